@@ -1,0 +1,145 @@
+/*
+ * strugepic_b200 -- C ABI of the B200-native StrugePIC symplectic PIC step.
+ *
+ * This is the drop-in boundary for the hot path of MoPHA/strugepic: the
+ * Hamiltonian-splitting sub-flows and composition drivers of
+ * include/strugepic_propagators.hpp.  The reference has no FFI of its own (its
+ * public interface is a C++ header API over AMReX containers), so each entry
+ * point below cites the reference interface it replaces; the C++ header
+ * include/strugepic_b200.hpp re-provides the reference's template names
+ * (Theta_map1/2/4<W>, G_Theta<comp,W>, G_Theta_E<W>, G_Theta_B, E_source,
+ * SimulationIO) as thin inline wrappers over these calls, and INTEGRATION.md
+ * shows the binding a reference maintainer would add.
+ *
+ * Conventions (those of every shipped reference driver, e.g.
+ * test/single_particle/main.cpp:106-107): ProbLo = 0, dx = dy = dz = 1,
+ * c = eps0 = mu0 = 1, all arithmetic FP64.  Host field buffers are
+ * [comp][k][j][i] over the VALID cells of this rank's brick (the layout of
+ * amrex::Array4 without guard cells); particle buffers are SoA.
+ *
+ * All functions return 0 on success and a negative SPIC_E* code otherwise;
+ * spic_last_error() gives the message.  Work is enqueued on the context's CUDA
+ * stream; calls that return data to the host synchronise that stream.
+ * There is no CPU fallback: spic_create fails when no sm_100 device is present.
+ */
+#ifndef STRUGEPIC_B200_H
+#define STRUGEPIC_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SPIC_OK 0
+#define SPIC_EINVAL (-1)   /* bad argument / unsupported configuration            */
+#define SPIC_ECUDA (-2)    /* CUDA runtime error                                   */
+#define SPIC_ENODEV (-3)   /* no usable GPU                                        */
+#define SPIC_ECFL (-4)     /* a particle moved >= 1 cell in one sub-flow           */
+#define SPIC_ENCCL (-5)    /* NCCL error / NCCL not loadable                       */
+#define SPIC_EIO (-6)      /* checkpoint file error                                */
+#define SPIC_ECAPACITY (-7)/* a device buffer (movers, migration) overflowed       */
+
+/* interpolation variants: src/interpolation/interpolation.cpp:19-84 and 87-157 */
+#define SPIC_INTERP_P8R2 0 /* 8th-order piecewise polynomial on [-2,2], W_range 2 */
+#define SPIC_INTERP_PWL 1  /* piecewise linear on [-1,1], W_range 1               */
+
+#define SPIC_FIELD_E 0
+#define SPIC_FIELD_B 1
+
+/* Theta_map4 coefficients.  The reference evaluates 1/(2*l+1) in integer
+ * arithmetic (include/strugepic_propagators.hpp:578) so alpha = 1, beta = -1. */
+#define SPIC_MAP4_REFERENCE 0
+#define SPIC_MAP4_YOSHIDA 1 /* alpha = 1/(2 - 2^(1/3)), the intended 4th-order scheme */
+
+/* particle engines */
+#define SPIC_ENGINE_BINNED 0 /* cell-binned SoA, warp-per-cell kernels (default) */
+#define SPIC_ENGINE_DIRECT 1 /* thread-per-particle, global atomics (diagnostic) */
+
+typedef struct spic_ctx spic_ctx;
+
+typedef struct spic_config {
+  int32_t n_cell[3];   /* GLOBAL domain in cells (x, y, z)                        */
+  int32_t periodic[3]; /* Geometry::isPeriodic; MABC acts on x when x is a wall   */
+  int32_t ng;          /* guard width, >= interpolation range (0: use the range)  */
+  int32_t interp;      /* SPIC_INTERP_*                                           */
+  int32_t map4_mode;   /* SPIC_MAP4_*                                             */
+  int32_t engine;      /* SPIC_ENGINE_*                                           */
+  int32_t device;      /* CUDA device ordinal                                     */
+  int32_t nranks;      /* z-slab decomposition: n_cell[2] % nranks == 0           */
+  int32_t rank;
+  int32_t reserved[7]; /* must be 0                                               */
+} spic_config;
+
+/* ---- lifetime -------------------------------------------------------------- */
+int spic_create(const spic_config* cfg, spic_ctx** out);
+int spic_destroy(spic_ctx* ctx);
+const char* spic_last_error(const spic_ctx* ctx); /* ctx may be NULL: last create error */
+int spic_sync(spic_ctx* ctx);
+/* this rank's brick: lo[3], n[3] in cells */
+int spic_local_box(const spic_ctx* ctx, int32_t lo[3], int32_t n[3]);
+
+/* ---- multi-GPU (replaces AMReX FillBoundary/SumBoundary/Redistribute over MPI,
+ *      SURVEY.md section 2.3).  id is an ncclUniqueId (128 bytes) from rank 0. ---- */
+int spic_comm_unique_id(void* id128);
+int spic_comm_init(spic_ctx* ctx, const void* id128);
+
+/* ---- state transfer (MultiFab / ParticleContainer contents) ------------------- */
+/* set_uniform_field: src/strugepic_util.cpp:26-41 */
+int spic_set_uniform_field(spic_ctx* ctx, int which, const double val[3]);
+int spic_set_field(spic_ctx* ctx, int which, const double* host);
+int spic_get_field(spic_ctx* ctx, int which, double* host);
+/* One species = one (q, m) pair, as every reference loader produces
+ * (src/strugepic_util.cpp:273-274).  Positions are GLOBAL coordinates; particles
+ * outside this rank's slab are rejected.  Returns the species id (>= 0). */
+int spic_add_species(spic_ctx* ctx, double q, double m, int64_t n, const double* x, const double* y,
+                     const double* z, const double* vx, const double* vy, const double* vz);
+/* add_particle_density(geom, P, uniform_density, ppc, m, q, v): src/strugepic_util.cpp:267-311,
+ * generated on the device from a counter-based RNG (strugepic_b200/synthetic.py is the
+ * host twin); per-particle charge q/ppc and mass m/ppc as in the reference. */
+int spic_load_uniform_plasma(spic_ctx* ctx, double q, double m, int32_t ppc, double v_th, uint64_t seed);
+int spic_num_species(const spic_ctx* ctx);
+int spic_num_particles(spic_ctx* ctx, int species, int64_t* n);
+int spic_get_particles(spic_ctx* ctx, int species, double* x, double* y, double* z, double* vx,
+                       double* vy, double* vz);
+int spic_set_particles(spic_ctx* ctx, int species, int64_t n, const double* x, const double* y,
+                       const double* z, const double* vx, const double* vy, const double* vz);
+
+/* ---- sub-flows (global updates: they own the guard-cell traffic) -------------- */
+/* G_Theta<comp,W>: include/strugepic_propagators.hpp:347-372 (kernel Theta, :80-244) */
+int spic_theta_axis(spic_ctx* ctx, int comp, double dt);
+/* G_Theta_E<W>: include/strugepic_propagators.hpp:52-71 (push_V_E :247-344, push_B_E cpp:93-95) */
+int spic_theta_E(spic_ctx* ctx, double dt);
+/* G_Theta_B: src/strugepic_propagators.cpp:102-113 (push_E_B cpp:97-99) */
+int spic_theta_B(spic_ctx* ctx, double dt);
+/* E_source::operator()(t): src/strugepic_propagators.cpp:22-41 */
+int spic_source(spic_ctx* ctx, int pos, int comp, double E0, double omega, double dt, double t);
+/* Theta_map1 / Theta_map2 / Theta_map4: include/strugepic_propagators.hpp:548-583; order in {1,2,4} */
+int spic_map(spic_ctx* ctx, int order, double dt);
+/* field_only step: examples/field_only/main.cpp:142-145 */
+int spic_field_only_step(spic_ctx* ctx, int pos, int comp, double E0, double omega, double dt, int step);
+
+/* ---- diagnostics ------------------------------------------------------------- */
+/* get_total_energy: src/strugepic_util.cpp:364-394; out = {field, kinetic}, summed over ranks */
+int spic_energy(spic_ctx* ctx, double out[2]);
+/* discrete Gauss residual G = div- E - rho, [k][j][i] over valid cells */
+int spic_gauss_residual(spic_ctx* ctx, double* host);
+
+/* ---- checkpoint / restart: SimulationIO::write(step,true) / read(step),
+ *      include/strugepic_util.hpp:126-132, src/strugepic_util.cpp:66-70 ---------- */
+int spic_checkpoint_write(spic_ctx* ctx, const char* path);
+int spic_checkpoint_read(spic_ctx* ctx, const char* path);
+
+/* ---- introspection for benchmarks --------------------------------------------- */
+int64_t spic_launch_count(const spic_ctx* ctx); /* kernels launched so far */
+/* CUDA-event time (ms) accumulated inside the particle kernels since the last reset */
+int spic_kernel_time_ms(spic_ctx* ctx, int reset, double* particle_ms, int64_t* particle_launches);
+int spic_set_option(spic_ctx* ctx, const char* name, double value);
+void* spic_stream(spic_ctx* ctx); /* cudaStream_t */
+/* FP64 FMA micro-benchmark for the roofline denominator: returns TFLOP/s */
+int spic_probe_fp64_tflops(int device, double seconds, double* tflops);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,570 @@
+// C-ABI layer: context, state transfer, global sub-flows and composition drivers.
+//
+// The "global update" functions below own the guard-cell protocol exactly as the
+// reference's G_* functions do (include/strugepic_propagators.hpp:52-71, 347-372;
+// src/strugepic_propagators.cpp:102-113), with AMReX's FillBoundary / setBndry /
+// SumBoundary / Redistribute replaced by device kernels (+ NCCL across z slabs).
+#include <math.h>
+#include <stdio.h>
+#include <string.h>
+
+#include "engine.cuh"
+#include "spic_internal.cuh"
+
+using namespace spic;
+
+struct spic_ctx : public spic::Ctx {};
+
+namespace {
+std::string g_create_error;
+
+int fail(Ctx* c, int code, const std::string& msg) {
+  if (c) c->err = msg;
+  else g_create_error = msg;
+  return code;
+}
+
+int check_flags(Ctx* c) {
+  int h[2] = {0, 0};
+  cudaError_t e = cudaMemcpyAsync(h, c->d_flags, sizeof h, cudaMemcpyDeviceToHost, c->stream);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+  if (e != cudaSuccess) return fail(c, SPIC_ECUDA, std::string("device error: ") + cudaGetErrorString(e));
+  if (h[0] & 1) return fail(c, SPIC_ECFL, "a particle moved >= 1 cell in one sub-flow (|v*dt| must be < 1)");
+  if (h[0] & 2) return fail(c, SPIC_ECFL, "a particle left a non-periodic domain");
+  if (h[1]) return fail(c, SPIC_ECAPACITY, "a device particle buffer overflowed (movers / migration / tail)");
+  return SPIC_OK;
+}
+
+int alloc_soa(Ctx* c, ParticleSoA& p, long n) {
+  for (int d = 0; d < 3; ++d) {
+    SPIC_CUDA_CHECK(c, cudaMalloc(&p.x[d], sizeof(double) * (size_t)(n > 0 ? n : 1)));
+    SPIC_CUDA_CHECK(c, cudaMalloc(&p.v[d], sizeof(double) * (size_t)(n > 0 ? n : 1)));
+  }
+  return SPIC_OK;
+}
+void free_soa(ParticleSoA& p) {
+  for (int d = 0; d < 3; ++d) {
+    if (p.x[d]) cudaFree(p.x[d]);
+    if (p.v[d]) cudaFree(p.v[d]);
+    p.x[d] = p.v[d] = nullptr;
+  }
+}
+
+// guard refresh of a field: neighbour slabs over NCCL when decomposed, then the
+// local periodic images (FillBoundary semantics)
+int halo_fill(Ctx* c, double* F) {
+  if (c->cfg.nranks > 1) {
+    int rc = comm_exchange_fill(c, F);
+    if (rc) return rc;
+  }
+  launch_fill_boundary(c, F, c->g.zlocal != 0);
+  return SPIC_OK;
+}
+int halo_sum(Ctx* c, double* F, int comp) {
+  launch_sum_boundary(c, F, comp, c->g.zlocal != 0);
+  if (c->cfg.nranks > 1) return comm_exchange_sum(c, F, comp);
+  return SPIC_OK;
+}
+}  // namespace
+
+extern "C" {
+
+const char* spic_last_error(const spic_ctx* ctx) { return ctx ? ctx->err.c_str() : g_create_error.c_str(); }
+
+int spic_create(const spic_config* cfg, spic_ctx** out) {
+  if (!cfg || !out) return fail(nullptr, SPIC_EINVAL, "null argument");
+  *out = nullptr;
+  if (cfg->interp != SPIC_INTERP_P8R2 && cfg->interp != SPIC_INTERP_PWL)
+    return fail(nullptr, SPIC_EINVAL, "interp must be SPIC_INTERP_P8R2 or SPIC_INTERP_PWL");
+  const int W = cfg->interp == SPIC_INTERP_P8R2 ? 2 : 1;
+  const int ng = cfg->ng == 0 ? W : cfg->ng;
+  if (ng < W) return fail(nullptr, SPIC_EINVAL, "ng must be >= the interpolation range");
+  const int nranks = cfg->nranks <= 0 ? 1 : cfg->nranks;
+  for (int d = 0; d < 3; ++d)
+    if (cfg->n_cell[d] < 1) return fail(nullptr, SPIC_EINVAL, "n_cell must be >= 1");
+  if (cfg->rank < 0 || cfg->rank >= nranks) return fail(nullptr, SPIC_EINVAL, "rank out of range");
+  if (cfg->n_cell[2] % nranks) return fail(nullptr, SPIC_EINVAL, "n_cell[2] must be divisible by nranks");
+  if (nranks > 1 && !cfg->periodic[2]) return fail(nullptr, SPIC_EINVAL, "z must be periodic when nranks > 1");
+  if (nranks > 1 && cfg->n_cell[2] / nranks < ng)
+    return fail(nullptr, SPIC_EINVAL, "each z slab must be at least ng cells thick");
+
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+    return fail(nullptr, SPIC_ENODEV, "no CUDA device: strugepic_b200 has no CPU fallback");
+  if (cfg->device < 0 || cfg->device >= ndev) return fail(nullptr, SPIC_EINVAL, "device ordinal out of range");
+  cudaDeviceProp prop;
+  if (cudaGetDeviceProperties(&prop, cfg->device) != cudaSuccess || prop.major < 10)
+    return fail(nullptr, SPIC_ENODEV, "device is not sm_100 class (this library is built for sm_100a only)");
+  if (cudaSetDevice(cfg->device) != cudaSuccess) return fail(nullptr, SPIC_ECUDA, "cudaSetDevice failed");
+
+  spic_ctx* c = new spic_ctx();
+  c->cfg = *cfg;
+  c->cfg.ng = ng;
+  c->cfg.nranks = nranks;
+  c->W = W;
+  c->sm_count = prop.multiProcessorCount;
+  Grid& g = c->g;
+  for (int d = 0; d < 3; ++d) {
+    g.gn[d] = cfg->n_cell[d];
+    g.n[d] = cfg->n_cell[d];
+    g.per[d] = cfg->periodic[d] ? 1 : 0;
+  }
+  g.n[2] = cfg->n_cell[2] / nranks;
+  g.z0 = cfg->rank * g.n[2];
+  g.zlocal = nranks == 1 ? 1 : 0;
+  g.ng = ng;
+  g.pj = (g.n[0] + 2 * ng + 1) & ~1L;
+  g.pk = g.pj * (g.n[1] + 2 * ng);
+  g.pc = g.pk * (g.n[2] + 2 * ng);
+
+  auto bail = [&](const char* what) {
+    std::string m = std::string(what) + ": " + cudaGetErrorString(cudaGetLastError());
+    spic_destroy(c);
+    return fail(nullptr, SPIC_ECUDA, m);
+  };
+  if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess) return bail("stream");
+  cudaEventCreate(&c->ev0);
+  cudaEventCreate(&c->ev1);
+  const size_t fbytes = sizeof(double) * (size_t)c->field_elems();
+  if (cudaMalloc(&c->E, fbytes) != cudaSuccess) return bail("cudaMalloc E");
+  if (cudaMalloc(&c->B, fbytes) != cudaSuccess) return bail("cudaMalloc B");
+  cudaMemsetAsync(c->E, 0, fbytes, c->stream);
+  cudaMemsetAsync(c->B, 0, fbytes, c->stream);
+  c->scratch_elems = 3 * g.cells() + 4096;
+  if (cudaMalloc(&c->scratch, sizeof(double) * (size_t)c->scratch_elems) != cudaSuccess) return bail("cudaMalloc scratch");
+  if (cudaMalloc(&c->d_flags, 8 * sizeof(int)) != cudaSuccess) return bail("cudaMalloc flags");
+  cudaMemsetAsync(c->d_flags, 0, 8 * sizeof(int), c->stream);
+  if (cudaStreamSynchronize(c->stream) != cudaSuccess) return bail("init");
+  *out = c;
+  return SPIC_OK;
+}
+
+int spic_destroy(spic_ctx* c) {
+  if (!c) return SPIC_OK;
+  cudaSetDevice(c->cfg.device);
+  if (c->stream) cudaStreamSynchronize(c->stream);
+  comm_destroy(c);
+  for (auto& s : c->sp) {
+    free_soa(s.d);
+    engine_free_species(c, s);
+  }
+  engine_destroy(c);
+  if (c->E) cudaFree(c->E);
+  if (c->B) cudaFree(c->B);
+  if (c->scratch) cudaFree(c->scratch);
+  if (c->d_flags) cudaFree(c->d_flags);
+  if (c->ev0) cudaEventDestroy(c->ev0);
+  if (c->ev1) cudaEventDestroy(c->ev1);
+  if (c->stream) cudaStreamDestroy(c->stream);
+  delete c;
+  return SPIC_OK;
+}
+
+int spic_sync(spic_ctx* c) {
+  if (!c) return SPIC_EINVAL;
+  cudaSetDevice(c->cfg.device);
+  return check_flags(c);
+}
+
+int spic_local_box(const spic_ctx* c, int32_t lo[3], int32_t n[3]) {
+  if (!c) return SPIC_EINVAL;
+  lo[0] = lo[1] = 0;
+  lo[2] = c->g.z0;
+  for (int d = 0; d < 3; ++d) n[d] = c->g.n[d];
+  return SPIC_OK;
+}
+
+// ---- fields ---------------------------------------------------------------------
+int spic_set_uniform_field(spic_ctx* c, int which, const double val[3]) {
+  if (!c || (which != SPIC_FIELD_E && which != SPIC_FIELD_B)) return SPIC_EINVAL;
+  cudaSetDevice(c->cfg.device);
+  double* F = which == SPIC_FIELD_E ? c->E : c->B;
+  launch_set_uniform(c, F, val);
+  return halo_fill(c, F);
+}
+int spic_set_field(spic_ctx* c, int which, const double* host) {
+  if (!c || !host || (which != SPIC_FIELD_E && which != SPIC_FIELD_B)) return SPIC_EINVAL;
+  cudaSetDevice(c->cfg.device);
+  double* F = which == SPIC_FIELD_E ? c->E : c->B;
+  const size_t bytes = sizeof(double) * 3 * (size_t)c->g.cells();
+  SPIC_CUDA_CHECK(c, cudaMemcpyAsync(c->scratch, host, bytes, cudaMemcpyHostToDevice, c->stream));
+  launch_unpack_field(c, F, c->scratch);
+  int rc = halo_fill(c, F);  // as the drivers do after init (test/single_particle/main.cpp:132-133)
+  if (rc) return rc;
+  SPIC_CUDA_CHECK(c, cudaStreamSynchronize(c->stream));
+  return SPIC_OK;
+}
+int spic_get_field(spic_ctx* c, int which, double* host) {
+  if (!c || !host || (which != SPIC_FIELD_E && which != SPIC_FIELD_B)) return SPIC_EINVAL;
+  cudaSetDevice(c->cfg.device);
+  const double* F = which == SPIC_FIELD_E ? c->E : c->B;
+  const size_t bytes = sizeof(double) * 3 * (size_t)c->g.cells();
+  launch_pack_field(c, F, c->scratch);
+  SPIC_CUDA_CHECK(c, cudaMemcpyAsync(host, c->scratch, bytes, cudaMemcpyDeviceToHost, c->stream));
+  return check_flags(c);
+}
+
+// ---- particles --------------------------------------------------------------------
+int spic_num_species(const spic_ctx* c) { return c ? (int)c->sp.size() : SPIC_EINVAL; }
+
+static int upload_list(spic_ctx* c, Species& s, int64_t n, const double* const* hx, const double* const* hv) {
+  free_soa(s.d);
+  s.nd = s.capd = 0;
+  int rc = alloc_soa(c, s.d, n);
+  if (rc) return rc;
+  s.capd = n;
+  s.nd = n;
+  for (int d = 0; d < 3; ++d) {
+    SPIC_CUDA_CHECK(c, cudaMemcpyAsync(s.d.x[d], hx[d], sizeof(double) * (size_t)n, cudaMemcpyHostToDevice, c->stream));
+    SPIC_CUDA_CHECK(c, cudaMemcpyAsync(s.d.v[d], hv[d], sizeof(double) * (size_t)n, cudaMemcpyHostToDevice, c->stream));
+  }
+  SPIC_CUDA_CHECK(c, cudaStreamSynchronize(c->stream));
+  return SPIC_OK;
+}
+
+int spic_add_species(spic_ctx* c, double q, double m, int64_t n, const double* x, const double* y, const double* z,
+                     const double* vx, const double* vy, const double* vz) {
+  if (!c || n < 0 || m == 0.0) return SPIC_EINVAL;
+  if (n > 0 && (!x || !y || !z || !vx || !vy || !vz)) return fail(c, SPIC_EINVAL, "null particle array");
+  cudaSetDevice(c->cfg.device);
+  Species s;
+  s.q = q;
+  s.m = m;
+  c->sp.push_back(s);
+  const int id = (int)c->sp.size() - 1;
+  int rc = spic_set_particles(c, id, n, x, y, z, vx, vy, vz);
+  if (rc) {
+    c->sp.pop_back();
+    return rc;
+  }
+  return id;
+}
+
+int spic_set_particles(spic_ctx* c, int species, int64_t n, const double* x, const double* y, const double* z,
+                       const double* vx, const double* vy, const double* vz) {
+  if (!c || species < 0 || species >= (int)c->sp.size() || n < 0) return SPIC_EINVAL;
+  cudaSetDevice(c->cfg.device);
+  Species& s = c->sp[species];
+  // every particle must sit inside this rank's slab (and inside the domain)
+  const double zlo = (double)c->g.z0, zhi = (double)(c->g.z0 + c->g.n[2]);
+  for (int64_t i = 0; i < n; ++i) {
+    if (!(x[i] >= 0.0 && x[i] < c->g.gn[0] && y[i] >= 0.0 && y[i] < c->g.gn[1] && z[i] >= zlo && z[i] < zhi))
+      return fail(c, SPIC_EINVAL, "particle outside this rank's brick");
+  }
+  const double* hx[3] = {x, y, z};
+  const double* hv[3] = {vx, vy, vz};
+  engine_free_species(c, s);
+  int rc = upload_list(c, s, n, hx, hv);
+  if (rc) return rc;
+  return engine_ingest(c, s);  // BINNED: move the list into cell bins
+}
+
+int spic_load_uniform_plasma(spic_ctx* c, double q, double m, int32_t ppc, double v_th, uint64_t seed) {
+  if (!c || ppc < 1 || m == 0.0) return SPIC_EINVAL;
+  cudaSetDevice(c->cfg.device);
+  Species s;
+  s.q = q / ppc;  // q_c, m_c: src/strugepic_util.cpp:273-274
+  s.m = m / ppc;
+  const long n = c->g.cells() * ppc;
+  int rc = alloc_soa(c, s.d, n);
+  if (rc) return rc;
+  s.nd = s.capd = n;
+  launch_load_uniform(c, s.d, n, ppc, v_th, seed);
+  c->sp.push_back(s);
+  rc = engine_ingest(c, c->sp.back());
+  if (rc) return rc;
+  return (int)c->sp.size() - 1;
+}
+
+int spic_num_particles(spic_ctx* c, int species, int64_t* n) {
+  if (!c || !n || species < 0 || species >= (int)c->sp.size()) return SPIC_EINVAL;
+  cudaSetDevice(c->cfg.device);
+  long nb = 0;
+  int rc = engine_count(c, c->sp[species], &nb);
+  if (rc) return rc;
+  *n = nb + c->sp[species].nd;
+  return SPIC_OK;
+}
+
+int spic_get_particles(spic_ctx* c, int species, double* x, double* y, double* z, double* vx, double* vy, double* vz) {
+  if (!c || species < 0 || species >= (int)c->sp.size()) return SPIC_EINVAL;
+  cudaSetDevice(c->cfg.device);
+  Species& s = c->sp[species];
+  double* hx[3] = {x, y, z};
+  double* hv[3] = {vx, vy, vz};
+  long nb = 0;
+  int rc = engine_gather(c, s, hx, hv, &nb);  // binned particles first (cell order)
+  if (rc) return rc;
+  for (int d = 0; d < 3 && s.nd > 0; ++d) {
+    SPIC_CUDA_CHECK(c, cudaMemcpyAsync(hx[d] + nb, s.d.x[d], sizeof(double) * (size_t)s.nd, cudaMemcpyDeviceToHost, c->stream));
+    SPIC_CUDA_CHECK(c, cudaMemcpyAsync(hv[d] + nb, s.d.v[d], sizeof(double) * (size_t)s.nd, cudaMemcpyDeviceToHost, c->stream));
+  }
+  return check_flags(c);
+}
+
+// ---- sub-flows ------------------------------------------------------------------------
+int spic_theta_axis(spic_ctx* c, int comp, double dt) {
+  if (!c || comp < 0 || comp > 2) return SPIC_EINVAL;
+  cudaSetDevice(c->cfg.device);
+  int rc = halo_fill(c, c->B);  // B.FillBoundary            hpp:350
+  if (rc) return rc;
+  launch_zero_guards(c, c->E);  // E.setBndry(0)             hpp:351-352
+  for (auto& s : c->sp) {       // Theta<comp,W,...> per tile hpp:353-365
+    rc = engine_theta_axis(c, s, comp, dt);
+    if (rc) return rc;
+    launch_theta_axis_direct(c, s.d, s.nd, s.q, s.m, comp, dt);
+  }
+  rc = halo_sum(c, c->E, comp);  // E.SumBoundary             hpp:367
+  if (rc) return rc;
+  if (comp == 2 && c->cfg.nranks > 1) rc = comm_migrate(c);  // P.Redistribute across slabs, hpp:368
+  return rc;
+}
+
+int spic_theta_E(spic_ctx* c, double dt) {
+  if (!c) return SPIC_EINVAL;
+  cudaSetDevice(c->cfg.device);
+  int rc = halo_fill(c, c->E);  // E.FillBoundary  hpp:56
+  if (rc) return rc;
+  for (auto& s : c->sp) {       // push_V_E        hpp:57-62
+    rc = engine_push_v_e(c, s, dt);
+    if (rc) return rc;
+    launch_push_v_e_direct(c, s.d, s.nd, s.q, s.m, dt);
+  }
+  launch_curl_E_into_B(c, dt);  // push_B_E        hpp:63-68
+  return SPIC_OK;
+}
+
+int spic_theta_B(spic_ctx* c, double dt) {
+  if (!c) return SPIC_EINVAL;
+  cudaSetDevice(c->cfg.device);
+  int rc = halo_fill(c, c->B);  // cpp:104
+  if (rc) return rc;
+  launch_curl_B_into_E(c, dt);  // cpp:105-110
+  return SPIC_OK;
+}
+
+int spic_source(spic_ctx* c, int pos, int comp, double E0, double omega, double dt, double t) {
+  if (!c || comp < 0 || comp > 2) return SPIC_EINVAL;
+  cudaSetDevice(c->cfg.device);
+  if (pos >= 0 && pos < c->g.n[0]) launch_source(c, pos, comp, 2 * E0 * sin(omega * t) * dt);  // cpp:32-36
+  return halo_fill(c, c->E);                                                                   // cpp:40
+}
+
+static int map2(spic_ctx* c, double dt) {  // hpp:559-572
+  int rc;
+  if ((rc = spic_theta_E(c, dt / 2))) return rc;
+  if ((rc = spic_theta_axis(c, 0, dt / 2))) return rc;
+  if ((rc = spic_theta_axis(c, 1, dt / 2))) return rc;
+  if ((rc = spic_theta_axis(c, 2, dt / 2))) return rc;
+  if ((rc = spic_theta_B(c, dt))) return rc;
+  if ((rc = spic_theta_axis(c, 2, dt / 2))) return rc;
+  if ((rc = spic_theta_axis(c, 1, dt / 2))) return rc;
+  if ((rc = spic_theta_axis(c, 0, dt / 2))) return rc;
+  return spic_theta_E(c, dt / 2);
+}
+
+int spic_map(spic_ctx* c, int order, double dt) {
+  if (!c) return SPIC_EINVAL;
+  int rc;
+  if (order == 1) {  // hpp:548-557
+    if ((rc = spic_theta_B(c, dt))) return rc;
+    if ((rc = spic_theta_E(c, dt))) return rc;
+    if ((rc = spic_theta_axis(c, 2, dt))) return rc;
+    if ((rc = spic_theta_axis(c, 1, dt))) return rc;
+    return spic_theta_axis(c, 0, dt);
+  }
+  if (order == 2) return map2(c, dt);
+  if (order == 4) {  // hpp:574-583; alpha = 1, beta = -1 in the reference (integer division at :578)
+    const double alpha = c->cfg.map4_mode == SPIC_MAP4_YOSHIDA ? 1.0 / (2.0 - cbrt(2.0)) : 1.0;
+    const double beta = 1 - 2 * alpha;
+    if ((rc = map2(c, alpha * dt))) return rc;
+    if ((rc = map2(c, beta * dt))) return rc;
+    return map2(c, alpha * dt);
+  }
+  return fail(c, SPIC_EINVAL, "order must be 1, 2 or 4");
+}
+
+int spic_field_only_step(spic_ctx* c, int pos, int comp, double E0, double omega, double dt, int step) {
+  int rc;  // examples/field_only/main.cpp:142-145
+  if ((rc = spic_theta_E(c, dt / 2))) return rc;
+  if ((rc = spic_source(c, pos, comp, E0, omega, dt, dt * step))) return rc;
+  if ((rc = spic_theta_B(c, dt))) return rc;
+  return spic_theta_E(c, dt / 2);
+}
+
+// ---- diagnostics ---------------------------------------------------------------------
+int spic_energy(spic_ctx* c, double out[2]) {
+  if (!c || !out) return SPIC_EINVAL;
+  cudaSetDevice(c->cfg.device);
+  double ss[6];
+  field_energy(c, ss);
+  double* acc = c->scratch + 1024 * 3 + 8;
+  SPIC_CUDA_CHECK(c, cudaMemsetAsync(acc, 0, sizeof(double), c->stream));
+  for (auto& s : c->sp) {
+    int rc = engine_kinetic(c, s, acc);
+    if (rc) return rc;
+    launch_kinetic_energy(c, s.d, s.nd, s.m, acc);
+  }
+  double kin = 0;
+  SPIC_CUDA_CHECK(c, cudaMemcpyAsync(&kin, acc, sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+  int rc = check_flags(c);
+  if (rc) return rc;
+  double v[2] = {0.5 * (ss[0] + ss[1] + ss[2] + ss[3] + ss[4] + ss[5]), kin};  // util.cpp:388-393, dV = 1
+  if (c->cfg.nranks > 1 && (rc = comm_allreduce_sum(c, v, 2))) return rc;
+  out[0] = v[0];
+  out[1] = v[1];
+  return SPIC_OK;
+}
+
+int spic_gauss_residual(spic_ctx* c, double* host) {
+  if (!c || !host) return SPIC_EINVAL;
+  if (c->cfg.nranks > 1) return fail(c, SPIC_EINVAL, "gauss residual is a single-rank diagnostic");
+  cudaSetDevice(c->cfg.device);
+  int rc = halo_fill(c, c->E);
+  if (rc) return rc;
+  double* out = c->scratch;
+  const size_t bytes = sizeof(double) * (size_t)c->g.cells();
+  SPIC_CUDA_CHECK(c, cudaMemsetAsync(out, 0, bytes, c->stream));
+  for (auto& s : c->sp) {
+    rc = engine_deposit_rho(c, s, out);
+    if (rc) return rc;
+    launch_deposit_rho(c, s.d, s.nd, s.q, out);
+  }
+  launch_gauss_div(c, out);
+  SPIC_CUDA_CHECK(c, cudaMemcpyAsync(host, out, bytes, cudaMemcpyDeviceToHost, c->stream));
+  return check_flags(c);
+}
+
+// ---- checkpoint -------------------------------------------------------------------------
+// Own binary format (the reference delegates to AMReX VisMF / ParticleContainer::Checkpoint,
+// include/strugepic_util.hpp:126-132): header, E, B (valid cells, [c][k][j][i]), then per
+// species q, m, n and the six SoA arrays.  One file per rank.
+struct CkptHeader {
+  char magic[8];
+  int32_t version, interp, n_cell[3], periodic[3], nranks, rank, nspecies, pad;
+};
+
+int spic_checkpoint_write(spic_ctx* c, const char* path) {
+  if (!c || !path) return SPIC_EINVAL;
+  cudaSetDevice(c->cfg.device);
+  FILE* f = fopen(path, "wb");
+  if (!f) return fail(c, SPIC_EIO, std::string("cannot open ") + path);
+  CkptHeader h{};
+  memcpy(h.magic, "SPICB200", 8);
+  h.version = 1;
+  h.interp = c->cfg.interp;
+  for (int d = 0; d < 3; ++d) {
+    h.n_cell[d] = c->g.gn[d];
+    h.periodic[d] = c->g.per[d];
+  }
+  h.nranks = c->cfg.nranks;
+  h.rank = c->cfg.rank;
+  h.nspecies = (int)c->sp.size();
+  bool ok = fwrite(&h, sizeof h, 1, f) == 1;
+  std::vector<double> buf(3 * (size_t)c->g.cells());
+  for (int w = 0; w < 2 && ok; ++w) {
+    int rc = spic_get_field(c, w, buf.data());
+    if (rc) {
+      fclose(f);
+      return rc;
+    }
+    ok = fwrite(buf.data(), sizeof(double), buf.size(), f) == buf.size();
+  }
+  for (int s = 0; s < (int)c->sp.size() && ok; ++s) {
+    int64_t n = 0;
+    int rc = spic_num_particles(c, s, &n);
+    if (rc) {
+      fclose(f);
+      return rc;
+    }
+    std::vector<double> p(6 * (size_t)n + 1);
+    rc = spic_get_particles(c, s, &p[0], &p[n], &p[2 * n], &p[3 * n], &p[4 * n], &p[5 * n]);
+    if (rc) {
+      fclose(f);
+      return rc;
+    }
+    double qm[2] = {c->sp[s].q, c->sp[s].m};
+    ok = fwrite(qm, sizeof(double), 2, f) == 2 && fwrite(&n, sizeof n, 1, f) == 1 &&
+         fwrite(p.data(), sizeof(double), 6 * (size_t)n, f) == 6 * (size_t)n;
+  }
+  ok = (fclose(f) == 0) && ok;
+  return ok ? SPIC_OK : fail(c, SPIC_EIO, std::string("short write to ") + path);
+}
+
+int spic_checkpoint_read(spic_ctx* c, const char* path) {
+  if (!c || !path) return SPIC_EINVAL;
+  cudaSetDevice(c->cfg.device);
+  FILE* f = fopen(path, "rb");
+  if (!f) return fail(c, SPIC_EIO, std::string("cannot open ") + path);
+  CkptHeader h{};
+  if (fread(&h, sizeof h, 1, f) != 1 || memcmp(h.magic, "SPICB200", 8) != 0 || h.version != 1) {
+    fclose(f);
+    return fail(c, SPIC_EIO, "not a strugepic_b200 checkpoint");
+  }
+  if (h.interp != c->cfg.interp || h.nranks != c->cfg.nranks || h.rank != c->cfg.rank || h.n_cell[0] != c->g.gn[0] ||
+      h.n_cell[1] != c->g.gn[1] || h.n_cell[2] != c->g.gn[2]) {
+    fclose(f);
+    return fail(c, SPIC_EIO, "checkpoint geometry / decomposition does not match this context");
+  }
+  std::vector<double> buf(3 * (size_t)c->g.cells());
+  for (int w = 0; w < 2; ++w) {
+    if (fread(buf.data(), sizeof(double), buf.size(), f) != buf.size()) {
+      fclose(f);
+      return fail(c, SPIC_EIO, "truncated checkpoint (fields)");
+    }
+    int rc = spic_set_field(c, w, buf.data());
+    if (rc) {
+      fclose(f);
+      return rc;
+    }
+  }
+  for (auto& s : c->sp) {
+    free_soa(s.d);
+    engine_free_species(c, s);
+  }
+  c->sp.clear();
+  for (int s = 0; s < h.nspecies; ++s) {
+    double qm[2];
+    int64_t n = 0;
+    if (fread(qm, sizeof(double), 2, f) != 2 || fread(&n, sizeof n, 1, f) != 1 || n < 0) {
+      fclose(f);
+      return fail(c, SPIC_EIO, "truncated checkpoint (species header)");
+    }
+    std::vector<double> p(6 * (size_t)n + 1);
+    if (fread(p.data(), sizeof(double), 6 * (size_t)n, f) != 6 * (size_t)n) {
+      fclose(f);
+      return fail(c, SPIC_EIO, "truncated checkpoint (particles)");
+    }
+    int rc = spic_add_species(c, qm[0], qm[1], n, &p[0], &p[n], &p[2 * n], &p[3 * n], &p[4 * n], &p[5 * n]);
+    if (rc < 0) {
+      fclose(f);
+      return rc;
+    }
+  }
+  fclose(f);
+  return SPIC_OK;
+}
+
+// ---- introspection ------------------------------------------------------------------------
+int64_t spic_launch_count(const spic_ctx* c) { return c ? c->launches : 0; }
+int spic_kernel_time_ms(spic_ctx* c, int reset, double* particle_ms, int64_t* particle_launches) {
+  if (!c) return SPIC_EINVAL;
+  if (particle_ms) *particle_ms = c->particle_ms;
+  if (particle_launches) *particle_launches = c->particle_launches;
+  if (reset) {
+    c->particle_ms = 0;
+    c->particle_launches = 0;
+  }
+  return SPIC_OK;
+}
+int spic_set_option(spic_ctx* c, const char* name, double value) {
+  if (!c || !name) return SPIC_EINVAL;
+  if (!strcmp(name, "time_kernels")) {
+    c->time_kernels = value != 0;
+    return SPIC_OK;
+  }
+  return engine_set_option(c, name, value);
+}
+void* spic_stream(spic_ctx* c) { return c ? (void*)c->stream : nullptr; }
+
+}  // extern "C"

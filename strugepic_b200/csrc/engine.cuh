@@ -1,0 +1,27 @@
+// Interfaces of the binned particle engine (particles_binned.cu) and of the
+// multi-GPU layer (comm.cu) used by the C-ABI layer (api.cu).
+#pragma once
+#include "spic_internal.cuh"
+
+namespace spic {
+
+// ---- cell-binned engine ------------------------------------------------------------
+int engine_ingest(Ctx* c, Species& s);  // move s.d (direct list) into cell bins (no-op for ENGINE_DIRECT)
+void engine_free_species(Ctx* c, Species& s);
+void engine_destroy(Ctx* c);
+int engine_count(Ctx* c, Species& s, long* nb);
+int engine_gather(Ctx* c, Species& s, double* hx[3], double* hv[3], long* nb);
+int engine_theta_axis(Ctx* c, Species& s, int comp, double dt);
+int engine_push_v_e(Ctx* c, Species& s, double dt);
+int engine_kinetic(Ctx* c, Species& s, double* acc);
+int engine_deposit_rho(Ctx* c, Species& s, double* out);
+int engine_set_option(Ctx* c, const char* name, double value);
+
+// ---- z-slab decomposition over NCCL --------------------------------------------------
+int comm_exchange_fill(Ctx* c, double* F);           // owner planes -> neighbour guard planes
+int comm_exchange_sum(Ctx* c, double* F, int comp);  // guard planes added into the neighbour's owner planes
+int comm_migrate(Ctx* c);                            // particles that crossed a slab face change rank
+int comm_allreduce_sum(Ctx* c, double* v, int n);
+void comm_destroy(Ctx* c);
+
+}  // namespace spic

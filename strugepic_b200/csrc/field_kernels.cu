@@ -1,0 +1,352 @@
+// Field-only kernels: guard-cell protocol, curl sweeps, MABC, source, norms.
+//
+// Reference behaviour restated here (paths relative to /root/reference):
+//   E_curl / curl_fdiff_1   src/strugepic_propagators.cpp:71-80, 54-60
+//   B_curl / curl_bdiff_1   src/strugepic_propagators.cpp:82-91, 63-69
+//   push_ff, construct_interior, MABC_bad<X>
+//                           include/strugepic_propagators.hpp:512-527, 499-510, 447-476
+//   E_source::operator()    src/strugepic_propagators.cpp:22-41
+//   FillBoundary / setBndry / SumBoundary call sites
+//                           include/strugepic_propagators.hpp:56, 350-352, 367
+// These are HBM-streaming stencils (72 B per cell per curl sweep); grids are sized
+// in whole waves of the SM count and rows are read with the x index fastest.
+#include "spic_internal.cuh"
+
+namespace spic {
+
+namespace {
+
+constexpr int kBlock = 256;
+
+inline int grid_for(const Ctx* c, long n, int block = kBlock) {
+  long b = (n + block - 1) / block;
+  const long cap = (long)c->sm_count * 16;  // grid-stride beyond 16 resident blocks per SM
+  if (b > cap) b = cap;
+  if (b < 1) b = 1;
+  return (int)b;
+}
+
+// periodic image of a (possibly guard) index into [0,n); returns false beyond a wall
+__device__ __forceinline__ bool image_of(int idx, int n, int per, int& out) {
+  if (idx >= 0 && idx < n) {
+    out = idx;
+    return true;
+  }
+  if (!per) return false;
+  int r = idx % n;
+  out = r < 0 ? r + n : r;
+  return true;
+}
+
+__global__ void k_fill_boundary(Grid g, double* __restrict__ F, int z_too) {
+  const int gx = g.n[0] + 2 * g.ng, gy = g.n[1] + 2 * g.ng, gz = g.n[2] + 2 * g.ng;
+  const long total = (long)gx * gy * gz;
+  for (long t = blockIdx.x * (long)blockDim.x + threadIdx.x; t < total; t += (long)gridDim.x * blockDim.x) {
+    const int i = (int)(t % gx) - g.ng;
+    const int j = (int)((t / gx) % gy) - g.ng;
+    const int k = (int)(t / ((long)gx * gy)) - g.ng;
+    const bool vi = i >= 0 && i < g.n[0], vj = j >= 0 && j < g.n[1], vk = k >= 0 && k < g.n[2];
+    if (vi && vj && vk) continue;
+    int si, sj, sk;
+    if (!image_of(i, g.n[0], g.per[0], si)) continue;
+    if (!image_of(j, g.n[1], g.per[1], sj)) continue;
+    if (z_too) {
+      if (!image_of(k, g.n[2], g.per[2], sk)) continue;
+    } else {
+      // z guards of the valid (i,j) columns arrive from the neighbour rank
+      if (vi && vj) continue;
+      sk = k;
+    }
+    const long d = g.at(i, j, k), s = g.at(si, sj, sk);
+    F[d] = F[s];
+    F[d + g.pc] = F[s + g.pc];
+    F[d + 2 * g.pc] = F[s + 2 * g.pc];
+  }
+}
+
+__global__ void k_zero_guards(Grid g, double* __restrict__ F) {
+  const int gx = g.n[0] + 2 * g.ng, gy = g.n[1] + 2 * g.ng, gz = g.n[2] + 2 * g.ng;
+  const long total = (long)gx * gy * gz;
+  for (long t = blockIdx.x * (long)blockDim.x + threadIdx.x; t < total; t += (long)gridDim.x * blockDim.x) {
+    const int i = (int)(t % gx) - g.ng;
+    const int j = (int)((t / gx) % gy) - g.ng;
+    const int k = (int)(t / ((long)gx * gy)) - g.ng;
+    if (i >= 0 && i < g.n[0] && j >= 0 && j < g.n[1] && k >= 0 && k < g.n[2]) continue;
+    const long d = g.at(i, j, k);
+    F[d] = 0.0;
+    F[d + g.pc] = 0.0;
+    F[d + 2 * g.pc] = 0.0;
+  }
+}
+
+// Owner-centric fold: each valid cell adds up its guard images in a fixed order
+// (deterministic; no atomics).  With z_too == 0 the z images are folded by the
+// neighbour exchange instead and the x/y fold also runs over the z guard planes.
+__global__ void k_sum_boundary(Grid g, double* __restrict__ F, int comp, int z_too) {
+  const int klo = z_too ? 0 : -g.ng, khi = z_too ? g.n[2] : g.n[2] + g.ng;
+  const long total = (long)g.n[0] * g.n[1] * (khi - klo);
+  double* Fc = F + (long)comp * g.pc;
+  for (long t = blockIdx.x * (long)blockDim.x + threadIdx.x; t < total; t += (long)gridDim.x * blockDim.x) {
+    const int i = (int)(t % g.n[0]);
+    const int j = (int)((t / g.n[0]) % g.n[1]);
+    const int k = (int)(t / ((long)g.n[0] * g.n[1])) + klo;
+    const bool ei = g.per[0] && (i < g.ng || i >= g.n[0] - g.ng);
+    const bool ej = g.per[1] && (j < g.ng || j >= g.n[1] - g.ng);
+    const bool ek = z_too && g.per[2] && (k < g.ng || k >= g.n[2] - g.ng);
+    if (!(ei || ej || ek)) continue;
+    const int ax = ei ? (g.ng + g.n[0] - 1) / g.n[0] : 0;
+    const int ay = ej ? (g.ng + g.n[1] - 1) / g.n[1] : 0;
+    const int az = ek ? (g.ng + g.n[2] - 1) / g.n[2] : 0;
+    double acc = Fc[g.at(i, j, k)];
+    for (int c = -az; c <= az; ++c) {
+      const int kk = k + c * g.n[2];
+      if (kk < -g.ng || kk >= g.n[2] + g.ng) continue;
+      for (int b = -ay; b <= ay; ++b) {
+        const int jj = j + b * g.n[1];
+        if (jj < -g.ng || jj >= g.n[1] + g.ng) continue;
+        for (int a = -ax; a <= ax; ++a) {
+          const int ii = i + a * g.n[0];
+          if (ii < -g.ng || ii >= g.n[0] + g.ng) continue;
+          if (a == 0 && b == 0 && c == 0) continue;
+          acc += Fc[g.at(ii, jj, kk)];
+        }
+      }
+    }
+    Fc[g.at(i, j, k)] = acc;
+  }
+}
+
+// MABC_bad<X>: A <- (1-dt) A + dt A(i +- 1) on the two global x faces, 3 components
+__global__ void k_mabc_x(Grid g, double* __restrict__ A, double dt) {
+  const long total = (long)g.n[1] * g.n[2];
+  const int Lo = 0, Hi = g.gn[0] - 1;
+  for (long t = blockIdx.x * (long)blockDim.x + threadIdx.x; t < total; t += (long)gridDim.x * blockDim.x) {
+    const int j = (int)(t % g.n[1]), k = (int)(t / g.n[1]);
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      const long lo = g.at(Lo, j, k, c), hi = g.at(Hi, j, k, c);
+      const double a_lo = (1 - dt) * A[lo] + A[lo + 1] * dt;
+      const double a_hi = (1 - dt) * A[hi] + A[hi - 1] * dt;
+      A[lo] = a_lo;
+      if (Hi != Lo) A[hi] = a_hi;
+    }
+  }
+}
+
+struct Interior {
+  int lo[3], hi[3];  // inclusive, local indices
+};
+
+// FWD = true : B -= dt * curl+ E   (E_curl, forward differences)
+// FWD = false: E += dt * curl- B   (B_curl, backward differences)
+template <bool FWD>
+__global__ void __launch_bounds__(kBlock) k_curl(Grid g, const double* __restrict__ S, double* __restrict__ T,
+                                                 Interior in, double dt) {
+  const int nx = in.hi[0] - in.lo[0] + 1, ny = in.hi[1] - in.lo[1] + 1, nz = in.hi[2] - in.lo[2] + 1;
+  const long total = (long)nx * ny * nz;
+  const long sj = g.pj, sk = g.pk, sc = g.pc;
+  for (long t = blockIdx.x * (long)blockDim.x + threadIdx.x; t < total; t += (long)gridDim.x * blockDim.x) {
+    const int i = (int)(t % nx) + in.lo[0];
+    const int j = (int)((t / nx) % ny) + in.lo[1];
+    const int k = (int)(t / ((long)nx * ny)) + in.lo[2];
+    const long o = g.at(i, j, k);
+    const double sx = S[o], sy = S[o + sc], sz = S[o + 2 * sc];
+    double r0, r1, r2;
+    if (FWD) {
+      r0 = (S[o + sj + 2 * sc] - sz) - (S[o + sk + sc] - sy);
+      r1 = (S[o + sk] - sx) - (S[o + 1 + 2 * sc] - sz);
+      r2 = (S[o + 1 + sc] - sy) - (S[o + sj] - sx);
+      T[o] = T[o] - dt * r0;
+      T[o + sc] = T[o + sc] - dt * r1;
+      T[o + 2 * sc] = T[o + 2 * sc] - dt * r2;
+    } else {
+      r0 = (sz - S[o - sj + 2 * sc]) - (sy - S[o - sk + sc]);
+      r1 = (sx - S[o - sk]) - (sz - S[o - 1 + 2 * sc]);
+      r2 = (sy - S[o - 1 + sc]) - (sx - S[o - sj]);
+      T[o] = T[o] + dt * r0;
+      T[o + sc] = T[o + sc] + dt * r1;
+      T[o + 2 * sc] = T[o + 2 * sc] + dt * r2;
+    }
+  }
+}
+
+__global__ void k_source(Grid g, double* __restrict__ E, int pos, int comp, double amp) {
+  const long total = (long)g.n[1] * g.n[2];
+  for (long t = blockIdx.x * (long)blockDim.x + threadIdx.x; t < total; t += (long)gridDim.x * blockDim.x) {
+    const int j = (int)(t % g.n[1]), k = (int)(t / g.n[1]);
+    E[g.at(pos, j, k, comp)] += amp;
+  }
+}
+
+__global__ void k_set_uniform(Grid g, double* __restrict__ F, double v0, double v1, double v2) {
+  const long total = g.cells();
+  for (long t = blockIdx.x * (long)blockDim.x + threadIdx.x; t < total; t += (long)gridDim.x * blockDim.x) {
+    const int i = (int)(t % g.n[0]);
+    const int j = (int)((t / g.n[0]) % g.n[1]);
+    const int k = (int)(t / ((long)g.n[0] * g.n[1]));
+    const long o = g.at(i, j, k);
+    F[o] = v0;
+    F[o + g.pc] = v1;
+    F[o + 2 * g.pc] = v2;
+  }
+}
+
+template <bool PACK>
+__global__ void k_pack(Grid g, double* __restrict__ F, double* __restrict__ P) {
+  const long nc = g.cells(), total = nc * 3;
+  for (long t = blockIdx.x * (long)blockDim.x + threadIdx.x; t < total; t += (long)gridDim.x * blockDim.x) {
+    const int c = (int)(t / nc);
+    const long r = t % nc;
+    const int i = (int)(r % g.n[0]);
+    const int j = (int)((r / g.n[0]) % g.n[1]);
+    const int k = (int)(r / ((long)g.n[0] * g.n[1]));
+    if (PACK)
+      P[t] = F[g.at(i, j, k, c)];
+    else
+      F[g.at(i, j, k, c)] = P[t];
+  }
+}
+
+// per-block partial sums of squares of the 3 components of F over valid cells
+__global__ void __launch_bounds__(kBlock) k_sumsq(Grid g, const double* __restrict__ F, double* __restrict__ part) {
+  double a[3] = {0, 0, 0};
+  const long total = g.cells();
+  for (long t = blockIdx.x * (long)blockDim.x + threadIdx.x; t < total; t += (long)gridDim.x * blockDim.x) {
+    const int i = (int)(t % g.n[0]);
+    const int j = (int)((t / g.n[0]) % g.n[1]);
+    const int k = (int)(t / ((long)g.n[0] * g.n[1]));
+    const long o = g.at(i, j, k);
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      const double v = F[o + c * g.pc];
+      a[c] = fma(v, v, a[c]);
+    }
+  }
+  __shared__ double sh[3][kBlock / 32];
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
+    double v = a[c];
+    for (int s = 16; s > 0; s >>= 1) v += __shfl_xor_sync(0xffffffffu, v, s);
+    if ((threadIdx.x & 31) == 0) sh[c][threadIdx.x >> 5] = v;
+  }
+  __syncthreads();
+  if (threadIdx.x < 3) {
+    double v = 0;
+    for (int w = 0; w < kBlock / 32; ++w) v += sh[threadIdx.x][w];
+    part[blockIdx.x * 3 + threadIdx.x] = v;
+  }
+}
+__global__ void k_final_sum(const double* __restrict__ part, int nblocks, int width, double* __restrict__ out) {
+  if (threadIdx.x < width) {
+    double v = 0;
+    for (int b = 0; b < nblocks; ++b) v += part[b * width + threadIdx.x];
+    out[threadIdx.x] = v;
+  }
+}
+
+__global__ void k_gauss_div(Grid g, const double* __restrict__ E, double* __restrict__ out) {
+  const long total = g.cells();
+  for (long t = blockIdx.x * (long)blockDim.x + threadIdx.x; t < total; t += (long)gridDim.x * blockDim.x) {
+    const int i = (int)(t % g.n[0]);
+    const int j = (int)((t / g.n[0]) % g.n[1]);
+    const int k = (int)(t / ((long)g.n[0] * g.n[1]));
+    const long o = g.at(i, j, k);
+    out[t] += (E[o] - E[o - 1]) + (E[o + g.pc] - E[o + g.pc - g.pj]) + (E[o + 2 * g.pc] - E[o + 2 * g.pc - g.pk]);
+  }
+}
+
+Interior make_interior(const Grid& g) {  // construct_interior<d,1>, hpp:499-510
+  Interior in;
+  for (int d = 0; d < 3; ++d) {
+    in.lo[d] = 0;
+    in.hi[d] = g.n[d] - 1;
+  }
+  for (int d = 0; d < 2; ++d)
+    if (!g.per[d]) {
+      in.lo[d] += 1;
+      in.hi[d] -= 1;
+    }
+  if (!g.per[2]) {  // walls in z only touch the first / last slab
+    if (g.z0 == 0) in.lo[2] += 1;
+    if (g.z0 + g.n[2] == g.gn[2]) in.hi[2] -= 1;
+  }
+  return in;
+}
+
+bool all_periodic(const Grid& g) { return g.per[0] && g.per[1] && g.per[2]; }
+
+}  // namespace
+
+void launch_fill_boundary(Ctx* c, double* F, bool z_too) {
+  const int gx = c->g.n[0] + 2 * c->g.ng, gy = c->g.n[1] + 2 * c->g.ng, gz = c->g.n[2] + 2 * c->g.ng;
+  k_fill_boundary<<<grid_for(c, (long)gx * gy * gz), kBlock, 0, c->stream>>>(c->g, F, z_too ? 1 : 0);
+  c->launches++;
+}
+void launch_zero_guards(Ctx* c, double* F) {
+  const int gx = c->g.n[0] + 2 * c->g.ng, gy = c->g.n[1] + 2 * c->g.ng, gz = c->g.n[2] + 2 * c->g.ng;
+  k_zero_guards<<<grid_for(c, (long)gx * gy * gz), kBlock, 0, c->stream>>>(c->g, F);
+  c->launches++;
+}
+void launch_sum_boundary(Ctx* c, double* F, int comp, bool z_too) {
+  const long total = (long)c->g.n[0] * c->g.n[1] * (c->g.n[2] + (z_too ? 0 : 2 * c->g.ng));
+  k_sum_boundary<<<grid_for(c, total), kBlock, 0, c->stream>>>(c->g, F, comp, z_too ? 1 : 0);
+  c->launches++;
+}
+void launch_curl_E_into_B(Ctx* c, double dt) {
+  if (!all_periodic(c->g)) {  // push_ff: ExteriorF(Target) first (hpp:516-523)
+    k_mabc_x<<<grid_for(c, (long)c->g.n[1] * c->g.n[2]), kBlock, 0, c->stream>>>(c->g, c->B, dt);
+    c->launches++;
+  }
+  const Interior in = make_interior(c->g);
+  const long total = (long)(in.hi[0] - in.lo[0] + 1) * (in.hi[1] - in.lo[1] + 1) * (in.hi[2] - in.lo[2] + 1);
+  if (total <= 0) return;
+  k_curl<true><<<grid_for(c, total), kBlock, 0, c->stream>>>(c->g, c->E, c->B, in, dt);
+  c->launches++;
+}
+void launch_curl_B_into_E(Ctx* c, double dt) {
+  if (!all_periodic(c->g)) {
+    k_mabc_x<<<grid_for(c, (long)c->g.n[1] * c->g.n[2]), kBlock, 0, c->stream>>>(c->g, c->E, dt);
+    c->launches++;
+  }
+  const Interior in = make_interior(c->g);
+  const long total = (long)(in.hi[0] - in.lo[0] + 1) * (in.hi[1] - in.lo[1] + 1) * (in.hi[2] - in.lo[2] + 1);
+  if (total <= 0) return;
+  k_curl<false><<<grid_for(c, total), kBlock, 0, c->stream>>>(c->g, c->B, c->E, in, dt);
+  c->launches++;
+}
+void launch_source(Ctx* c, int pos, int comp, double amp) {
+  k_source<<<grid_for(c, (long)c->g.n[1] * c->g.n[2]), kBlock, 0, c->stream>>>(c->g, c->E, pos, comp, amp);
+  c->launches++;
+}
+void launch_set_uniform(Ctx* c, double* F, const double v[3]) {
+  k_set_uniform<<<grid_for(c, c->g.cells()), kBlock, 0, c->stream>>>(c->g, F, v[0], v[1], v[2]);
+  c->launches++;
+}
+void launch_pack_field(Ctx* c, const double* F, double* packed) {
+  k_pack<true><<<grid_for(c, c->g.cells() * 3), kBlock, 0, c->stream>>>(c->g, const_cast<double*>(F), packed);
+  c->launches++;
+}
+void launch_unpack_field(Ctx* c, double* F, const double* packed) {
+  k_pack<false><<<grid_for(c, c->g.cells() * 3), kBlock, 0, c->stream>>>(c->g, F, const_cast<double*>(packed));
+  c->launches++;
+}
+void field_energy(Ctx* c, double* out6) {
+  // scratch layout: [0, 1024*3) partials, then 6 results
+  int nb = grid_for(c, c->g.cells());
+  if (nb > 1024) nb = 1024;
+  double* part = c->scratch;
+  double* res = c->scratch + 1024 * 3;
+  for (int f = 0; f < 2; ++f) {
+    k_sumsq<<<nb, kBlock, 0, c->stream>>>(c->g, f == 0 ? c->E : c->B, part);
+    k_final_sum<<<1, 32, 0, c->stream>>>(part, nb, 3, res + 3 * f);
+    c->launches += 2;
+  }
+  cudaMemcpyAsync(out6, res, 6 * sizeof(double), cudaMemcpyDeviceToHost, c->stream);
+  cudaStreamSynchronize(c->stream);
+}
+void launch_gauss_div(Ctx* c, double* out) {
+  k_gauss_div<<<grid_for(c, c->g.cells()), kBlock, 0, c->stream>>>(c->g, c->E, out);
+  c->launches++;
+}
+
+}  // namespace spic

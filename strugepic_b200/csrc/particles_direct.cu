@@ -1,0 +1,260 @@
+// Thread-per-particle sub-flow kernels (engine DIRECT, and the unbinned tail of
+// engine BINNED).  Any particle order, fields read through L1/L2, deposition with
+// native FP64 global reductions (RED.E.ADD.F64).
+//
+// Reference behaviour restated (paths relative to /root/reference):
+//   Theta<comp,W,F_SEG,F_PART>   include/strugepic_propagators.hpp:80-244
+//   construct_segments           src/strugepic_util.cpp:160-174
+//   segment_reflect/particle_reflect  include/strugepic_util.hpp:172-186
+//   push_V_E<W>                  include/strugepic_propagators.hpp:247-344
+//   Redistribute (periodic wrap) include/strugepic_propagators.hpp:368
+//   get_total_energy (kinetic)   src/strugepic_util.cpp:364-380
+// The triple sums are factorised (sum over the push axis innermost, then u, then
+// l); this changes rounding by O(1e-16) relative, see DESIGN.md "parity budget".
+#include "particle_math.cuh"
+#include "spic_internal.cuh"
+
+namespace spic {
+namespace {
+
+constexpr int kBlock = 128;
+
+template <class I, int A>
+__global__ void __launch_bounds__(kBlock)
+    k_theta_axis_direct(Grid g, ParticleSoA p, long n, double* __restrict__ E, const double* __restrict__ B,
+                        double q, double qm, double dt, int* __restrict__ flags) {
+  constexpr int U = (A + 1) % 3, L = (A + 2) % 3;  // hpp:90-91
+  const long i = blockIdx.x * (long)blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const long st[3] = {1, g.pj, g.pk};
+
+  double xa = p.x[A][i];
+  const double xu = p.x[U][i], xl = p.x[L][i];
+  double va = p.v[A][i];
+  int cell[3];
+  cell[A] = (int)floor(xa);
+  cell[U] = (int)floor(xu);
+  cell[L] = (int)floor(xl);
+
+  double uW1[I::NW1], lW1[I::NW1], uWp[I::NWP], lWp[I::NWP];
+  eval_w1<I>(xl, cell[L], lW1);
+  eval_wp<I>(xl, cell[L], lWp);
+  eval_w1<I>(xu, cell[U], uW1);
+  eval_wp<I>(xu, cell[U], uWp);
+
+  Segments sg = make_segments<I, A>(g, xa, xa + dt * va, flags);
+
+  cell[2] -= g.z0;  // local k
+  double r1 = 0, r2 = 0;
+  const double nq = -q;  // -E_coef, hpp:114,215 (Ics = Cs = 1)
+  double* Ea = E + (long)A * g.pc;
+  const double* Bu = B + (long)U * g.pc;
+  const double* Bl = B + (long)L * g.pc;
+  for (int s = 0; s < sg.n; ++s) {
+    const int ca = sg.cell[s];
+    double Iw[I::NWP];
+    eval_iwp<I>(sg.pt[s], sg.pt[s + 1], ca, Iw);
+    int cc[3] = {cell[0], cell[1], cell[2]};
+    cc[A] = ca - (A == 2 ? g.z0 : 0);
+    const long base = g.at(cc[0], cc[1], cc[2]) + (1 - I::W) * (st[A] + st[U] + st[L]);
+#pragma unroll
+    for (int tl = 0; tl < I::NW1; ++tl) {
+      double a1 = 0, a2 = 0;
+#pragma unroll
+      for (int tu = 0; tu < I::NW1; ++tu) {
+        const long row = base + tl * st[L] + tu * st[U];
+        const double mul = nq * (lW1[tl] * uW1[tu]);
+        double s1 = 0, s2 = 0;
+#pragma unroll
+        for (int tc = 0; tc < I::NWP; ++tc) {
+          const long idx = row + tc * st[A];
+          atomicAdd(&Ea[idx], mul * Iw[tc]);  // hpp:215
+          s1 = fma(__ldg(&Bu[idx]), Iw[tc], s1);
+          s2 = fma(__ldg(&Bl[idx]), Iw[tc], s2);
+        }
+        a1 = fma(uW1[tu], s1, a1);
+        if (tu < I::NWP) a2 = fma(uWp[tu], s2, a2);
+      }
+      if (tl < I::NWP) r1 = fma(lWp[tl], a1, r1);  // hpp:216
+      r2 = fma(-lW1[tl], a2, r2);                  // hpp:217
+    }
+  }
+
+  if (sg.reflected) {  // particle_reflect, util.hpp:182-186
+    xa = sg.pt[2];
+    va = -va;
+    p.v[A][i] = va;
+  } else {
+    xa = xa + dt * va;  // hpp:237
+  }
+  p.x[A][i] = wrap_periodic(xa, g.gn[A], g.per[A], flags);
+  p.v[L][i] += qm * r1;  // hpp:240
+  p.v[U][i] += qm * r2;  // hpp:241
+}
+
+template <class I>
+__global__ void __launch_bounds__(kBlock)
+    k_push_v_e_direct(Grid g, ParticleSoA p, long n, const double* __restrict__ E, double coef) {
+  const long i = blockIdx.x * (long)blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const double x = p.x[0][i], y = p.x[1][i], z = p.x[2][i];
+  const int cx = (int)floor(x), cy = (int)floor(y), cz = (int)floor(z);
+  double w1x[I::NW1], w1y[I::NW1], w1z[I::NW1], wpx[I::NWP], wpy[I::NWP], wpz[I::NWP];
+  eval_w1<I>(x, cx, w1x);
+  eval_w1<I>(y, cy, w1y);
+  eval_w1<I>(z, cz, w1z);
+  eval_wp<I>(x, cx, wpx);
+  eval_wp<I>(y, cy, wpy);
+  eval_wp<I>(z, cz, wpz);
+  const long base = g.at(cx, cy, cz - g.z0) + (1 - I::W) * (1 + g.pj + g.pk);
+  double dv[3];
+  gather_E<I>(E + base, g.pj, g.pk, g.pc, w1x, w1y, w1z, wpx, wpy, wpz, dv,
+              [](const double* ptr) { return __ldg(ptr); });
+  p.v[0][i] = fma(dv[0], coef, p.v[0][i]);  // hpp:339-341
+  p.v[1][i] = fma(dv[1], coef, p.v[1][i]);
+  p.v[2][i] = fma(dv[2], coef, p.v[2][i]);
+}
+
+__global__ void __launch_bounds__(256) k_kinetic(ParticleSoA p, long n, double half_m, double* __restrict__ accum) {
+  double a = 0;
+  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x) {
+    const double vx = p.v[0][i], vy = p.v[1][i], vz = p.v[2][i];
+    a += half_m * (vx * vx + vy * vy + vz * vz);
+  }
+  for (int s = 16; s > 0; s >>= 1) a += __shfl_xor_sync(0xffffffffu, a, s);
+  __shared__ double sh[8];
+  if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = a;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double t = 0;
+    for (int w = 0; w < 8; ++w) t += sh[w];
+    atomicAdd(accum, t);
+  }
+}
+
+// rho deposit for the Gauss diagnostic: out[cell] -= q W1 W1 W1 (periodic images folded)
+template <class I>
+__global__ void __launch_bounds__(kBlock) k_deposit_rho(Grid g, ParticleSoA p, long n, double q, double* __restrict__ out) {
+  const long i = blockIdx.x * (long)blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const double x = p.x[0][i], y = p.x[1][i], z = p.x[2][i];
+  const int cx = (int)floor(x), cy = (int)floor(y), cz = (int)floor(z);
+  double w1x[I::NW1], w1y[I::NW1], w1z[I::NW1];
+  eval_w1<I>(x, cx, w1x);
+  eval_w1<I>(y, cy, w1y);
+  eval_w1<I>(z, cz, w1z);
+#pragma unroll
+  for (int tk = 0; tk < I::NW1; ++tk)
+#pragma unroll
+    for (int tj = 0; tj < I::NW1; ++tj)
+#pragma unroll
+      for (int ti = 0; ti < I::NW1; ++ti) {
+        int ii = cx + ti + 1 - I::W, jj = cy + tj + 1 - I::W, kk = cz + tk + 1 - I::W;
+        if (g.per[0]) ii = (ii % g.gn[0] + g.gn[0]) % g.gn[0];
+        if (g.per[1]) jj = (jj % g.gn[1] + g.gn[1]) % g.gn[1];
+        if (g.per[2]) kk = (kk % g.gn[2] + g.gn[2]) % g.gn[2];
+        if (ii < 0 || ii >= g.gn[0] || jj < 0 || jj >= g.gn[1] || kk < 0 || kk >= g.gn[2]) continue;
+        atomicAdd(&out[((long)kk * g.gn[1] + jj) * g.gn[0] + ii], -q * w1x[ti] * w1y[tj] * w1z[tk]);
+      }
+}
+
+__global__ void __launch_bounds__(256)
+    k_load_uniform(Grid g, ParticleSoA p, long n, int ppc, double vth, uint64_t seed) {
+  for (long t = blockIdx.x * (long)blockDim.x + threadIdx.x; t < n; t += (long)gridDim.x * blockDim.x) {
+    const long cell = t / ppc;
+    const int i = (int)(cell % g.n[0]);
+    const int j = (int)((cell / g.n[0]) % g.n[1]);
+    const int k = (int)(cell / ((long)g.n[0] * g.n[1])) + g.z0;
+    const uint64_t gcell = ((uint64_t)k * g.gn[1] + j) * g.gn[0] + i;
+    const uint64_t gid = gcell * (uint64_t)ppc + (uint64_t)(t % ppc);
+    double xyz[3], vel[3];
+    synth_particle(seed, gid, vth, xyz, vel);
+    p.x[0][t] = (double)i + xyz[0];
+    p.x[1][t] = (double)j + xyz[1];
+    p.x[2][t] = (double)k + xyz[2];
+    p.v[0][t] = vel[0];
+    p.v[1][t] = vel[1];
+    p.v[2][t] = vel[2];
+  }
+}
+
+struct KernelTimer {
+  Ctx* c;
+  explicit KernelTimer(Ctx* ctx) : c(ctx) {
+    if (c->time_kernels) cudaEventRecord(c->ev0, c->stream);
+  }
+  ~KernelTimer() {
+    c->particle_launches++;
+    if (c->time_kernels) {
+      cudaEventRecord(c->ev1, c->stream);
+      cudaEventSynchronize(c->ev1);
+      float ms = 0;
+      cudaEventElapsedTime(&ms, c->ev0, c->ev1);
+      c->particle_ms += ms;
+    }
+  }
+};
+
+template <class I>
+void theta_axis_dispatch(Ctx* c, const ParticleSoA& p, long n, double q, double m, int comp, double dt) {
+  const int grid = (int)((n + kBlock - 1) / kBlock);
+  const double qm = q / m;  // B_coef, hpp:113
+  if (comp == 0)
+    k_theta_axis_direct<I, 0><<<grid, kBlock, 0, c->stream>>>(c->g, p, n, c->E, c->B, q, qm, dt, c->d_flags);
+  else if (comp == 1)
+    k_theta_axis_direct<I, 1><<<grid, kBlock, 0, c->stream>>>(c->g, p, n, c->E, c->B, q, qm, dt, c->d_flags);
+  else
+    k_theta_axis_direct<I, 2><<<grid, kBlock, 0, c->stream>>>(c->g, p, n, c->E, c->B, q, qm, dt, c->d_flags);
+}
+
+}  // namespace
+
+void launch_theta_axis_direct(Ctx* c, const ParticleSoA& p, long n, double q, double m, int comp, double dt) {
+  if (n <= 0) return;
+  KernelTimer t(c);
+  if (c->cfg.interp == SPIC_INTERP_P8R2)
+    theta_axis_dispatch<InterpP8R2>(c, p, n, q, m, comp, dt);
+  else
+    theta_axis_dispatch<InterpPWL>(c, p, n, q, m, comp, dt);
+  c->launches++;
+}
+
+void launch_push_v_e_direct(Ctx* c, const ParticleSoA& p, long n, double q, double m, double dt) {
+  if (n <= 0) return;
+  KernelTimer t(c);
+  const int grid = (int)((n + kBlock - 1) / kBlock);
+  const double coef = dt * q / m;  // hpp:267
+  if (c->cfg.interp == SPIC_INTERP_P8R2)
+    k_push_v_e_direct<InterpP8R2><<<grid, kBlock, 0, c->stream>>>(c->g, p, n, c->E, coef);
+  else
+    k_push_v_e_direct<InterpPWL><<<grid, kBlock, 0, c->stream>>>(c->g, p, n, c->E, coef);
+  c->launches++;
+}
+
+void launch_kinetic_energy(Ctx* c, const ParticleSoA& p, long n, double m, double* accum) {
+  if (n <= 0) return;
+  long b = (n + 255) / 256;
+  if (b > (long)c->sm_count * 8) b = (long)c->sm_count * 8;
+  k_kinetic<<<(int)b, 256, 0, c->stream>>>(p, n, 0.5 * m, accum);
+  c->launches++;
+}
+
+void launch_deposit_rho(Ctx* c, const ParticleSoA& p, long n, double q, double* out) {
+  if (n <= 0) return;
+  const int grid = (int)((n + kBlock - 1) / kBlock);
+  if (c->cfg.interp == SPIC_INTERP_P8R2)
+    k_deposit_rho<InterpP8R2><<<grid, kBlock, 0, c->stream>>>(c->g, p, n, q, out);
+  else
+    k_deposit_rho<InterpPWL><<<grid, kBlock, 0, c->stream>>>(c->g, p, n, q, out);
+  c->launches++;
+}
+
+void launch_load_uniform(Ctx* c, const ParticleSoA& p, long n, int ppc, double vth, uint64_t seed) {
+  if (n <= 0) return;
+  long b = (n + 255) / 256;
+  if (b > (long)c->sm_count * 16) b = (long)c->sm_count * 16;
+  k_load_uniform<<<(int)b, 256, 0, c->stream>>>(c->g, p, n, ppc, vth, seed);
+  c->launches++;
+}
+
+}  // namespace spic

@@ -1,0 +1,107 @@
+// Internal types shared by the kernels and the C-ABI layer (not installed).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <string>
+#include <vector>
+
+#include "../../include/strugepic_b200.h"
+#include "interp.cuh"
+
+namespace spic {
+
+// Geometry of this rank's brick as the kernels see it.  Field arrays are
+// [comp][k][j][i] (amrex::Array4 order) with ng guard cells on every side; the
+// x pitch is padded to an even number of doubles so that every row starts on a
+// 16-byte boundary (TMA / 128-bit loads).
+struct Grid {
+  int n[3];    // local valid cells
+  int gn[3];   // global cells
+  int per[3];  // global periodicity
+  int ng;
+  int z0;      // global k of local k = 0
+  int zlocal;  // 1: z periodicity is resolved inside this brick (nranks == 1)
+  long pj, pk, pc;
+  __host__ __device__ long at(int i, int j, int k) const {
+    return (long)(i + ng) + (long)(j + ng) * pj + (long)(k + ng) * pk;
+  }
+  __host__ __device__ long at(int i, int j, int k, int c) const { return at(i, j, k) + (long)c * pc; }
+  __host__ __device__ long cells() const { return (long)n[0] * n[1] * n[2]; }
+};
+
+struct ParticleSoA {
+  double* x[3];
+  double* v[3];
+};
+
+// Cell-binned particle store of one species (engine BINNED).  Bin c occupies slots
+// [start[c], start[c+1]) of the SoA arrays; the first count[c] slots are live and
+// every live particle satisfies floor(pos) == cell c.  Particles that do not fit
+// their bin live in the unbinned tail list and go through the direct kernels.
+struct Species {
+  double q = 0, m = 0;
+  // direct list (engine DIRECT: all particles; engine BINNED: overflow tail)
+  ParticleSoA d{};
+  long nd = 0, capd = 0;
+  // binned store
+  ParticleSoA b{};
+  long slots = 0;          // allocated slots in b
+  long* start = nullptr;   // [cells+1]
+  int* count = nullptr;    // [cells]
+  long nb = 0;             // live binned particles (host mirror, refreshed on demand)
+};
+
+struct Ctx;
+
+// ---- field kernels (field_kernels.cu) ------------------------------------------
+void launch_fill_boundary(Ctx* c, double* F, bool z_too);
+void launch_zero_guards(Ctx* c, double* F);
+void launch_sum_boundary(Ctx* c, double* F, int comp, bool z_too);
+void launch_curl_E_into_B(Ctx* c, double dt);  // push_B_E
+void launch_curl_B_into_E(Ctx* c, double dt);  // push_E_B
+void launch_source(Ctx* c, int pos, int comp, double amp);
+void launch_set_uniform(Ctx* c, double* F, const double v[3]);
+void field_energy(Ctx* c, double* out_sumsq6);  // sum of squares of the 6 components (valid cells)
+void launch_pack_field(Ctx* c, const double* F, double* packed);    // guarded -> [c][k][j][i] valid
+void launch_unpack_field(Ctx* c, double* F, const double* packed);  // valid -> guarded
+void launch_gauss_div(Ctx* c, double* out);                          // out += div- E
+
+// ---- particle kernels, thread per particle (particles_direct.cu) ----------------
+void launch_theta_axis_direct(Ctx* c, const ParticleSoA& p, long n, double q, double m, int comp, double dt);
+void launch_push_v_e_direct(Ctx* c, const ParticleSoA& p, long n, double q, double m, double dt);
+void launch_kinetic_energy(Ctx* c, const ParticleSoA& p, long n, double m, double* accum);
+void launch_deposit_rho(Ctx* c, const ParticleSoA& p, long n, double q, double* out);
+void launch_load_uniform(Ctx* c, const ParticleSoA& p, long n, int ppc, double vth, uint64_t seed);
+
+struct Ctx {
+  spic_config cfg{};
+  Grid g{};
+  int W = 2;
+  double* E = nullptr;
+  double* B = nullptr;
+  double* scratch = nullptr;  // >= 3 * cells doubles (pack/unpack, reductions, gauss)
+  long scratch_elems = 0;
+  int* d_flags = nullptr;     // [0]: CFL violation, [1]: capacity overflow
+  std::vector<Species> sp;
+  cudaStream_t stream = nullptr;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  int sm_count = 148;
+  int64_t launches = 0;
+  double particle_ms = 0;
+  int64_t particle_launches = 0;
+  bool time_kernels = false;
+  std::string err;
+  long field_elems() const { return g.pc * 3; }
+};
+
+#define SPIC_CUDA_CHECK(ctx, expr)                                                         \
+  do {                                                                                     \
+    cudaError_t _e = (expr);                                                               \
+    if (_e != cudaSuccess) {                                                               \
+      (ctx)->err = std::string(#expr) + ": " + cudaGetErrorString(_e);                     \
+      return SPIC_ECUDA;                                                                   \
+    }                                                                                      \
+  } while (0)
+
+}  // namespace spic
