@@ -310,9 +310,11 @@ int spic_theta_axis(spic_ctx* c, int comp, double dt) {
   if (rc) return rc;
   launch_zero_guards(c, c->E);  // E.setBndry(0)             hpp:351-352
   for (auto& s : c->sp) {       // Theta<comp,W,...> per tile hpp:353-365
-    rc = engine_theta_axis(c, s, comp, dt);
-    if (rc) return rc;
-    launch_theta_axis_direct(c, s.d, s.nd, s.q, s.m, comp, dt);
+    if (s.binned) {
+      if ((rc = engine_theta_axis(c, s, comp, dt))) return rc;
+    } else {
+      launch_theta_axis_direct(c, s.d, s.nd, nullptr, s.q, s.m, comp, dt);
+    }
   }
   rc = halo_sum(c, c->E, comp);  // E.SumBoundary             hpp:367
   if (rc) return rc;
@@ -326,9 +328,11 @@ int spic_theta_E(spic_ctx* c, double dt) {
   int rc = halo_fill(c, c->E);  // E.FillBoundary  hpp:56
   if (rc) return rc;
   for (auto& s : c->sp) {       // push_V_E        hpp:57-62
-    rc = engine_push_v_e(c, s, dt);
-    if (rc) return rc;
-    launch_push_v_e_direct(c, s.d, s.nd, s.q, s.m, dt);
+    if (s.binned) {
+      if ((rc = engine_push_v_e(c, s, dt))) return rc;
+    } else {
+      launch_push_v_e_direct(c, s.d, s.nd, nullptr, s.q, s.m, dt);
+    }
   }
   launch_curl_E_into_B(c, dt);  // push_B_E        hpp:63-68
   return SPIC_OK;
@@ -363,8 +367,15 @@ static int map2(spic_ctx* c, double dt) {  // hpp:559-572
   return spic_theta_E(c, dt / 2);
 }
 
+static int map_body(spic_ctx* c, int order, double dt);
 int spic_map(spic_ctx* c, int order, double dt) {
   if (!c) return SPIC_EINVAL;
+  cudaSetDevice(c->cfg.device);
+  int rc = map_body(c, order, dt);
+  if (rc) return rc;
+  return engine_maintain(c);  // re-bin when the overflow tail has grown
+}
+static int map_body(spic_ctx* c, int order, double dt) {
   int rc;
   if (order == 1) {  // hpp:548-557
     if ((rc = spic_theta_B(c, dt))) return rc;
@@ -401,9 +412,12 @@ int spic_energy(spic_ctx* c, double out[2]) {
   double* acc = c->scratch + 1024 * 3 + 8;
   SPIC_CUDA_CHECK(c, cudaMemsetAsync(acc, 0, sizeof(double), c->stream));
   for (auto& s : c->sp) {
-    int rc = engine_kinetic(c, s, acc);
-    if (rc) return rc;
-    launch_kinetic_energy(c, s.d, s.nd, s.m, acc);
+    if (s.binned) {
+      int rc = engine_kinetic(c, s, acc);
+      if (rc) return rc;
+    } else {
+      launch_kinetic_energy(c, s.d, s.nd, nullptr, s.m, acc);
+    }
   }
   double kin = 0;
   SPIC_CUDA_CHECK(c, cudaMemcpyAsync(&kin, acc, sizeof(double), cudaMemcpyDeviceToHost, c->stream));
@@ -426,9 +440,11 @@ int spic_gauss_residual(spic_ctx* c, double* host) {
   const size_t bytes = sizeof(double) * (size_t)c->g.cells();
   SPIC_CUDA_CHECK(c, cudaMemsetAsync(out, 0, bytes, c->stream));
   for (auto& s : c->sp) {
-    rc = engine_deposit_rho(c, s, out);
-    if (rc) return rc;
-    launch_deposit_rho(c, s.d, s.nd, s.q, out);
+    if (s.binned) {
+      if ((rc = engine_deposit_rho(c, s, out))) return rc;
+    } else {
+      launch_deposit_rho(c, s.d, s.nd, nullptr, s.q, out);
+    }
   }
   launch_gauss_div(c, out);
   SPIC_CUDA_CHECK(c, cudaMemcpyAsync(host, out, bytes, cudaMemcpyDeviceToHost, c->stream));

@@ -84,6 +84,8 @@ SPIC_DI void gather_E(const double* E0, long sj, long sk, long sc, const double 
     ax = fma(w1z[tk], bx, ax);
     ay = fma(w1z[tk], by, ay);
     if (tk < I::NWP) az = fma(wpz[tk], bz, az);
+    // keep ptxas from hoisting the whole stencil's loads above the arithmetic (register blow-up)
+    asm volatile("" ::: "memory");
   }
   dv[0] = ax;
   dv[1] = ay;

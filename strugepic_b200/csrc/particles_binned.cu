@@ -1,14 +1,880 @@
-// placeholder: binned engine not yet implemented -- everything stays in the direct list
+// Cell-binned particle engine (SPIC_ENGINE_BINNED): the hot path.
+//
+// Data layout.  Per species, SoA arrays x,y,z,vx,vy,vz over `slots`; cell c (x
+// fastest) owns slots [start[c], start[c+1]) of which the first count[c] are live.
+// Invariant: a live particle of bin c has floor(pos) == cell c.  Bins carry ~25 %
+// slack so that the few particles that change cell per sub-flow (0.4 % at
+// v_th*dt = 0.005) can be re-filed without re-sorting the store.
+//
+// theta_axis kernel (reference: Theta<comp,W,..>, include/strugepic_propagators.hpp:80-244).
+// One warp owns one cell at a time:
+//   stage    the cell's B stencil (NWP x NW1 x NW1 points x 2 components) into shared memory;
+//   phase A  thread per particle: weights, segments, B gather from shared memory (all lanes
+//            read the same addresses -> broadcast), position / velocity update;
+//   phase B  cell-centric deposition: lane (l,u) keeps the NWP accumulators of its stencil
+//            column in REGISTERS and walks the warp's particles, reading their weights from
+//            shared memory.  No atomics, no shuffles in the inner loop: the per-particle
+//            `E(cell) += ...` of hpp:215 becomes one DFMA per stencil point;
+//   flush    once per cell: NWP x NW1 x NW1 native FP64 reductions (RED.E.ADD.F64) to HBM;
+//   re-file  stayers are compacted in place; movers go to a mover list and are inserted
+//            into their new bin by k_insert_movers (or migrate to the neighbour rank).
+// Only the second segment of a cell-crossing particle (a different stencil) takes the
+// per-particle atomic path.
+//
+// push_V_E kernel (hpp:247-344): warp per cell, E stencil (NW1^3 x 3) staged in shared
+// memory, thread per particle, velocities updated in place.
+#include <cub/device/device_reduce.cuh>
+#include <cub/device/device_scan.cuh>
+#include <cub/iterator/transform_input_iterator.cuh>
+
+#include <string.h>
+
 #include "engine.cuh"
+#include "particle_math.cuh"
+
 namespace spic {
-int engine_ingest(Ctx*, Species&) { return SPIC_OK; }
-void engine_free_species(Ctx*, Species&) {}
-void engine_destroy(Ctx*) {}
-int engine_count(Ctx*, Species&, long* nb) { *nb = 0; return SPIC_OK; }
-int engine_gather(Ctx*, Species&, double**, double**, long* nb) { *nb = 0; return SPIC_OK; }
-int engine_theta_axis(Ctx*, Species&, int, double) { return SPIC_OK; }
-int engine_push_v_e(Ctx*, Species&, double) { return SPIC_OK; }
-int engine_kinetic(Ctx*, Species&, double*) { return SPIC_OK; }
-int engine_deposit_rho(Ctx*, Species&, double*) { return SPIC_OK; }
-int engine_set_option(Ctx* c, const char*, double) { c->err = "unknown option"; return SPIC_EINVAL; }
+
+struct ToLong {
+  __host__ __device__ long operator()(int v) const { return (long)v; }
+};
+
+struct MoverList {
+  double* x[3];
+  double* v[3];
+  int* dest;  // >= 0: local cell; -1 / -2: leaves through the low / high z face of the slab
+  unsigned* n;
+  unsigned cap;
+};
+
+struct EngineState {
+  MoverList mv{};
+  void* cub_tmp = nullptr;
+  size_t cub_bytes = 0;
+  double mover_frac = 0.0;  // 0: automatic
+  int cells_per_block = 64;
+  unsigned long long* d_scalar = nullptr;  // small device scratch (8 words)
+};
+
+namespace {
+
+constexpr int kWarps = 8;
+constexpr int kThreads = kWarps * 32;
+
+EngineState* eng(Ctx* c) {
+  if (!c->engine) c->engine = new EngineState();
+  return static_cast<EngineState*>(c->engine);
+}
+
+// ------------------------------------------------------------------------------------
+// theta_axis, binned
+// ------------------------------------------------------------------------------------
+template <class I, int A>
+__global__ void __launch_bounds__(kThreads, 2)
+    k_theta_axis_binned(Grid g, ParticleSoA p, const long* __restrict__ start, int* __restrict__ count,
+                        double* __restrict__ E, const double* __restrict__ B, double q, double qm, double dt,
+                        MoverList mv, int* __restrict__ flags, long ncell, int cells_per_block) {
+  constexpr int U = (A + 1) % 3, L = (A + 2) % 3;  // hpp:90-91
+  constexpr int NW1 = I::NW1, NWP = I::NWP;
+  constexpr int LU = NW1 * NW1;     // stencil columns (l,u)
+  constexpr int PER = 32 / LU;      // particles handled per phase-B iteration
+  constexpr int SW = 2 * NW1 + NWP; // doubles per particle in the weight scratch
+  constexpr int NST = NWP * LU;     // stencil points per component
+  extern __shared__ double smem[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  double* sB = smem + warp * (2 * NST + 32 * SW);  // [2][NST]: B_u then B_l
+  double* sW = sB + 2 * NST;                       // [32][SW]
+  const long st[3] = {1, g.pj, g.pk};
+  const int lu = lane % LU, sub = lane / LU;
+  const int my_tl = lu / NW1, my_tu = lu % NW1;
+  const double nq = -q;  // -E_coef (hpp:114; Ics = Cs = 1)
+  double* Ea = E + (long)A * g.pc;
+  const double* Bu = B + (long)U * g.pc;
+  const double* Bl = B + (long)L * g.pc;
+  const long cstride[3] = {1, g.n[0], (long)g.n[0] * g.n[1]};
+
+  const long cbeg = (long)blockIdx.x * cells_per_block;
+  long cend = cbeg + cells_per_block;
+  if (cend > ncell) cend = ncell;
+  for (long cell = cbeg + warp; cell < cend; cell += kWarps) {
+    const int cnt = count[cell];
+    if (cnt == 0) continue;
+    const long s0 = start[cell];
+    int cc[3];  // local cell coordinates
+    cc[0] = (int)(cell % g.n[0]);
+    cc[1] = (int)((cell / g.n[0]) % g.n[1]);
+    cc[2] = (int)(cell / cstride[2]);
+    const int homeA = cc[A] + (A == 2 ? g.z0 : 0);  // global index along the push axis
+    const int homeU = cc[U] + (U == 2 ? g.z0 : 0);
+    const int homeL = cc[L] + (L == 2 ? g.z0 : 0);
+    const long base = g.at(cc[0], cc[1], cc[2]) + (1 - I::W) * (st[A] + st[U] + st[L]);
+
+    __syncwarp();
+    for (int s = lane; s < 2 * NST; s += 32) {  // stage the B stencil of this cell
+      const int r = s % NST;
+      const int tc = r % NWP, tu = (r / NWP) % NW1, tl = r / (NWP * NW1);
+      const long idx = base + tc * st[A] + tu * st[U] + tl * st[L];
+      sB[s] = __ldg(s < NST ? &Bu[idx] : &Bl[idx]);
+    }
+    __syncwarp();
+
+    double acc[NWP];
+#pragma unroll
+    for (int t = 0; t < NWP; ++t) acc[t] = 0.0;
+    int wp = 0;  // stayers written so far (compaction pointer)
+
+    for (int off = 0; off < cnt; off += 32) {
+      const bool valid = off + lane < cnt;
+      const long idx = s0 + off + lane;
+      // ---- phase A: thread per particle -------------------------------------------------
+      double xa = (double)homeA + 0.5, xu = (double)homeU + 0.5, xl = (double)homeL + 0.5;
+      double va = 0.0, vu = 0.0, vl = 0.0;
+      if (valid) {
+        xa = p.x[A][idx];
+        xu = p.x[U][idx];
+        xl = p.x[L][idx];
+        va = p.v[A][idx];
+        vu = p.v[U][idx];
+        vl = p.v[L][idx];
+      }
+      double uW1[NW1], lW1[NW1], uWp[NWP], lWp[NWP];
+      eval_w1<I>(xl, homeL, lW1);
+      eval_wp<I>(xl, homeL, lWp);
+      eval_w1<I>(xu, homeU, uW1);
+      eval_wp<I>(xu, homeU, uWp);
+      Segments sg = make_segments<I, A>(g, xa, xa + dt * va, flags);
+      double I0[NWP];
+      eval_iwp<I>(sg.pt[0], sg.pt[1], homeA, I0);
+
+      double r1 = 0, r2 = 0;
+#pragma unroll
+      for (int tl = 0; tl < NW1; ++tl) {  // first segment: B gather from the staged stencil
+        double a1 = 0, a2 = 0;
+#pragma unroll
+        for (int tu = 0; tu < NW1; ++tu) {
+          double s1 = 0, s2 = 0;
+#pragma unroll
+          for (int tc = 0; tc < NWP; ++tc) {
+            s1 = fma(sB[(tl * NW1 + tu) * NWP + tc], I0[tc], s1);
+            if (tu < NWP) s2 = fma(sB[NST + (tl * NW1 + tu) * NWP + tc], I0[tc], s2);
+          }
+          a1 = fma(uW1[tu], s1, a1);
+          if (tu < NWP) a2 = fma(uWp[tu], s2, a2);
+        }
+        if (tl < NWP) r1 = fma(lWp[tl], a1, r1);  // hpp:216
+        r2 = fma(-lW1[tl], a2, r2);               // hpp:217
+        asm volatile("" ::: "memory");            // bound load hoisting (register pressure)
+      }
+      if (sg.n == 2) {  // second segment lives in another stencil: per-particle path (rare)
+        double I1[NWP];
+        eval_iwp<I>(sg.pt[1], sg.pt[2], sg.cell[1], I1);
+        const long base2 = base + (long)(sg.cell[1] - homeA) * st[A];
+#pragma unroll
+        for (int tl = 0; tl < NW1; ++tl) {
+          double a1 = 0, a2 = 0;
+#pragma unroll
+          for (int tu = 0; tu < NW1; ++tu) {
+            const long row = base2 + tl * st[L] + tu * st[U];
+            const double mul = nq * (lW1[tl] * uW1[tu]);
+            double s1 = 0, s2 = 0;
+#pragma unroll
+            for (int tc = 0; tc < NWP; ++tc) {
+              const long j = row + tc * st[A];
+              atomicAdd(&Ea[j], mul * I1[tc]);  // hpp:215
+              s1 = fma(__ldg(&Bu[j]), I1[tc], s1);
+              if (tu < NWP) s2 = fma(__ldg(&Bl[j]), I1[tc], s2);
+            }
+            a1 = fma(uW1[tu], s1, a1);
+            if (tu < NWP) a2 = fma(uWp[tu], s2, a2);
+          }
+          if (tl < NWP) r1 = fma(lWp[tl], a1, r1);
+          r2 = fma(-lW1[tl], a2, r2);
+        }
+      }
+      // position / velocity update (hpp:230-241) and periodic wrap (Redistribute, hpp:368)
+      double xa_new;
+      if (sg.reflected) {
+        xa_new = sg.pt[2];
+        va = -va;
+      } else {
+        xa_new = xa + dt * va;
+      }
+      xa_new = wrap_periodic(xa_new, g.gn[A], g.per[A], flags);
+      vl = fma(qm, r1, vl);
+      vu = fma(qm, r2, vu);
+      const int newA = (int)floor(xa_new);
+      const bool moves = valid && newA != homeA;
+
+      // weights of the first segment for phase B: -q*W1_l, W1_u, I   (hpp:194,215)
+      {
+        double* w = sW + lane * SW;
+#pragma unroll
+        for (int t = 0; t < NW1; ++t) w[t] = nq * lW1[t];
+#pragma unroll
+        for (int t = 0; t < NW1; ++t) w[NW1 + t] = uW1[t];
+#pragma unroll
+        for (int t = 0; t < NWP; ++t) w[2 * NW1 + t] = valid ? I0[t] : 0.0;
+      }
+      __syncwarp();
+      // ---- phase B: lane (l,u) accumulates its stencil column over the warp's particles ----
+#pragma unroll 4
+      for (int it = 0; it < 32 / PER; ++it) {
+        const double* w = sW + (it * PER + sub) * SW;
+        const double ab = w[my_tl] * w[NW1 + my_tu];
+#pragma unroll
+        for (int t = 0; t < NWP; ++t) acc[t] = fma(ab, w[2 * NW1 + t], acc[t]);
+      }
+      __syncwarp();
+
+      // ---- re-file: stayers compacted in place, movers to the list ---------------------------
+      const unsigned stay_mask = __ballot_sync(0xffffffffu, valid && !moves);
+      const unsigned move_mask = __ballot_sync(0xffffffffu, moves);
+      const int nstay = __popc(stay_mask);
+      if (valid && !moves) {
+        const long dst = s0 + wp + __popc(stay_mask & ((1u << lane) - 1u));
+        if (dst == idx) {  // nothing ahead of us left: only the changed components move
+          p.x[A][dst] = xa_new;
+          p.v[U][dst] = vu;
+          p.v[L][dst] = vl;
+          if (!g.per[A]) p.v[A][dst] = va;
+        } else {
+          p.x[A][dst] = xa_new;
+          p.x[U][dst] = xu;
+          p.x[L][dst] = xl;
+          p.v[A][dst] = va;
+          p.v[U][dst] = vu;
+          p.v[L][dst] = vl;
+        }
+      }
+      if (move_mask) {
+        unsigned basei = 0;
+        const int leader = __ffs(move_mask) - 1;
+        if (lane == leader) basei = atomicAdd(mv.n, (unsigned)__popc(move_mask));
+        basei = __shfl_sync(0xffffffffu, basei, leader);
+        if (moves) {
+          const unsigned m = basei + __popc(move_mask & ((1u << lane) - 1u));
+          if (m < mv.cap) {
+            int dest;
+            if (A == 2) {
+              const int knew = newA - g.z0;
+              dest = knew < 0 ? -1 : (knew >= g.n[2] ? -2 : (int)(cell + (long)(knew - cc[2]) * cstride[2]));
+            } else {
+              dest = (int)(cell + (long)(newA - homeA) * cstride[A]);
+            }
+            mv.x[A][m] = xa_new;
+            mv.x[U][m] = xu;
+            mv.x[L][m] = xl;
+            mv.v[A][m] = va;
+            mv.v[U][m] = vu;
+            mv.v[L][m] = vl;
+            mv.dest[m] = dest;
+          } else {
+            atomicOr(&flags[1], 1);
+          }
+        }
+      }
+      wp += nstay;
+      __syncwarp();
+    }
+
+    // ---- flush: one reduction per stencil point and cell -----------------------------------
+#pragma unroll
+    for (int t = 0; t < NWP; ++t) {
+#pragma unroll
+      for (int s = LU; s < 32; s <<= 1) acc[t] += __shfl_xor_sync(0xffffffffu, acc[t], s);
+    }
+    if (sub == 0) {
+      const long row = base + my_tl * st[L] + my_tu * st[U];
+#pragma unroll
+      for (int t = 0; t < NWP; ++t) atomicAdd(&Ea[row + t * st[A]], acc[t]);
+    }
+    if (lane == 0) count[cell] = wp;
+  }
+}
+
+// movers -> their new bin (or the tail when the bin is full)
+__global__ void __launch_bounds__(256)
+    k_insert_movers(MoverList mv, ParticleSoA b, const long* __restrict__ start, int* __restrict__ count,
+                    ParticleSoA tail, unsigned long long* __restrict__ tail_n, long tail_cap, int* __restrict__ flags) {
+  const unsigned n = min(*mv.n, mv.cap);
+  for (unsigned m = blockIdx.x * blockDim.x + threadIdx.x; m < n; m += gridDim.x * blockDim.x) {
+    const int dest = mv.dest[m];
+    if (dest < 0) continue;  // handled by the migration kernels (comm.cu)
+    const int cap = (int)(start[dest + 1] - start[dest]);
+    const int slot = atomicAdd(&count[dest], 1);
+    if (slot < cap) {
+      const long d = start[dest] + slot;
+#pragma unroll
+      for (int k = 0; k < 3; ++k) {
+        b.x[k][d] = mv.x[k][m];
+        b.v[k][d] = mv.v[k][m];
+      }
+    } else {
+      atomicSub(&count[dest], 1);
+      const unsigned long long t = atomicAdd(tail_n, 1ull);
+      if ((long)t < tail_cap) {
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+          tail.x[k][t] = mv.x[k][m];
+          tail.v[k][t] = mv.v[k][m];
+        }
+      } else {
+        atomicOr(&flags[1], 2);
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------
+// push_V_E, binned
+// ------------------------------------------------------------------------------------
+template <class I>
+__global__ void __launch_bounds__(kThreads, 2)
+    k_push_v_e_binned(Grid g, ParticleSoA p, const long* __restrict__ start, const int* __restrict__ count,
+                      const double* __restrict__ E, double coef, long ncell, int cells_per_block) {
+  constexpr int NW1 = I::NW1, NWP = I::NWP;
+  constexpr int NS = NW1 * NW1 * NW1;
+  extern __shared__ double smem[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  double* sE = smem + warp * 3 * NS;  // [3][NW1][NW1][NW1]
+  const long cstride2 = (long)g.n[0] * g.n[1];
+  const long cbeg = (long)blockIdx.x * cells_per_block;
+  long cend = cbeg + cells_per_block;
+  if (cend > ncell) cend = ncell;
+  for (long cell = cbeg + warp; cell < cend; cell += kWarps) {
+    const int cnt = count[cell];
+    if (cnt == 0) continue;
+    const long s0 = start[cell];
+    const int ci = (int)(cell % g.n[0]), cj = (int)((cell / g.n[0]) % g.n[1]), ck = (int)(cell / cstride2);
+    const long base = g.at(ci, cj, ck) + (1 - I::W) * (1 + g.pj + g.pk);
+    __syncwarp();
+    for (int s = lane; s < 3 * NS; s += 32) {
+      const int comp = s / NS, r = s % NS;
+      const int ti = r % NW1, tj = (r / NW1) % NW1, tk = r / (NW1 * NW1);
+      sE[s] = __ldg(&E[base + ti + tj * g.pj + tk * g.pk + comp * g.pc]);
+    }
+    __syncwarp();
+    for (int off = lane; off < cnt; off += 32) {
+      const long idx = s0 + off;
+      const double x = p.x[0][idx], y = p.x[1][idx], z = p.x[2][idx];
+      double w1x[NW1], w1y[NW1], w1z[NW1], wpx[NWP], wpy[NWP], wpz[NWP];
+      eval_w1<I>(x, ci, w1x);
+      eval_w1<I>(y, cj, w1y);
+      eval_w1<I>(z, ck + g.z0, w1z);
+      eval_wp<I>(x, ci, wpx);
+      eval_wp<I>(y, cj, wpy);
+      eval_wp<I>(z, ck + g.z0, wpz);
+      double dv[3];
+      gather_E<I>(sE, (long)NW1, (long)NW1 * NW1, (long)NS, w1x, w1y, w1z, wpx, wpy, wpz, dv,
+                  [](const double* ptr) { return *ptr; });
+      p.v[0][idx] = fma(dv[0], coef, p.v[0][idx]);  // hpp:339-341
+      p.v[1][idx] = fma(dv[1], coef, p.v[1][idx]);
+      p.v[2][idx] = fma(dv[2], coef, p.v[2][idx]);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------
+// diagnostics / transfers over the binned store (warp per cell)
+// ------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+    k_kinetic_binned(ParticleSoA p, const long* __restrict__ start, const int* __restrict__ count, long ncell,
+                     double half_m, double* __restrict__ accum) {
+  const int lane = threadIdx.x & 31;
+  const long wid = (blockIdx.x * (long)blockDim.x + threadIdx.x) >> 5, nw = ((long)gridDim.x * blockDim.x) >> 5;
+  double a = 0;
+  for (long cell = wid; cell < ncell; cell += nw) {
+    const int cnt = count[cell];
+    const long s0 = start[cell];
+    for (int i = lane; i < cnt; i += 32) {
+      const double vx = p.v[0][s0 + i], vy = p.v[1][s0 + i], vz = p.v[2][s0 + i];
+      a += half_m * (vx * vx + vy * vy + vz * vz);
+    }
+  }
+  for (int s = 16; s > 0; s >>= 1) a += __shfl_xor_sync(0xffffffffu, a, s);
+  __shared__ double sh[8];
+  if (lane == 0) sh[threadIdx.x >> 5] = a;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double t = 0;
+    for (int w = 0; w < 8; ++w) t += sh[w];
+    atomicAdd(accum, t);
+  }
+}
+
+// packed[prefix[cell] + i] = arr[start[cell] + i]
+__global__ void __launch_bounds__(256)
+    k_pack_bins(const double* __restrict__ arr, const long* __restrict__ start, const int* __restrict__ count,
+                const long* __restrict__ prefix, long ncell, double* __restrict__ packed) {
+  const int lane = threadIdx.x & 31;
+  const long wid = (blockIdx.x * (long)blockDim.x + threadIdx.x) >> 5, nw = ((long)gridDim.x * blockDim.x) >> 5;
+  for (long cell = wid; cell < ncell; cell += nw) {
+    const int cnt = count[cell];
+    const long s0 = start[cell], d0 = prefix[cell];
+    for (int i = lane; i < cnt; i += 32) packed[d0 + i] = arr[s0 + i];
+  }
+}
+
+// ---- rebin ---------------------------------------------------------------------------
+__device__ __forceinline__ long cell_of(const Grid& g, double x, double y, double z) {
+  int i = (int)floor(x), j = (int)floor(y), k = (int)floor(z) - g.z0;
+  i = min(max(i, 0), g.n[0] - 1);
+  j = min(max(j, 0), g.n[1] - 1);
+  k = min(max(k, 0), g.n[2] - 1);
+  return ((long)k * g.n[1] + j) * g.n[0] + i;
+}
+
+__global__ void k_count_tail(Grid g, ParticleSoA t, long n, const unsigned long long* __restrict__ n_dev,
+                             int* __restrict__ newcount) {
+  if (n_dev) n = (long)*n_dev;
+  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x)
+    atomicAdd(&newcount[cell_of(g, t.x[0][i], t.x[1][i], t.x[2][i])], 1);
+}
+
+struct CapOf {  // bin capacity for a live count: ~25 % slack, multiple of 8 slots
+  __host__ __device__ long operator()(int n) const {
+    const int slack = n / 4 > 8 ? n / 4 : 8;
+    return (long)((n + slack + 7) & ~7);
+  }
+};
+
+// perm[new slot] = source slot (old bins: index < old_slots; tail: old_slots + t)
+__global__ void __launch_bounds__(256)
+    k_perm_bins(const long* __restrict__ ostart, const int* __restrict__ ocount, const long* __restrict__ nstart,
+                long ncell, unsigned* __restrict__ perm) {
+  const int lane = threadIdx.x & 31;
+  const long wid = (blockIdx.x * (long)blockDim.x + threadIdx.x) >> 5, nw = ((long)gridDim.x * blockDim.x) >> 5;
+  for (long cell = wid; cell < ncell; cell += nw) {
+    const int cnt = ocount[cell];
+    const long s0 = ostart[cell], d0 = nstart[cell];
+    for (int i = lane; i < cnt; i += 32) perm[d0 + i] = (unsigned)(s0 + i);
+  }
+}
+__global__ void k_perm_tail(Grid g, ParticleSoA t, long n, const unsigned long long* __restrict__ n_dev,
+                            const long* __restrict__ nstart, int* __restrict__ fill, long old_slots,
+                            unsigned* __restrict__ perm) {
+  if (n_dev) n = (long)*n_dev;
+  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x) {
+    const long cell = cell_of(g, t.x[0][i], t.x[1][i], t.x[2][i]);
+    const int slot = atomicAdd(&fill[cell], 1);
+    perm[nstart[cell] + slot] = (unsigned)(old_slots + i);
+  }
+}
+__global__ void __launch_bounds__(256)
+    k_gather_perm(const double* __restrict__ obins, const double* __restrict__ tail, long old_slots,
+                  const unsigned* __restrict__ perm, const long* __restrict__ nstart, const int* __restrict__ ncount,
+                  long ncell, double* __restrict__ out) {
+  const int lane = threadIdx.x & 31;
+  const long wid = (blockIdx.x * (long)blockDim.x + threadIdx.x) >> 5, nw = ((long)gridDim.x * blockDim.x) >> 5;
+  for (long cell = wid; cell < ncell; cell += nw) {
+    const int cnt = ncount[cell];
+    const long d0 = nstart[cell];
+    for (int i = lane; i < cnt; i += 32) {
+      const long src = (long)perm[d0 + i];
+      out[d0 + i] = src < old_slots ? obins[src] : tail[src - old_slots];
+    }
+  }
+}
+
+int grid_warps(const Ctx* c, long ncell) {
+  long b = (ncell * 32 + 255) / 256;
+  const long cap = (long)c->sm_count * 16;
+  return (int)(b > cap ? cap : (b < 1 ? 1 : b));
+}
+
+int ensure_cub(Ctx* c, size_t bytes) {
+  EngineState* e = eng(c);
+  if (bytes > e->cub_bytes) {
+    if (e->cub_tmp) cudaFree(e->cub_tmp);
+    e->cub_tmp = nullptr;
+    SPIC_CUDA_CHECK(c, cudaMalloc(&e->cub_tmp, bytes));
+    e->cub_bytes = bytes;
+  }
+  return SPIC_OK;
+}
+
+int ensure_movers(Ctx* c, long n_total) {
+  EngineState* e = eng(c);
+  double frac = e->mover_frac > 0 ? e->mover_frac : (n_total < (1L << 26) ? 0.5 : 1.0 / 16);
+  long want = (long)(n_total * frac) + 65536;
+  if (want > 0xfffffff0L) want = 0xfffffff0L;
+  if ((long)e->mv.cap >= want) return SPIC_OK;
+  for (int d = 0; d < 3; ++d) {
+    if (e->mv.x[d]) cudaFree(e->mv.x[d]);
+    if (e->mv.v[d]) cudaFree(e->mv.v[d]);
+    SPIC_CUDA_CHECK(c, cudaMalloc(&e->mv.x[d], sizeof(double) * want));
+    SPIC_CUDA_CHECK(c, cudaMalloc(&e->mv.v[d], sizeof(double) * want));
+  }
+  if (e->mv.dest) cudaFree(e->mv.dest);
+  SPIC_CUDA_CHECK(c, cudaMalloc(&e->mv.dest, sizeof(int) * want));
+  if (!e->mv.n) {
+    SPIC_CUDA_CHECK(c, cudaMalloc(&e->mv.n, sizeof(unsigned) * 4));
+    SPIC_CUDA_CHECK(c, cudaMemsetAsync(e->mv.n, 0, sizeof(unsigned) * 4, c->stream));
+  }
+  if (!e->d_scalar) SPIC_CUDA_CHECK(c, cudaMalloc(&e->d_scalar, sizeof(unsigned long long) * 8));
+  e->mv.cap = (unsigned)want;
+  return SPIC_OK;
+}
+
+void free_soa_local(ParticleSoA& p) {
+  for (int d = 0; d < 3; ++d) {
+    if (p.x[d]) cudaFree(p.x[d]);
+    if (p.v[d]) cudaFree(p.v[d]);
+    p.x[d] = p.v[d] = nullptr;
+  }
+}
+
+long tail_capacity(long n_total) {
+  long t = n_total / 32 + 65536;
+  return t;
+}
+
+// Rebuild the bins of species s from its current bins + tail (tail_n_host < 0: read *d_nd).
+int rebin(Ctx* c, Species& s, long tail_n_host) {
+  const long ncell = c->g.cells();
+  int rc;
+  if (!s.d_nd) {
+    SPIC_CUDA_CHECK(c, cudaMalloc(&s.d_nd, sizeof(unsigned long long)));
+    SPIC_CUDA_CHECK(c, cudaMemsetAsync(s.d_nd, 0, sizeof(unsigned long long), c->stream));
+  }
+  long tail_n = tail_n_host;
+  if (tail_n < 0) {
+    unsigned long long h = 0;
+    SPIC_CUDA_CHECK(c, cudaMemcpyAsync(&h, s.d_nd, sizeof h, cudaMemcpyDeviceToHost, c->stream));
+    SPIC_CUDA_CHECK(c, cudaStreamSynchronize(c->stream));
+    tail_n = (long)h < s.capd ? (long)h : s.capd;
+  }
+  int* ncount = nullptr;
+  int* fill = nullptr;
+  long* nstart = nullptr;
+  SPIC_CUDA_CHECK(c, cudaMalloc(&ncount, sizeof(int) * (ncell + 1)));
+  SPIC_CUDA_CHECK(c, cudaMalloc(&nstart, sizeof(long) * (ncell + 1)));
+  if (s.count)
+    SPIC_CUDA_CHECK(c, cudaMemcpyAsync(ncount, s.count, sizeof(int) * ncell, cudaMemcpyDeviceToDevice, c->stream));
+  else
+    SPIC_CUDA_CHECK(c, cudaMemsetAsync(ncount, 0, sizeof(int) * ncell, c->stream));
+  SPIC_CUDA_CHECK(c, cudaMemsetAsync(ncount + ncell, 0, sizeof(int), c->stream));
+  if (tail_n > 0) {
+    long b = (tail_n + 255) / 256;
+    if (b > (long)c->sm_count * 32) b = (long)c->sm_count * 32;
+    k_count_tail<<<(int)b, 256, 0, c->stream>>>(c->g, s.d, tail_n, nullptr, ncount);
+    c->launches++;
+  }
+  // capacities -> exclusive scan -> new starts (ncell + 1 entries; the last is the slot total)
+  {
+    cub::TransformInputIterator<long, CapOf, const int*> caps(ncount, CapOf());
+    size_t bytes = 0;
+    cub::DeviceScan::ExclusiveSum(nullptr, bytes, caps, nstart, (int)(ncell + 1), c->stream);
+    if ((rc = ensure_cub(c, bytes))) return rc;
+    cub::DeviceScan::ExclusiveSum(eng(c)->cub_tmp, bytes, caps, nstart, (int)(ncell + 1), c->stream);
+    c->launches++;
+  }
+  long new_slots = 0;
+  SPIC_CUDA_CHECK(c, cudaMemcpyAsync(&new_slots, nstart + ncell, sizeof(long), cudaMemcpyDeviceToHost, c->stream));
+  SPIC_CUDA_CHECK(c, cudaStreamSynchronize(c->stream));
+  if (new_slots + 1 >= 0xffffffffL || s.slots + tail_n >= 0xffffffffL) {
+    cudaFree(ncount);
+    cudaFree(nstart);
+    c->err = "more than 2^32 particle slots on one rank: decompose over more GPUs";
+    return SPIC_EINVAL;
+  }
+  unsigned* perm = nullptr;
+  SPIC_CUDA_CHECK(c, cudaMalloc(&perm, sizeof(unsigned) * (size_t)(new_slots + 1)));
+  if (s.count) {
+    k_perm_bins<<<grid_warps(c, ncell), 256, 0, c->stream>>>(s.start, s.count, nstart, ncell, perm);
+    c->launches++;
+  }
+  if (tail_n > 0) {
+    SPIC_CUDA_CHECK(c, cudaMalloc(&fill, sizeof(int) * ncell));
+    if (s.count)
+      SPIC_CUDA_CHECK(c, cudaMemcpyAsync(fill, s.count, sizeof(int) * ncell, cudaMemcpyDeviceToDevice, c->stream));
+    else
+      SPIC_CUDA_CHECK(c, cudaMemsetAsync(fill, 0, sizeof(int) * ncell, c->stream));
+    long b = (tail_n + 255) / 256;
+    if (b > (long)c->sm_count * 32) b = (long)c->sm_count * 32;
+    k_perm_tail<<<(int)b, 256, 0, c->stream>>>(c->g, s.d, tail_n, nullptr, nstart, fill, s.slots, perm);
+    c->launches++;
+  }
+  // permute the six arrays one at a time (peak extra memory: one array + perm)
+  for (int a = 0; a < 6; ++a) {
+    double*& old_b = a < 3 ? s.b.x[a] : s.b.v[a - 3];
+    const double* tl = a < 3 ? s.d.x[a] : s.d.v[a - 3];
+    double* out = nullptr;
+    SPIC_CUDA_CHECK(c, cudaMalloc(&out, sizeof(double) * (size_t)(new_slots + 1)));
+    k_gather_perm<<<grid_warps(c, ncell), 256, 0, c->stream>>>(old_b, tl, s.slots, perm, nstart, ncount, ncell, out);
+    c->launches++;
+    SPIC_CUDA_CHECK(c, cudaStreamSynchronize(c->stream));
+    if (old_b) cudaFree(old_b);
+    old_b = out;
+  }
+  cudaFree(perm);
+  if (fill) cudaFree(fill);
+  if (s.start) cudaFree(s.start);
+  if (s.count) cudaFree(s.count);
+  s.start = nstart;
+  s.count = ncount;
+  s.slots = new_slots;
+  s.binned = true;
+  // live total (for buffer sizing) and an empty tail of the right capacity
+  {
+    size_t bytes = 0;
+    long* d_sum = reinterpret_cast<long*>(c->scratch);
+    cub::TransformInputIterator<long, ToLong, const int*> it(ncount, ToLong());
+    cub::DeviceReduce::Sum(nullptr, bytes, it, d_sum, (int)ncell, c->stream);
+    if ((rc = ensure_cub(c, bytes))) return rc;
+    cub::DeviceReduce::Sum(eng(c)->cub_tmp, bytes, it, d_sum, (int)ncell, c->stream);
+    c->launches++;
+    SPIC_CUDA_CHECK(c, cudaMemcpyAsync(&s.n_total, d_sum, sizeof(long), cudaMemcpyDeviceToHost, c->stream));
+    SPIC_CUDA_CHECK(c, cudaStreamSynchronize(c->stream));
+  }
+  const long want_tail = tail_capacity(s.n_total);
+  if (s.capd != want_tail) {
+    free_soa_local(s.d);
+    for (int d = 0; d < 3; ++d) {
+      SPIC_CUDA_CHECK(c, cudaMalloc(&s.d.x[d], sizeof(double) * want_tail));
+      SPIC_CUDA_CHECK(c, cudaMalloc(&s.d.v[d], sizeof(double) * want_tail));
+    }
+    s.capd = want_tail;
+  }
+  s.nd = 0;
+  SPIC_CUDA_CHECK(c, cudaMemsetAsync(s.d_nd, 0, sizeof(unsigned long long), c->stream));
+  return ensure_movers(c, s.n_total);
+}
+
+template <class I>
+void theta_axis_binned_dispatch(Ctx* c, Species& s, int comp, double dt) {
+  EngineState* e = eng(c);
+  const long ncell = c->g.cells();
+  const int cpb = e->cells_per_block;
+  const int grid = (int)((ncell + cpb - 1) / cpb);
+  constexpr int per_warp = 2 * I::NWP * I::NW1 * I::NW1 + 32 * (2 * I::NW1 + I::NWP);
+  const size_t smem = sizeof(double) * kWarps * per_warp;
+  const double qm = s.q / s.m;
+  if (comp == 0)
+    k_theta_axis_binned<I, 0><<<grid, kThreads, smem, c->stream>>>(c->g, s.b, s.start, s.count, c->E, c->B, s.q, qm, dt,
+                                                                  e->mv, c->d_flags, ncell, cpb);
+  else if (comp == 1)
+    k_theta_axis_binned<I, 1><<<grid, kThreads, smem, c->stream>>>(c->g, s.b, s.start, s.count, c->E, c->B, s.q, qm, dt,
+                                                                  e->mv, c->d_flags, ncell, cpb);
+  else
+    k_theta_axis_binned<I, 2><<<grid, kThreads, smem, c->stream>>>(c->g, s.b, s.start, s.count, c->E, c->B, s.q, qm, dt,
+                                                                  e->mv, c->d_flags, ncell, cpb);
+  c->launches++;
+}
+
+}  // namespace
+
+// ---- engine interface -------------------------------------------------------------------
+int engine_ingest(Ctx* c, Species& s) {
+  if (c->cfg.engine != SPIC_ENGINE_BINNED || s.nd == 0) return SPIC_OK;
+  return rebin(c, s, s.nd);
+}
+
+void engine_free_species(Ctx*, Species& s) {
+  free_soa_local(s.b);
+  if (s.start) cudaFree(s.start);
+  if (s.count) cudaFree(s.count);
+  if (s.d_nd) cudaFree(s.d_nd);
+  s.start = nullptr;
+  s.count = nullptr;
+  s.d_nd = nullptr;
+  s.slots = 0;
+  s.binned = false;
+}
+
+void engine_destroy(Ctx* c) {
+  if (!c->engine) return;
+  EngineState* e = static_cast<EngineState*>(c->engine);
+  for (int d = 0; d < 3; ++d) {
+    if (e->mv.x[d]) cudaFree(e->mv.x[d]);
+    if (e->mv.v[d]) cudaFree(e->mv.v[d]);
+  }
+  if (e->mv.dest) cudaFree(e->mv.dest);
+  if (e->mv.n) cudaFree(e->mv.n);
+  if (e->cub_tmp) cudaFree(e->cub_tmp);
+  if (e->d_scalar) cudaFree(e->d_scalar);
+  delete e;
+  c->engine = nullptr;
+}
+
+static int tail_count(Ctx* c, Species& s, long* n) {
+  unsigned long long h = 0;
+  SPIC_CUDA_CHECK(c, cudaMemcpyAsync(&h, s.d_nd, sizeof h, cudaMemcpyDeviceToHost, c->stream));
+  SPIC_CUDA_CHECK(c, cudaStreamSynchronize(c->stream));
+  *n = (long)h < s.capd ? (long)h : s.capd;
+  return SPIC_OK;
+}
+
+int engine_count(Ctx* c, Species& s, long* nb) {
+  *nb = 0;
+  if (!s.binned) return SPIC_OK;
+  const long ncell = c->g.cells();
+  cub::TransformInputIterator<long, ToLong, const int*> it(s.count, ToLong());
+  size_t bytes = 0;
+  long* d_sum = reinterpret_cast<long*>(c->scratch);
+  cub::DeviceReduce::Sum(nullptr, bytes, it, d_sum, (int)ncell, c->stream);
+  int rc = ensure_cub(c, bytes);
+  if (rc) return rc;
+  cub::DeviceReduce::Sum(eng(c)->cub_tmp, bytes, it, d_sum, (int)ncell, c->stream);
+  c->launches++;
+  long live = 0, tail = 0;
+  SPIC_CUDA_CHECK(c, cudaMemcpyAsync(&live, d_sum, sizeof(long), cudaMemcpyDeviceToHost, c->stream));
+  if ((rc = tail_count(c, s, &tail))) return rc;
+  s.nd = tail;  // host mirror: api.cu adds s.nd
+  *nb = live;
+  return SPIC_OK;
+}
+
+int engine_gather(Ctx* c, Species& s, double* hx[3], double* hv[3], long* nb) {
+  *nb = 0;
+  if (!s.binned) return SPIC_OK;
+  const long ncell = c->g.cells();
+  long live = 0;
+  int rc = engine_count(c, s, &live);
+  if (rc) return rc;
+  long* prefix = nullptr;
+  double* packed = nullptr;
+  SPIC_CUDA_CHECK(c, cudaMalloc(&prefix, sizeof(long) * (ncell + 1)));
+  SPIC_CUDA_CHECK(c, cudaMalloc(&packed, sizeof(double) * (size_t)(live + 1)));
+  cub::TransformInputIterator<long, ToLong, const int*> it(s.count, ToLong());
+  size_t bytes = 0;
+  cub::DeviceScan::ExclusiveSum(nullptr, bytes, it, prefix, (int)ncell, c->stream);
+  if ((rc = ensure_cub(c, bytes))) return rc;
+  cub::DeviceScan::ExclusiveSum(eng(c)->cub_tmp, bytes, it, prefix, (int)ncell, c->stream);
+  c->launches++;
+  for (int a = 0; a < 6; ++a) {
+    const double* src = a < 3 ? s.b.x[a] : s.b.v[a - 3];
+    double* dst = a < 3 ? hx[a] : hv[a - 3];
+    k_pack_bins<<<grid_warps(c, ncell), 256, 0, c->stream>>>(src, s.start, s.count, prefix, ncell, packed);
+    c->launches++;
+    SPIC_CUDA_CHECK(c, cudaMemcpyAsync(dst, packed, sizeof(double) * (size_t)live, cudaMemcpyDeviceToHost, c->stream));
+    SPIC_CUDA_CHECK(c, cudaStreamSynchronize(c->stream));
+  }
+  cudaFree(prefix);
+  cudaFree(packed);
+  *nb = live;
+  return SPIC_OK;
+}
+
+int engine_theta_axis(Ctx* c, Species& s, int comp, double dt) {
+  if (!s.binned) return SPIC_OK;
+  EngineState* e = eng(c);
+  {
+    KernelTimer t(c);
+    if (c->cfg.interp == SPIC_INTERP_P8R2)
+      theta_axis_binned_dispatch<InterpP8R2>(c, s, comp, dt);
+    else
+      theta_axis_binned_dispatch<InterpPWL>(c, s, comp, dt);
+  }
+  // the tail runs through the thread-per-particle kernel BEFORE new overflow can join it
+  launch_theta_axis_direct(c, s.d, s.capd, s.d_nd, s.q, s.m, comp, dt);
+  int nb = (int)((e->mv.cap + 255) / 256);
+  if (nb > c->sm_count * 8) nb = c->sm_count * 8;
+  k_insert_movers<<<nb, 256, 0, c->stream>>>(e->mv, s.b, s.start, s.count, s.d, s.d_nd, s.capd, c->d_flags);
+  c->launches++;
+  if (c->cfg.nranks > 1 && comp == 2) {
+    int rc = comm_collect_leavers(c, s, e->mv.x, e->mv.v, e->mv.dest, e->mv.n, e->mv.cap);
+    if (rc) return rc;
+  }
+  SPIC_CUDA_CHECK(c, cudaMemsetAsync(e->mv.n, 0, sizeof(unsigned), c->stream));
+  return SPIC_OK;
+}
+
+int engine_push_v_e(Ctx* c, Species& s, double dt) {
+  if (!s.binned) return SPIC_OK;
+  EngineState* e = eng(c);
+  const long ncell = c->g.cells();
+  const int cpb = e->cells_per_block;
+  const int grid = (int)((ncell + cpb - 1) / cpb);
+  const double coef = dt * s.q / s.m;  // hpp:267
+  {
+    KernelTimer t(c);
+    if (c->cfg.interp == SPIC_INTERP_P8R2) {
+      const size_t smem = sizeof(double) * kWarps * 3 * 64;
+      k_push_v_e_binned<InterpP8R2><<<grid, kThreads, smem, c->stream>>>(c->g, s.b, s.start, s.count, c->E, coef, ncell, cpb);
+    } else {
+      const size_t smem = sizeof(double) * kWarps * 3 * 8;
+      k_push_v_e_binned<InterpPWL><<<grid, kThreads, smem, c->stream>>>(c->g, s.b, s.start, s.count, c->E, coef, ncell, cpb);
+    }
+    c->launches++;
+  }
+  launch_push_v_e_direct(c, s.d, s.capd, s.d_nd, s.q, s.m, dt);
+  return SPIC_OK;
+}
+
+int engine_kinetic(Ctx* c, Species& s, double* acc) {
+  if (!s.binned) return SPIC_OK;
+  const long ncell = c->g.cells();
+  k_kinetic_binned<<<grid_warps(c, ncell), 256, 0, c->stream>>>(s.b, s.start, s.count, ncell, 0.5 * s.m, acc);
+  c->launches++;
+  launch_kinetic_energy(c, s.d, s.capd, s.d_nd, s.m, acc);
+  return SPIC_OK;
+}
+
+// Gauss diagnostic: pack each bin array and reuse the thread-per-particle rho deposit
+int engine_deposit_rho(Ctx* c, Species& s, double* out) {
+  if (!s.binned) return SPIC_OK;
+  const long ncell = c->g.cells();
+  long live = 0;
+  int rc = engine_count(c, s, &live);
+  if (rc) return rc;
+  long* prefix = nullptr;
+  SPIC_CUDA_CHECK(c, cudaMalloc(&prefix, sizeof(long) * (ncell + 1)));
+  cub::TransformInputIterator<long, ToLong, const int*> it(s.count, ToLong());
+  size_t bytes = 0;
+  cub::DeviceScan::ExclusiveSum(nullptr, bytes, it, prefix, (int)ncell, c->stream);
+  if ((rc = ensure_cub(c, bytes))) return rc;
+  cub::DeviceScan::ExclusiveSum(eng(c)->cub_tmp, bytes, it, prefix, (int)ncell, c->stream);
+  ParticleSoA tmp{};
+  for (int d = 0; d < 3; ++d) {
+    SPIC_CUDA_CHECK(c, cudaMalloc(&tmp.x[d], sizeof(double) * (size_t)(live + 1)));
+    k_pack_bins<<<grid_warps(c, ncell), 256, 0, c->stream>>>(s.b.x[d], s.start, s.count, prefix, ncell, tmp.x[d]);
+    c->launches++;
+  }
+  launch_deposit_rho(c, tmp, live, nullptr, s.q, out);
+  launch_deposit_rho(c, s.d, s.capd, s.d_nd, s.q, out);
+  SPIC_CUDA_CHECK(c, cudaStreamSynchronize(c->stream));
+  for (int d = 0; d < 3; ++d) cudaFree(tmp.x[d]);
+  cudaFree(prefix);
+  return SPIC_OK;
+}
+
+int engine_maintain(Ctx* c) {
+  // rebin a species whose overflow tail has grown past ~0.4 % of its particles
+  for (auto& s : c->sp) {
+    if (!s.binned) continue;
+    long tail = 0;
+    int rc = tail_count(c, s, &tail);
+    if (rc) return rc;
+    if (tail > s.n_total / 256 + 1024 || tail >= s.capd) {
+      if ((rc = rebin(c, s, tail))) return rc;
+    }
+  }
+  return SPIC_OK;
+}
+
+int engine_force_rebin(Ctx* c) {
+  for (auto& s : c->sp)
+    if (s.binned) {
+      int rc = rebin(c, s, -1);
+      if (rc) return rc;
+    }
+  return SPIC_OK;
+}
+
+int engine_set_option(Ctx* c, const char* name, double value) {
+  EngineState* e = eng(c);
+  if (!strcmp(name, "mover_frac")) {
+    e->mover_frac = value;
+    return SPIC_OK;
+  }
+  if (!strcmp(name, "cells_per_block")) {
+    if (value < 1) return SPIC_EINVAL;
+    e->cells_per_block = (int)value;
+    return SPIC_OK;
+  }
+  if (!strcmp(name, "rebin")) return engine_force_rebin(c);
+  c->err = std::string("unknown option ") + name;
+  return SPIC_EINVAL;
+}
+
 }  // namespace spic

@@ -21,10 +21,12 @@ constexpr int kBlock = 128;
 
 template <class I, int A>
 __global__ void __launch_bounds__(kBlock)
-    k_theta_axis_direct(Grid g, ParticleSoA p, long n, double* __restrict__ E, const double* __restrict__ B,
-                        double q, double qm, double dt, int* __restrict__ flags) {
+    k_theta_axis_direct(Grid g, ParticleSoA p, long n, const unsigned long long* __restrict__ n_dev,
+                        double* __restrict__ E, const double* __restrict__ B, double q, double qm, double dt,
+                        int* __restrict__ flags) {
   constexpr int U = (A + 1) % 3, L = (A + 2) % 3;  // hpp:90-91
   const long i = blockIdx.x * (long)blockDim.x + threadIdx.x;
+  if (n_dev) n = (long)*n_dev;
   if (i >= n) return;
   const long st[3] = {1, g.pj, g.pk};
 
@@ -94,8 +96,10 @@ __global__ void __launch_bounds__(kBlock)
 
 template <class I>
 __global__ void __launch_bounds__(kBlock)
-    k_push_v_e_direct(Grid g, ParticleSoA p, long n, const double* __restrict__ E, double coef) {
+    k_push_v_e_direct(Grid g, ParticleSoA p, long n, const unsigned long long* __restrict__ n_dev,
+                      const double* __restrict__ E, double coef) {
   const long i = blockIdx.x * (long)blockDim.x + threadIdx.x;
+  if (n_dev) n = (long)*n_dev;
   if (i >= n) return;
   const double x = p.x[0][i], y = p.x[1][i], z = p.x[2][i];
   const int cx = (int)floor(x), cy = (int)floor(y), cz = (int)floor(z);
@@ -115,8 +119,10 @@ __global__ void __launch_bounds__(kBlock)
   p.v[2][i] = fma(dv[2], coef, p.v[2][i]);
 }
 
-__global__ void __launch_bounds__(256) k_kinetic(ParticleSoA p, long n, double half_m, double* __restrict__ accum) {
+__global__ void __launch_bounds__(256) k_kinetic(ParticleSoA p, long n, const unsigned long long* __restrict__ n_dev,
+                                                 double half_m, double* __restrict__ accum) {
   double a = 0;
+  if (n_dev) n = (long)*n_dev;
   for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x) {
     const double vx = p.v[0][i], vy = p.v[1][i], vz = p.v[2][i];
     a += half_m * (vx * vx + vy * vy + vz * vz);
@@ -134,8 +140,11 @@ __global__ void __launch_bounds__(256) k_kinetic(ParticleSoA p, long n, double h
 
 // rho deposit for the Gauss diagnostic: out[cell] -= q W1 W1 W1 (periodic images folded)
 template <class I>
-__global__ void __launch_bounds__(kBlock) k_deposit_rho(Grid g, ParticleSoA p, long n, double q, double* __restrict__ out) {
+__global__ void __launch_bounds__(kBlock) k_deposit_rho(Grid g, ParticleSoA p, long n,
+                                                        const unsigned long long* __restrict__ n_dev, double q,
+                                                        double* __restrict__ out) {
   const long i = blockIdx.x * (long)blockDim.x + threadIdx.x;
+  if (n_dev) n = (long)*n_dev;
   if (i >= n) return;
   const double x = p.x[0][i], y = p.x[1][i], z = p.x[2][i];
   const int cx = (int)floor(x), cy = (int)floor(y), cz = (int)floor(z);
@@ -178,74 +187,61 @@ __global__ void __launch_bounds__(256)
   }
 }
 
-struct KernelTimer {
-  Ctx* c;
-  explicit KernelTimer(Ctx* ctx) : c(ctx) {
-    if (c->time_kernels) cudaEventRecord(c->ev0, c->stream);
-  }
-  ~KernelTimer() {
-    c->particle_launches++;
-    if (c->time_kernels) {
-      cudaEventRecord(c->ev1, c->stream);
-      cudaEventSynchronize(c->ev1);
-      float ms = 0;
-      cudaEventElapsedTime(&ms, c->ev0, c->ev1);
-      c->particle_ms += ms;
-    }
-  }
-};
-
 template <class I>
-void theta_axis_dispatch(Ctx* c, const ParticleSoA& p, long n, double q, double m, int comp, double dt) {
+void theta_axis_dispatch(Ctx* c, const ParticleSoA& p, long n, const unsigned long long* n_dev, double q, double m,
+                         int comp, double dt) {
   const int grid = (int)((n + kBlock - 1) / kBlock);
   const double qm = q / m;  // B_coef, hpp:113
   if (comp == 0)
-    k_theta_axis_direct<I, 0><<<grid, kBlock, 0, c->stream>>>(c->g, p, n, c->E, c->B, q, qm, dt, c->d_flags);
+    k_theta_axis_direct<I, 0><<<grid, kBlock, 0, c->stream>>>(c->g, p, n, n_dev, c->E, c->B, q, qm, dt, c->d_flags);
   else if (comp == 1)
-    k_theta_axis_direct<I, 1><<<grid, kBlock, 0, c->stream>>>(c->g, p, n, c->E, c->B, q, qm, dt, c->d_flags);
+    k_theta_axis_direct<I, 1><<<grid, kBlock, 0, c->stream>>>(c->g, p, n, n_dev, c->E, c->B, q, qm, dt, c->d_flags);
   else
-    k_theta_axis_direct<I, 2><<<grid, kBlock, 0, c->stream>>>(c->g, p, n, c->E, c->B, q, qm, dt, c->d_flags);
+    k_theta_axis_direct<I, 2><<<grid, kBlock, 0, c->stream>>>(c->g, p, n, n_dev, c->E, c->B, q, qm, dt, c->d_flags);
 }
 
 }  // namespace
 
-void launch_theta_axis_direct(Ctx* c, const ParticleSoA& p, long n, double q, double m, int comp, double dt) {
+void launch_theta_axis_direct(Ctx* c, const ParticleSoA& p, long n, const unsigned long long* n_dev, double q,
+                              double m, int comp, double dt) {
   if (n <= 0) return;
   KernelTimer t(c);
   if (c->cfg.interp == SPIC_INTERP_P8R2)
-    theta_axis_dispatch<InterpP8R2>(c, p, n, q, m, comp, dt);
+    theta_axis_dispatch<InterpP8R2>(c, p, n, n_dev, q, m, comp, dt);
   else
-    theta_axis_dispatch<InterpPWL>(c, p, n, q, m, comp, dt);
+    theta_axis_dispatch<InterpPWL>(c, p, n, n_dev, q, m, comp, dt);
   c->launches++;
 }
 
-void launch_push_v_e_direct(Ctx* c, const ParticleSoA& p, long n, double q, double m, double dt) {
+void launch_push_v_e_direct(Ctx* c, const ParticleSoA& p, long n, const unsigned long long* n_dev, double q, double m,
+                            double dt) {
   if (n <= 0) return;
   KernelTimer t(c);
   const int grid = (int)((n + kBlock - 1) / kBlock);
   const double coef = dt * q / m;  // hpp:267
   if (c->cfg.interp == SPIC_INTERP_P8R2)
-    k_push_v_e_direct<InterpP8R2><<<grid, kBlock, 0, c->stream>>>(c->g, p, n, c->E, coef);
+    k_push_v_e_direct<InterpP8R2><<<grid, kBlock, 0, c->stream>>>(c->g, p, n, n_dev, c->E, coef);
   else
-    k_push_v_e_direct<InterpPWL><<<grid, kBlock, 0, c->stream>>>(c->g, p, n, c->E, coef);
+    k_push_v_e_direct<InterpPWL><<<grid, kBlock, 0, c->stream>>>(c->g, p, n, n_dev, c->E, coef);
   c->launches++;
 }
 
-void launch_kinetic_energy(Ctx* c, const ParticleSoA& p, long n, double m, double* accum) {
+void launch_kinetic_energy(Ctx* c, const ParticleSoA& p, long n, const unsigned long long* n_dev, double m,
+                           double* accum) {
   if (n <= 0) return;
   long b = (n + 255) / 256;
   if (b > (long)c->sm_count * 8) b = (long)c->sm_count * 8;
-  k_kinetic<<<(int)b, 256, 0, c->stream>>>(p, n, 0.5 * m, accum);
+  k_kinetic<<<(int)b, 256, 0, c->stream>>>(p, n, n_dev, 0.5 * m, accum);
   c->launches++;
 }
 
-void launch_deposit_rho(Ctx* c, const ParticleSoA& p, long n, double q, double* out) {
+void launch_deposit_rho(Ctx* c, const ParticleSoA& p, long n, const unsigned long long* n_dev, double q, double* out) {
   if (n <= 0) return;
   const int grid = (int)((n + kBlock - 1) / kBlock);
   if (c->cfg.interp == SPIC_INTERP_P8R2)
-    k_deposit_rho<InterpP8R2><<<grid, kBlock, 0, c->stream>>>(c->g, p, n, q, out);
+    k_deposit_rho<InterpP8R2><<<grid, kBlock, 0, c->stream>>>(c->g, p, n, n_dev, q, out);
   else
-    k_deposit_rho<InterpPWL><<<grid, kBlock, 0, c->stream>>>(c->g, p, n, q, out);
+    k_deposit_rho<InterpPWL><<<grid, kBlock, 0, c->stream>>>(c->g, p, n, n_dev, q, out);
   c->launches++;
 }
 

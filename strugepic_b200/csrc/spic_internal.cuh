@@ -35,21 +35,23 @@ struct ParticleSoA {
   double* v[3];
 };
 
-// Cell-binned particle store of one species (engine BINNED).  Bin c occupies slots
-// [start[c], start[c+1]) of the SoA arrays; the first count[c] slots are live and
-// every live particle satisfies floor(pos) == cell c.  Particles that do not fit
-// their bin live in the unbinned tail list and go through the direct kernels.
+// One species = one (q, m).  Engine DIRECT keeps every particle in the list `d`
+// (count `nd` on the host).  Engine BINNED keeps them in cell bins: bin c occupies
+// slots [start[c], start[c+1]) of the SoA arrays `b`; the first count[c] slots are
+// live and every live particle satisfies floor(pos) == cell c.  Particles that do
+// not fit their bin overflow into the tail list `d` (count on the device, *d_nd)
+// and go through the thread-per-particle kernels until the next rebin.
 struct Species {
   double q = 0, m = 0;
-  // direct list (engine DIRECT: all particles; engine BINNED: overflow tail)
   ParticleSoA d{};
   long nd = 0, capd = 0;
-  // binned store
+  unsigned long long* d_nd = nullptr;  // device count of `d` (BINNED); null => use nd
   ParticleSoA b{};
-  long slots = 0;          // allocated slots in b
-  long* start = nullptr;   // [cells+1]
-  int* count = nullptr;    // [cells]
-  long nb = 0;             // live binned particles (host mirror, refreshed on demand)
+  long slots = 0;         // allocated slots in b
+  long* start = nullptr;  // [cells+1]
+  int* count = nullptr;   // [cells]
+  long n_total = 0;       // particles of this species on this rank at the last rebin
+  bool binned = false;
 };
 
 struct Ctx;
@@ -68,10 +70,14 @@ void launch_unpack_field(Ctx* c, double* F, const double* packed);  // valid -> 
 void launch_gauss_div(Ctx* c, double* out);                          // out += div- E
 
 // ---- particle kernels, thread per particle (particles_direct.cu) ----------------
-void launch_theta_axis_direct(Ctx* c, const ParticleSoA& p, long n, double q, double m, int comp, double dt);
-void launch_push_v_e_direct(Ctx* c, const ParticleSoA& p, long n, double q, double m, double dt);
-void launch_kinetic_energy(Ctx* c, const ParticleSoA& p, long n, double m, double* accum);
-void launch_deposit_rho(Ctx* c, const ParticleSoA& p, long n, double q, double* out);
+// n = host upper bound of the list length; n_dev (optional) = exact count on the device
+void launch_theta_axis_direct(Ctx* c, const ParticleSoA& p, long n, const unsigned long long* n_dev, double q,
+                              double m, int comp, double dt);
+void launch_push_v_e_direct(Ctx* c, const ParticleSoA& p, long n, const unsigned long long* n_dev, double q, double m,
+                            double dt);
+void launch_kinetic_energy(Ctx* c, const ParticleSoA& p, long n, const unsigned long long* n_dev, double m,
+                           double* accum);
+void launch_deposit_rho(Ctx* c, const ParticleSoA& p, long n, const unsigned long long* n_dev, double q, double* out);
 void launch_load_uniform(Ctx* c, const ParticleSoA& p, long n, int ppc, double vth, uint64_t seed);
 
 struct Ctx {
@@ -91,8 +97,29 @@ struct Ctx {
   double particle_ms = 0;
   int64_t particle_launches = 0;
   bool time_kernels = false;
+  void* engine = nullptr;  // EngineState (particles_binned.cu)
+  void* comm = nullptr;    // CommState (comm.cu)
   std::string err;
   long field_elems() const { return g.pc * 3; }
+};
+
+// Brackets one particle-kernel launch: counts it and, when the "time_kernels" option is
+// on, accumulates its CUDA-event duration (used by bench.py for the roofline figure).
+struct KernelTimer {
+  Ctx* c;
+  explicit KernelTimer(Ctx* ctx) : c(ctx) {
+    if (c->time_kernels) cudaEventRecord(c->ev0, c->stream);
+  }
+  ~KernelTimer() {
+    c->particle_launches++;
+    if (c->time_kernels) {
+      cudaEventRecord(c->ev1, c->stream);
+      cudaEventSynchronize(c->ev1);
+      float ms = 0;
+      cudaEventElapsedTime(&ms, c->ev0, c->ev1);
+      c->particle_ms += ms;
+    }
+  }
 };
 
 #define SPIC_CUDA_CHECK(ctx, expr)                                                         \

@@ -1,0 +1,68 @@
+"""CPU tests: the C-ABI library loads and exports exactly what include/strugepic_b200.h declares."""
+import ctypes as C
+import os
+import re
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _declared():
+    src = open(os.path.join(ROOT, "include", "strugepic_b200.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(spic_[A-Za-z0-9_]+)\s*\(", src)))
+
+
+def test_library_exports_every_declared_symbol():
+    from strugepic_b200 import _lib
+    lib = _lib.load()
+    names = _declared()
+    assert len(names) >= 25
+    for n in names:
+        assert hasattr(lib, n), "missing export " + n
+    assert sorted(_lib.SIGNATURES) == names, "ctypes table and header disagree"
+
+
+def test_header_compiles_as_c():
+    import subprocess
+    import tempfile
+    with tempfile.TemporaryDirectory() as d:
+        p = os.path.join(d, "t.c")
+        open(p, "w").write('#include "strugepic_b200.h"\nint main(void){spic_config c; (void)c; return 0;}\n')
+        subprocess.check_call(["gcc", "-std=c99", "-Wall", "-Werror", "-I", os.path.join(ROOT, "include"), "-c", p,
+                               "-o", os.path.join(d, "t.o")])
+
+
+def test_no_silent_fallback_without_gpu():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    import strugepic_b200 as spic
+    with pytest.raises(spic.SpicError) as e:
+        spic.Simulation((8, 8, 8))
+    assert e.value.code == -3  # SPIC_ENODEV
+
+
+def test_product_never_imports_the_oracle():
+    pkg = os.path.join(ROOT, "strugepic_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h", ".hpp")):
+                txt = open(os.path.join(dirpath, f)).read()
+                assert "import oracle" not in txt and "from oracle" not in txt and "liboracle" not in txt, f
+
+
+def test_synthetic_generator_statistics():
+    import numpy as np
+    from strugepic_b200 import synthetic
+    x, y, z, vx, vy, vz = synthetic.uniform_plasma((6, 5, 4), 16, 0.01, 12345)
+    assert len(x) == 6 * 5 * 4 * 16
+    assert np.all((x >= 0) & (x < 6)) and np.all((y >= 0) & (y < 5)) and np.all((z >= 0) & (z < 4))
+    # cell-major order, ppc per cell
+    assert np.array_equal(np.floor(x[::16]).astype(int)[:6], np.arange(6))
+    for v in (vx, vy, vz):
+        assert abs(np.std(v) - 0.01) < 5e-4 and abs(np.mean(v)) < 1e-3
+    # slab generation is a slice of the global generation
+    xs = synthetic.uniform_plasma((6, 5, 4), 16, 0.01, 12345, z_range=(2, 4))
+    assert np.array_equal(xs[0], x[len(x) // 2:]) and np.array_equal(xs[5], vz[len(x) // 2:])

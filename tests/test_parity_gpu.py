@@ -1,0 +1,251 @@
+"""GPU parity tests (-m gpu): the CUDA library, called through the C ABI, against the oracle.
+
+Tolerances.  The kernels use FMA contraction and factorised stencil sums, and deposition is
+a floating-point reduction whose order differs from the reference's serial particle loop, so
+results are not bit-identical.  north_star budgets 1e-11 relative per step; measured
+differences are ~1e-15 per sub-flow.  We assert TOL_STEP = 1e-11 per map step (fields
+relative to max|F|, positions absolute in cells, velocities relative to max|v|).
+"""
+import os
+import sys
+
+import numpy as np
+import pytest
+
+import oracle as ora
+import util
+
+pytestmark = pytest.mark.gpu
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.join(HERE, "golden"))
+import make_golden  # noqa: E402
+
+TOL_STEP = 1e-11
+ENGINES = [0, 1]  # SPIC_ENGINE_BINNED, SPIC_ENGINE_DIRECT
+
+
+def spic():
+    import strugepic_b200
+    return strugepic_b200
+
+
+def gpu_sim(c, engine, **kw):
+    s = spic().Simulation(c["n_cell"], periodic=c["periodic"], interp=c["interp"], engine=engine, **kw)
+    util.load_state(s, c["E"], c["B"], c["parts"], c["q"], c["m"])
+    return s
+
+
+@pytest.mark.parametrize("engine", ENGINES)
+@pytest.mark.parametrize("name", sorted(make_golden.CASES))
+def test_golden_vectors(name, engine):
+    """Committed vectors generated from the reference's own code (tests/golden/make_golden.py)."""
+    c = make_golden.build_case(name)
+    g = np.load(os.path.join(HERE, "golden", name + ".npz"))
+    s = gpu_sim(c, engine)
+    util.run(s, c["schedule"])
+    nsteps = len(c["schedule"])
+    errs = util.compare_states((g["E1"], g["B1"], g["P1"]), util.state_of(s), TOL_STEP * nsteps, TOL_STEP * nsteps,
+                               box=c["n_cell"])
+    en = np.array(s.get_total_energy())
+    assert np.allclose(en, g["energy1"], rtol=1e-11, atol=0), (en, g["energy1"])
+    print(name, errs)
+
+
+@pytest.mark.parametrize("engine", ENGINES)
+@pytest.mark.parametrize("interp", [0, 1])
+@pytest.mark.parametrize("periodic", [(1, 1, 1), (0, 1, 1)])
+def test_every_subflow_against_oracle(interp, periodic, engine):
+    n_cell = (16, 9, 6)
+    W = 2 if interp == 0 else 1
+    E, B = util.rng_fields(n_cell, 21)
+    parts = util.plasma(n_cell, 6, 0.25, 21, periodic, W)
+    q, m = -1.0 / 6, 100.0 / 6
+    o = ora.best_oracle(n_cell, periodic=periodic, interp=interp)
+    s = spic().Simulation(n_cell, periodic=periodic, interp=interp, engine=engine)
+    for t in (o, s):
+        util.load_state(t, E, B, parts, q, m)
+    ops = [("E", 0.3), ("axis", 0, 0.4), ("axis", 1, -0.4), ("axis", 2, 0.5), ("B", 0.7),
+           ("source", 5, 2, 0.2, 0.3, 0.5, 1.5), ("axis", 2, -0.5), ("axis", 0, 0.25), ("E", -0.3)]
+    for n, op in enumerate(ops, 1):
+        util.apply(o, op)
+        util.apply(s, op)
+        util.compare_states(util.state_of(o), util.state_of(s), TOL_STEP * n, TOL_STEP * n, box=n_cell)
+
+
+@pytest.mark.parametrize("engine", ENGINES)
+@pytest.mark.parametrize("order", [1, 2, 4])
+def test_maps_many_cell_crossings(order, engine):
+    """32^3 x 8 ppc, hot plasma (10 % of the particles change cell per sub-flow), 5 steps."""
+    n_cell = (32, 32, 32)
+    E, B = util.rng_fields(n_cell, 31, 0.2)
+    parts = util.plasma(n_cell, 8, 0.2, 31)
+    q, m = -1.0 / 8, 100.0 / 8
+    o = ora.best_oracle(n_cell, interp=0)
+    s = spic().Simulation(n_cell, interp=0, engine=engine)
+    for t in (o, s):
+        util.load_state(t, E, B, parts, q, m)
+    for _ in range(5):
+        o.map(order, 0.5)
+        s.map(order, 0.5)
+    util.compare_states(util.state_of(o), util.state_of(s), TOL_STEP * 5, TOL_STEP * 5, box=n_cell)
+    assert s.num_particles() == len(parts[0])
+
+
+@pytest.mark.parametrize("engine", ENGINES)
+def test_tiny_and_ragged_boxes(engine):
+    """Edge shapes of the reference's own decks: 4x4x1 (energy.input), odd sizes, guard > box."""
+    for n_cell, ng in (((4, 4, 1), 3), ((5, 3, 2), 2), ((15, 15, 2), 3)):
+        E, B = util.rng_fields(n_cell, 41)
+        parts = util.plasma(n_cell, 5, 0.2, 41)
+        o = ora.best_oracle(n_cell, interp=0, ng=ng)
+        s = spic().Simulation(n_cell, interp=0, ng=ng, engine=engine)
+        for t in (o, s):
+            util.load_state(t, E, B, parts, -0.2, 20.0)
+        for _ in range(3):
+            o.map(2, 0.5)
+            s.map(2, 0.5)
+        util.compare_states(util.state_of(o), util.state_of(s), 3 * TOL_STEP, 3 * TOL_STEP, box=n_cell)
+
+
+@pytest.mark.parametrize("engine", ENGINES)
+def test_empty_species_and_field_only(engine):
+    """No particles: field_only schedule with source + MABC (examples/field_only/main.cpp:142-145)."""
+    n_cell = (64, 4, 4)
+    o = ora.best_oracle(n_cell, periodic=(0, 1, 1), interp=0, ng=3)
+    s = spic().Simulation(n_cell, periodic=(0, 1, 1), interp=0, ng=3, engine=engine)
+    z = np.zeros((3, 4, 4, 64))
+    for t in (o, s):
+        util.load_state(t, z, z, [np.zeros(0)] * 6, -1.0, 1.0)
+    for step in range(120):
+        for op in (("E", 0.25), ("source", 4, 1, 0.1, 0.3, 0.5, 0.5 * step), ("B", 0.5), ("E", 0.25)):
+            util.apply(o, op)
+        s.field_only_step(4, 1, 0.1, 0.3, 0.5, step)
+    Eo, Bo, _ = util.state_of(o)
+    Es, Bs, _ = util.state_of(s)
+    assert util.rel_err(Es, Eo) < 1e-12 and util.rel_err(Bs, Bo) < 1e-12
+    assert np.max(np.abs(Eo)) > 1e-2
+    assert s.get_total_energy()[0] == pytest.approx(o.energy()[0], rel=1e-12)
+
+
+@pytest.mark.parametrize("engine", ENGINES)
+def test_single_particle_decks(engine):
+    """cyclotron.input known answers and reflection.input flip steps."""
+    Q_E, M_E = -1.60217662e-19, 9.427127615688092e-16
+    s = spic().Simulation((12, 12, 12), interp=0, ng=3, engine=engine)
+    B = np.zeros((3, 12, 12, 12))
+    B[2] = 58.8395
+    s.set_field(0, np.zeros_like(B))
+    s.set_field(1, B)
+    s.add_species(Q_E, M_E, [6.0], [4.0], [6.0], [0.01], [0.0], [0.01])
+    s.Theta_map1(0.5)
+    got = [float(t[0]) for t in s.get_particles()]
+    assert got == pytest.approx([6.005, 4.0, 6.005, 0.01, 4.9999997388179764e-05, 0.01], rel=1e-13, abs=1e-18)
+    for _ in range(1255):
+        s.Theta_map1(0.5)
+    x, y, z = [float(t[0]) for t in s.get_particles()[:3]]
+    assert (x, y, z) == pytest.approx((5.9968209017141412, 4.000013001059183, 0.28000000000058278), rel=1e-10)
+
+    r = spic().Simulation((15, 15, 2), periodic=(0, 1, 1), interp=0, ng=3, engine=engine)
+    zf = np.zeros((3, 2, 15, 15))
+    r.set_field(0, zf)
+    r.set_field(1, zf)
+    r.add_species(Q_E, M_E, [7.0], [7.0], [1.0], [0.1], [0.0], [0.0])
+    flips, prev = [], 0.1
+    for step in range(1, 300):
+        r.Theta_map1(0.5)
+        vx = float(r.get_particles()[3][0])
+        if vx * prev < 0:
+            flips.append(step)
+        prev = vx
+    assert flips == [100, 280]
+
+
+@pytest.mark.parametrize("engine", ENGINES)
+def test_gauss_law_and_energy_at_scale(engine):
+    """Check #2 and #3 of north_star on the energy_conservation config (64^3, 8 ppc, W8, map2):
+    the discrete Gauss residual must not move beyond round-off and H must stay in the reference's
+    envelope (map2 within [-3.12e-4, 0] relative)."""
+    n_cell = (64, 64, 64)
+    s = spic().Simulation(n_cell, interp=0, engine=engine)
+    s.set_uniform_field(0, [1, 1, 1])
+    s.set_uniform_field(1, [1, 1, 1])
+    s.add_particle_density_uniform(8, 100.0, -1.0, 0.01, seed=12345)
+    assert s.num_particles() == 64 ** 3 * 8
+    g0 = s.gauss_residual()
+    h0 = sum(s.get_total_energy())
+    for _ in range(20):
+        s.Theta_map2(0.5)
+    g1 = s.gauss_residual()
+    h1 = sum(s.get_total_energy())
+    drift = float(np.max(np.abs(g1 - g0)))
+    assert drift < 1e-12 * max(1.0, float(np.max(np.abs(g0)))), drift
+    assert -4e-4 < (h1 - h0) / h0 < 1e-6, (h1 - h0) / h0
+    s.Theta_map4(0.5)
+    assert float(np.max(np.abs(s.gauss_residual() - g0))) < 1e-12 * max(1.0, float(np.max(np.abs(g0))))
+
+
+@pytest.mark.parametrize("engine", ENGINES)
+def test_device_loader_is_the_numpy_twin(engine):
+    from strugepic_b200 import synthetic
+    n_cell = (10, 7, 5)
+    s = spic().Simulation(n_cell, interp=0, engine=engine)
+    s.add_particle_density_uniform(4, 100.0, -1.0, 0.01, seed=777)
+    got = np.stack(s.get_particles())
+    want = np.stack(synthetic.uniform_plasma(n_cell, 4, 0.01, 777))
+    got = got[:, util.match_particles(want, got)]
+    assert np.array_equal(got, want)
+
+
+@pytest.mark.parametrize("engine", ENGINES)
+def test_energy_tracks_oracle(engine):
+    n_cell = (16, 16, 16)
+    parts = util.plasma(n_cell, 8, 0.01, 12345)
+    E = np.ones((3, 16, 16, 16))
+    o = ora.best_oracle(n_cell, interp=0)
+    s = spic().Simulation(n_cell, interp=0, engine=engine)
+    for t in (o, s):
+        util.load_state(t, E, E.copy(), parts, -1.0 / 8, 100.0 / 8)
+    for step in range(30):
+        o.map(2, 0.5)
+        s.map(2, 0.5)
+        ho, hs = sum(o.energy()), sum(s.get_total_energy())
+        assert abs(hs - ho) / ho < 1e-9, step
+
+
+@pytest.mark.parametrize("engine", ENGINES)
+def test_checkpoint_roundtrip(tmp_path, engine):
+    n_cell = (12, 8, 6)
+    c = dict(n_cell=n_cell, periodic=(1, 1, 1), interp=0, q=-0.25, m=25.0)
+    c["E"], c["B"] = util.rng_fields(n_cell, 51)
+    c["parts"] = util.plasma(n_cell, 4, 0.2, 51)
+    a = gpu_sim(c, engine)
+    a.Theta_map2(0.5)
+    a.checkpoint(tmp_path / "ck.bin")
+    b = spic().Simulation(n_cell, interp=0, engine=engine)
+    b.restart(tmp_path / "ck.bin")
+    for t in (a, b):
+        t.Theta_map2(0.5)
+    util.compare_states(util.state_of(a), util.state_of(b), 1e-13, 1e-13, box=n_cell)
+    with pytest.raises(spic().SpicError):
+        spic().Simulation((12, 8, 7), interp=0).restart(tmp_path / "ck.bin")
+
+
+def test_errors_are_reported():
+    sp = spic()
+    with pytest.raises(sp.SpicError):
+        sp.Simulation((8, 8, 8), interp=0, ng=1)  # ng < interpolation range
+    s = sp.Simulation((8, 8, 8), interp=0)
+    s.set_uniform_field(1, [0, 0, 0])
+    with pytest.raises(sp.SpicError):
+        s.add_species(-1.0, 1.0, [9.0], [1.0], [1.0], [0.0], [0.0], [0.0])  # outside the box
+    s.add_species(-1.0, 1.0, [4.0], [4.0], [4.0], [5.0], [0.0], [0.0])  # |v dt| = 2.5 cells
+    s.G_Theta(0, 0.5)
+    with pytest.raises(sp.SpicError) as e:
+        s.sync()
+    assert e.value.code == -4  # SPIC_ECFL
+
+
+def test_fp64_probe_runs():
+    tf = spic().probe_fp64_tflops(0, 0.2)
+    assert 5.0 < tf < 80.0, tf
