@@ -1,0 +1,426 @@
+#!/usr/bin/env python
+"""bench.py -- particle-steps/s of the W8, 4th-order-composition symplectic PIC step.
+
+    python bench.py --gpus N --steps K --warmup W            (ours: hand-written sm_100a kernels)
+    python bench.py --impl reference --gpus N --steps K --warmup W   (the reference's CPU code)
+
+A "step" is one `Theta_map4` (include/strugepic_propagators.hpp:574-583 of the reference:
+3 x map2 = 18 axis sub-flows + 6 Theta_E + 3 Theta_B) over a uniform thermal plasma.
+
+Workload.  BASELINE.json quotes the metric on `examples/full: 512^3 cells x 64 ppc`, which
+is 8.59e9 particles = 412 GB of FP64 phase space and does not fit one B200 (180 GB).  The
+per-GPU brick measured here is the largest same-physics case that does: 256^3 cells x 64 ppc
+= 1.07e9 particles (51.5 GB SoA, 64 GB with bin slack), W8 (P8R2), dt = 0.5, v_th = 0.01,
+q = -1, m = 100, E = 0, B = (0,0,1), fully periodic.  With N GPUs the
+global box is 256 x 256 x (256 N) cut into z slabs (weak scaling).
+
+Keys: `value` = particle-steps/s with the state resident in HBM, CUDA-event timed on the
+library's stream, max over ranks; `e2e` = the same step driven through the C ABI with HOST
+buffers: fields and particles uploaded from pinned host memory (spic_set_field /
+spic_set_particles), one spic_map(4), fields and particles read back (spic_get_*), all inside
+the timed region; `roofline` = the dominant kernel (theta_axis, 18 of the 24 particle launches
+of a step) in algorithmic bytes (72 B per particle per sub-flow) over its own CUDA-event
+duration against MEASURED_PEAKS.json; `roofline_fp64` = the same launch in algorithmic FP64
+flops (718 per particle per sub-flow) against the DFMA rate measured here by
+spic_probe_fp64_tflops -- W8 is FP64-pipe bound, so that is the binding roof;
+`cpu_baseline` / `--impl reference` = the reference's own sources (oracle/_ref, compiled
+unmodified; else the C port) on every host core, one independent 16^3 x 64 ppc brick per
+core (the communication-free upper bound of its MPI build).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "particle-steps/s (W8, 4th-order split)"
+UNIT = "particle-steps/s"
+BYTES_PER_SUBFLOW = 72.0        # R 6 doubles, W 3 doubles per particle per sub-flow
+FLOP_AXIS, FLOP_PUSHVE = 718.0, 842.0   # SURVEY 8d, W8, factorised count
+FLOP_AXIS_PWL, FLOP_PUSHVE_PWL = 80.0, 100.0
+SUBFLOWS_PER_STEP = 24          # map4: 18 axis + 6 push_V_E
+CPU_BRICK, CPU_PPC = 16, 64     # per-core sample of the reference arm
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--n", type=int, default=256, help="cells per side of one GPU's brick")
+    ap.add_argument("--ppc", type=int, default=64)
+    ap.add_argument("--interp", default="p8r2", choices=["p8r2", "pwl"])
+    ap.add_argument("--order", type=int, default=4, choices=[1, 2, 4])
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--e2e-steps", type=int, default=2)
+    ap.add_argument("--cpu-steps", type=int, default=3)
+    ap.add_argument("--cores", type=int, default=0, help="reference arm: worker processes (0 = all)")
+    return ap.parse_args()
+
+
+def workload_name(a, n_gpus):
+    return ("uniform plasma %dx%dx%d cells, %d ppc, %s, Theta_map%d, dt=0.5, v_th=0.01 "
+            "(stand-in for examples/full 512^3 x 64 ppc = 412 GB, which does not fit one B200)"
+            % (a.n, a.n, a.n * n_gpus, a.ppc, "W8/P8R2" if a.interp == "p8r2" else "PWL", a.order))
+
+
+# ------------------------------------------------------------------------------------------
+# reference arm: the reference's CPU implementation on every host core
+# ------------------------------------------------------------------------------------------
+def _cpu_worker(conn, interp, order, seed):
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import numpy as np
+    import oracle as ora  # the reference's own code (oracle/_ref) or its C port: CPU baseline only
+    from strugepic_b200 import synthetic
+    n_cell = (CPU_BRICK,) * 3
+    try:
+        o = ora.RefOracle(n_cell, interp=interp, ng=2 if interp == 0 else 1, fast=True) \
+            if ora.have_ref(interp, fast=True) else ora.PortOracle(n_cell, interp=interp, fast=True)
+    except Exception as e:  # noqa: BLE001
+        conn.send(("error", repr(e)))
+        return
+    E = np.zeros((3,) + n_cell)
+    B = np.zeros((3,) + n_cell)
+    B[2] = 1.0
+    o.set_field(0, E)
+    o.set_field(1, B)
+    parts = synthetic.uniform_plasma(n_cell, CPU_PPC, 0.01, seed)
+    o.set_particles(*parts, -1.0 / CPU_PPC, 100.0 / CPU_PPC)
+    conn.send(("ready", o.kind, o.num_particles()))
+    while True:
+        cmd = conn.recv()
+        if cmd == "stop":
+            break
+        t0 = time.perf_counter()
+        o.map(order, 0.5)
+        conn.send(time.perf_counter() - t0)
+
+
+def run_reference(a, steps, warmup, cores=0):
+    """Times `steps` Theta_map steps of the reference's CPU code on `cores` processes."""
+    import multiprocessing as mp
+    interp = 0 if a.interp == "p8r2" else 1
+    ncores = cores or len(os.sched_getaffinity(0))
+    ctx = mp.get_context("fork")
+    procs = []
+    for r in range(ncores):
+        pc, cc = ctx.Pipe()
+        p = ctx.Process(target=_cpu_worker, args=(cc, interp, a.order, 1000 + r), daemon=True)
+        p.start()
+        procs.append((p, pc))
+    kind, npart = "port", 0
+    for _, pc in procs:
+        msg = pc.recv()
+        if msg[0] == "error":
+            raise RuntimeError("reference worker failed: " + msg[1])
+        kind, npart = msg[1], npart + msg[2]
+    times = []
+    for s in range(warmup + steps):
+        t0 = time.perf_counter()
+        for _, pc in procs:
+            pc.send("step")
+        for _, pc in procs:
+            pc.recv()
+        dt = time.perf_counter() - t0  # max over the workers: the step ends when the last core ends
+        if s >= warmup:
+            times.append(dt)
+    for p, pc in procs:
+        pc.send("stop")
+    for p, _ in procs:
+        p.join(timeout=10)
+    total = sum(times)
+    return {"value": npart * steps / total, "ms_per_step": 1e3 * total / steps, "cores": ncores,
+            "kind": "reference" if kind == "reference" else "port", "particles": npart,
+            "sample": "%d independent %d^3 x %d ppc bricks (one per host core, %d particles in all), "
+                      "%d Theta_map%d steps after %d warm-up, %s" %
+                      (ncores, CPU_BRICK, CPU_PPC, npart, steps, a.order, warmup,
+                       "reference sources compiled unmodified (oracle/_ref, -O3 -mavx2 -mfma)"
+                       if kind == "reference" else "C port of the reference (oracle/port, -O3 -mavx2 -mfma)")}
+
+
+def reference_main(a):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    r = run_reference(a, a.steps, a.warmup, a.cores)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": r["value"], "unit": UNIT, "n_gpus": a.gpus,
+        "steps": a.steps, "warmup": a.warmup, "ms_per_step": r["ms_per_step"], "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": workload_name(a, a.gpus), "sample": r["sample"]},
+        "cpu_baseline": {"value": r["value"], "unit": UNIT, "cores": r["cores"], "kind": r["kind"],
+                         "sample": r["sample"]},
+        "e2e": {"value": r["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+    return 0
+
+
+# ------------------------------------------------------------------------------------------
+# our arm
+# ------------------------------------------------------------------------------------------
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md)."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, device):
+        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", "-i", str(device), "--query-gpu=" + self.Q,
+                                       "--format=csv,noheader,nounits", "-lms", "200"],
+                                      stdout=self.f, stderr=subprocess.DEVNULL)
+        except OSError:
+            self.p = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
+        if self.p is None:
+            return out
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.p.kill()
+        self.f.flush()
+        self.f.seek(0)
+        sm, mx, reasons, power = [], [], set(), []
+        for ln in self.f.read().splitlines():
+            t = [x.strip() for x in ln.split(",")]
+            if len(t) < 8:
+                continue
+            try:
+                sm.append(float(t[0]))
+                mx.append(float(t[1]))
+                power.append(float(t[2]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), t[4:8]):
+                if v.lower() == "active":
+                    reasons.add(name)
+        self.f.close()
+        os.unlink(self.f.name)
+        if sm:
+            sm.sort()
+            out = {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": max(mx), "reasons": sorted(reasons),
+                   "power_w_max": max(power), "samples": len(sm)}
+        return out
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.isfile(p):
+        return json.load(open(p)), "measured (MEASURED_PEAKS.json)"
+    return {"hbm_gbs": 6650.0}, "fallback (B200_PROFILING.md)"
+
+
+def ncu_traffic():
+    """DRAM bytes per theta_axis launch from the committed ncu --set full capture (profiles/)."""
+    p = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.isfile(p):
+        return json.load(open(p))
+    return None
+
+
+def ours_main(a):
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    cpu = None
+    if rank == 0 and world == 1 and not a.no_cpu:
+        # reference CPU code timed beside us, BEFORE CUDA is initialised (fork-safe), rank 0, N=1 only
+        try:
+            cpu = run_reference(a, a.cpu_steps, 1, a.cores)
+        except Exception as e:  # noqa: BLE001
+            cpu = {"error": repr(e)}
+
+    import numpy as np
+    import torch
+    import strugepic_b200 as spic  # raises ImportError when the CUDA library is missing: no fallback
+
+    torch.cuda.set_device(local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+
+    def allmax(x):
+        if dist is None:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def allsum(x):
+        if dist is None:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        return float(t.item())
+
+    interp = spic.P8R2 if a.interp == "p8r2" else spic.PWL
+    n_cell = (a.n, a.n, a.n * world)
+    sim = spic.Simulation(n_cell, interp=interp, device=local, nranks=world, rank=rank)
+    if world > 1:
+        uid = torch.zeros(128, dtype=torch.uint8, device="cuda")
+        if rank == 0:
+            uid = torch.tensor(list(spic.comm_unique_id()), dtype=torch.uint8, device="cuda")
+        dist.broadcast(uid, 0)
+        sim.comm_init(bytes(uid.cpu().tolist()))
+    sim.set_uniform_field(spic.FIELD_E, [0.0, 0.0, 0.0])
+    sim.set_uniform_field(spic.FIELD_B, [0.0, 0.0, 1.0])
+    sim.add_particle_density_uniform(a.ppc, 100.0, -1.0, 0.01, seed=12345)
+    sim.sync()
+    npart_local = sim.num_particles()
+    npart = int(allsum(float(npart_local)))
+    fp64_peak = spic.probe_fp64_tflops(local, 0.5)
+
+    stream = torch.cuda.ExternalStream(sim.stream())
+    for _ in range(a.warmup):
+        sim.map(a.order, 0.5)
+    sim.sync()
+
+    # ---- timed region: K steps, state resident in HBM --------------------------------------
+    sim.set_option("time_kernels", 1)
+    sim.kernel_times(reset=True)
+    l0 = sim.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    sampler = ClockSampler(local)
+    torch.cuda.synchronize()
+    barrier()
+    e0.record(stream)
+    for _ in range(a.steps):
+        sim.map(a.order, 0.5)
+    e1.record(stream)
+    sim.sync()
+    torch.cuda.synchronize()
+    barrier()
+    clocks = sampler.stop()
+    ms = allmax(e0.elapsed_time(e1))
+    launches = sim.launch_count() - l0
+    kt = sim.kernel_times(reset=True)
+    sim.set_option("time_kernels", 0)
+    value = npart * a.steps / (ms * 1e-3)
+
+    # ---- roofline of the dominant kernel (theta_axis) ----------------------------------------
+    peaks, peak_src = measured_peaks()
+    ax_ms, ax_n = kt["theta_axis"]
+    pv_ms, pv_n = kt["push_V_E"]
+    ax_avg = ax_ms / max(ax_n, 1)
+    f_axis = FLOP_AXIS if a.interp == "p8r2" else FLOP_AXIS_PWL
+    f_pv = FLOP_PUSHVE if a.interp == "p8r2" else FLOP_PUSHVE_PWL
+    achieved = BYTES_PER_SUBFLOW * npart_local / (ax_avg * 1e-3) / 1e9 if ax_n else 0.0
+    traffic = ncu_traffic()
+    roofline = {"kernel": "k_theta_axis_binned", "bound": "hbm", "achieved": achieved, "peak": peaks["hbm_gbs"],
+                "unit": "GB/s", "frac": achieved / peaks["hbm_gbs"],
+                "traffic": traffic["theta_axis_bytes_per_launch"] if traffic else None,
+                "peak_source": peak_src, "avg_launch_ms": ax_avg, "launches_timed": ax_n,
+                "algorithmic_bytes_per_launch": BYTES_PER_SUBFLOW * npart_local,
+                "share_of_step": ax_ms / ms if ms else None,
+                "note": "W8 is FP64-pipe bound (10 flop/B > ridge 5.8): see roofline_fp64 for the binding roof"}
+    ach_tf = f_axis * npart_local / (ax_avg * 1e-3) / 1e12 if ax_n else 0.0
+    step_tf = (18 * f_axis + 6 * f_pv) * npart_local * a.steps / (ms * 1e-3) / 1e12 if a.order == 4 else None
+    roofline_fp64 = {"kernel": "k_theta_axis_binned", "bound": "fp64", "achieved": ach_tf, "peak": fp64_peak,
+                     "unit": "TFLOP/s", "frac": ach_tf / fp64_peak if fp64_peak else None,
+                     "peak_source": "measured here: spic_probe_fp64_tflops (dependent-free DFMA chains, all SMs)",
+                     "algorithmic_flop_per_particle": f_axis,
+                     "whole_step_tflops": step_tf, "whole_step_frac": step_tf / fp64_peak if step_tf else None,
+                     "push_V_E_avg_ms": pv_ms / max(pv_n, 1),
+                     "push_V_E_tflops": f_pv * npart_local / (pv_ms / max(pv_n, 1) * 1e-3) / 1e12 if pv_n else None}
+
+    # ---- e2e: the same step through the C ABI with HOST buffers ------------------------------
+    e2e = None
+    if not a.no_e2e:
+        e2e = run_e2e(a, sim, spic, np, torch, npart_local, npart, barrier, allmax)
+
+    energy = sim.get_total_energy()
+    sim.close()
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
+            "ms_per_step": ms / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic",
+            "config": {"workload": workload_name(a, world), "particles": npart, "cells": a.n ** 3 * world,
+                       "parallelism": "z-slab x%d" % world,
+                       "l2": "inputs (%.1f GB of particle state per GPU) exceed the 126 MB L2; no flush needed"
+                             % (48e-9 * npart_local)},
+            "clocks": clocks, "e2e": e2e, "gpu_launches": launches,
+            "roofline": roofline, "roofline_fp64": roofline_fp64,
+            "cell_updates_per_s": a.n ** 3 * world * a.steps / (ms * 1e-3),
+            "kernel_ms_per_step": {k: v[0] / a.steps for k, v in kt.items()},
+            "energy_after": energy,
+        }
+        if cpu is not None and "error" not in cpu:
+            line["cpu_baseline"] = {"value": cpu["value"], "unit": UNIT, "cores": cpu["cores"], "kind": cpu["kind"],
+                                    "sample": cpu["sample"]}
+        elif cpu is not None:
+            line["cpu_baseline"] = cpu
+        print(json.dumps(line))
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
+    return 0
+
+
+def run_e2e(a, sim, spic, np, torch, npart_local, npart, barrier, allmax):
+    """Upload (pinned host -> device, re-bin), one Theta_map, read back: all timed."""
+    avail = 0
+    try:
+        for ln in open("/proc/meminfo"):
+            if ln.startswith("MemAvailable"):
+                avail = int(ln.split()[1]) * 1024
+    except OSError:
+        pass
+    need = 48 * npart_local + 2 * 24 * a.n ** 3
+    if avail and need * 1.3 > avail:
+        return {"value": None, "unit": UNIT, "skipped": "host RAM: need %.0f GB pinned, %.0f GB available"
+                % (need / 1e9, avail / 1e9)}
+    host_p = [torch.empty(npart_local, dtype=torch.float64, pin_memory=True).numpy() for _ in range(6)]
+    host_f = [torch.empty((3, a.n, a.n, a.n), dtype=torch.float64, pin_memory=True).numpy() for _ in range(2)]
+    sim.get_particles(0, out=host_p)
+    sim.get_field(spic.FIELD_E, out=host_f[0])
+    sim.get_field(spic.FIELD_B, out=host_f[1])
+    sim.sync()
+    h2d = d2h = sum(t.nbytes for t in host_p) + sum(t.nbytes for t in host_f)
+    times = []
+    for s in range(1 + a.e2e_steps):
+        torch.cuda.synchronize()
+        barrier()
+        t0 = time.perf_counter()
+        sim.set_field(spic.FIELD_E, host_f[0])
+        sim.set_field(spic.FIELD_B, host_f[1])
+        sim.set_particles(0, *host_p)
+        sim.map(a.order, 0.5)
+        sim.get_field(spic.FIELD_E, out=host_f[0])
+        sim.get_field(spic.FIELD_B, out=host_f[1])
+        sim.get_particles(0, out=host_p)
+        sim.sync()
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        barrier()
+        if s >= 1:
+            times.append(allmax(dt))
+    t = sum(times) / len(times)
+    return {"value": npart / t, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+            "ms_per_step": 1e3 * t, "steps": a.e2e_steps,
+            "path": "spic_set_field x2 + spic_set_particles (pinned host -> HBM, re-binned) + spic_map + "
+                    "spic_get_field x2 + spic_get_particles (HBM -> pinned host), wall clock, max over ranks"}
+
+
+if __name__ == "__main__":
+    args = parse()
+    sys.exit(reference_main(args) if args.impl == "reference" else ours_main(args))

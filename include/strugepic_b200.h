@@ -134,6 +134,11 @@ int spic_checkpoint_read(spic_ctx* ctx, const char* path);
 int64_t spic_launch_count(const spic_ctx* ctx); /* kernels launched so far */
 /* CUDA-event time (ms) accumulated inside the particle kernels since the last reset */
 int spic_kernel_time_ms(spic_ctx* ctx, int reset, double* particle_ms, int64_t* particle_launches);
+/* Same, per kernel kind: [0] theta_axis (Theta, hpp:80-244), [1] push_V_E (hpp:247-344),
+ * [2] curl sweeps (cpp:71-91), [3] other timed launches (overflow-tail kernels).
+ * With option "time_kernels" = 1 every such launch is bracketed by a CUDA-event pair on
+ * the context's stream (no synchronisation); this call synchronises and sums them. */
+int spic_kernel_times(spic_ctx* ctx, int reset, double ms[4], int64_t launches[4]);
 int spic_set_option(spic_ctx* ctx, const char* name, double value);
 void* spic_stream(spic_ctx* ctx); /* cudaStream_t */
 /* FP64 FMA micro-benchmark for the roofline denominator: returns TFLOP/s */

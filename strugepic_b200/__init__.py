@@ -55,6 +55,15 @@ def probe_fp64_tflops(device=0, seconds=1.0):
     return out.value
 
 
+def comm_unique_id():
+    """ncclUniqueId (128 bytes) to be created on rank 0 and broadcast to every rank."""
+    buf = C.create_string_buffer(128)
+    rc = _lib.load().spic_comm_unique_id(buf)
+    if rc:
+        raise SpicError(rc, "ncclGetUniqueId failed (NCCL not loadable?)")
+    return buf.raw
+
+
 class Simulation:
     """One rank's brick: fields E, B and the particle species, resident in HBM."""
 
@@ -199,6 +208,15 @@ class Simulation:
     # -- introspection -------------------------------------------------------------------------
     def launch_count(self):
         return int(self.lib.spic_launch_count(self.h))
+
+    def kernel_times(self, reset=False):
+        """{kind: (ms, launches)} for theta_axis / push_V_E / curl / other (CUDA events, own stream)."""
+        ms, n = (C.c_double * 4)(), (C.c_int64 * 4)()
+        self._ck(self.lib.spic_kernel_times(self.h, int(reset), C.byref(ms), C.byref(n)))
+        return {k: (ms[i], n[i]) for i, k in enumerate(("theta_axis", "push_V_E", "curl", "other"))}
+
+    def stream(self):
+        return self.lib.spic_stream(self.h)
 
     def kernel_time_ms(self, reset=False):
         ms, n = C.c_double(0), C.c_int64(0)

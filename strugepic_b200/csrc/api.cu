@@ -15,8 +15,53 @@ using namespace spic;
 
 struct spic_ctx : public spic::Ctx {};
 
+namespace spic {
+static cudaEvent_t take_event(Ctx* c) {
+  cudaEvent_t e = nullptr;
+  if (!c->event_pool.empty()) {
+    e = c->event_pool.back();
+    c->event_pool.pop_back();
+  } else {
+    cudaEventCreate(&e);
+  }
+  return e;
+}
+KernelTimer::KernelTimer(Ctx* ctx, int k) : c(ctx), kind(k) {
+  if (c->time_kernels && c->timed.size() < 65536) {
+    cudaEvent_t e0 = take_event(c);
+    e1 = take_event(c);
+    cudaEventRecord(e0, c->stream);
+    c->timed.push_back({e0, e1, kind});
+  }
+}
+KernelTimer::~KernelTimer() {
+  c->kind_launches[kind]++;
+  if (e1) cudaEventRecord(e1, c->stream);
+}
+// fold the recorded event pairs into kind_ms (synchronises the stream)
+static void collect_timed(Ctx* c) {
+  if (c->timed.empty()) return;
+  cudaStreamSynchronize(c->stream);
+  for (auto& t : c->timed) {
+    float ms = 0;
+    if (cudaEventElapsedTime(&ms, t.e0, t.e1) == cudaSuccess) c->kind_ms[t.kind] += ms;
+    c->event_pool.push_back(t.e0);
+    c->event_pool.push_back(t.e1);
+  }
+  c->timed.clear();
+}
+}  // namespace spic
+
 namespace {
 std::string g_create_error;
+
+__global__ void k_check_inside(Grid g, ParticleSoA p, long n, int* __restrict__ bad) {
+  const double zlo = (double)g.z0, zhi = (double)(g.z0 + g.n[2]);
+  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x) {
+    const double x = p.x[0][i], y = p.x[1][i], z = p.x[2][i];
+    if (!(x >= 0.0 && x < g.gn[0] && y >= 0.0 && y < g.gn[1] && z >= zlo && z < zhi)) *bad = 1;
+  }
+}
 
 int fail(Ctx* c, int code, const std::string& msg) {
   if (c) c->err = msg;
@@ -153,6 +198,11 @@ int spic_destroy(spic_ctx* c) {
   if (c->B) cudaFree(c->B);
   if (c->scratch) cudaFree(c->scratch);
   if (c->d_flags) cudaFree(c->d_flags);
+  for (auto& t : c->timed) {
+    cudaEventDestroy(t.e0);
+    cudaEventDestroy(t.e1);
+  }
+  for (auto e : c->event_pool) cudaEventDestroy(e);
   if (c->ev0) cudaEventDestroy(c->ev0);
   if (c->ev1) cudaEventDestroy(c->ev1);
   if (c->stream) cudaStreamDestroy(c->stream);
@@ -245,17 +295,28 @@ int spic_set_particles(spic_ctx* c, int species, int64_t n, const double* x, con
   if (!c || species < 0 || species >= (int)c->sp.size() || n < 0) return SPIC_EINVAL;
   cudaSetDevice(c->cfg.device);
   Species& s = c->sp[species];
-  // every particle must sit inside this rank's slab (and inside the domain)
-  const double zlo = (double)c->g.z0, zhi = (double)(c->g.z0 + c->g.n[2]);
-  for (int64_t i = 0; i < n; ++i) {
-    if (!(x[i] >= 0.0 && x[i] < c->g.gn[0] && y[i] >= 0.0 && y[i] < c->g.gn[1] && z[i] >= zlo && z[i] < zhi))
-      return fail(c, SPIC_EINVAL, "particle outside this rank's brick");
-  }
+  if (n > 0 && (!x || !y || !z || !vx || !vy || !vz)) return fail(c, SPIC_EINVAL, "null particle array");
   const double* hx[3] = {x, y, z};
   const double* hv[3] = {vx, vy, vz};
   engine_free_species(c, s);
   int rc = upload_list(c, s, n, hx, hv);
   if (rc) return rc;
+  // every particle must sit inside this rank's slab (and inside the domain): checked on the device
+  if (n > 0) {
+    SPIC_CUDA_CHECK(c, cudaMemsetAsync(c->d_flags + 2, 0, sizeof(int), c->stream));
+    long b = (n + 255) / 256;
+    if (b > (long)c->sm_count * 16) b = (long)c->sm_count * 16;
+    k_check_inside<<<(int)b, 256, 0, c->stream>>>(c->g, s.d, n, c->d_flags + 2);
+    c->launches++;
+    int bad = 0;
+    SPIC_CUDA_CHECK(c, cudaMemcpyAsync(&bad, c->d_flags + 2, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    SPIC_CUDA_CHECK(c, cudaStreamSynchronize(c->stream));
+    if (bad) {
+      free_soa(s.d);
+      s.nd = s.capd = 0;
+      return fail(c, SPIC_EINVAL, "particle outside this rank's brick");
+    }
+  }
   return engine_ingest(c, s);  // BINNED: move the list into cell bins
 }
 
@@ -563,14 +624,27 @@ int spic_checkpoint_read(spic_ctx* c, const char* path) {
 
 // ---- introspection ------------------------------------------------------------------------
 int64_t spic_launch_count(const spic_ctx* c) { return c ? c->launches : 0; }
-int spic_kernel_time_ms(spic_ctx* c, int reset, double* particle_ms, int64_t* particle_launches) {
+int spic_kernel_times(spic_ctx* c, int reset, double ms[4], int64_t launches[4]) {
   if (!c) return SPIC_EINVAL;
-  if (particle_ms) *particle_ms = c->particle_ms;
-  if (particle_launches) *particle_launches = c->particle_launches;
-  if (reset) {
-    c->particle_ms = 0;
-    c->particle_launches = 0;
+  cudaSetDevice(c->cfg.device);
+  collect_timed(c);
+  for (int k = 0; k < KT_KINDS; ++k) {
+    if (ms) ms[k] = c->kind_ms[k];
+    if (launches) launches[k] = c->kind_launches[k];
+    if (reset) {
+      c->kind_ms[k] = 0;
+      c->kind_launches[k] = 0;
+    }
   }
+  return SPIC_OK;
+}
+int spic_kernel_time_ms(spic_ctx* c, int reset, double* particle_ms, int64_t* particle_launches) {
+  double ms[4];
+  int64_t n[4];
+  int rc = spic_kernel_times(c, reset, ms, n);
+  if (rc) return rc;
+  if (particle_ms) *particle_ms = ms[KT_AXIS] + ms[KT_PUSHVE];
+  if (particle_launches) *particle_launches = n[KT_AXIS] + n[KT_PUSHVE];
   return SPIC_OK;
 }
 int spic_set_option(spic_ctx* c, const char* name, double value) {

@@ -300,6 +300,7 @@ void launch_curl_E_into_B(Ctx* c, double dt) {
   const Interior in = make_interior(c->g);
   const long total = (long)(in.hi[0] - in.lo[0] + 1) * (in.hi[1] - in.lo[1] + 1) * (in.hi[2] - in.lo[2] + 1);
   if (total <= 0) return;
+  KernelTimer t(c, KT_CURL);
   k_curl<true><<<grid_for(c, total), kBlock, 0, c->stream>>>(c->g, c->E, c->B, in, dt);
   c->launches++;
 }
@@ -311,6 +312,7 @@ void launch_curl_B_into_E(Ctx* c, double dt) {
   const Interior in = make_interior(c->g);
   const long total = (long)(in.hi[0] - in.lo[0] + 1) * (in.hi[1] - in.lo[1] + 1) * (in.hi[2] - in.lo[2] + 1);
   if (total <= 0) return;
+  KernelTimer t(c, KT_CURL);
   k_curl<false><<<grid_for(c, total), kBlock, 0, c->stream>>>(c->g, c->B, c->E, in, dt);
   c->launches++;
 }

@@ -759,7 +759,7 @@ int engine_theta_axis(Ctx* c, Species& s, int comp, double dt) {
   if (!s.binned) return SPIC_OK;
   EngineState* e = eng(c);
   {
-    KernelTimer t(c);
+    KernelTimer t(c, KT_AXIS);
     if (c->cfg.interp == SPIC_INTERP_P8R2)
       theta_axis_binned_dispatch<InterpP8R2>(c, s, comp, dt);
     else
@@ -787,7 +787,7 @@ int engine_push_v_e(Ctx* c, Species& s, double dt) {
   const int grid = (int)((ncell + cpb - 1) / cpb);
   const double coef = dt * s.q / s.m;  // hpp:267
   {
-    KernelTimer t(c);
+    KernelTimer t(c, KT_PUSHVE);
     if (c->cfg.interp == SPIC_INTERP_P8R2) {
       const size_t smem = sizeof(double) * kWarps * 3 * 64;
       k_push_v_e_binned<InterpP8R2><<<grid, kThreads, smem, c->stream>>>(c->g, s.b, s.start, s.count, c->E, coef, ncell, cpb);

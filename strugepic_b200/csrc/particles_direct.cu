@@ -205,7 +205,7 @@ void theta_axis_dispatch(Ctx* c, const ParticleSoA& p, long n, const unsigned lo
 void launch_theta_axis_direct(Ctx* c, const ParticleSoA& p, long n, const unsigned long long* n_dev, double q,
                               double m, int comp, double dt) {
   if (n <= 0) return;
-  KernelTimer t(c);
+  KernelTimer t(c, n_dev ? KT_OTHER : KT_AXIS);  // n_dev: the (small) overflow tail of the binned engine
   if (c->cfg.interp == SPIC_INTERP_P8R2)
     theta_axis_dispatch<InterpP8R2>(c, p, n, n_dev, q, m, comp, dt);
   else
@@ -216,7 +216,7 @@ void launch_theta_axis_direct(Ctx* c, const ParticleSoA& p, long n, const unsign
 void launch_push_v_e_direct(Ctx* c, const ParticleSoA& p, long n, const unsigned long long* n_dev, double q, double m,
                             double dt) {
   if (n <= 0) return;
-  KernelTimer t(c);
+  KernelTimer t(c, n_dev ? KT_OTHER : KT_PUSHVE);
   const int grid = (int)((n + kBlock - 1) / kBlock);
   const double coef = dt * q / m;  // hpp:267
   if (c->cfg.interp == SPIC_INTERP_P8R2)

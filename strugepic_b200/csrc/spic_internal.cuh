@@ -94,32 +94,32 @@ struct Ctx {
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   int sm_count = 148;
   int64_t launches = 0;
-  double particle_ms = 0;
-  int64_t particle_launches = 0;
   bool time_kernels = false;
+  struct TimedLaunch {
+    cudaEvent_t e0, e1;
+    int kind;
+  };
+  std::vector<TimedLaunch> timed;       // event pairs recorded since the last reset
+  std::vector<cudaEvent_t> event_pool;  // recycled events
+  double kind_ms[4] = {0, 0, 0, 0};
+  int64_t kind_launches[4] = {0, 0, 0, 0};
   void* engine = nullptr;  // EngineState (particles_binned.cu)
   void* comm = nullptr;    // CommState (comm.cu)
   std::string err;
   long field_elems() const { return g.pc * 3; }
 };
 
-// Brackets one particle-kernel launch: counts it and, when the "time_kernels" option is
-// on, accumulates its CUDA-event duration (used by bench.py for the roofline figure).
+// Brackets one hot-kernel launch: counts it and, when the "time_kernels" option is on,
+// records a CUDA-event pair around it on the context's stream WITHOUT synchronising, so
+// the timed region of bench.py is not perturbed; spic_kernel_times() reads the pairs
+// back after the region.  kind: 0 theta_axis, 1 push_V_E, 2 curl sweeps, 3 other.
+enum { KT_AXIS = 0, KT_PUSHVE = 1, KT_CURL = 2, KT_OTHER = 3, KT_KINDS = 4 };
 struct KernelTimer {
   Ctx* c;
-  explicit KernelTimer(Ctx* ctx) : c(ctx) {
-    if (c->time_kernels) cudaEventRecord(c->ev0, c->stream);
-  }
-  ~KernelTimer() {
-    c->particle_launches++;
-    if (c->time_kernels) {
-      cudaEventRecord(c->ev1, c->stream);
-      cudaEventSynchronize(c->ev1);
-      float ms = 0;
-      cudaEventElapsedTime(&ms, c->ev0, c->ev1);
-      c->particle_ms += ms;
-    }
-  }
+  int kind;
+  cudaEvent_t e1 = nullptr;
+  KernelTimer(Ctx* ctx, int k);
+  ~KernelTimer();
 };
 
 #define SPIC_CUDA_CHECK(ctx, expr)                                                         \
