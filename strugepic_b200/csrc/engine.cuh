@@ -16,12 +16,16 @@ int engine_push_v_e(Ctx* c, Species& s, double dt);
 int engine_kinetic(Ctx* c, Species& s, double* acc);
 int engine_deposit_rho(Ctx* c, Species& s, double* out);
 int engine_set_option(Ctx* c, const char* name, double value);
-int engine_maintain(Ctx* c);  // called between steps: rebin species whose overflow tail has grown
+int engine_maintain(Ctx* c);
+// file n particles (device arrays, positions inside this rank's slab) into their bins / the tail
+int engine_insert_list(Ctx* c, Species& s, double* const x[3], double* const v[3], long n);  // called between steps: rebin species whose overflow tail has grown
 
 // ---- z-slab decomposition over NCCL --------------------------------------------------
 int comm_exchange_fill(Ctx* c, double* F);           // owner planes -> neighbour guard planes
 int comm_exchange_sum(Ctx* c, double* F, int comp);  // guard planes added into the neighbour's owner planes
-int comm_migrate(Ctx* c);                            // particles that crossed a slab face change rank
+int comm_migrate(Ctx* c);
+int comm_migrate_species(Ctx* c, Species& s);       // exchange the packed leavers of one species
+int comm_init(Ctx* c, const void* id128);                            // particles that crossed a slab face change rank
 // movers with dest -1 / -2 (left through the low / high z face) are copied to the send buffers
 int comm_collect_leavers(Ctx* c, Species& s, double* const mx[3], double* const mv[3], const int* dest,
                          const unsigned* n, unsigned cap);

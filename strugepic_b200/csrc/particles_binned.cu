@@ -324,6 +324,41 @@ __global__ void __launch_bounds__(256)
   }
 }
 
+// particles arriving from a neighbour rank -> their bin (or the tail)
+__device__ __forceinline__ long cell_of(const Grid& g, double x, double y, double z);
+__global__ void __launch_bounds__(256)
+    k_insert_arrivals(Grid g, const double* ax0, const double* ax1, const double* ax2, const double* av0,
+                      const double* av1, const double* av2, long n, ParticleSoA b, const long* __restrict__ start,
+                      int* __restrict__ count, ParticleSoA tail, unsigned long long* __restrict__ tail_n, long tail_cap,
+                      int* __restrict__ flags) {
+  for (long m = blockIdx.x * (long)blockDim.x + threadIdx.x; m < n; m += (long)gridDim.x * blockDim.x) {
+    const double px[3] = {ax0[m], ax1[m], ax2[m]}, pv[3] = {av0[m], av1[m], av2[m]};
+    const long dest = cell_of(g, px[0], px[1], px[2]);
+    const int cap = (int)(start[dest + 1] - start[dest]);
+    const int slot = atomicAdd(&count[dest], 1);
+    if (slot < cap) {
+      const long d = start[dest] + slot;
+#pragma unroll
+      for (int k = 0; k < 3; ++k) {
+        b.x[k][d] = px[k];
+        b.v[k][d] = pv[k];
+      }
+    } else {
+      atomicSub(&count[dest], 1);
+      const unsigned long long t = atomicAdd(tail_n, 1ull);
+      if ((long)t < tail_cap) {
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+          tail.x[k][t] = px[k];
+          tail.v[k][t] = pv[k];
+        }
+      } else {
+        atomicOr(&flags[1], 2);
+      }
+    }
+  }
+}
+
 // ------------------------------------------------------------------------------------
 // push_V_E, binned
 // ------------------------------------------------------------------------------------
@@ -629,6 +664,8 @@ int rebin(Ctx* c, Species& s, long tail_n_host) {
   const long want_tail = tail_capacity(s.n_total);
   if (s.capd != want_tail) {
     free_soa_local(s.d);
+    free_soa_local(s.d2);
+    s.capd2 = 0;
     for (int d = 0; d < 3; ++d) {
       SPIC_CUDA_CHECK(c, cudaMalloc(&s.d.x[d], sizeof(double) * want_tail));
       SPIC_CUDA_CHECK(c, cudaMalloc(&s.d.v[d], sizeof(double) * want_tail));
@@ -665,7 +702,8 @@ void theta_axis_binned_dispatch(Ctx* c, Species& s, int comp, double dt) {
 
 // ---- engine interface -------------------------------------------------------------------
 int engine_ingest(Ctx* c, Species& s) {
-  if (c->cfg.engine != SPIC_ENGINE_BINNED || s.nd == 0) return SPIC_OK;
+  // (with nranks > 1 even an empty species is binned: every rank takes part in the exchanges)
+  if (c->cfg.engine != SPIC_ENGINE_BINNED || (s.nd == 0 && c->cfg.nranks == 1)) return SPIC_OK;
   return rebin(c, s, s.nd);
 }
 
@@ -674,6 +712,10 @@ void engine_free_species(Ctx*, Species& s) {
   if (s.start) cudaFree(s.start);
   if (s.count) cudaFree(s.count);
   if (s.d_nd) cudaFree(s.d_nd);
+  free_soa_local(s.d2);
+  if (s.d2_nd) cudaFree(s.d2_nd);
+  s.d2_nd = nullptr;
+  s.capd2 = 0;
   s.start = nullptr;
   s.count = nullptr;
   s.d_nd = nullptr;
@@ -776,6 +818,20 @@ int engine_theta_axis(Ctx* c, Species& s, int comp, double dt) {
     if (rc) return rc;
   }
   SPIC_CUDA_CHECK(c, cudaMemsetAsync(e->mv.n, 0, sizeof(unsigned), c->stream));
+  return SPIC_OK;
+}
+
+int engine_insert_list(Ctx* c, Species& s, double* const x[3], double* const v[3], long n) {
+  if (n <= 0) return SPIC_OK;
+  if (!s.binned) {
+    c->err = "engine_insert_list: species is not binned";
+    return SPIC_EINVAL;
+  }
+  long b = (n + 255) / 256;
+  if (b > (long)c->sm_count * 8) b = (long)c->sm_count * 8;
+  k_insert_arrivals<<<(int)b, 256, 0, c->stream>>>(c->g, x[0], x[1], x[2], v[0], v[1], v[2], n, s.b, s.start, s.count,
+                                                   s.d, s.d_nd, s.capd, c->d_flags);
+  c->launches++;
   return SPIC_OK;
 }
 

@@ -46,6 +46,9 @@ struct Species {
   ParticleSoA d{};
   long nd = 0, capd = 0;
   unsigned long long* d_nd = nullptr;  // device count of `d` (BINNED); null => use nd
+  ParticleSoA d2{};                    // spare tail (multi-GPU: the tail is split into stayers / leavers)
+  unsigned long long* d2_nd = nullptr;
+  long capd2 = 0;
   ParticleSoA b{};
   long slots = 0;         // allocated slots in b
   long* start = nullptr;  // [cells+1]

@@ -1,0 +1,85 @@
+"""Worker of tests/test_multi_gpu.py: one process per GPU (torchrun), z-slab decomposition over NCCL.
+
+Every rank owns one slab of the same global problem; after the schedule rank 0 gathers the slabs
+and compares the global state with the oracle run on the undecomposed box (the reference's own
+multi-box test strategy: max_grid_size < n_cell).
+"""
+import os
+import sys
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+for p in (ROOT, os.path.join(ROOT, "oracle"), HERE):
+    sys.path.insert(0, p)
+
+import oracle as ora  # noqa: E402
+import strugepic_b200 as spic  # noqa: E402
+import util  # noqa: E402
+
+
+def main():
+    rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
+    local = int(os.environ.get("LOCAL_RANK", rank))
+    dist.init_process_group("gloo")
+    torch.cuda.set_device(local)
+    case = sys.argv[1] if len(sys.argv) > 1 else "p8"
+    interp = 0 if case.startswith("p8") else 1
+    nz = 4 * world if case.endswith("thin") else 6 * world
+    n_cell = (12, 10, nz)
+    ppc, vth = 6, 0.25
+    E, B = util.rng_fields(n_cell, 77, 0.3)
+    parts = util.plasma(n_cell, ppc, vth, 77)
+    q, m = -1.0 / ppc, 100.0 / ppc
+
+    s = spic.Simulation(n_cell, interp=interp, device=local, nranks=world, rank=rank)
+    ids = [spic.comm_unique_id() if rank == 0 else None]
+    dist.broadcast_object_list(ids, src=0)
+    s.comm_init(ids[0])
+    k0, k1 = s.lo[2], s.lo[2] + s.n[2]
+    assert s.n[2] == nz // world
+    s.set_field(0, E[:, k0:k1])
+    s.set_field(1, B[:, k0:k1])
+    mine = (parts[2] >= k0) & (parts[2] < k1)
+    s.add_species(q, m, *[t[mine] for t in parts])
+
+    schedule = [("map", 1, 0.5), ("map", 2, 0.5), ("map", 2, 0.5), ("map", 4, 0.5),
+                ("E", 0.2), ("axis", 2, -0.7), ("axis", 2, 0.7), ("B", 0.3)]
+    util.run(s, schedule)
+    s.sync()
+    en = s.get_total_energy()
+    Es, Bs, Ps = util.state_of(s)
+    assert np.all((Ps[2] >= k0) & (Ps[2] < k1)), "a particle sits outside its rank's slab"
+    gathered = [None] * world
+    dist.gather_object((Es, Bs, Ps, en), gathered if rank == 0 else None, dst=0)
+    ok = True
+    if rank == 0:
+        Eg = np.concatenate([g[0] for g in gathered], axis=1)
+        Bg = np.concatenate([g[1] for g in gathered], axis=1)
+        Pg = np.concatenate([g[2] for g in gathered], axis=1)
+        o = ora.best_oracle(n_cell, interp=interp)
+        util.load_state(o, E, B, parts, q, m)
+        util.run(o, schedule)
+        try:
+            assert Pg.shape[1] == len(parts[0]), "particle count changed: %d != %d" % (Pg.shape[1], len(parts[0]))
+            moved = sum(int(g[2].shape[1]) for g in gathered)
+            errs = util.compare_states(util.state_of(o), (Eg, Bg, Pg), 1e-10, 1e-10, box=n_cell)
+            eo = o.energy()
+            for g in gathered:  # every rank holds the allreduced energy
+                assert np.allclose(g[3], eo, rtol=1e-10), (g[3], eo)
+            print("multi-gpu parity ok case=%s world=%d particles=%d errs=%s" % (case, world, moved, errs))
+        except AssertionError as e:
+            print("MULTI-GPU PARITY FAILED:", e)
+            ok = False
+    flag = [ok]
+    dist.broadcast_object_list(flag, src=0)
+    s.close()
+    dist.destroy_process_group()
+    sys.exit(0 if flag[0] else 1)
+
+
+if __name__ == "__main__":
+    main()
