@@ -54,7 +54,7 @@ def parse():
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--n", type=int, default=256, help="cells per side of one GPU's brick")
+    ap.add_argument("--cells", dest="n", type=int, default=256, help="cells per side of one GPU's brick")
     ap.add_argument("--ppc", type=int, default=64)
     ap.add_argument("--interp", default="p8r2", choices=["p8r2", "pwl"])
     ap.add_argument("--order", type=int, default=4, choices=[1, 2, 4])

@@ -105,6 +105,18 @@ struct InterpP8R2 {
     return a >= 2.0 ? 1.0 : (a < -1.0 ? 0.0 : v);
   }
 
+  // In-cell tap forms (the binned kernels): the argument is KNOWN to lie in the closed range of
+  // the tap's piece (particle inside its bin cell, segment inside its cell), so the support tests
+  // of poly_util.hpp:32,42-47 can only fire at a piece end point -- and there every piece
+  // polynomial evaluates EXACTLY (dyadic coefficients, dyadic argument) to the value the test
+  // would return (0 or 1).  Same bits as w1_tap / wp_tap / iwp_tap, without DSETP/FSEL.
+  template <int T>
+  static SPIC_HDI double w1_in(double a) { return w1_piece<3 - T>(a); }
+  template <int T>
+  static SPIC_HDI double wp_in(double a) { return wp_piece<2 - T>(a); }
+  template <int T>
+  static SPIC_HDI double iwp_in(double a) { return iwp_piece<2 - T>(a); }
+
   // general-argument forms (diagnostics, tests): dynamic piece like the reference
   static SPIC_HDI double W1(double x) {
     if (x >= 2.0 || x <= -2.0) return 0.0;
@@ -169,6 +181,12 @@ struct InterpPWL {
   static SPIC_HDI double wp_tap(double a) { return Wp(a); }
   template <int T>
   static SPIC_HDI double iwp_tap(double a) { return IWp_cdf(a); }
+  template <int T>
+  static SPIC_HDI double w1_in(double a) { return W1(a); }
+  template <int T>
+  static SPIC_HDI double wp_in(double a) { return Wp(a); }
+  template <int T>
+  static SPIC_HDI double iwp_in(double a) { return IWp_cdf(a); }
 };
 
 // Fill w1[0..NW1) and wp[0..NWP) for a particle at normalised coordinate x in cell c:
@@ -219,6 +237,42 @@ SPIC_HDI void eval_iwp(double s, double e, int cell, double (&out)[I::NWP]) {
   } else {
     const double c0 = (double)(cell + 0 - I::W + 1);
     out[0] = I::template iwp_tap<0>(e - c0) - I::template iwp_tap<0>(s - c0);
+  }
+}
+
+// ---- in-cell forms: f = x - cell in [0,1) is exact, so f - o has the bits of x - (cell + o) ----------
+template <class I>
+SPIC_HDI void eval_w1_in(double f, double (&out)[I::NW1]) {
+  if (I::NW1 == 4) {
+    out[0] = I::template w1_in<0>(f + 1.0);
+    out[1] = I::template w1_in<1>(f);
+    out[I::NW1 > 2 ? 2 : 0] = I::template w1_in<2>(f - 1.0);
+    out[I::NW1 > 3 ? 3 : 0] = I::template w1_in<3>(f - 2.0);
+  } else {
+    out[0] = I::template w1_in<0>(f);
+    out[1] = I::template w1_in<1>(f - 1.0);
+  }
+}
+template <class I>
+SPIC_HDI void eval_wp_in(double f, double (&out)[I::NWP]) {
+  if (I::NWP == 3) {
+    out[0] = I::template wp_in<0>(f + 1.0);
+    out[I::NWP > 1 ? 1 : 0] = I::template wp_in<1>(f);
+    out[I::NWP > 2 ? 2 : 0] = I::template wp_in<2>(f - 1.0);
+  } else {
+    out[0] = I::template wp_in<0>(f);
+  }
+}
+// I[t] = I_Wp(s - cc, e - cc) for a segment [s,e] inside cell `cell`; hc = (double)cell
+template <class I>
+SPIC_HDI void eval_iwp_in(double s, double e, double hc, double (&out)[I::NWP]) {
+  if (I::NWP == 3) {
+    const double c0 = hc - 1.0, c2 = hc + 1.0;
+    out[0] = I::template iwp_in<0>(e - c0) - I::template iwp_in<0>(s - c0);
+    out[I::NWP > 1 ? 1 : 0] = I::template iwp_in<1>(e - hc) - I::template iwp_in<1>(s - hc);
+    out[I::NWP > 2 ? 2 : 0] = I::template iwp_in<2>(e - c2) - I::template iwp_in<2>(s - c2);
+  } else {
+    out[0] = I::template iwp_in<0>(e - hc) - I::template iwp_in<0>(s - hc);
   }
 }
 

@@ -52,6 +52,8 @@ struct EngineState {
   size_t cub_bytes = 0;
   double mover_frac = 0.0;  // 0: automatic
   int cells_per_block = 64;
+  int axis_kernel = 2;   // 1: k_theta_axis_binned, 2: k_theta_axis_v2 (cp.async pipelined)
+  int pushve_kernel = 2;
   unsigned long long* d_scalar = nullptr;  // small device scratch (8 words)
 };
 
@@ -291,6 +293,383 @@ __global__ void __launch_bounds__(kThreads, 2)
   }
 }
 
+// ------------------------------------------------------------------------------------
+// theta_axis, binned, v2: software-pipelined warp-per-cell kernel.
+//
+// Same algorithm and data layout as k_theta_axis_binned above; what changes is how the
+// warp is fed (ncu of v1: 28-41 % of the stall samples were long_scoreboard on the particle /
+// stencil loads, 21 % of the instructions were the LDS-bound deposition loop):
+//   * the block's bin counts / starts are read once into shared memory;
+//   * particle batches (32 x 6 doubles) and the B stencil of the NEXT batch / cell are staged
+//     into shared memory with cp.async (LDGSTS) while the current batch computes: global
+//     latency is hidden behind arithmetic without spending registers on prefetch;
+//   * weights use the in-cell tap forms (no DSETP/FSEL, no I2F per tap; same bits);
+//   * the stencil rows are padded to 4 doubles and read with LDS.128;
+//   * deposition: lane (tu, sub) keeps the NW1 x NWP accumulators of its u-column for the
+//     particles p = sub (mod 32/NW1); per particle 2 LDS.128 + 1 LDS.64 + 2 LDS.128 feed
+//     NWP DMUL + NW1*NWP DFMA (v1: 5 LDS.64 per 1 DMUL + NWP DFMA).
+// ------------------------------------------------------------------------------------
+constexpr int kMaxCellsPerBlock = 128;
+
+__device__ __forceinline__ void cp_async8(double* smem_dst, const double* gsrc) {
+  const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"(d), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+  asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory");
+}
+// N consecutive doubles from 16-byte aligned shared memory with LDS.128 (reads N rounded up to even)
+template <int N>
+__device__ __forceinline__ void lds_row(const double* src, double (&out)[N]) {
+  const double2* r = reinterpret_cast<const double2*>(src);
+#pragma unroll
+  for (int i = 0; i < (N + 1) / 2; ++i) {
+    const double2 t = r[i];
+    out[2 * i] = t.x;
+    if (2 * i + 1 < N) out[2 * i + 1 < N ? 2 * i + 1 : 0] = t.y;
+  }
+}
+
+template <class I>
+struct AxisV2Layout {
+  static constexpr int NW1 = I::NW1, NWP = I::NWP;
+  static constexpr int NROW = NW1 * NW1;             // (l,u) rows per component, NWP doubles each
+  static constexpr int SBC = NROW * NWP + 2;         // one component of the stencil (+ pad, even)
+  static constexpr int SB = 2 * SBC;                 // one stencil buffer: B_u then B_l
+  static constexpr int SW = NWP == 3 ? 14 : 6;       // weight record: a[NW1] b[NW1] I[NWP] pad
+  static constexpr int SP = 6 * 32;                  // one particle batch
+  static constexpr int RS = 36;                      // row pitch of the per-lane accumulator rows
+  static constexpr int SA = NW1 * NWP * RS;          // deposition accumulators parked between batches
+  static constexpr int PER_WARP = 2 * SP + 2 * SB + 32 * SW + SA;
+  static_assert(SBC % 2 == 0 && SP % 2 == 0 && SW % 2 == 0, "16-byte alignment of the sub-buffers");
+};
+
+template <class I, int A>
+__global__ void __launch_bounds__(kThreads, 2)
+    k_theta_axis_v2(Grid g, ParticleSoA p, const long* __restrict__ start, int* __restrict__ count,
+                    double* __restrict__ E, const double* __restrict__ B, double q, double qm, double dt, MoverList mv,
+                    int* __restrict__ flags, long ncell, int cells_per_block) {
+  constexpr int U = (A + 1) % 3, L = (A + 2) % 3;  // hpp:90-91
+  constexpr int NW1 = I::NW1, NWP = I::NWP;
+  using Lay = AxisV2Layout<I>;
+  constexpr int NROW = Lay::NROW, SBC = Lay::SBC, SB = Lay::SB, SW = Lay::SW, SP = Lay::SP, RS = Lay::RS;
+  constexpr int NSUB = 32 / NW1;  // particle subsets in the deposition phase
+  extern __shared__ __align__(16) double smem[];
+  __shared__ int s_cnt[kMaxCellsPerBlock];
+  __shared__ long s_start[kMaxCellsPerBlock];
+  __shared__ long s_base[kMaxCellsPerBlock];   // stencil corner (-W+1 in every direction) of the cell
+  __shared__ int s_cc[kMaxCellsPerBlock][3];   // local cell coordinates
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  double* sPart = smem + warp * Lay::PER_WARP;  // [2][6][32]
+  double* sBst = sPart + 2 * SP;                // [2][2][SBC]
+  double* sW = sBst + 2 * SB;                   // [32][SW]
+  double* sAcc = sW + 32 * SW;                  // [NW1*NWP][RS]
+  const long st[3] = {1, g.pj, g.pk};
+  const long stA = st[A], stU = st[U], stL = st[L];
+  const double nq = -q;  // -E_coef (hpp:114; Ics = Cs = 1)
+  double* Ea = E + (long)A * g.pc;
+  const double* Bu = B + (long)U * g.pc;
+  const double* Bl = B + (long)L * g.pc;
+
+  const long cbeg = (long)blockIdx.x * cells_per_block;
+  int nloc = cells_per_block;
+  if (cbeg + nloc > ncell) nloc = (int)(ncell - cbeg);
+  for (int t = threadIdx.x; t < nloc; t += kThreads) {
+    const long cell = cbeg + t;
+    const int cx = (int)(cell % g.n[0]), cy = (int)((cell / g.n[0]) % g.n[1]);
+    const int cz = (int)(cell / ((long)g.n[0] * g.n[1]));
+    s_cnt[t] = count[cell];
+    s_start[t] = start[cell];
+    s_cc[t][0] = cx;
+    s_cc[t][1] = cy;
+    s_cc[t][2] = cz;
+    s_base[t] = g.at(cx, cy, cz) + (1 - I::W) * (stA + stU + stL);
+  }
+  __syncthreads();
+
+  // stage batch (ci, off) into particle buffer pb; with off == 0 also the cell's stencil into bb
+  auto prefetch = [&](int ci, int off, int pb, int bb) {
+    if (off + lane < s_cnt[ci]) {
+      const long src = s_start[ci] + off + lane;
+      double* d = sPart + pb * SP + lane;
+      cp_async8(d + 0 * 32, p.x[A] + src);
+      cp_async8(d + 1 * 32, p.x[U] + src);
+      cp_async8(d + 2 * 32, p.x[L] + src);
+      cp_async8(d + 3 * 32, p.v[A] + src);
+      cp_async8(d + 4 * 32, p.v[U] + src);
+      cp_async8(d + 5 * 32, p.v[L] + src);
+    }
+    if (off == 0) {
+      const long base = s_base[ci];
+      double* d = sBst + bb * SB;
+#pragma unroll
+      for (int s = lane; s < 2 * NROW * NWP; s += 32) {
+        const int comp = s / (NROW * NWP), r = s % (NROW * NWP);
+        const int tc = r % NWP, tu = (r / NWP) % NW1, tl = r / (NWP * NW1);
+        const long idx = base + tc * stA + tu * stU + tl * stL;
+        cp_async8(d + comp * SBC + r, (comp ? Bl : Bu) + idx);
+      }
+    }
+    cp_async_commit();
+  };
+  auto next_cell = [&](int ci) {
+    ci += kWarps;
+    while (ci < nloc && s_cnt[ci] == 0) ci += kWarps;
+    return ci;
+  };
+
+  int ci = warp < nloc && s_cnt[warp] != 0 ? warp : next_cell(warp);
+  int off = 0, pb = 0, bb = 0;
+  if (ci < nloc) prefetch(ci, 0, 0, 0);
+
+  // per-cell state
+  int wp = 0, cnt = 0, homeA = 0;
+  long base = 0, s0 = 0;
+  double hA = 0, hU = 0, hL = 0;
+  bool wall_cell = false;
+  const int tuB = lane % NW1, subB = lane / NW1;
+
+  while (ci < nloc) {
+    // ---- issue the next batch's loads, then wait for the current batch ----------------------
+    int nci = ci, noff = off + 32;
+    if (noff >= s_cnt[ci]) {
+      nci = next_cell(ci);
+      noff = 0;
+    }
+    if (nci < nloc) prefetch(nci, noff, pb ^ 1, noff == 0 ? bb ^ 1 : bb);
+    else cp_async_commit();
+    cp_async_wait<1>();
+    __syncwarp();
+
+    if (off == 0) {  // new cell
+      cnt = s_cnt[ci];
+      s0 = s_start[ci];
+      base = s_base[ci];
+      homeA = s_cc[ci][A] + (A == 2 ? g.z0 : 0);
+      hA = (double)homeA;
+      hU = (double)(s_cc[ci][U] + (U == 2 ? g.z0 : 0));
+      hL = (double)(s_cc[ci][L] + (L == 2 ? g.z0 : 0));
+      // a particle sitting in a reflect cell reflects even without leaving it (util.hpp:174)
+      wall_cell = !g.per[A] && (homeA == I::W || homeA == g.gn[A] - 1 - I::W);
+      wp = 0;
+    }
+    const double* sBu = sBst + bb * SB;
+    const double* sBl = sBu + SBC;
+    const double* sP = sPart + pb * SP + lane;
+    const bool valid = off + lane < cnt;
+    const long idx = s0 + off + lane;
+
+    // ---- phase A: thread per particle ---------------------------------------------------------
+    // (padding lanes carry a resting particle at the cell centre: v = 0 makes every I exactly 0)
+    double xa = hA + 0.5, xu = hU + 0.5, xl = hL + 0.5, va = 0.0, vu = 0.0, vl = 0.0;
+    if (valid) {
+      xa = sP[0 * 32];
+      xu = sP[1 * 32];
+      xl = sP[2 * 32];
+      va = sP[3 * 32];
+      vu = sP[4 * 32];
+      vl = sP[5 * 32];
+    }
+    double uW1[NW1], lW1[NW1], uWp[NWP], lWp[NWP], I0[NWP];
+    {
+      const double fl = xl - hL, fu = xu - hU;  // exact: the particle lies inside its bin cell
+      eval_w1_in<I>(fl, lW1);
+      eval_wp_in<I>(fl, lWp);
+      eval_w1_in<I>(fu, uW1);
+      eval_wp_in<I>(fu, uWp);
+    }
+    const double x1 = xa + dt * va;
+    // construct_segments (util.cpp:160-174): floor(x1) == homeA  <=>  hA <= x1 < hA + 1
+    const bool crosses = !(x1 >= hA && x1 < hA + 1.0) || wall_cell;
+    eval_iwp_in<I>(xa, crosses ? xa : x1, hA, I0);
+    double r1 = 0, r2 = 0, xa_new = x1;
+    int newA = homeA;
+    if (crosses) {  // rare: <= 2 segments, reflection, periodic wrap -- the general path
+      Segments sg = make_segments<I, A>(g, xa, x1, flags);
+      eval_iwp_in<I>(sg.pt[0], sg.pt[1], hA, I0);
+      if (sg.n == 2) {  // the second segment lives in another stencil: per-particle atomics
+        double I1[NWP];
+        eval_iwp<I>(sg.pt[1], sg.pt[2], sg.cell[1], I1);
+        const long base2 = base + (long)(sg.cell[1] - homeA) * stA;
+#pragma unroll 1
+        for (int tl = 0; tl < NW1; ++tl) {
+          double a1 = 0, a2 = 0;
+#pragma unroll
+          for (int tu = 0; tu < NW1; ++tu) {
+            const long row = base2 + tl * stL + tu * stU;
+            const double mul = nq * (lW1[tl] * uW1[tu]);
+            double s1 = 0, s2 = 0;
+#pragma unroll
+            for (int tc = 0; tc < NWP; ++tc) {
+              const long j = row + tc * stA;
+              atomicAdd(&Ea[j], mul * I1[tc]);  // hpp:215
+              s1 = fma(__ldg(&Bu[j]), I1[tc], s1);
+              if (tu < NWP) s2 = fma(__ldg(&Bl[j]), I1[tc], s2);
+            }
+            a1 = fma(uW1[tu], s1, a1);
+            if (tu < NWP) a2 = fma(uWp[tu], s2, a2);
+          }
+          if (tl < NWP) r1 = fma(lWp[tl], a1, r1);
+          r2 = fma(-lW1[tl], a2, r2);
+        }
+      }
+      if (sg.reflected) {  // hpp:230-238
+        xa_new = sg.pt[2];
+        va = -va;
+      }
+      xa_new = wrap_periodic(xa_new, g.gn[A], g.per[A], flags);  // Redistribute, hpp:368
+      newA = (int)floor(xa_new);
+    }
+    // weights of the first segment for the deposition phase: -q*W1_l, W1_u, I   (hpp:194,215)
+    {
+      double2* w = reinterpret_cast<double2*>(sW + lane * SW);
+#pragma unroll
+      for (int t = 0; t < NW1 / 2; ++t) w[t] = make_double2(nq * lW1[2 * t], nq * lW1[2 * t + 1]);
+#pragma unroll
+      for (int t = 0; t < NW1 / 2; ++t) w[NW1 / 2 + t] = make_double2(uW1[2 * t], uW1[2 * t + 1]);
+      if (NWP == 3) {
+        w[NW1] = make_double2(I0[0], I0[NWP > 1 ? 1 : 0]);
+        sW[lane * SW + 2 * NW1 + 2] = I0[NWP - 1];
+      } else {
+        sW[lane * SW + 2 * NW1] = I0[0];
+      }
+    }
+#pragma unroll
+    for (int tl = 0; tl < NW1; ++tl) {  // first segment: B gather from the staged stencil
+      double a1 = 0, a2 = 0;
+      {
+        double bu[NW1 * NWP];
+        lds_row<NW1 * NWP>(sBu + tl * NW1 * NWP, bu);
+#pragma unroll
+        for (int tu = 0; tu < NW1; ++tu) {
+          double s1 = 0;
+#pragma unroll
+          for (int tc = 0; tc < NWP; ++tc) s1 = fma(bu[tu * NWP + tc], I0[tc], s1);
+          a1 = fma(uW1[tu], s1, a1);
+        }
+      }
+      {
+        double bl[NWP * NWP];
+        lds_row<NWP * NWP>(sBl + tl * NW1 * NWP, bl);
+#pragma unroll
+        for (int tu = 0; tu < NWP; ++tu) {
+          double s2 = 0;
+#pragma unroll
+          for (int tc = 0; tc < NWP; ++tc) s2 = fma(bl[tu * NWP + tc], I0[tc], s2);
+          a2 = fma(uWp[tu], s2, a2);
+        }
+      }
+      if (tl < NWP) r1 = fma(lWp[tl < NWP ? tl : 0], a1, r1);  // hpp:216
+      r2 = fma(-lW1[tl], a2, r2);                             // hpp:217
+      asm volatile("" ::: "memory");                          // bound load hoisting (register pressure)
+    }
+    vl = fma(qm, r1, vl);  // hpp:240-241
+    vu = fma(qm, r2, vu);
+    const bool moves = valid && newA != homeA;
+    __syncwarp();
+
+    // ---- deposition: lane (tu, sub) accumulates its u-column over particles sub, sub+NSUB, ... ----
+    // (the accumulators live in registers only here; between the batches of a cell they are parked
+    //  in shared memory so that phase A keeps its registers for the Horner chains)
+    double acc[NW1][NWP];
+#pragma unroll
+    for (int k = 0; k < NW1; ++k)
+#pragma unroll
+      for (int t = 0; t < NWP; ++t) acc[k][t] = off == 0 ? 0.0 : sAcc[(k * NWP + t) * RS + lane];
+#pragma unroll
+    for (int it = 0; it < NW1; ++it) {
+      const double* w = sW + (it * NSUB + subB) * SW;
+      double a[NW1], In[NWP];
+      lds_row<NW1>(w, a);
+      lds_row<NWP>(w + 2 * NW1, In);
+      const double b = w[NW1 + tuB];
+#pragma unroll
+      for (int t = 0; t < NWP; ++t) {
+        const double bI = b * In[t];
+#pragma unroll
+        for (int k = 0; k < NW1; ++k) acc[k][t] = fma(a[k], bI, acc[k][t]);
+      }
+    }
+
+    // ---- re-file: stayers compacted in place, movers to the list ---------------------------------
+    const unsigned stay_mask = __ballot_sync(0xffffffffu, valid && !moves);
+    const unsigned move_mask = __ballot_sync(0xffffffffu, moves);
+    if (valid && !moves) {
+      const long dst = s0 + wp + __popc(stay_mask & ((1u << lane) - 1u));
+      if (dst == idx) {  // nothing ahead of us left: only the changed components move
+        p.x[A][dst] = xa_new;
+        p.v[U][dst] = vu;
+        p.v[L][dst] = vl;
+        if (!g.per[A]) p.v[A][dst] = va;
+      } else {
+        p.x[A][dst] = xa_new;
+        p.x[U][dst] = xu;
+        p.x[L][dst] = xl;
+        p.v[A][dst] = va;
+        p.v[U][dst] = vu;
+        p.v[L][dst] = vl;
+      }
+    }
+    if (move_mask) {
+      unsigned basei = 0;
+      const int leader = __ffs(move_mask) - 1;
+      if (lane == leader) basei = atomicAdd(mv.n, (unsigned)__popc(move_mask));
+      basei = __shfl_sync(0xffffffffu, basei, leader);
+      if (moves) {
+        const unsigned m = basei + __popc(move_mask & ((1u << lane) - 1u));
+        if (m < mv.cap) {
+          const long cell = cbeg + ci;
+          int dest;
+          if (A == 2) {
+            const int knew = newA - g.z0;
+            dest = knew < 0 ? -1
+                            : (knew >= g.n[2] ? -2 : (int)(cell + (long)(knew - s_cc[ci][2]) * g.n[0] * g.n[1]));
+          } else {
+            dest = (int)(cell + (long)(newA - homeA) * (A == 0 ? 1 : g.n[0]));
+          }
+          mv.x[A][m] = xa_new;
+          mv.x[U][m] = xu;
+          mv.x[L][m] = xl;
+          mv.v[A][m] = va;
+          mv.v[U][m] = vu;
+          mv.v[L][m] = vl;
+          mv.dest[m] = dest;
+        } else {
+          atomicOr(&flags[1], 1);
+        }
+      }
+    }
+    wp += __popc(stay_mask);
+
+#pragma unroll
+    for (int k = 0; k < NW1; ++k)
+#pragma unroll
+      for (int t = 0; t < NWP; ++t) sAcc[(k * NWP + t) * RS + lane] = acc[k][t];
+    if (nci != ci) {
+      // ---- last batch of the cell: sum the particle subsets through shared memory, then one
+      //      native FP64 reduction (RED.E.ADD.F64) per stencil point -------------------------------
+      const double* red = sAcc;
+      __syncwarp();
+      for (int o = lane; o < NW1 * NWP * NW1; o += 32) {
+        const int kt = o / NW1, tu = o % NW1;
+        double sum = 0.0;
+#pragma unroll
+        for (int sb = 0; sb < NSUB; ++sb) sum += red[kt * RS + tu + NW1 * sb];
+        atomicAdd(&Ea[base + tu * stU + (kt / NWP) * stL + (kt % NWP) * stA], sum);
+      }
+      if (lane == 0) count[cbeg + ci] = wp;
+    }
+    __syncwarp();  // every lane is done with this batch's buffers before they are refilled
+    if (noff == 0) bb ^= 1;
+    pb ^= 1;
+    ci = nci;
+    off = noff;
+  }
+  cp_async_wait<0>();
+}
+
 // movers -> their new bin (or the tail when the bin is full)
 __global__ void __launch_bounds__(256)
     k_insert_movers(MoverList mv, ParticleSoA b, const long* __restrict__ start, int* __restrict__ count,
@@ -406,6 +785,156 @@ __global__ void __launch_bounds__(kThreads, 2)
       p.v[2][idx] = fma(dv[2], coef, p.v[2][idx]);
     }
   }
+}
+
+// ------------------------------------------------------------------------------------
+// push_V_E, binned, v2: the same cp.async pipeline as k_theta_axis_v2 (particle batches and the
+// E stencil of the next batch / cell staged in shared memory while the current one computes),
+// in-cell tap forms, stencil rows (4 doubles along x) read with LDS.128.
+// ------------------------------------------------------------------------------------
+template <class I>
+struct PushV2Layout {
+  static constexpr int NW1 = I::NW1;
+  static constexpr int NS = NW1 * NW1 * NW1;  // stencil points per component
+  static constexpr int SE = 3 * NS;           // one stencil buffer
+  static constexpr int SP = 6 * 32;
+  static constexpr int PER_WARP = 2 * SP + 2 * SE;
+};
+
+template <class I>
+__global__ void __launch_bounds__(kThreads, 2)
+    k_push_v_e_v2(Grid g, ParticleSoA p, const long* __restrict__ start, const int* __restrict__ count,
+                  const double* __restrict__ E, double coef, long ncell, int cells_per_block) {
+  constexpr int NW1 = I::NW1, NWP = I::NWP;
+  using Lay = PushV2Layout<I>;
+  constexpr int NS = Lay::NS, SE = Lay::SE, SP = Lay::SP;
+  extern __shared__ __align__(16) double smem[];
+  __shared__ int s_cnt[kMaxCellsPerBlock];
+  __shared__ long s_start[kMaxCellsPerBlock];
+  __shared__ long s_base[kMaxCellsPerBlock];
+  __shared__ int s_cc[kMaxCellsPerBlock][3];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  double* sPart = smem + warp * Lay::PER_WARP;  // [2][3][32]: positions (velocities are RMW in HBM)
+  double* sEst = sPart + 2 * SP;                // [2][3][NW1][NW1][NW1]
+  const long cbeg = (long)blockIdx.x * cells_per_block;
+  int nloc = cells_per_block;
+  if (cbeg + nloc > ncell) nloc = (int)(ncell - cbeg);
+  for (int t = threadIdx.x; t < nloc; t += kThreads) {
+    const long cell = cbeg + t;
+    const int cx = (int)(cell % g.n[0]), cy = (int)((cell / g.n[0]) % g.n[1]);
+    const int cz = (int)(cell / ((long)g.n[0] * g.n[1]));
+    s_cnt[t] = count[cell];
+    s_start[t] = start[cell];
+    s_cc[t][0] = cx;
+    s_cc[t][1] = cy;
+    s_cc[t][2] = cz;
+    s_base[t] = g.at(cx, cy, cz) + (1 - I::W) * (1 + g.pj + g.pk);
+  }
+  __syncthreads();
+
+  auto prefetch = [&](int ci, int off, int pb, int bb) {
+    if (off + lane < s_cnt[ci]) {
+      const long src = s_start[ci] + off + lane;
+      double* d = sPart + pb * SP + lane;
+      cp_async8(d + 0 * 32, p.x[0] + src);
+      cp_async8(d + 1 * 32, p.x[1] + src);
+      cp_async8(d + 2 * 32, p.x[2] + src);
+      cp_async8(d + 3 * 32, p.v[0] + src);
+      cp_async8(d + 4 * 32, p.v[1] + src);
+      cp_async8(d + 5 * 32, p.v[2] + src);
+    }
+    if (off == 0) {
+      const long base = s_base[ci];
+      double* d = sEst + bb * SE;
+#pragma unroll
+      for (int s = lane; s < 3 * NS; s += 32) {
+        const int comp = s / NS, r = s % NS;
+        const int ti = r % NW1, tj = (r / NW1) % NW1, tk = r / (NW1 * NW1);
+        cp_async8(d + s, E + base + ti + tj * g.pj + tk * g.pk + comp * g.pc);
+      }
+    }
+    cp_async_commit();
+  };
+  auto next_cell = [&](int ci) {
+    ci += kWarps;
+    while (ci < nloc && s_cnt[ci] == 0) ci += kWarps;
+    return ci;
+  };
+
+  int ci = warp < nloc && s_cnt[warp] != 0 ? warp : next_cell(warp);
+  int off = 0, pb = 0, bb = 0;
+  if (ci < nloc) prefetch(ci, 0, 0, 0);
+  while (ci < nloc) {
+    int nci = ci, noff = off + 32;
+    if (noff >= s_cnt[ci]) {
+      nci = next_cell(ci);
+      noff = 0;
+    }
+    if (nci < nloc) prefetch(nci, noff, pb ^ 1, noff == 0 ? bb ^ 1 : bb);
+    else cp_async_commit();
+    cp_async_wait<1>();
+    __syncwarp();
+
+    if (off + lane < s_cnt[ci]) {
+      const long idx = s_start[ci] + off + lane;
+      const double* sP = sPart + pb * SP + lane;
+      const double* sE = sEst + bb * SE;
+      const double fx = sP[0] - (double)s_cc[ci][0], fy = sP[32] - (double)s_cc[ci][1],
+                   fz = sP[64] - (double)(s_cc[ci][2] + g.z0);  // exact: inside the bin cell
+      double w1x[NW1], w1y[NW1], w1z[NW1], wpx[NWP], wpy[NWP], wpz[NWP];
+      eval_w1_in<I>(fx, w1x);
+      eval_w1_in<I>(fy, w1y);
+      eval_w1_in<I>(fz, w1z);
+      eval_wp_in<I>(fx, wpx);
+      eval_wp_in<I>(fy, wpy);
+      eval_wp_in<I>(fz, wpz);
+      // hpp:322-338, factorised: dv_x = sum_k W1z sum_j W1y sum_i E_x Wpx   etc.
+      double ax = 0, ay = 0, az = 0;
+#pragma unroll
+      for (int tk = 0; tk < NW1; ++tk) {
+        double bx = 0, by = 0, bz = 0;
+#pragma unroll
+        for (int tj = 0; tj < NW1; ++tj) {
+          const double* row = sE + (tk * NW1 + tj) * NW1;
+          double ex[NW1];
+          lds_row<NW1>(row, ex);
+          double cx = 0;
+#pragma unroll
+          for (int ti = 0; ti < NWP; ++ti) cx = fma(ex[ti], wpx[ti], cx);
+          bx = fma(w1y[tj], cx, bx);
+          if (tj < NWP) {
+            double ey[NW1];
+            lds_row<NW1>(row + NS, ey);
+            double cy = 0;
+#pragma unroll
+            for (int ti = 0; ti < NW1; ++ti) cy = fma(ey[ti], w1x[ti], cy);
+            by = fma(wpy[tj < NWP ? tj : 0], cy, by);
+          }
+          if (tk < NWP) {
+            double ez[NW1];
+            lds_row<NW1>(row + 2 * NS, ez);
+            double cz = 0;
+#pragma unroll
+            for (int ti = 0; ti < NW1; ++ti) cz = fma(ez[ti], w1x[ti], cz);
+            bz = fma(w1y[tj], cz, bz);
+          }
+        }
+        ax = fma(w1z[tk], bx, ax);
+        ay = fma(w1z[tk], by, ay);
+        if (tk < NWP) az = fma(wpz[tk < NWP ? tk : 0], bz, az);
+        asm volatile("" ::: "memory");  // bound load hoisting (register pressure)
+      }
+      p.v[0][idx] = fma(ax, coef, sP[96]);  // hpp:339-341
+      p.v[1][idx] = fma(ay, coef, sP[128]);
+      p.v[2][idx] = fma(az, coef, sP[160]);
+    }
+    __syncwarp();
+    if (noff == 0) bb ^= 1;
+    pb ^= 1;
+    ci = nci;
+    off = noff;
+  }
+  cp_async_wait<0>();
 }
 
 // ------------------------------------------------------------------------------------
@@ -678,6 +1207,33 @@ int rebin(Ctx* c, Species& s, long tail_n_host) {
 }
 
 template <class I>
+int theta_axis_v2_dispatch(Ctx* c, Species& s, int comp, double dt) {
+  EngineState* e = eng(c);
+  const long ncell = c->g.cells();
+  const int cpb = e->cells_per_block;
+  const int grid = (int)((ncell + cpb - 1) / cpb);
+  const size_t smem = sizeof(double) * kWarps * AxisV2Layout<I>::PER_WARP;
+  const double qm = s.q / s.m;
+  static bool attr_set[3] = {false, false, false};
+#define SPIC_LAUNCH_V2(AX)                                                                                        \
+  do {                                                                                                            \
+    if (!attr_set[AX]) {                                                                                          \
+      SPIC_CUDA_CHECK(c, cudaFuncSetAttribute(k_theta_axis_v2<I, AX>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                                              (int)smem));                                                        \
+      attr_set[AX] = true;                                                                                        \
+    }                                                                                                             \
+    k_theta_axis_v2<I, AX><<<grid, kThreads, smem, c->stream>>>(c->g, s.b, s.start, s.count, c->E, c->B, s.q, qm, dt, \
+                                                                e->mv, c->d_flags, ncell, cpb);                   \
+  } while (0)
+  if (comp == 0) SPIC_LAUNCH_V2(0);
+  else if (comp == 1) SPIC_LAUNCH_V2(1);
+  else SPIC_LAUNCH_V2(2);
+#undef SPIC_LAUNCH_V2
+  c->launches++;
+  return SPIC_OK;
+}
+
+template <class I>
 void theta_axis_binned_dispatch(Ctx* c, Species& s, int comp, double dt) {
   EngineState* e = eng(c);
   const long ncell = c->g.cells();
@@ -802,10 +1358,16 @@ int engine_theta_axis(Ctx* c, Species& s, int comp, double dt) {
   EngineState* e = eng(c);
   {
     KernelTimer t(c, KT_AXIS);
-    if (c->cfg.interp == SPIC_INTERP_P8R2)
-      theta_axis_binned_dispatch<InterpP8R2>(c, s, comp, dt);
-    else
-      theta_axis_binned_dispatch<InterpPWL>(c, s, comp, dt);
+    if (e->axis_kernel == 1) {
+      if (c->cfg.interp == SPIC_INTERP_P8R2)
+        theta_axis_binned_dispatch<InterpP8R2>(c, s, comp, dt);
+      else
+        theta_axis_binned_dispatch<InterpPWL>(c, s, comp, dt);
+    } else {
+      const int rc = c->cfg.interp == SPIC_INTERP_P8R2 ? theta_axis_v2_dispatch<InterpP8R2>(c, s, comp, dt)
+                                                       : theta_axis_v2_dispatch<InterpPWL>(c, s, comp, dt);
+      if (rc) return rc;
+    }
   }
   // the tail runs through the thread-per-particle kernel BEFORE new overflow can join it
   launch_theta_axis_direct(c, s.d, s.capd, s.d_nd, s.q, s.m, comp, dt);
@@ -844,7 +1406,21 @@ int engine_push_v_e(Ctx* c, Species& s, double dt) {
   const double coef = dt * s.q / s.m;  // hpp:267
   {
     KernelTimer t(c, KT_PUSHVE);
-    if (c->cfg.interp == SPIC_INTERP_P8R2) {
+    if (e->pushve_kernel != 1) {
+      if (c->cfg.interp == SPIC_INTERP_P8R2) {
+        const size_t smem = sizeof(double) * kWarps * PushV2Layout<InterpP8R2>::PER_WARP;
+        static bool attr = false;
+        if (!attr) {
+          SPIC_CUDA_CHECK(c, cudaFuncSetAttribute(k_push_v_e_v2<InterpP8R2>,
+                                                  cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+          attr = true;
+        }
+        k_push_v_e_v2<InterpP8R2><<<grid, kThreads, smem, c->stream>>>(c->g, s.b, s.start, s.count, c->E, coef, ncell, cpb);
+      } else {
+        const size_t smem = sizeof(double) * kWarps * PushV2Layout<InterpPWL>::PER_WARP;
+        k_push_v_e_v2<InterpPWL><<<grid, kThreads, smem, c->stream>>>(c->g, s.b, s.start, s.count, c->E, coef, ncell, cpb);
+      }
+    } else if (c->cfg.interp == SPIC_INTERP_P8R2) {
       const size_t smem = sizeof(double) * kWarps * 3 * 64;
       k_push_v_e_binned<InterpP8R2><<<grid, kThreads, smem, c->stream>>>(c->g, s.b, s.start, s.count, c->E, coef, ncell, cpb);
     } else {
@@ -923,8 +1499,16 @@ int engine_set_option(Ctx* c, const char* name, double value) {
     e->mover_frac = value;
     return SPIC_OK;
   }
+  if (!strcmp(name, "axis_kernel")) {
+    e->axis_kernel = (int)value;
+    return SPIC_OK;
+  }
+  if (!strcmp(name, "pushve_kernel")) {
+    e->pushve_kernel = (int)value;
+    return SPIC_OK;
+  }
   if (!strcmp(name, "cells_per_block")) {
-    if (value < 1) return SPIC_EINVAL;
+    if (value < 1 || value > kMaxCellsPerBlock) return SPIC_EINVAL;
     e->cells_per_block = (int)value;
     return SPIC_OK;
   }
