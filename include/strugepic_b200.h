@@ -125,10 +125,29 @@ int spic_energy(spic_ctx* ctx, double out[2]);
 /* discrete Gauss residual G = div- E - rho, [k][j][i] over valid cells */
 int spic_gauss_residual(spic_ctx* ctx, double* host);
 
+/* get_particle_number_density<W>: include/strugepic_util.hpp:30-85; [k][j][i] over valid cells */
+int spic_number_density(spic_ctx* ctx, double* host);
+/* SimulationIO::write<W>(step) plot output (E, B, number density): include/strugepic_util.hpp:133-143 */
+int spic_plot_write(spic_ctx* ctx, const char* path);
+
 /* ---- checkpoint / restart: SimulationIO::write(step,true) / read(step),
  *      include/strugepic_util.hpp:126-132, src/strugepic_util.cpp:66-70 ---------- */
 int spic_checkpoint_write(spic_ctx* ctx, const char* path);
 int spic_checkpoint_read(spic_ctx* ctx, const char* path);
+
+/* ---- interpolation interface: W1, Wp, I_W1, I_Wp, interpolation_range of
+ *      include/strugepic_w.hpp:12-16 (defaults: src/interpolation/interpolation.cpp:19-84 P8R2,
+ *      87-157 PWL).  Host evaluation of the same inline code the kernels use. ---------------- */
+double spic_W1(int interp, double x);
+double spic_Wp(int interp, double x);
+double spic_I_W1(int interp, double a, double b);
+double spic_I_Wp(int interp, double a, double b);
+int spic_interpolation_range(int interp);
+/* the in-cell tap forms of the binned kernels: W1/Wp at f - (tap - W + 1), f = x - cell in [0,1);
+ * I_Wp(s - cc, e - cc), cc = cell + tap - W + 1, for a segment [s,e] inside `cell` */
+double spic_tap_W1(int interp, int tap, double f);
+double spic_tap_Wp(int interp, int tap, double f);
+double spic_tap_IWp(int interp, int tap, double s, double e, int cell);
 
 /* ---- introspection for benchmarks --------------------------------------------- */
 int64_t spic_launch_count(const spic_ctx* ctx); /* kernels launched so far */

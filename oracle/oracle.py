@@ -81,6 +81,7 @@ class _Base:
         self._theta_B = self._f("theta_B", None, [vp, d])
         self._source = self._f("source", None, [vp, i, i, d, d, d, d])
         self._energy = self._f("energy", None, [vp, _dp])
+        self._number_density = self._f("number_density", None, [vp, _dp])
 
     # -- state -----------------------------------------------------------------
     def set_field(self, which, arr):
@@ -126,6 +127,12 @@ class _Base:
         out = np.zeros(2)
         self._energy(self.h, _p(out))
         return float(out[0]), float(out[1])
+
+    def number_density(self):
+        """get_particle_number_density<W> (include/strugepic_util.hpp:30-85), [k][j][i] valid cells."""
+        out = np.empty((self.n[2], self.n[1], self.n[0]))
+        self._number_density(self.h, _p(out))
+        return out
 
     def close(self):
         if getattr(self, "h", None):

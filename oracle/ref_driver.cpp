@@ -15,6 +15,7 @@
 //   get_total_energy    src/strugepic_util.cpp:364-394
 //   W1/Wp/I_W1/I_Wp     src/interpolation/interpolation.cpp
 //   construct_segments  src/strugepic_util.cpp:160-174
+//   get_particle_number_density<W>  include/strugepic_util.hpp:30-85
 #include "strugepic_propagators.hpp"
 #include "strugepic_util.hpp"
 #include "strugepic_w.hpp"
@@ -145,6 +146,17 @@ void oref_source(void* h, int pos, int comp, double E0, double omega, double dt,
   Sim* s = static_cast<Sim*>(h);
   E_source src(s->geom, *s->E, pos, comp, E0, omega, dt);
   src(t);
+}
+// get_particle_number_density<W>: include/strugepic_util.hpp:30-85; dst = [k][j][i] valid cells
+void oref_number_density(void* h, double* dst) {
+  Sim* s = static_cast<Sim*>(h);
+  amrex::MultiFab Pdens(s->ba, s->dm, 1, s->ng);
+  get_particle_number_density<WRANGE>(s->geom, *s->P, Pdens);
+  auto a = Pdens.fab().array();
+  long q = 0;
+  for (int k = 0; k < s->n[2]; ++k)
+    for (int j = 0; j < s->n[1]; ++j)
+      for (int i = 0; i < s->n[0]; ++i) dst[q++] = a(i, j, k, 0);
 }
 void oref_energy(void* h, double* out) {
   Sim* s = static_cast<Sim*>(h);

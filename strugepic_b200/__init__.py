@@ -47,6 +47,23 @@ def interpolation_range(interp):
     return 2 if interp == P8R2 else 1
 
 
+def W1(x, interp=P8R2):
+    """W1 of include/strugepic_w.hpp:12 (host evaluation of the kernels' inline code)."""
+    return _lib.load().spic_W1(interp, x)
+
+
+def Wp(x, interp=P8R2):
+    return _lib.load().spic_Wp(interp, x)
+
+
+def I_W1(a, b, interp=P8R2):
+    return _lib.load().spic_I_W1(interp, a, b)
+
+
+def I_Wp(a, b, interp=P8R2):
+    return _lib.load().spic_I_Wp(interp, a, b)
+
+
 def probe_fp64_tflops(device=0, seconds=1.0):
     out = C.c_double(0)
     rc = _lib.load().spic_probe_fp64_tflops(device, seconds, C.byref(out))
@@ -62,6 +79,21 @@ def comm_unique_id():
     if rc:
         raise SpicError(rc, "ncclGetUniqueId failed (NCCL not loadable?)")
     return buf.raw
+
+
+def read_plot(path):
+    """Reader of `Simulation.write_plot` files -> dict(n_cell, lo, n, E, B, n_density)."""
+    with open(path, "rb") as f:
+        raw = f.read()
+    assert raw[:8] == b"SPICPLT1", "not a strugepic_b200 plot file"
+    hdr = np.frombuffer(raw, dtype=np.int32, count=14, offset=8)
+    n_cell, lo, n = hdr[2:5], hdr[5:8], hdr[8:11]
+    cells = int(n[0]) * int(n[1]) * int(n[2])
+    data = np.frombuffer(raw, dtype=np.float64, count=7 * cells, offset=8 + 14 * 4)
+    shp = (int(n[2]), int(n[1]), int(n[0]))
+    return {"n_cell": tuple(int(t) for t in n_cell), "lo": tuple(int(t) for t in lo), "n": tuple(int(t) for t in n),
+            "interp": int(hdr[1]), "E": data[:3 * cells].reshape((3,) + shp),
+            "B": data[3 * cells:6 * cells].reshape((3,) + shp), "n_density": data[6 * cells:].reshape(shp)}
 
 
 class Simulation:
@@ -198,6 +230,16 @@ class Simulation:
         out = np.empty((self.n[2], self.n[1], self.n[0]))
         self._ck(self.lib.spic_gauss_residual(self.h, _p(out)))
         return out
+
+    def number_density(self):
+        """get_particle_number_density<W> (include/strugepic_util.hpp:30-85), [k][j][i] valid cells."""
+        out = np.empty((self.n[2], self.n[1], self.n[0]))
+        self._ck(self.lib.spic_number_density(self.h, _p(out)))
+        return out
+
+    def write_plot(self, path):
+        """SimulationIO::write<W>(step) plot output: E, B and the number density of this rank's brick."""
+        self._ck(self.lib.spic_plot_write(self.h, str(path).encode()))
 
     def checkpoint(self, path):
         self._ck(self.lib.spic_checkpoint_write(self.h, str(path).encode()))

@@ -41,8 +41,18 @@ SIGNATURES = {
     "spic_field_only_step": (i32, [vp, i32, i32, dbl, dbl, dbl, i32]),
     "spic_energy": (i32, [vp, _dp]),
     "spic_gauss_residual": (i32, [vp, _dp]),
+    "spic_number_density": (i32, [vp, _dp]),
+    "spic_plot_write": (i32, [vp, C.c_char_p]),
     "spic_checkpoint_write": (i32, [vp, C.c_char_p]),
     "spic_checkpoint_read": (i32, [vp, C.c_char_p]),
+    "spic_W1": (dbl, [i32, dbl]),
+    "spic_Wp": (dbl, [i32, dbl]),
+    "spic_I_W1": (dbl, [i32, dbl, dbl]),
+    "spic_I_Wp": (dbl, [i32, dbl, dbl]),
+    "spic_interpolation_range": (i32, [i32]),
+    "spic_tap_W1": (dbl, [i32, i32, dbl]),
+    "spic_tap_Wp": (dbl, [i32, i32, dbl]),
+    "spic_tap_IWp": (dbl, [i32, i32, dbl, dbl, i32]),
     "spic_launch_count": (i64, [vp]),
     "spic_kernel_time_ms": (i32, [vp, i32, _dp, C.POINTER(i64)]),
     "spic_kernel_times": (i32, [vp, i32, C.POINTER(C.c_double * 4), C.POINTER(C.c_int64 * 4)]),

@@ -512,6 +512,65 @@ int spic_gauss_residual(spic_ctx* c, double* host) {
   return check_flags(c);
 }
 
+// get_particle_number_density<W>(geom, P, P_dens): include/strugepic_util.hpp:30-85
+int spic_number_density(spic_ctx* c, double* host) {
+  if (!c || !host) return SPIC_EINVAL;
+  cudaSetDevice(c->cfg.device);
+  double* nd = nullptr;
+  const size_t gbytes = sizeof(double) * (size_t)c->g.pc;
+  SPIC_CUDA_CHECK(c, cudaMalloc(&nd, gbytes));
+  cudaMemsetAsync(nd, 0, gbytes, c->stream);  // P_dens.setVal(0); setBndry(0)   util.hpp:32-33
+  int rc = SPIC_OK;
+  for (auto& s : c->sp) {
+    if (s.binned) rc = engine_number_density(c, s, nd);
+    else launch_number_density(c, s.d, s.nd, nullptr, nd);
+    if (rc) break;
+  }
+  if (!rc) rc = halo_sum(c, nd, 0);  // P_dens.SumBoundary   util.hpp:84
+  if (!rc) {
+    launch_pack_scalar(c, nd, c->scratch);
+    cudaMemcpyAsync(host, c->scratch, sizeof(double) * (size_t)c->g.cells(), cudaMemcpyDeviceToHost, c->stream);
+    rc = check_flags(c);
+  }
+  cudaFree(nd);
+  return rc;
+}
+
+// SimulationIO::write<W>(step) without checkpoint flag (include/strugepic_util.hpp:133-143): the
+// reference writes three AMReX plotfiles (plt_E, plt_B, plt_Pdens); here one binary file per rank:
+// header, E, B ([3][k][j][i] valid cells each), number density ([k][j][i]).  Reader:
+// strugepic_b200.read_plot().
+struct PlotHeader {
+  char magic[8];
+  int32_t version, interp, n_cell[3], lo[3], n[3], nranks, rank, pad;
+};
+int spic_plot_write(spic_ctx* c, const char* path) {
+  if (!c || !path) return SPIC_EINVAL;
+  cudaSetDevice(c->cfg.device);
+  const size_t cells = (size_t)c->g.cells();
+  std::vector<double> buf(7 * cells);
+  int rc;
+  if ((rc = spic_get_field(c, SPIC_FIELD_E, buf.data()))) return rc;
+  if ((rc = spic_get_field(c, SPIC_FIELD_B, buf.data() + 3 * cells))) return rc;
+  if ((rc = spic_number_density(c, buf.data() + 6 * cells))) return rc;
+  PlotHeader h{};
+  memcpy(h.magic, "SPICPLT1", 8);
+  h.version = 1;
+  h.interp = c->cfg.interp;
+  for (int d = 0; d < 3; ++d) {
+    h.n_cell[d] = c->g.gn[d];
+    h.n[d] = c->g.n[d];
+    h.lo[d] = d == 2 ? c->g.z0 : 0;
+  }
+  h.nranks = c->cfg.nranks;
+  h.rank = c->cfg.rank;
+  FILE* f = fopen(path, "wb");
+  if (!f) return fail(c, SPIC_EIO, std::string("cannot open ") + path);
+  bool ok = fwrite(&h, sizeof h, 1, f) == 1 && fwrite(buf.data(), sizeof(double), buf.size(), f) == buf.size();
+  ok = (fclose(f) == 0) && ok;
+  return ok ? SPIC_OK : fail(c, SPIC_EIO, std::string("short write to ") + path);
+}
+
 // ---- checkpoint -------------------------------------------------------------------------
 // Own binary format (the reference delegates to AMReX VisMF / ParticleContainer::Checkpoint,
 // include/strugepic_util.hpp:126-132): header, E, B (valid cells, [c][k][j][i]), then per
@@ -620,6 +679,50 @@ int spic_checkpoint_read(spic_ctx* c, const char* path) {
   }
   fclose(f);
   return SPIC_OK;
+}
+
+// ---- interpolation interface (include/strugepic_w.hpp:12-16), host evaluation of the very
+//      same code the kernels inline (csrc/interp.cuh) ------------------------------------------
+double spic_W1(int interp, double x) { return interp == SPIC_INTERP_PWL ? InterpPWL::W1(x) : InterpP8R2::W1(x); }
+double spic_Wp(int interp, double x) { return interp == SPIC_INTERP_PWL ? InterpPWL::Wp(x) : InterpP8R2::Wp(x); }
+double spic_I_W1(int interp, double a, double b) {
+  return interp == SPIC_INTERP_PWL ? InterpPWL::I_W1(a, b) : InterpP8R2::I_W1(a, b);
+}
+double spic_I_Wp(int interp, double a, double b) {
+  return interp == SPIC_INTERP_PWL ? InterpPWL::I_Wp(a, b) : InterpP8R2::I_Wp(a, b);
+}
+int spic_interpolation_range(int interp) { return interp == SPIC_INTERP_PWL ? InterpPWL::W : InterpP8R2::W; }
+// The in-cell tap forms used by the binned kernels (f = x - cell in [0,1), tap t): exposed so that
+// the CPU test-suite can pin them bit for bit against the general forms.
+double spic_tap_W1(int interp, int tap, double f) {
+  if (interp == SPIC_INTERP_PWL) {
+    double o[InterpPWL::NW1];
+    eval_w1_in<InterpPWL>(f, o);
+    return tap >= 0 && tap < InterpPWL::NW1 ? o[tap] : 0.0;
+  }
+  double o[InterpP8R2::NW1];
+  eval_w1_in<InterpP8R2>(f, o);
+  return tap >= 0 && tap < InterpP8R2::NW1 ? o[tap] : 0.0;
+}
+double spic_tap_Wp(int interp, int tap, double f) {
+  if (interp == SPIC_INTERP_PWL) {
+    double o[InterpPWL::NWP];
+    eval_wp_in<InterpPWL>(f, o);
+    return tap >= 0 && tap < InterpPWL::NWP ? o[tap] : 0.0;
+  }
+  double o[InterpP8R2::NWP];
+  eval_wp_in<InterpP8R2>(f, o);
+  return tap >= 0 && tap < InterpP8R2::NWP ? o[tap] : 0.0;
+}
+double spic_tap_IWp(int interp, int tap, double s, double e, int cell) {
+  if (interp == SPIC_INTERP_PWL) {
+    double o[InterpPWL::NWP];
+    eval_iwp_in<InterpPWL>(s, e, (double)cell, o);
+    return tap >= 0 && tap < InterpPWL::NWP ? o[tap] : 0.0;
+  }
+  double o[InterpP8R2::NWP];
+  eval_iwp_in<InterpP8R2>(s, e, (double)cell, o);
+  return tap >= 0 && tap < InterpP8R2::NWP ? o[tap] : 0.0;
 }
 
 // ---- introspection ------------------------------------------------------------------------

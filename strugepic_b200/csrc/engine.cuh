@@ -15,6 +15,7 @@ int engine_theta_axis(Ctx* c, Species& s, int comp, double dt);
 int engine_push_v_e(Ctx* c, Species& s, double dt);
 int engine_kinetic(Ctx* c, Species& s, double* acc);
 int engine_deposit_rho(Ctx* c, Species& s, double* out);
+int engine_number_density(Ctx* c, Species& s, double* nd);  // nd: one guarded component
 int engine_set_option(Ctx* c, const char* name, double value);
 int engine_maintain(Ctx* c);
 // file n particles (device arrays, positions inside this rank's slab) into their bins / the tail

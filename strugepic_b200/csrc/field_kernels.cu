@@ -255,6 +255,17 @@ __global__ void k_gauss_div(Grid g, const double* __restrict__ E, double* __rest
   }
 }
 
+// one guarded component -> [k][j][i] over the valid cells
+__global__ void k_pack_scalar(Grid g, const double* __restrict__ F, double* __restrict__ packed) {
+  const long total = g.cells();
+  for (long t = blockIdx.x * (long)blockDim.x + threadIdx.x; t < total; t += (long)gridDim.x * blockDim.x) {
+    const int i = (int)(t % g.n[0]);
+    const int j = (int)((t / g.n[0]) % g.n[1]);
+    const int k = (int)(t / ((long)g.n[0] * g.n[1]));
+    packed[t] = F[g.at(i, j, k)];
+  }
+}
+
 Interior make_interior(const Grid& g) {  // construct_interior<d,1>, hpp:499-510
   Interior in;
   for (int d = 0; d < 3; ++d) {
@@ -330,6 +341,10 @@ void launch_pack_field(Ctx* c, const double* F, double* packed) {
 }
 void launch_unpack_field(Ctx* c, double* F, const double* packed) {
   k_pack<false><<<grid_for(c, c->g.cells() * 3), kBlock, 0, c->stream>>>(c->g, F, const_cast<double*>(packed));
+  c->launches++;
+}
+void launch_pack_scalar(Ctx* c, const double* F, double* packed) {
+  k_pack_scalar<<<grid_for(c, c->g.cells()), kBlock, 0, c->stream>>>(c->g, F, packed);
   c->launches++;
 }
 void field_energy(Ctx* c, double* out6) {

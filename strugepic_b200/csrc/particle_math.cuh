@@ -92,6 +92,25 @@ SPIC_DI void gather_E(const double* E0, long sj, long sk, long sc, const double 
   dv[2] = az;
 }
 
+// get_particle_number_density (include/strugepic_util.hpp:53-81): n(cell + o) += Wp Wp Wp over the
+// (2W-1)^3 Wp taps; `nd` is one guarded component (guards are folded by the caller: SumBoundary, :84)
+template <class I>
+SPIC_DI void deposit_number_density(const Grid& g, double x, double y, double z, double* __restrict__ nd) {
+  const int cx = (int)floor(x), cy = (int)floor(y), cz = (int)floor(z);
+  double wx[I::NWP], wy[I::NWP], wz[I::NWP];
+  eval_wp<I>(x, cx, wx);
+  eval_wp<I>(y, cy, wy);
+  eval_wp<I>(z, cz, wz);
+  const long base = g.at(cx + 1 - I::W, cy + 1 - I::W, cz - g.z0 + 1 - I::W);
+#pragma unroll
+  for (int ti = 0; ti < I::NWP; ++ti)
+#pragma unroll
+    for (int tj = 0; tj < I::NWP; ++tj)
+#pragma unroll
+      for (int tk = 0; tk < I::NWP; ++tk)
+        atomicAdd(&nd[base + ti + tj * g.pj + tk * g.pk], wx[ti] * wy[tj] * wz[tk]);  // util.hpp:76
+}
+
 // Counter-based synthetic particle (strugepic_b200/synthetic.py is the bit-identical
 // numpy twin): splitmix64 keyed by (seed, global particle id, draw index).  Position
 // offsets are U[0,1)^3; each velocity component is an Irwin-Hall(4) variate scaled to

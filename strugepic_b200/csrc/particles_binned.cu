@@ -361,6 +361,7 @@ __global__ void __launch_bounds__(kThreads, 2)
   __shared__ long s_start[kMaxCellsPerBlock];
   __shared__ long s_base[kMaxCellsPerBlock];   // stencil corner (-W+1 in every direction) of the cell
   __shared__ int s_cc[kMaxCellsPerBlock][3];   // local cell coordinates
+  __shared__ long s_soff[2 * NROW * NWP];      // stencil point -> offset from the corner (+ component)
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   double* sPart = smem + warp * Lay::PER_WARP;  // [2][6][32]
   double* sBst = sPart + 2 * SP;                // [2][2][SBC]
@@ -387,6 +388,11 @@ __global__ void __launch_bounds__(kThreads, 2)
     s_cc[t][2] = cz;
     s_base[t] = g.at(cx, cy, cz) + (1 - I::W) * (stA + stU + stL);
   }
+  for (int t = threadIdx.x; t < 2 * NROW * NWP; t += kThreads) {
+    const int comp = t / (NROW * NWP), r = t % (NROW * NWP);
+    const int tc = r % NWP, tu = (r / NWP) % NW1, tl = r / (NWP * NW1);
+    s_soff[t] = tc * stA + tu * stU + tl * stL + (long)(comp ? L : U) * g.pc;
+  }
   __syncthreads();
 
   // stage batch (ci, off) into particle buffer pb; with off == 0 also the cell's stencil into bb
@@ -402,15 +408,11 @@ __global__ void __launch_bounds__(kThreads, 2)
       cp_async8(d + 5 * 32, p.v[L] + src);
     }
     if (off == 0) {
-      const long base = s_base[ci];
+      const double* src = B + s_base[ci];
       double* d = sBst + bb * SB;
 #pragma unroll
-      for (int s = lane; s < 2 * NROW * NWP; s += 32) {
-        const int comp = s / (NROW * NWP), r = s % (NROW * NWP);
-        const int tc = r % NWP, tu = (r / NWP) % NW1, tl = r / (NWP * NW1);
-        const long idx = base + tc * stA + tu * stU + tl * stL;
-        cp_async8(d + comp * SBC + r, (comp ? Bl : Bu) + idx);
-      }
+      for (int s = lane; s < 2 * NROW * NWP; s += 32)
+        cp_async8(d + s + (s >= NROW * NWP ? SBC - NROW * NWP : 0), src + s_soff[s]);
     }
     cp_async_commit();
   };
@@ -483,6 +485,16 @@ __global__ void __launch_bounds__(kThreads, 2)
     const double x1 = xa + dt * va;
     // construct_segments (util.cpp:160-174): floor(x1) == homeA  <=>  hA <= x1 < hA + 1
     const bool crosses = !(x1 >= hA && x1 < hA + 1.0) || wall_cell;
+    if (crosses) {  // warm L1 with the neighbour cell's stencil; the loads come ~300 DFMAs later
+      const long base2 = base + (x1 < hA ? -stA : stA);
+#pragma unroll 1
+      for (int s = 0; s < 2 * NROW; ++s) {
+        const double* ptr = (s < NROW ? Bu : Bl) + base2 + (s % NW1) * stU + ((s / NW1) % NW1) * stL;
+#pragma unroll
+        for (int tc = 0; tc < NWP; tc += (A == 0 ? NWP - 1 > 0 ? NWP - 1 : 1 : 1))
+          asm volatile("prefetch.global.L1 [%0];" ::"l"(ptr + tc * stA));
+      }
+    }
     eval_iwp_in<I>(xa, crosses ? xa : x1, hA, I0);
     double r1 = 0, r2 = 0, xa_new = x1;
     int newA = homeA;
@@ -493,7 +505,7 @@ __global__ void __launch_bounds__(kThreads, 2)
         double I1[NWP];
         eval_iwp<I>(sg.pt[1], sg.pt[2], sg.cell[1], I1);
         const long base2 = base + (long)(sg.cell[1] - homeA) * stA;
-#pragma unroll 1
+#pragma unroll
         for (int tl = 0; tl < NW1; ++tl) {
           double a1 = 0, a2 = 0;
 #pragma unroll
@@ -538,16 +550,17 @@ __global__ void __launch_bounds__(kThreads, 2)
     }
 #pragma unroll
     for (int tl = 0; tl < NW1; ++tl) {  // first segment: B gather from the staged stencil
-      double a1 = 0, a2 = 0;
+      // (first terms are plain products: fma(a, b, +0) has the same bits and costs a zeroed register)
+      double a1, a2;
       {
         double bu[NW1 * NWP];
         lds_row<NW1 * NWP>(sBu + tl * NW1 * NWP, bu);
 #pragma unroll
         for (int tu = 0; tu < NW1; ++tu) {
-          double s1 = 0;
+          double s1 = bu[tu * NWP] * I0[0];
 #pragma unroll
-          for (int tc = 0; tc < NWP; ++tc) s1 = fma(bu[tu * NWP + tc], I0[tc], s1);
-          a1 = fma(uW1[tu], s1, a1);
+          for (int tc = 1; tc < NWP; ++tc) s1 = fma(bu[tu * NWP + tc], I0[tc], s1);
+          a1 = tu == 0 ? uW1[0] * s1 : fma(uW1[tu], s1, a1);
         }
       }
       {
@@ -555,10 +568,10 @@ __global__ void __launch_bounds__(kThreads, 2)
         lds_row<NWP * NWP>(sBl + tl * NW1 * NWP, bl);
 #pragma unroll
         for (int tu = 0; tu < NWP; ++tu) {
-          double s2 = 0;
+          double s2 = bl[tu * NWP] * I0[0];
 #pragma unroll
-          for (int tc = 0; tc < NWP; ++tc) s2 = fma(bl[tu * NWP + tc], I0[tc], s2);
-          a2 = fma(uWp[tu], s2, a2);
+          for (int tc = 1; tc < NWP; ++tc) s2 = fma(bl[tu * NWP + tc], I0[tc], s2);
+          a2 = tu == 0 ? uWp[0] * s2 : fma(uWp[tu], s2, a2);
         }
       }
       if (tl < NWP) r1 = fma(lWp[tl < NWP ? tl : 0], a1, r1);  // hpp:216
@@ -889,6 +902,7 @@ __global__ void __launch_bounds__(kThreads, 2)
       eval_wp_in<I>(fy, wpy);
       eval_wp_in<I>(fz, wpz);
       // hpp:322-338, factorised: dv_x = sum_k W1z sum_j W1y sum_i E_x Wpx   etc.
+      // (first terms are plain products: fma(a, b, +0) has the same bits and costs a zeroed register)
       double ax = 0, ay = 0, az = 0;
 #pragma unroll
       for (int tk = 0; tk < NW1; ++tk) {
@@ -898,30 +912,30 @@ __global__ void __launch_bounds__(kThreads, 2)
           const double* row = sE + (tk * NW1 + tj) * NW1;
           double ex[NW1];
           lds_row<NW1>(row, ex);
-          double cx = 0;
+          double cx = ex[0] * wpx[0];
 #pragma unroll
-          for (int ti = 0; ti < NWP; ++ti) cx = fma(ex[ti], wpx[ti], cx);
-          bx = fma(w1y[tj], cx, bx);
+          for (int ti = 1; ti < NWP; ++ti) cx = fma(ex[ti], wpx[ti], cx);
+          bx = tj == 0 ? w1y[0] * cx : fma(w1y[tj], cx, bx);
           if (tj < NWP) {
             double ey[NW1];
             lds_row<NW1>(row + NS, ey);
-            double cy = 0;
+            double cy = ey[0] * w1x[0];
 #pragma unroll
-            for (int ti = 0; ti < NW1; ++ti) cy = fma(ey[ti], w1x[ti], cy);
-            by = fma(wpy[tj < NWP ? tj : 0], cy, by);
+            for (int ti = 1; ti < NW1; ++ti) cy = fma(ey[ti], w1x[ti], cy);
+            by = tj == 0 ? wpy[0] * cy : fma(wpy[tj < NWP ? tj : 0], cy, by);
           }
           if (tk < NWP) {
             double ez[NW1];
             lds_row<NW1>(row + 2 * NS, ez);
-            double cz = 0;
+            double cz = ez[0] * w1x[0];
 #pragma unroll
-            for (int ti = 0; ti < NW1; ++ti) cz = fma(ez[ti], w1x[ti], cz);
-            bz = fma(w1y[tj], cz, bz);
+            for (int ti = 1; ti < NW1; ++ti) cz = fma(ez[ti], w1x[ti], cz);
+            bz = tj == 0 ? w1y[0] * cz : fma(w1y[tj], cz, bz);
           }
         }
-        ax = fma(w1z[tk], bx, ax);
-        ay = fma(w1z[tk], by, ay);
-        if (tk < NWP) az = fma(wpz[tk < NWP ? tk : 0], bz, az);
+        ax = tk == 0 ? w1z[0] * bx : fma(w1z[tk], bx, ax);
+        ay = tk == 0 ? w1z[0] * by : fma(w1z[tk], by, ay);
+        if (tk < NWP) az = tk == 0 ? wpz[0] * bz : fma(wpz[tk < NWP ? tk : 0], bz, az);
         asm volatile("" ::: "memory");  // bound load hoisting (register pressure)
       }
       p.v[0][idx] = fma(ax, coef, sP[96]);  // hpp:339-341
@@ -962,6 +976,20 @@ __global__ void __launch_bounds__(256)
     double t = 0;
     for (int w = 0; w < 8; ++w) t += sh[w];
     atomicAdd(accum, t);
+  }
+}
+
+template <class I>
+__global__ void __launch_bounds__(256)
+    k_number_density_binned(Grid g, ParticleSoA p, const long* __restrict__ start, const int* __restrict__ count,
+                            long ncell, double* __restrict__ nd) {
+  const int lane = threadIdx.x & 31;
+  const long wid = (blockIdx.x * (long)blockDim.x + threadIdx.x) >> 5, nw = ((long)gridDim.x * blockDim.x) >> 5;
+  for (long cell = wid; cell < ncell; cell += nw) {
+    const int cnt = count[cell];
+    const long s0 = start[cell];
+    for (int i = lane; i < cnt; i += 32)
+      deposit_number_density<I>(g, p.x[0][s0 + i], p.x[1][s0 + i], p.x[2][s0 + i], nd);
   }
 }
 
@@ -1467,6 +1495,18 @@ int engine_deposit_rho(Ctx* c, Species& s, double* out) {
   SPIC_CUDA_CHECK(c, cudaStreamSynchronize(c->stream));
   for (int d = 0; d < 3; ++d) cudaFree(tmp.x[d]);
   cudaFree(prefix);
+  return SPIC_OK;
+}
+
+int engine_number_density(Ctx* c, Species& s, double* nd) {
+  if (!s.binned) return SPIC_OK;
+  const long ncell = c->g.cells();
+  if (c->cfg.interp == SPIC_INTERP_P8R2)
+    k_number_density_binned<InterpP8R2><<<grid_warps(c, ncell), 256, 0, c->stream>>>(c->g, s.b, s.start, s.count, ncell, nd);
+  else
+    k_number_density_binned<InterpPWL><<<grid_warps(c, ncell), 256, 0, c->stream>>>(c->g, s.b, s.start, s.count, ncell, nd);
+  c->launches++;
+  launch_number_density(c, s.d, s.capd, s.d_nd, nd);
   return SPIC_OK;
 }
 

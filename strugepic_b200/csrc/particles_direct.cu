@@ -167,6 +167,16 @@ __global__ void __launch_bounds__(kBlock) k_deposit_rho(Grid g, ParticleSoA p, l
       }
 }
 
+template <class I>
+__global__ void __launch_bounds__(kBlock) k_number_density(Grid g, ParticleSoA p, long n,
+                                                           const unsigned long long* __restrict__ n_dev,
+                                                           double* __restrict__ nd) {
+  const long i = blockIdx.x * (long)blockDim.x + threadIdx.x;
+  if (n_dev) n = (long)*n_dev;
+  if (i >= n) return;
+  deposit_number_density<I>(g, p.x[0][i], p.x[1][i], p.x[2][i], nd);
+}
+
 __global__ void __launch_bounds__(256)
     k_load_uniform(Grid g, ParticleSoA p, long n, int ppc, double vth, uint64_t seed) {
   for (long t = blockIdx.x * (long)blockDim.x + threadIdx.x; t < n; t += (long)gridDim.x * blockDim.x) {
@@ -242,6 +252,16 @@ void launch_deposit_rho(Ctx* c, const ParticleSoA& p, long n, const unsigned lon
     k_deposit_rho<InterpP8R2><<<grid, kBlock, 0, c->stream>>>(c->g, p, n, n_dev, q, out);
   else
     k_deposit_rho<InterpPWL><<<grid, kBlock, 0, c->stream>>>(c->g, p, n, n_dev, q, out);
+  c->launches++;
+}
+
+void launch_number_density(Ctx* c, const ParticleSoA& p, long n, const unsigned long long* n_dev, double* nd) {
+  if (n <= 0) return;
+  const int grid = (int)((n + kBlock - 1) / kBlock);
+  if (c->cfg.interp == SPIC_INTERP_P8R2)
+    k_number_density<InterpP8R2><<<grid, kBlock, 0, c->stream>>>(c->g, p, n, n_dev, nd);
+  else
+    k_number_density<InterpPWL><<<grid, kBlock, 0, c->stream>>>(c->g, p, n, n_dev, nd);
   c->launches++;
 }
 

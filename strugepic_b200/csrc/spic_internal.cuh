@@ -71,6 +71,7 @@ void field_energy(Ctx* c, double* out_sumsq6);  // sum of squares of the 6 compo
 void launch_pack_field(Ctx* c, const double* F, double* packed);    // guarded -> [c][k][j][i] valid
 void launch_unpack_field(Ctx* c, double* F, const double* packed);  // valid -> guarded
 void launch_gauss_div(Ctx* c, double* out);                          // out += div- E
+void launch_pack_scalar(Ctx* c, const double* F, double* packed);   // one guarded component -> valid cells
 
 // ---- particle kernels, thread per particle (particles_direct.cu) ----------------
 // n = host upper bound of the list length; n_dev (optional) = exact count on the device
@@ -82,6 +83,8 @@ void launch_kinetic_energy(Ctx* c, const ParticleSoA& p, long n, const unsigned 
                            double* accum);
 void launch_deposit_rho(Ctx* c, const ParticleSoA& p, long n, const unsigned long long* n_dev, double q, double* out);
 void launch_load_uniform(Ctx* c, const ParticleSoA& p, long n, int ppc, double vth, uint64_t seed);
+// get_particle_number_density (include/strugepic_util.hpp:30-85): nd is ONE guarded component
+void launch_number_density(Ctx* c, const ParticleSoA& p, long n, const unsigned long long* n_dev, double* nd);
 
 struct Ctx {
   spic_config cfg{};

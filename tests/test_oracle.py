@@ -222,3 +222,23 @@ def test_map4_is_three_map2_with_unit_coefficients():
     util.load_state(c, E, B, parts, -0.5, 50.0)
     c.map(4, 0.3, yoshida=True)
     assert not np.array_equal(util.state_of(c)[0], util.state_of(a)[0])
+
+
+@needs_ref
+@pytest.mark.parametrize("interp", [0, 1])
+@pytest.mark.parametrize("periodic", [(1, 1, 1), (0, 1, 1)])
+def test_number_density_port_matches_reference(interp, periodic):
+    """get_particle_number_density<W> (include/strugepic_util.hpp:30-85): port == reference bit for bit,
+    and the deposit conserves the particle count (sum_i Wp(x - i) = 1) on a periodic box."""
+    n_cell = (9, 7, 5)
+    W = 2 if interp == 0 else 1
+    parts = util.plasma(n_cell, 5, 0.2, 61, periodic, W)
+    dens = []
+    for kind in ("ref", "port"):
+        o = util.make_oracle(kind, n_cell, periodic, interp)
+        z = np.zeros((3, 5, 7, 9))
+        util.load_state(o, z, z, parts, -1.0, 1.0)
+        dens.append(o.number_density())
+    assert np.array_equal(dens[0], dens[1])
+    if all(periodic):
+        assert abs(dens[0].sum() - len(parts[0])) < 1e-9 * len(parts[0])

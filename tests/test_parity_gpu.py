@@ -231,6 +231,48 @@ def test_checkpoint_roundtrip(tmp_path, engine):
         spic().Simulation((12, 8, 7), interp=0).restart(tmp_path / "ck.bin")
 
 
+@pytest.mark.parametrize("engine", ENGINES)
+@pytest.mark.parametrize("interp", [0, 1])
+@pytest.mark.parametrize("periodic", [(1, 1, 1), (0, 1, 1)])
+def test_number_density_and_plot_file(tmp_path, interp, periodic, engine):
+    """get_particle_number_density<W> + SimulationIO::write<W>(step) (include/strugepic_util.hpp:30-85, 133-143)."""
+    n_cell = (9, 7, 5)
+    W = 2 if interp == 0 else 1
+    E, B = util.rng_fields(n_cell, 61)
+    parts = util.plasma(n_cell, 5, 0.2, 61, periodic, W)
+    o = ora.best_oracle(n_cell, periodic=periodic, interp=interp)
+    s = spic().Simulation(n_cell, periodic=periodic, interp=interp, engine=engine)
+    for t in (o, s):
+        util.load_state(t, E, B, parts, -0.2, 20.0)
+    want = o.number_density()
+    got = s.number_density()
+    assert np.max(np.abs(got - want)) <= 1e-13 * np.max(np.abs(want))
+    s.write_plot(tmp_path / "plt0.spic")
+    plt = spic().read_plot(tmp_path / "plt0.spic")
+    assert plt["n_cell"] == n_cell and plt["n"] == n_cell and plt["interp"] == interp
+    assert np.array_equal(plt["E"], E) and np.array_equal(plt["B"], B)
+    assert np.array_equal(plt["n_density"], got)
+
+
+@pytest.mark.parametrize("variant", [1, 2])
+def test_kernel_variants_agree_with_oracle(variant):
+    """Both generations of the binned particle kernels stay covered (option axis_kernel / pushve_kernel)."""
+    n_cell = (16, 12, 8)
+    E, B = util.rng_fields(n_cell, 71, 0.3)
+    parts = util.plasma(n_cell, 40, 0.15, 71)   # > 32 per cell: several batches per bin
+    for interp in (0, 1):
+        o = ora.best_oracle(n_cell, interp=interp)
+        s = spic().Simulation(n_cell, interp=interp)
+        s.set_option("axis_kernel", variant)
+        s.set_option("pushve_kernel", variant)
+        for t in (o, s):
+            util.load_state(t, E, B, parts, -1.0 / 40, 100.0 / 40)
+        for t in (o, s):
+            t.map(2, 0.5)
+            t.map(1, 0.5)
+        util.compare_states(util.state_of(o), util.state_of(s), 2 * TOL_STEP, 2 * TOL_STEP, box=n_cell)
+
+
 def test_errors_are_reported():
     sp = spic()
     with pytest.raises(sp.SpicError):
