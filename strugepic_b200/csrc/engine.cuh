@@ -5,6 +5,54 @@
 
 namespace spic {
 
+struct MoverList {
+  double* x[3];
+  double* v[3];
+  int* dest;  // >= 0: local cell; -1 / -2: leaves through the low / high z face of the slab
+  unsigned* n;
+  unsigned cap;
+};
+
+struct EngineState {
+  MoverList mv{};
+  void* cub_tmp = nullptr;
+  size_t cub_bytes = 0;
+  double mover_frac = 0.0;  // 0: automatic
+  int cells_per_block = 64;
+  // particle-kernel generation: 1 warp-per-cell (k_*_binned), 2 cp.async pipelined warp-per-cell
+  // (k_*_v2), 3 particle-stream batches that span cells (k_*_v3, particles_stream.cu)
+  int axis_kernel = 3;
+  int pushve_kernel = 3;
+  unsigned long long* d_scalar = nullptr;  // small device scratch (8 words)
+};
+EngineState* eng(Ctx* c);
+
+// ---- shared-memory pipeline helpers (cp.async = LDGSTS) --------------------------------
+__device__ __forceinline__ void cp_async8(double* smem_dst, const double* gsrc) {
+  const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"(d), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+  asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory");
+}
+// N consecutive doubles from 16-byte aligned shared memory with LDS.128 (reads N rounded up to even)
+template <int N>
+__device__ __forceinline__ void lds_row(const double* src, double (&out)[N]) {
+  const double2* r = reinterpret_cast<const double2*>(src);
+#pragma unroll
+  for (int i = 0; i < (N + 1) / 2; ++i) {
+    const double2 t = r[i];
+    out[2 * i] = t.x;
+    if (2 * i + 1 < N) out[2 * i + 1 < N ? 2 * i + 1 : 0] = t.y;
+  }
+}
+
+// ---- particle-stream kernels (particles_stream.cu) ------------------------------------------
+int stream_theta_axis(Ctx* c, Species& s, int comp, double dt);
+int stream_push_v_e(Ctx* c, Species& s, double dt);
+
 // ---- cell-binned engine ------------------------------------------------------------
 int engine_ingest(Ctx* c, Species& s);  // move s.d (direct list) into cell bins (no-op for ENGINE_DIRECT)
 void engine_free_species(Ctx* c, Species& s);

@@ -38,34 +38,15 @@ struct ToLong {
   __host__ __device__ long operator()(int v) const { return (long)v; }
 };
 
-struct MoverList {
-  double* x[3];
-  double* v[3];
-  int* dest;  // >= 0: local cell; -1 / -2: leaves through the low / high z face of the slab
-  unsigned* n;
-  unsigned cap;
-};
-
-struct EngineState {
-  MoverList mv{};
-  void* cub_tmp = nullptr;
-  size_t cub_bytes = 0;
-  double mover_frac = 0.0;  // 0: automatic
-  int cells_per_block = 64;
-  int axis_kernel = 2;   // 1: k_theta_axis_binned, 2: k_theta_axis_v2 (cp.async pipelined)
-  int pushve_kernel = 2;
-  unsigned long long* d_scalar = nullptr;  // small device scratch (8 words)
-};
+EngineState* eng(Ctx* c) {
+  if (!c->engine) c->engine = new EngineState();
+  return static_cast<EngineState*>(c->engine);
+}
 
 namespace {
 
 constexpr int kWarps = 8;
 constexpr int kThreads = kWarps * 32;
-
-EngineState* eng(Ctx* c) {
-  if (!c->engine) c->engine = new EngineState();
-  return static_cast<EngineState*>(c->engine);
-}
 
 // ------------------------------------------------------------------------------------
 // theta_axis, binned
@@ -310,27 +291,6 @@ __global__ void __launch_bounds__(kThreads, 2)
 //     NWP DMUL + NW1*NWP DFMA (v1: 5 LDS.64 per 1 DMUL + NWP DFMA).
 // ------------------------------------------------------------------------------------
 constexpr int kMaxCellsPerBlock = 128;
-
-__device__ __forceinline__ void cp_async8(double* smem_dst, const double* gsrc) {
-  const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
-  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"(d), "l"(gsrc) : "memory");
-}
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
-template <int N>
-__device__ __forceinline__ void cp_async_wait() {
-  asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory");
-}
-// N consecutive doubles from 16-byte aligned shared memory with LDS.128 (reads N rounded up to even)
-template <int N>
-__device__ __forceinline__ void lds_row(const double* src, double (&out)[N]) {
-  const double2* r = reinterpret_cast<const double2*>(src);
-#pragma unroll
-  for (int i = 0; i < (N + 1) / 2; ++i) {
-    const double2 t = r[i];
-    out[2 * i] = t.x;
-    if (2 * i + 1 < N) out[2 * i + 1 < N ? 2 * i + 1 : 0] = t.y;
-  }
-}
 
 template <class I>
 struct AxisV2Layout {
@@ -1386,7 +1346,10 @@ int engine_theta_axis(Ctx* c, Species& s, int comp, double dt) {
   EngineState* e = eng(c);
   {
     KernelTimer t(c, KT_AXIS);
-    if (e->axis_kernel == 1) {
+    if (e->axis_kernel == 3) {
+      const int rc = stream_theta_axis(c, s, comp, dt);
+      if (rc) return rc;
+    } else if (e->axis_kernel == 1) {
       if (c->cfg.interp == SPIC_INTERP_P8R2)
         theta_axis_binned_dispatch<InterpP8R2>(c, s, comp, dt);
       else
@@ -1434,7 +1397,11 @@ int engine_push_v_e(Ctx* c, Species& s, double dt) {
   const double coef = dt * s.q / s.m;  // hpp:267
   {
     KernelTimer t(c, KT_PUSHVE);
-    if (e->pushve_kernel != 1) {
+    if (e->pushve_kernel == 3) {
+      const int rc = stream_push_v_e(c, s, dt);
+      if (rc) return rc;
+      c->launches--;  // counted below
+    } else if (e->pushve_kernel != 1) {
       if (c->cfg.interp == SPIC_INTERP_P8R2) {
         const size_t smem = sizeof(double) * kWarps * PushV2Layout<InterpP8R2>::PER_WARP;
         static bool attr = false;

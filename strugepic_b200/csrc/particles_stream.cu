@@ -1,0 +1,687 @@
+// Particle-stream kernels (generation 3 of the binned engine): the hot path.
+//
+// Data layout is the cell-binned SoA store of particles_binned.cu.  What changes against the
+// warp-per-cell kernels (k_*_v2) is the unit of work: a warp owns a run of consecutive cells and
+// walks their live particles as ONE stream cut into 32-particle batches, so a batch may span the
+// boundary between two cells.  With warp-per-cell batching a cell holding 65 particles costs three
+// batches (32 + 32 + 1); a thermal plasma at 64 ppc has ~47 % such cells, i.e. ~20 % of the issue
+// slots went to padding lanes (ncu: 1.16 batches per 32 particles already after 6 steps).  At low
+// ppc the gain is larger still (8 ppc: 2 cells per batch instead of 8 active lanes in 32).
+//
+//   * per block: bin counts / starts, stencil corners, cell coordinates of its cells -> shared memory;
+//     per warp: exclusive prefix of the counts of its cells (stream index -> cell);
+//   * per batch: lane -> (cell, slot); particle data and the stencil of every cell first touched by
+//     the NEXT batch are staged with cp.async (LDGSTS) while the current batch computes; stencils
+//     live in a small ring (a batch spans at most kSpan non-empty cells);
+//   * phase A (thread per particle) as in k_theta_axis_v2, with per-lane cell data;
+//   * deposition (theta_axis): one register-accumulated pass per cell present in the batch; the
+//     accumulators of a cell that continues into the next batch are parked in shared memory; a
+//     finished cell is flushed with one RED.ADD.F64 per stencil point;
+//   * re-file: stayers are compacted in place per cell, movers go to the mover list.
+//
+// Reference: Theta<comp,W,..> include/strugepic_propagators.hpp:80-244, push_V_E :247-344.
+#include "engine.cuh"
+#include "particle_math.cuh"
+
+namespace spic {
+
+namespace {
+
+constexpr int kWarps = 8;
+constexpr int kThreads = kWarps * 32;
+constexpr int kMaxCells = 64;          // cells per block (option cells_per_block, multiple of kWarps)
+constexpr int kSpan = 2;               // a batch spans at most kSpan non-empty cells
+constexpr int kRing = 2 * kSpan;       // stencil slots per warp: cells of the current + of the next batch
+constexpr unsigned kFull = 0xffffffffu;
+
+struct BlockTables {
+  int cnt[kMaxCells];
+  int pre[kMaxCells + kWarps + 1];  // per-warp exclusive prefix of cnt (warp w uses indices ci + w)
+  int slot[kMaxCells];              // ring slot holding the cell's stencil
+  int cc[kMaxCells][3];             // local cell coordinates
+  long start[kMaxCells];
+  long base[kMaxCells];             // stencil corner (-W+1 in every direction)
+  double home[kMaxCells][3];        // GLOBAL cell coordinates as doubles
+};
+
+__device__ __forceinline__ void load_tables(BlockTables& T, const Grid& g, const long* __restrict__ start,
+                                            const int* __restrict__ count, long cbeg, int nloc, long corner_off) {
+  for (int t = threadIdx.x; t < nloc; t += kThreads) {
+    const long cell = cbeg + t;
+    const int cx = (int)(cell % g.n[0]), cy = (int)((cell / g.n[0]) % g.n[1]);
+    const int cz = (int)(cell / ((long)g.n[0] * g.n[1]));
+    T.cnt[t] = count[cell];
+    T.start[t] = start[cell];
+    T.cc[t][0] = cx;
+    T.cc[t][1] = cy;
+    T.cc[t][2] = cz;
+    T.home[t][0] = (double)cx;
+    T.home[t][1] = (double)cy;
+    T.home[t][2] = (double)(cz + g.z0);
+    T.base[t] = g.at(cx, cy, cz) + corner_off;
+  }
+}
+
+// The warp's view of its particle stream.
+struct Stream {
+  const int* pre;  // pre[ci] for ci in [cbeg, cend]: stream index of the first particle of cell ci
+  int cbeg, cend, total;
+  __device__ __forceinline__ void init(BlockTables& T, int warp, int lane, int nloc, int ncw) {
+    cbeg = warp * ncw < nloc ? warp * ncw : nloc;
+    cend = cbeg + ncw < nloc ? cbeg + ncw : nloc;
+    int* p = T.pre + warp;
+    if (lane == 0) {
+      int acc = 0;
+      for (int ci = cbeg; ci < cend; ++ci) {
+        p[ci] = acc;
+        acc += T.cnt[ci];
+      }
+      p[cend] = acc;
+    }
+    __syncwarp();
+    pre = p;
+    total = p[cend];
+  }
+  // lane -> cell for the batch starting at stream index gbase.  `mc` only moves forward.  Valid lanes
+  // are a prefix of the warp; `heads` marks the first lane of every cell present in the batch.
+  __device__ __forceinline__ void locate(int gbase, int lane, int& mc, bool& valid, int& nvalid,
+                                         unsigned& heads) const {
+    const int gi = gbase + lane;
+    valid = gi < total;
+    if (valid)
+      while (gi >= pre[mc + 1]) ++mc;  // pre[cend] == total > gi ends the walk; empty cells are skipped
+    const int prev = __shfl_up_sync(kFull, mc, 1);
+    const bool head = valid && (lane == 0 || mc != prev);
+    heads = __ballot_sync(kFull, head);
+    // at most kSpan cells per batch: lanes of later cells wait for the next batch
+    const int group = __popc(heads & (0xffffffffu >> (31 - lane))) - 1;
+    valid = valid && group < kSpan;
+    const unsigned vm = __ballot_sync(kFull, valid);
+    nvalid = __popc(vm);
+    heads &= vm;
+  }
+};
+
+// ====================================================================================
+// push_V_E
+// ====================================================================================
+template <class I>
+struct PushLayout {
+  static constexpr int NW1 = I::NW1;
+  static constexpr int NS = NW1 * NW1 * NW1;  // stencil points per component
+  static constexpr int SE = 3 * NS;           // one stencil
+  static constexpr int SP = 6 * 32;           // one particle batch
+  static constexpr int PER_WARP = 2 * SP + kRing * SE;
+};
+
+template <class I>
+__global__ void __launch_bounds__(kThreads, 2)
+    k_push_v_e_v3(Grid g, ParticleSoA p, const long* __restrict__ start, const int* __restrict__ count,
+                  const double* __restrict__ E, double coef, long ncell, int cells_per_block) {
+  constexpr int NW1 = I::NW1, NWP = I::NWP;
+  using Lay = PushLayout<I>;
+  constexpr int NS = Lay::NS, SE = Lay::SE, SP = Lay::SP;
+  extern __shared__ __align__(16) double smem[];
+  __shared__ BlockTables T;
+  __shared__ long s_soff[SE];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  double* sPart = smem + warp * Lay::PER_WARP;  // [2][6][32]
+  double* sEst = sPart + 2 * SP;                // [kRing][3][NW1][NW1][NW1]
+  const long cbeg_blk = (long)blockIdx.x * cells_per_block;
+  int nloc = cells_per_block;
+  if (cbeg_blk + nloc > ncell) nloc = (int)(ncell - cbeg_blk);
+  load_tables(T, g, start, count, cbeg_blk, nloc, (1 - I::W) * (1 + g.pj + g.pk));
+  for (int t = threadIdx.x; t < SE; t += kThreads) {
+    const int comp = t / NS, r = t % NS;
+    s_soff[t] = (r % NW1) + ((r / NW1) % NW1) * g.pj + (r / (NW1 * NW1)) * g.pk + comp * g.pc;
+  }
+  __syncthreads();
+  Stream S;
+  S.init(T, warp, lane, nloc, cells_per_block / kWarps);
+
+  int staged = S.cbeg - 1, nstaged = 0;
+  // issue the loads of a located batch: particle data of its lanes + stencils of cells not staged yet
+  auto prefetch = [&](int gbase, int mc, bool valid, unsigned heads, int pb) {
+    if (valid) {
+      const long src = T.start[mc] + (gbase + lane - S.pre[mc]);
+      double* d = sPart + pb * SP + lane;
+      cp_async8(d + 0 * 32, p.x[0] + src);
+      cp_async8(d + 1 * 32, p.x[1] + src);
+      cp_async8(d + 2 * 32, p.x[2] + src);
+      cp_async8(d + 3 * 32, p.v[0] + src);
+      cp_async8(d + 4 * 32, p.v[1] + src);
+      cp_async8(d + 5 * 32, p.v[2] + src);
+    }
+    for (unsigned hm = heads; hm; hm &= hm - 1) {
+      const int X = __shfl_sync(kFull, mc, __ffs(hm) - 1);
+      if (X <= staged) continue;
+      const int sl = nstaged % kRing;
+      if (lane == 0) T.slot[X] = sl;
+      const double* src = E + T.base[X];
+      double* d = sEst + sl * SE;
+#pragma unroll
+      for (int s = lane; s < SE; s += 32) cp_async8(d + s, src + s_soff[s]);
+      staged = X;
+      ++nstaged;
+    }
+    cp_async_commit();
+  };
+
+  int gbase = 0, mc = S.cbeg, nvalid, pb = 0;
+  bool valid;
+  unsigned heads;
+  S.locate(gbase, lane, mc, valid, nvalid, heads);
+  if (nvalid > 0) prefetch(gbase, mc, valid, heads, 0);
+  while (nvalid > 0) {
+    int n_mc = mc, n_nvalid;
+    bool n_valid;
+    unsigned n_heads;
+    const int n_gbase = gbase + nvalid;
+    S.locate(n_gbase, lane, n_mc, n_valid, n_nvalid, n_heads);
+    if (n_nvalid > 0) prefetch(n_gbase, n_mc, n_valid, n_heads, pb ^ 1);
+    else cp_async_commit();
+    cp_async_wait<1>();
+    __syncwarp();
+
+    if (valid) {
+      const long idx = T.start[mc] + (gbase + lane - S.pre[mc]);
+      const double* sP = sPart + pb * SP + lane;
+      const double* sE = sEst + T.slot[mc] * SE;  // (valid lanes only: their cell has been staged)
+      // exact: the particle lies inside its bin cell
+      const double fx = sP[0] - T.home[mc][0], fy = sP[32] - T.home[mc][1], fz = sP[64] - T.home[mc][2];
+      double w1x[NW1], w1y[NW1], w1z[NW1], wpx[NWP], wpy[NWP], wpz[NWP];
+      eval_w1_in<I>(fx, w1x);
+      eval_w1_in<I>(fy, w1y);
+      eval_w1_in<I>(fz, w1z);
+      eval_wp_in<I>(fx, wpx);
+      eval_wp_in<I>(fy, wpy);
+      eval_wp_in<I>(fz, wpz);
+      // hpp:322-338, factorised: dv_x = sum_k W1z sum_j W1y sum_i E_x Wpx   etc.
+      // (first terms are plain products: fma(a, b, +0) has the same bits and costs a zeroed register)
+      double ax = 0, ay = 0, az = 0;
+#pragma unroll
+      for (int tk = 0; tk < NW1; ++tk) {
+        double bx = 0, by = 0, bz = 0;
+#pragma unroll
+        for (int tj = 0; tj < NW1; ++tj) {
+          const double* row = sE + (tk * NW1 + tj) * NW1;
+          double ex[NW1];
+          lds_row<NW1>(row, ex);
+          double cx = ex[0] * wpx[0];
+#pragma unroll
+          for (int ti = 1; ti < NWP; ++ti) cx = fma(ex[ti], wpx[ti], cx);
+          bx = tj == 0 ? w1y[0] * cx : fma(w1y[tj], cx, bx);
+          if (tj < NWP) {
+            double ey[NW1];
+            lds_row<NW1>(row + NS, ey);
+            double cy = ey[0] * w1x[0];
+#pragma unroll
+            for (int ti = 1; ti < NW1; ++ti) cy = fma(ey[ti], w1x[ti], cy);
+            by = tj == 0 ? wpy[0] * cy : fma(wpy[tj < NWP ? tj : 0], cy, by);
+          }
+          if (tk < NWP) {
+            double ez[NW1];
+            lds_row<NW1>(row + 2 * NS, ez);
+            double cz = ez[0] * w1x[0];
+#pragma unroll
+            for (int ti = 1; ti < NW1; ++ti) cz = fma(ez[ti], w1x[ti], cz);
+            bz = tj == 0 ? w1y[0] * cz : fma(w1y[tj], cz, bz);
+          }
+        }
+        ax = tk == 0 ? w1z[0] * bx : fma(w1z[tk], bx, ax);
+        ay = tk == 0 ? w1z[0] * by : fma(w1z[tk], by, ay);
+        if (tk < NWP) az = tk == 0 ? wpz[0] * bz : fma(wpz[tk < NWP ? tk : 0], bz, az);
+        asm volatile("" ::: "memory");  // bound load hoisting (register pressure)
+      }
+      p.v[0][idx] = fma(ax, coef, sP[96]);  // hpp:339-341
+      p.v[1][idx] = fma(ay, coef, sP[128]);
+      p.v[2][idx] = fma(az, coef, sP[160]);
+    }
+    __syncwarp();  // every lane is done with this batch's buffers before they are refilled
+    gbase = n_gbase;
+    mc = n_mc;
+    valid = n_valid;
+    nvalid = n_nvalid;
+    heads = n_heads;
+    pb ^= 1;
+  }
+  cp_async_wait<0>();
+}
+
+// ====================================================================================
+// theta_axis
+// ====================================================================================
+template <class I>
+struct AxisLayout {
+  static constexpr int NW1 = I::NW1, NWP = I::NWP;
+  static constexpr int NROW = NW1 * NW1;        // (l,u) rows per component, NWP doubles each
+  static constexpr int SBC = NROW * NWP + 2;    // one component of the stencil (+ pad, even)
+  static constexpr int SB = 2 * SBC;            // one stencil: B_u then B_l
+  static constexpr int SW = NWP == 3 ? 14 : 6;  // weight record: a[NW1] b[NW1] I[NWP] pad
+  static constexpr int SP = 6 * 32;             // one particle batch
+  static constexpr int RS = 36;                 // row pitch of the per-lane accumulator rows
+  static constexpr int SA = NW1 * NWP * RS;     // deposition accumulators (parked / reduced here)
+  static constexpr int PER_WARP = 2 * SP + kRing * SB + 32 * SW + SA;
+  static_assert(SBC % 2 == 0 && SP % 2 == 0 && SW % 2 == 0 && SB % 2 == 0, "16-byte alignment of the sub-buffers");
+};
+
+template <class I, int A>
+__global__ void __launch_bounds__(kThreads, 2)
+    k_theta_axis_v3(Grid g, ParticleSoA p, const long* __restrict__ start, int* __restrict__ count,
+                    double* __restrict__ E, const double* __restrict__ B, double q, double qm, double dt, MoverList mv,
+                    int* __restrict__ flags, long ncell, int cells_per_block) {
+  constexpr int U = (A + 1) % 3, L = (A + 2) % 3;  // hpp:90-91
+  constexpr int NW1 = I::NW1, NWP = I::NWP;
+  using Lay = AxisLayout<I>;
+  constexpr int NROW = Lay::NROW, SBC = Lay::SBC, SB = Lay::SB, SW = Lay::SW, SP = Lay::SP, RS = Lay::RS;
+  constexpr int NSUB = 32 / NW1;  // particle subsets in the deposition phase
+  extern __shared__ __align__(16) double smem[];
+  __shared__ BlockTables T;
+  __shared__ long s_soff[2 * NROW * NWP];  // stencil point -> offset from the corner (+ component)
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  double* sPart = smem + warp * Lay::PER_WARP;  // [2][6][32]
+  double* sBst = sPart + 2 * SP;                // [kRing][2][SBC]
+  double* sW = sBst + kRing * SB;               // [32][SW]
+  double* sAcc = sW + 32 * SW;                  // [NW1*NWP][RS]
+  const long st[3] = {1, g.pj, g.pk};
+  const long stA = st[A], stU = st[U], stL = st[L];
+  const double nq = -q;  // -E_coef (hpp:114; Ics = Cs = 1)
+  double* Ea = E + (long)A * g.pc;
+  const double* Bu = B + (long)U * g.pc;
+  const double* Bl = B + (long)L * g.pc;
+
+  const long cbeg_blk = (long)blockIdx.x * cells_per_block;
+  int nloc = cells_per_block;
+  if (cbeg_blk + nloc > ncell) nloc = (int)(ncell - cbeg_blk);
+  load_tables(T, g, start, count, cbeg_blk, nloc, (1 - I::W) * (stA + stU + stL));
+  for (int t = threadIdx.x; t < 2 * NROW * NWP; t += kThreads) {
+    const int comp = t / (NROW * NWP), r = t % (NROW * NWP);
+    const int tc = r % NWP, tu = (r / NWP) % NW1, tl = r / (NWP * NW1);
+    s_soff[t] = tc * stA + tu * stU + tl * stL + (long)(comp ? L : U) * g.pc;
+  }
+  __syncthreads();
+  Stream S;
+  S.init(T, warp, lane, nloc, cells_per_block / kWarps);
+
+  int staged = S.cbeg - 1, nstaged = 0;
+  auto prefetch = [&](int gbase, int mc, bool valid, unsigned heads, int pb) {
+    if (valid) {
+      const long src = T.start[mc] + (gbase + lane - S.pre[mc]);
+      double* d = sPart + pb * SP + lane;
+      cp_async8(d + 0 * 32, p.x[A] + src);
+      cp_async8(d + 1 * 32, p.x[U] + src);
+      cp_async8(d + 2 * 32, p.x[L] + src);
+      cp_async8(d + 3 * 32, p.v[A] + src);
+      cp_async8(d + 4 * 32, p.v[U] + src);
+      cp_async8(d + 5 * 32, p.v[L] + src);
+    }
+    for (unsigned hm = heads; hm; hm &= hm - 1) {
+      const int X = __shfl_sync(kFull, mc, __ffs(hm) - 1);
+      if (X <= staged) continue;
+      const int sl = nstaged % kRing;
+      if (lane == 0) T.slot[X] = sl;
+      const double* src = B + T.base[X];
+      double* d = sBst + sl * SB;
+#pragma unroll
+      for (int s = lane; s < 2 * NROW * NWP; s += 32)
+        cp_async8(d + s + (s >= NROW * NWP ? SBC - NROW * NWP : 0), src + s_soff[s]);
+      staged = X;
+      ++nstaged;
+    }
+    cp_async_commit();
+  };
+
+  const int tuB = lane % NW1, subB = lane / NW1;
+  const unsigned lanes_lt = (1u << lane) - 1u, lanes_le = 0xffffffffu >> (31 - lane);
+  int gbase = 0, mc = S.cbeg, nvalid, pb = 0;
+  bool valid;
+  unsigned heads;
+  int carry_cell = -1;  // cell whose deposition accumulators are parked in sAcc
+  int wp_cell = -1, wp_carry = 0;  // cell continuing from the previous batch and its stayers so far
+  S.locate(gbase, lane, mc, valid, nvalid, heads);
+  if (nvalid > 0) prefetch(gbase, mc, valid, heads, 0);
+
+  while (nvalid > 0) {
+    // ---- issue the next batch's loads, then wait for the current batch ----------------------
+    int n_mc = mc, n_nvalid;
+    bool n_valid;
+    unsigned n_heads;
+    const int n_gbase = gbase + nvalid;
+    S.locate(n_gbase, lane, n_mc, n_valid, n_nvalid, n_heads);
+    if (n_nvalid > 0) prefetch(n_gbase, n_mc, n_valid, n_heads, pb ^ 1);
+    else cp_async_commit();
+    cp_async_wait<1>();
+    __syncwarp();
+
+    // ---- per-lane cell data ----------------------------------------------------------------
+    const double hA = T.home[mc][A], hU = T.home[mc][U], hL = T.home[mc][L];
+    const long base = T.base[mc];
+    const int homeA = T.cc[mc][A] + (A == 2 ? g.z0 : 0);
+    // a particle sitting in a reflect cell reflects even without leaving it (util.hpp:174)
+    const bool wall_cell = !g.per[A] && (homeA == I::W || homeA == g.gn[A] - 1 - I::W);
+    const double* sBu = sBst + (valid ? T.slot[mc] : 0) * SB;  // padding lanes: any staged stencil
+    const double* sBl = sBu + SBC;
+    const double* sP = sPart + pb * SP + lane;
+    const long idx = T.start[mc] + (gbase + lane - S.pre[mc]);
+
+    // ---- phase A: thread per particle ---------------------------------------------------------
+    // (padding lanes carry a resting particle at the cell centre: v = 0 makes every I exactly 0)
+    double xa = hA + 0.5, xu = hU + 0.5, xl = hL + 0.5, va = 0.0, vu = 0.0, vl = 0.0;
+    if (valid) {
+      xa = sP[0 * 32];
+      xu = sP[1 * 32];
+      xl = sP[2 * 32];
+      va = sP[3 * 32];
+      vu = sP[4 * 32];
+      vl = sP[5 * 32];
+    }
+    double uW1[NW1], lW1[NW1], uWp[NWP], lWp[NWP], I0[NWP];
+    {
+      const double fl = xl - hL, fu = xu - hU;  // exact: the particle lies inside its bin cell
+      eval_w1_in<I>(fl, lW1);
+      eval_wp_in<I>(fl, lWp);
+      eval_w1_in<I>(fu, uW1);
+      eval_wp_in<I>(fu, uWp);
+    }
+    const double x1 = xa + dt * va;
+    // construct_segments (util.cpp:160-174): floor(x1) == homeA  <=>  hA <= x1 < hA + 1
+    const bool crosses = !(x1 >= hA && x1 < hA + 1.0) || wall_cell;
+    if (crosses) {  // warm L1 with the neighbour cell's stencil; the loads come ~300 DFMAs later
+      const long base2 = base + (x1 < hA ? -stA : stA);
+#pragma unroll 1
+      for (int s = 0; s < 2 * NROW; ++s) {
+        const double* ptr = (s < NROW ? Bu : Bl) + base2 + (s % NW1) * stU + ((s / NW1) % NW1) * stL;
+#pragma unroll
+        for (int tc = 0; tc < NWP; tc += (A == 0 && NWP > 1 ? NWP - 1 : 1))
+          asm volatile("prefetch.global.L1 [%0];" ::"l"(ptr + tc * stA));
+      }
+    }
+    eval_iwp_in<I>(xa, crosses ? xa : x1, hA, I0);
+    double r1 = 0, r2 = 0, xa_new = x1;
+    int newA = homeA;
+    if (crosses) {  // rare: <= 2 segments, reflection, periodic wrap -- the general path
+      Segments sg = make_segments<I, A>(g, xa, x1, flags);
+      eval_iwp_in<I>(sg.pt[0], sg.pt[1], hA, I0);
+      if (sg.n == 2) {  // the second segment lives in another stencil: per-particle atomics
+        double I1[NWP];
+        eval_iwp<I>(sg.pt[1], sg.pt[2], sg.cell[1], I1);
+        const long base2 = base + (long)(sg.cell[1] - homeA) * stA;
+#pragma unroll
+        for (int tl = 0; tl < NW1; ++tl) {
+          double a1 = 0, a2 = 0;
+#pragma unroll
+          for (int tu = 0; tu < NW1; ++tu) {
+            const long row = base2 + tl * stL + tu * stU;
+            const double mul = nq * (lW1[tl] * uW1[tu]);
+            double s1 = 0, s2 = 0;
+#pragma unroll
+            for (int tc = 0; tc < NWP; ++tc) {
+              const long j = row + tc * stA;
+              atomicAdd(&Ea[j], mul * I1[tc]);  // hpp:215
+              s1 = fma(__ldg(&Bu[j]), I1[tc], s1);
+              if (tu < NWP) s2 = fma(__ldg(&Bl[j]), I1[tc], s2);
+            }
+            a1 = fma(uW1[tu], s1, a1);
+            if (tu < NWP) a2 = fma(uWp[tu < NWP ? tu : 0], s2, a2);
+          }
+          if (tl < NWP) r1 = fma(lWp[tl < NWP ? tl : 0], a1, r1);
+          r2 = fma(-lW1[tl], a2, r2);
+        }
+      }
+      if (sg.reflected) {  // hpp:230-238
+        xa_new = sg.pt[2];
+        va = -va;
+      }
+      xa_new = wrap_periodic(xa_new, g.gn[A], g.per[A], flags);  // Redistribute, hpp:368
+      newA = (int)floor(xa_new);
+    }
+    // weights of the first segment for the deposition phase: -q*W1_l, W1_u, I   (hpp:194,215)
+    {
+      double2* w = reinterpret_cast<double2*>(sW + lane * SW);
+#pragma unroll
+      for (int t = 0; t < NW1 / 2; ++t) w[t] = make_double2(nq * lW1[2 * t], nq * lW1[2 * t + 1]);
+#pragma unroll
+      for (int t = 0; t < NW1 / 2; ++t) w[NW1 / 2 + t] = make_double2(uW1[2 * t], uW1[2 * t + 1]);
+      if (NWP == 3) {
+        w[NW1] = make_double2(I0[0], I0[NWP > 1 ? 1 : 0]);
+        sW[lane * SW + 2 * NW1 + 2] = I0[NWP - 1];
+      } else {
+        sW[lane * SW + 2 * NW1] = I0[0];
+      }
+    }
+#pragma unroll
+    for (int tl = 0; tl < NW1; ++tl) {  // first segment: B gather from the staged stencil
+      // (first terms are plain products: fma(a, b, +0) has the same bits and costs a zeroed register)
+      double a1, a2;
+      {
+        double bu[NW1 * NWP];
+        lds_row<NW1 * NWP>(sBu + tl * NW1 * NWP, bu);
+#pragma unroll
+        for (int tu = 0; tu < NW1; ++tu) {
+          double s1 = bu[tu * NWP] * I0[0];
+#pragma unroll
+          for (int tc = 1; tc < NWP; ++tc) s1 = fma(bu[tu * NWP + tc], I0[tc], s1);
+          a1 = tu == 0 ? uW1[0] * s1 : fma(uW1[tu], s1, a1);
+        }
+      }
+      {
+        double bl[NWP * NWP];
+        lds_row<NWP * NWP>(sBl + tl * NW1 * NWP, bl);
+#pragma unroll
+        for (int tu = 0; tu < NWP; ++tu) {
+          double s2 = bl[tu * NWP] * I0[0];
+#pragma unroll
+          for (int tc = 1; tc < NWP; ++tc) s2 = fma(bl[tu * NWP + tc], I0[tc], s2);
+          a2 = tu == 0 ? uWp[0] * s2 : fma(uWp[tu], s2, a2);
+        }
+      }
+      if (tl < NWP) r1 = fma(lWp[tl < NWP ? tl : 0], a1, r1);  // hpp:216
+      r2 = fma(-lW1[tl], a2, r2);                             // hpp:217
+      asm volatile("" ::: "memory");                          // bound load hoisting (register pressure)
+    }
+    vl = fma(qm, r1, vl);  // hpp:240-241
+    vu = fma(qm, r2, vu);
+    const bool moves = valid && newA != homeA;
+    __syncwarp();
+
+    // ---- deposition: one pass per cell present in the batch ---------------------------------------
+    // lane (tu, sub) accumulates the NW1 x NWP points of its u-column over particles sub, sub+NSUB, ...
+    const int gend = gbase + nvalid;
+    for (unsigned hm = heads; hm;) {
+      const int lo = __ffs(hm) - 1;
+      hm &= hm - 1;
+      const int hi = hm ? __ffs(hm) - 1 : nvalid;
+      const int X = __shfl_sync(kFull, mc, lo);
+      const bool complete = S.pre[X + 1] <= gend;  // all particles of X have been seen
+      double acc[NW1][NWP];
+      const bool resume = X == carry_cell;
+#pragma unroll
+      for (int k = 0; k < NW1; ++k)
+#pragma unroll
+        for (int t = 0; t < NWP; ++t) acc[k][t] = resume ? sAcc[(k * NWP + t) * RS + lane] : 0.0;
+#pragma unroll
+      for (int it = 0; it < NW1; ++it) {
+        if ((it + 1) * NSUB <= lo || it * NSUB >= hi) continue;  // no particle of X in this slice
+        const int pidx = it * NSUB + subB;
+        const bool inr = pidx >= lo && pidx < hi;
+        const double* w = sW + pidx * SW;
+        double a[NW1], In[NWP];
+        lds_row<NW1>(w, a);
+        lds_row<NWP>(w + 2 * NW1, In);
+        const double b = inr ? w[NW1 + tuB] : 0.0;
+#pragma unroll
+        for (int t = 0; t < NWP; ++t) {
+          const double bI = b * In[t];
+#pragma unroll
+          for (int k = 0; k < NW1; ++k) acc[k][t] = fma(a[k], bI, acc[k][t]);
+        }
+      }
+      __syncwarp();
+#pragma unroll
+      for (int k = 0; k < NW1; ++k)
+#pragma unroll
+        for (int t = 0; t < NWP; ++t) sAcc[(k * NWP + t) * RS + lane] = acc[k][t];
+      if (complete) {
+        // sum the particle subsets through shared memory, then one native FP64 reduction
+        // (RED.E.ADD.F64) per stencil point
+        __syncwarp();
+        const long bX = T.base[X];
+        for (int o = lane; o < NW1 * NWP * NW1; o += 32) {
+          const int kt = o / NW1, tu = o % NW1;
+          double sum = 0.0;
+#pragma unroll
+          for (int sb = 0; sb < NSUB; ++sb) sum += sAcc[kt * RS + tu + NW1 * sb];
+          atomicAdd(&Ea[bX + tu * stU + (kt / NWP) * stL + (kt % NWP) * stA], sum);
+        }
+        carry_cell = -1;
+        __syncwarp();
+      } else {
+        carry_cell = X;  // continues in the next batch (always as its first cell)
+      }
+    }
+
+    // ---- re-file: stayers compacted in place per cell, movers to the list -------------------------
+    const bool stay = valid && !moves;
+    const unsigned stay_mask = __ballot_sync(kFull, stay);
+    const unsigned move_mask = __ballot_sync(kFull, moves);
+    // my cell's lanes in this batch: [lo_my, hi_my)
+    const int lo_my = 31 - __clz(heads & lanes_le);
+    const unsigned later = heads & ~lanes_le;
+    const int hi_my = later ? __ffs(later) - 1 : nvalid;
+    const unsigned group = (hi_my >= 32 ? 0xffffffffu : (1u << hi_my) - 1u) & ~((1u << lo_my) - 1u);
+    const int wbase = mc == wp_cell ? wp_carry : 0;
+    const int stayers = wbase + __popc(stay_mask & group);  // live particles of my cell so far
+    const bool complete_my = S.pre[mc + 1] <= gend;
+    if (stay) {
+      const long dst = T.start[mc] + wbase + __popc(stay_mask & group & lanes_lt);
+      if (dst == idx) {  // nothing ahead of us left: only the changed components move
+        p.x[A][dst] = xa_new;
+        p.v[U][dst] = vu;
+        p.v[L][dst] = vl;
+        if (!g.per[A]) p.v[A][dst] = va;
+      } else {
+        p.x[A][dst] = xa_new;
+        p.x[U][dst] = xu;
+        p.x[L][dst] = xl;
+        p.v[A][dst] = va;
+        p.v[U][dst] = vu;
+        p.v[L][dst] = vl;
+      }
+    }
+    if (valid && lane == lo_my && complete_my) count[cbeg_blk + mc] = stayers;
+    if (move_mask) {
+      unsigned basei = 0;
+      const int leader = __ffs(move_mask) - 1;
+      if (lane == leader) basei = atomicAdd(mv.n, (unsigned)__popc(move_mask));
+      basei = __shfl_sync(kFull, basei, leader);
+      if (moves) {
+        const unsigned m = basei + __popc(move_mask & lanes_lt);
+        if (m < mv.cap) {
+          const long cell = cbeg_blk + mc;
+          int dest;
+          if (A == 2) {
+            const int knew = newA - g.z0;
+            dest = knew < 0 ? -1
+                            : (knew >= g.n[2] ? -2 : (int)(cell + (long)(knew - T.cc[mc][2]) * g.n[0] * g.n[1]));
+          } else {
+            dest = (int)(cell + (long)(newA - homeA) * (A == 0 ? 1 : g.n[0]));
+          }
+          mv.x[A][m] = xa_new;
+          mv.x[U][m] = xu;
+          mv.x[L][m] = xl;
+          mv.v[A][m] = va;
+          mv.v[U][m] = vu;
+          mv.v[L][m] = vl;
+          mv.dest[m] = dest;
+        } else {
+          atomicOr(&flags[1], 1);
+        }
+      }
+    }
+    {  // the last cell of the batch may continue: carry its compaction pointer
+      const int last = nvalid - 1;
+      const int l_mc = __shfl_sync(kFull, mc, last);
+      const int l_stayers = __shfl_sync(kFull, stayers, last);
+      const bool l_complete = __shfl_sync(kFull, (int)complete_my, last) != 0;
+      wp_cell = l_complete ? -1 : l_mc;
+      wp_carry = l_stayers;
+    }
+    __syncwarp();  // every lane is done with this batch's buffers before they are refilled
+    gbase = n_gbase;
+    mc = n_mc;
+    valid = n_valid;
+    nvalid = n_nvalid;
+    heads = n_heads;
+    pb ^= 1;
+  }
+  cp_async_wait<0>();
+}
+
+template <class K>
+int set_smem(Ctx* c, K kernel, size_t smem, bool& done) {
+  if (!done) {
+    SPIC_CUDA_CHECK(c, cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    done = true;
+  }
+  return SPIC_OK;
+}
+
+int stream_cpb(Ctx* c) {
+  int cpb = eng(c)->cells_per_block;
+  cpb = (cpb / kWarps) * kWarps;
+  if (cpb < kWarps) cpb = kWarps;
+  if (cpb > kMaxCells) cpb = kMaxCells;
+  return cpb;
+}
+
+template <class I>
+int axis_dispatch(Ctx* c, Species& s, int comp, double dt) {
+  EngineState* e = eng(c);
+  const long ncell = c->g.cells();
+  const int cpb = stream_cpb(c);
+  const int grid = (int)((ncell + cpb - 1) / cpb);
+  const size_t smem = sizeof(double) * kWarps * AxisLayout<I>::PER_WARP;
+  const double qm = s.q / s.m;
+  static bool attr[3] = {false, false, false};
+  int rc;
+#define SPIC_LAUNCH_AXIS(AX)                                                                                       \
+  do {                                                                                                             \
+    if ((rc = set_smem(c, k_theta_axis_v3<I, AX>, smem, attr[AX]))) return rc;                                     \
+    k_theta_axis_v3<I, AX><<<grid, kThreads, smem, c->stream>>>(c->g, s.b, s.start, s.count, c->E, c->B, s.q, qm,  \
+                                                                dt, e->mv, c->d_flags, ncell, cpb);                \
+  } while (0)
+  if (comp == 0) SPIC_LAUNCH_AXIS(0);
+  else if (comp == 1) SPIC_LAUNCH_AXIS(1);
+  else SPIC_LAUNCH_AXIS(2);
+#undef SPIC_LAUNCH_AXIS
+  c->launches++;
+  return SPIC_OK;
+}
+
+template <class I>
+int push_dispatch(Ctx* c, Species& s, double dt) {
+  const long ncell = c->g.cells();
+  const int cpb = stream_cpb(c);
+  const int grid = (int)((ncell + cpb - 1) / cpb);
+  const size_t smem = sizeof(double) * kWarps * PushLayout<I>::PER_WARP;
+  const double coef = dt * s.q / s.m;  // hpp:267
+  static bool attr = false;
+  int rc;
+  if ((rc = set_smem(c, k_push_v_e_v3<I>, smem, attr))) return rc;
+  k_push_v_e_v3<I><<<grid, kThreads, smem, c->stream>>>(c->g, s.b, s.start, s.count, c->E, coef, ncell, cpb);
+  c->launches++;
+  return SPIC_OK;
+}
+
+}  // namespace
+
+int stream_theta_axis(Ctx* c, Species& s, int comp, double dt) {
+  return c->cfg.interp == SPIC_INTERP_P8R2 ? axis_dispatch<InterpP8R2>(c, s, comp, dt)
+                                           : axis_dispatch<InterpPWL>(c, s, comp, dt);
+}
+
+int stream_push_v_e(Ctx* c, Species& s, double dt) {
+  return c->cfg.interp == SPIC_INTERP_P8R2 ? push_dispatch<InterpP8R2>(c, s, dt) : push_dispatch<InterpPWL>(c, s, dt);
+}
+
+}  // namespace spic

@@ -251,10 +251,10 @@ def test_number_density_and_plot_file(tmp_path, interp, periodic, engine):
     plt = spic().read_plot(tmp_path / "plt0.spic")
     assert plt["n_cell"] == n_cell and plt["n"] == n_cell and plt["interp"] == interp
     assert np.array_equal(plt["E"], E) and np.array_equal(plt["B"], B)
-    assert np.array_equal(plt["n_density"], got)
+    assert np.allclose(plt["n_density"], got, rtol=1e-13, atol=0)  # atomics: the order of additions varies
 
 
-@pytest.mark.parametrize("variant", [1, 2])
+@pytest.mark.parametrize("variant", [1, 2, 3])
 def test_kernel_variants_agree_with_oracle(variant):
     """Both generations of the binned particle kernels stay covered (option axis_kernel / pushve_kernel)."""
     n_cell = (16, 12, 8)
