@@ -36,12 +36,8 @@ constexpr unsigned kFull = 0xffffffffu;
 
 struct BlockTables {
   int cnt[kMaxCells];
-  int pre[kMaxCells + kWarps + 1];  // per-warp exclusive prefix of cnt (warp w uses indices ci + w)
-  int slot[kMaxCells];              // ring slot holding the cell's stencil
-  int cc[kMaxCells][3];             // local cell coordinates
   long start[kMaxCells];
-  long base[kMaxCells];             // stencil corner (-W+1 in every direction)
-  double home[kMaxCells][3];        // GLOBAL cell coordinates as doubles
+  long base[kMaxCells];  // stencil corner (-W+1 in every direction)
 };
 
 __device__ __forceinline__ void load_tables(BlockTables& T, const Grid& g, const long* __restrict__ start,
@@ -52,53 +48,87 @@ __device__ __forceinline__ void load_tables(BlockTables& T, const Grid& g, const
     const int cz = (int)(cell / ((long)g.n[0] * g.n[1]));
     T.cnt[t] = count[cell];
     T.start[t] = start[cell];
-    T.cc[t][0] = cx;
-    T.cc[t][1] = cy;
-    T.cc[t][2] = cz;
-    T.home[t][0] = (double)cx;
-    T.home[t][1] = (double)cy;
-    T.home[t][2] = (double)(cz + g.z0);
     T.base[t] = g.at(cx, cy, cz) + corner_off;
   }
 }
 
-// The warp's view of its particle stream.
-struct Stream {
-  const int* pre;  // pre[ci] for ci in [cbeg, cend]: stream index of the first particle of cell ci
-  int cbeg, cend, total;
-  __device__ __forceinline__ void init(BlockTables& T, int warp, int lane, int nloc, int ncw) {
-    cbeg = warp * ncw < nloc ? warp * ncw : nloc;
-    cend = cbeg + ncw < nloc ? cbeg + ncw : nloc;
-    int* p = T.pre + warp;
-    if (lane == 0) {
-      int acc = 0;
-      for (int ci = cbeg; ci < cend; ++ci) {
-        p[ci] = acc;
-        acc += T.cnt[ci];
-      }
-      p[cend] = acc;
-    }
-    __syncwarp();
-    pre = p;
-    total = p[cend];
+// One batch of the warp's particle stream: lanes [0, n0) hold particles off0.. of cell c0, lanes
+// [n0, n0 + n1) the first n1 particles of cell c1.  Everything here is warp-uniform.
+struct Batch {
+  int c0, off0, n0, c1, n1;
+  int slot0, slot1;    // stencil ring slots of c0 / c1
+  bool done0, done1;   // the batch holds the last particle of c0 / c1
+  __device__ __forceinline__ int n() const { return n0 + n1; }
+  // the next batch waits in two registers while the current one computes (register pressure)
+  __device__ __forceinline__ unsigned pack() const {
+    return (unsigned)c0 | ((unsigned)c1 << 7) | ((unsigned)n0 << 14) | ((unsigned)n1 << 20) |
+           ((unsigned)slot0 << 26) | ((unsigned)slot1 << 28) | ((unsigned)done0 << 30) | ((unsigned)done1 << 31);
   }
-  // lane -> cell for the batch starting at stream index gbase.  `mc` only moves forward.  Valid lanes
-  // are a prefix of the warp; `heads` marks the first lane of every cell present in the batch.
-  __device__ __forceinline__ void locate(int gbase, int lane, int& mc, bool& valid, int& nvalid,
-                                         unsigned& heads) const {
-    const int gi = gbase + lane;
-    valid = gi < total;
-    if (valid)
-      while (gi >= pre[mc + 1]) ++mc;  // pre[cend] == total > gi ends the walk; empty cells are skipped
-    const int prev = __shfl_up_sync(kFull, mc, 1);
-    const bool head = valid && (lane == 0 || mc != prev);
-    heads = __ballot_sync(kFull, head);
-    // at most kSpan cells per batch: lanes of later cells wait for the next batch
-    const int group = __popc(heads & (0xffffffffu >> (31 - lane))) - 1;
-    valid = valid && group < kSpan;
-    const unsigned vm = __ballot_sync(kFull, valid);
-    nvalid = __popc(vm);
-    heads &= vm;
+  __device__ __forceinline__ void unpack(unsigned w, int off) {
+    c0 = w & 127;
+    c1 = (w >> 7) & 127;
+    n0 = (w >> 14) & 63;
+    n1 = (w >> 20) & 63;
+    slot0 = (w >> 26) & 3;
+    slot1 = (w >> 28) & 3;
+    done0 = (w >> 30) & 1;
+    done1 = (w >> 31) & 1;
+    off0 = off;
+  }
+};
+static_assert(kMaxCells <= 128 && kRing <= 4, "Batch::pack field widths");
+
+// Walks the non-empty cells [cur, cend) of the warp and cuts them into batches.
+struct Cutter {
+  int cur, rem, cend;  // current cell, its particles not yet handed out, end of the warp's cells
+  int seq;             // stencils staged so far (ring position)
+  int slot_cur;        // ring slot of `cur` when part of it has already been handed out
+  __device__ __forceinline__ void skip_empty(const BlockTables& T) {
+    while (cur < cend && T.cnt[cur] == 0) ++cur;
+    rem = cur < cend ? T.cnt[cur] : 0;
+  }
+  __device__ __forceinline__ void init(const BlockTables& T, int cbeg, int cend_) {
+    cur = cbeg;
+    cend = cend_;
+    seq = 0;
+    slot_cur = 0;
+    skip_empty(T);
+  }
+  // stage0 / stage1: the batch touches c0 / c1 for the first time (its stencil must be staged)
+  __device__ __forceinline__ Batch next(const BlockTables& T, bool& stage0, bool& stage1) {
+    Batch b;
+    b.c0 = b.c1 = cur;
+    b.off0 = b.n0 = b.n1 = 0;
+    b.slot0 = b.slot1 = 0;
+    b.done0 = b.done1 = false;
+    stage0 = stage1 = false;
+    if (cur >= cend) return b;
+    const int cnt0 = T.cnt[cur];
+    b.off0 = cnt0 - rem;
+    b.n0 = rem < 32 ? rem : 32;
+    stage0 = b.off0 == 0;
+    if (stage0) slot_cur = (seq++) % kRing;
+    b.slot0 = slot_cur;
+    rem -= b.n0;
+    b.done0 = rem == 0;
+    if (b.done0) {
+      ++cur;
+      skip_empty(T);
+      if (b.n0 < 32 && cur < cend) {
+        b.c1 = cur;
+        b.n1 = rem < 32 - b.n0 ? rem : 32 - b.n0;
+        stage1 = true;
+        slot_cur = (seq++) % kRing;
+        b.slot1 = slot_cur;
+        rem -= b.n1;
+        b.done1 = rem == 0;
+        if (b.done1) {
+          ++cur;
+          skip_empty(T);
+        }
+      }
+    }
+    return b;
   }
 };
 
@@ -136,14 +166,24 @@ __global__ void __launch_bounds__(kThreads, 2)
     s_soff[t] = (r % NW1) + ((r / NW1) % NW1) * g.pj + (r / (NW1 * NW1)) * g.pk + comp * g.pc;
   }
   __syncthreads();
-  Stream S;
-  S.init(T, warp, lane, nloc, cells_per_block / kWarps);
+  const int ncw = cells_per_block / kWarps;
+  const int wbeg = warp * ncw < nloc ? warp * ncw : nloc, wend = wbeg + ncw < nloc ? wbeg + ncw : nloc;
+  Cutter cut;
+  cut.init(T, wbeg, wend);
 
-  int staged = S.cbeg - 1, nstaged = 0;
-  // issue the loads of a located batch: particle data of its lanes + stencils of cells not staged yet
-  auto prefetch = [&](int gbase, int mc, bool valid, unsigned heads, int pb) {
-    if (valid) {
-      const long src = T.start[mc] + (gbase + lane - S.pre[mc]);
+  auto stage = [&](int X, int sl) {
+    const double* src = E + T.base[X];
+    double* d = sEst + sl * SE;
+#pragma unroll
+    for (int s = lane; s < SE; s += 32) cp_async8(d + s, src + s_soff[s]);
+  };
+  // my slot in the particle arrays for batch b (lanes >= b.n() hold no particle)
+  auto my_index = [&](const Batch& b) {
+    return lane < b.n0 ? T.start[b.c0] + b.off0 + lane : T.start[b.c1] + (lane - b.n0);
+  };
+  auto prefetch = [&](const Batch& b, bool st0, bool st1, int pb) {
+    if (lane < b.n()) {
+      const long src = my_index(b);
       double* d = sPart + pb * SP + lane;
       cp_async8(d + 0 * 32, p.x[0] + src);
       cp_async8(d + 1 * 32, p.x[1] + src);
@@ -152,43 +192,35 @@ __global__ void __launch_bounds__(kThreads, 2)
       cp_async8(d + 4 * 32, p.v[1] + src);
       cp_async8(d + 5 * 32, p.v[2] + src);
     }
-    for (unsigned hm = heads; hm; hm &= hm - 1) {
-      const int X = __shfl_sync(kFull, mc, __ffs(hm) - 1);
-      if (X <= staged) continue;
-      const int sl = nstaged % kRing;
-      if (lane == 0) T.slot[X] = sl;
-      const double* src = E + T.base[X];
-      double* d = sEst + sl * SE;
-#pragma unroll
-      for (int s = lane; s < SE; s += 32) cp_async8(d + s, src + s_soff[s]);
-      staged = X;
-      ++nstaged;
-    }
+    if (st0) stage(b.c0, b.slot0);
+    if (st1) stage(b.c1, b.slot1);
     cp_async_commit();
   };
 
-  int gbase = 0, mc = S.cbeg, nvalid, pb = 0;
-  bool valid;
-  unsigned heads;
-  S.locate(gbase, lane, mc, valid, nvalid, heads);
-  if (nvalid > 0) prefetch(gbase, mc, valid, heads, 0);
-  while (nvalid > 0) {
-    int n_mc = mc, n_nvalid;
-    bool n_valid;
-    unsigned n_heads;
-    const int n_gbase = gbase + nvalid;
-    S.locate(n_gbase, lane, n_mc, n_valid, n_nvalid, n_heads);
-    if (n_nvalid > 0) prefetch(n_gbase, n_mc, n_valid, n_heads, pb ^ 1);
-    else cp_async_commit();
+  bool st0, st1;
+  Batch b = cut.next(T, st0, st1);
+  int pb = 0;
+  if (b.n() > 0) prefetch(b, st0, st1, 0);
+  while (b.n() > 0) {
+    unsigned nb_w;
+    int nb_off;
+    {
+      const Batch nb = cut.next(T, st0, st1);
+      if (nb.n() > 0) prefetch(nb, st0, st1, pb ^ 1);
+      else cp_async_commit();
+      nb_w = nb.pack();
+      nb_off = nb.off0;
+    }
     cp_async_wait<1>();
     __syncwarp();
 
-    if (valid) {
-      const long idx = T.start[mc] + (gbase + lane - S.pre[mc]);
+    if (lane < b.n()) {
+      const long idx = my_index(b);
       const double* sP = sPart + pb * SP + lane;
-      const double* sE = sEst + T.slot[mc] * SE;  // (valid lanes only: their cell has been staged)
-      // exact: the particle lies inside its bin cell
-      const double fx = sP[0] - T.home[mc][0], fy = sP[32] - T.home[mc][1], fz = sP[64] - T.home[mc][2];
+      const double* sE = sEst + (lane < b.n0 ? b.slot0 : b.slot1) * SE;
+      // the particle lies inside its bin cell: x - floor(x) is the exact in-cell coordinate
+      const double x = sP[0], y = sP[32], z = sP[64];
+      const double fx = x - floor(x), fy = y - floor(y), fz = z - floor(z);
       double w1x[NW1], w1y[NW1], w1z[NW1], wpx[NWP], wpy[NWP], wpz[NWP];
       eval_w1_in<I>(fx, w1x);
       eval_w1_in<I>(fy, w1y);
@@ -238,11 +270,7 @@ __global__ void __launch_bounds__(kThreads, 2)
       p.v[2][idx] = fma(az, coef, sP[160]);
     }
     __syncwarp();  // every lane is done with this batch's buffers before they are refilled
-    gbase = n_gbase;
-    mc = n_mc;
-    valid = n_valid;
-    nvalid = n_nvalid;
-    heads = n_heads;
+    b.unpack(nb_w, nb_off);
     pb ^= 1;
   }
   cp_async_wait<0>();
@@ -300,13 +328,24 @@ __global__ void __launch_bounds__(kThreads, 2)
     s_soff[t] = tc * stA + tu * stU + tl * stL + (long)(comp ? L : U) * g.pc;
   }
   __syncthreads();
-  Stream S;
-  S.init(T, warp, lane, nloc, cells_per_block / kWarps);
+  const int ncw = cells_per_block / kWarps;
+  const int wbeg = warp * ncw < nloc ? warp * ncw : nloc, wend = wbeg + ncw < nloc ? wbeg + ncw : nloc;
+  Cutter cut;
+  cut.init(T, wbeg, wend);
 
-  int staged = S.cbeg - 1, nstaged = 0;
-  auto prefetch = [&](int gbase, int mc, bool valid, unsigned heads, int pb) {
-    if (valid) {
-      const long src = T.start[mc] + (gbase + lane - S.pre[mc]);
+  auto stage = [&](int X, int sl) {
+    const double* src = B + T.base[X];
+    double* d = sBst + sl * SB;
+#pragma unroll
+    for (int s = lane; s < 2 * NROW * NWP; s += 32)
+      cp_async8(d + s + (s >= NROW * NWP ? SBC - NROW * NWP : 0), src + s_soff[s]);
+  };
+  auto my_index = [&](const Batch& b) {
+    return lane < b.n0 ? T.start[b.c0] + b.off0 + lane : T.start[b.c1] + (lane - b.n0);
+  };
+  auto prefetch = [&](const Batch& b, bool st0, bool st1, int pb) {
+    if (lane < b.n()) {
+      const long src = my_index(b);
       double* d = sPart + pb * SP + lane;
       cp_async8(d + 0 * 32, p.x[A] + src);
       cp_async8(d + 1 * 32, p.x[U] + src);
@@ -315,58 +354,44 @@ __global__ void __launch_bounds__(kThreads, 2)
       cp_async8(d + 4 * 32, p.v[U] + src);
       cp_async8(d + 5 * 32, p.v[L] + src);
     }
-    for (unsigned hm = heads; hm; hm &= hm - 1) {
-      const int X = __shfl_sync(kFull, mc, __ffs(hm) - 1);
-      if (X <= staged) continue;
-      const int sl = nstaged % kRing;
-      if (lane == 0) T.slot[X] = sl;
-      const double* src = B + T.base[X];
-      double* d = sBst + sl * SB;
-#pragma unroll
-      for (int s = lane; s < 2 * NROW * NWP; s += 32)
-        cp_async8(d + s + (s >= NROW * NWP ? SBC - NROW * NWP : 0), src + s_soff[s]);
-      staged = X;
-      ++nstaged;
-    }
+    if (st0) stage(b.c0, b.slot0);
+    if (st1) stage(b.c1, b.slot1);
     cp_async_commit();
   };
 
   const int tuB = lane % NW1, subB = lane / NW1;
-  const unsigned lanes_lt = (1u << lane) - 1u, lanes_le = 0xffffffffu >> (31 - lane);
-  int gbase = 0, mc = S.cbeg, nvalid, pb = 0;
-  bool valid;
-  unsigned heads;
-  int carry_cell = -1;  // cell whose deposition accumulators are parked in sAcc
-  int wp_cell = -1, wp_carry = 0;  // cell continuing from the previous batch and its stayers so far
-  S.locate(gbase, lane, mc, valid, nvalid, heads);
-  if (nvalid > 0) prefetch(gbase, mc, valid, heads, 0);
+  const unsigned lanes_lt = (1u << lane) - 1u;
+  bool st0, st1;
+  Batch b = cut.next(T, st0, st1);
+  int pb = 0;
+  int wp0 = 0;  // stayers of b.c0 written by earlier batches (compaction pointer)
+  if (b.n() > 0) prefetch(b, st0, st1, 0);
 
-  while (nvalid > 0) {
+  while (b.n() > 0) {
     // ---- issue the next batch's loads, then wait for the current batch ----------------------
-    int n_mc = mc, n_nvalid;
-    bool n_valid;
-    unsigned n_heads;
-    const int n_gbase = gbase + nvalid;
-    S.locate(n_gbase, lane, n_mc, n_valid, n_nvalid, n_heads);
-    if (n_nvalid > 0) prefetch(n_gbase, n_mc, n_valid, n_heads, pb ^ 1);
-    else cp_async_commit();
+    unsigned nb_w;
+    int nb_off;
+    {
+      const Batch nb = cut.next(T, st0, st1);
+      if (nb.n() > 0) prefetch(nb, st0, st1, pb ^ 1);
+      else cp_async_commit();
+      nb_w = nb.pack();
+      nb_off = nb.off0;
+    }
     cp_async_wait<1>();
     __syncwarp();
 
-    // ---- per-lane cell data ----------------------------------------------------------------
-    const double hA = T.home[mc][A], hU = T.home[mc][U], hL = T.home[mc][L];
-    const long base = T.base[mc];
-    const int homeA = T.cc[mc][A] + (A == 2 ? g.z0 : 0);
-    // a particle sitting in a reflect cell reflects even without leaving it (util.hpp:174)
-    const bool wall_cell = !g.per[A] && (homeA == I::W || homeA == g.gn[A] - 1 - I::W);
-    const double* sBu = sBst + (valid ? T.slot[mc] : 0) * SB;  // padding lanes: any staged stencil
+    const int nvalid = b.n();
+    const bool valid = lane < nvalid, second = lane >= b.n0;
+    const int mc = second ? b.c1 : b.c0;  // my cell (block-local index)
+    const double* sBu = sBst + (second ? b.slot1 : b.slot0) * SB;
     const double* sBl = sBu + SBC;
     const double* sP = sPart + pb * SP + lane;
-    const long idx = T.start[mc] + (gbase + lane - S.pre[mc]);
+    const long idx = my_index(b);
 
     // ---- phase A: thread per particle ---------------------------------------------------------
-    // (padding lanes carry a resting particle at the cell centre: v = 0 makes every I exactly 0)
-    double xa = hA + 0.5, xu = hU + 0.5, xl = hL + 0.5, va = 0.0, vu = 0.0, vl = 0.0;
+    // (padding lanes carry a resting particle: v = 0 makes every I exactly 0)
+    double xa = 0.5, xu = 0.5, xl = 0.5, va = 0.0, vu = 0.0, vl = 0.0;
     if (valid) {
       xa = sP[0 * 32];
       xu = sP[1 * 32];
@@ -375,18 +400,24 @@ __global__ void __launch_bounds__(kThreads, 2)
       vu = sP[4 * 32];
       vl = sP[5 * 32];
     }
+    // the particle lies inside its bin cell: floor(x) is the cell, x - floor(x) is exact
+    const double hA = floor(xa);
     double uW1[NW1], lW1[NW1], uWp[NWP], lWp[NWP], I0[NWP];
     {
-      const double fl = xl - hL, fu = xu - hU;  // exact: the particle lies inside its bin cell
+      const double fl = xl - floor(xl), fu = xu - floor(xu);
       eval_w1_in<I>(fl, lW1);
       eval_wp_in<I>(fl, lWp);
       eval_w1_in<I>(fu, uW1);
       eval_wp_in<I>(fu, uWp);
     }
     const double x1 = xa + dt * va;
-    // construct_segments (util.cpp:160-174): floor(x1) == homeA  <=>  hA <= x1 < hA + 1
-    const bool crosses = !(x1 >= hA && x1 < hA + 1.0) || wall_cell;
+    // construct_segments (util.cpp:160-174): floor(x1) == homeA  <=>  hA <= x1 < hA + 1;
+    // a particle sitting in a reflect cell reflects even without leaving it (util.hpp:174)
+    bool crosses = !(x1 >= hA && x1 < hA + 1.0);
+    if (!g.per[A]) crosses = crosses || (valid && (hA == (double)I::W || hA == (double)(g.gn[A] - 1 - I::W)));
+    long base = 0;
     if (crosses) {  // warm L1 with the neighbour cell's stencil; the loads come ~300 DFMAs later
+      base = T.base[mc];
       const long base2 = base + (x1 < hA ? -stA : stA);
 #pragma unroll 1
       for (int s = 0; s < 2 * NROW; ++s) {
@@ -398,8 +429,10 @@ __global__ void __launch_bounds__(kThreads, 2)
     }
     eval_iwp_in<I>(xa, crosses ? xa : x1, hA, I0);
     double r1 = 0, r2 = 0, xa_new = x1;
-    int newA = homeA;
+    bool moves = false;
+    int dest = 0;
     if (crosses) {  // rare: <= 2 segments, reflection, periodic wrap -- the general path
+      const int homeA = (int)hA;
       Segments sg = make_segments<I, A>(g, xa, x1, flags);
       eval_iwp_in<I>(sg.pt[0], sg.pt[1], hA, I0);
       if (sg.n == 2) {  // the second segment lives in another stencil: per-particle atomics
@@ -433,7 +466,17 @@ __global__ void __launch_bounds__(kThreads, 2)
         va = -va;
       }
       xa_new = wrap_periodic(xa_new, g.gn[A], g.per[A], flags);  // Redistribute, hpp:368
-      newA = (int)floor(xa_new);
+      const int newA = (int)floor(xa_new);
+      moves = valid && newA != homeA;
+      if (moves) {  // destination bin (or -1 / -2: leaves through the low / high z face of the slab)
+        const long cell = cbeg_blk + mc;
+        if (A == 2) {
+          const int knew = newA - g.z0, kold = homeA - g.z0;
+          dest = knew < 0 ? -1 : (knew >= g.n[2] ? -2 : (int)(cell + (long)(knew - kold) * g.n[0] * g.n[1]));
+        } else {
+          dest = (int)(cell + (long)(newA - homeA) * (A == 0 ? 1 : g.n[0]));
+        }
+      }
     }
     // weights of the first segment for the deposition phase: -q*W1_l, W1_u, I   (hpp:194,215)
     {
@@ -481,20 +524,18 @@ __global__ void __launch_bounds__(kThreads, 2)
     }
     vl = fma(qm, r1, vl);  // hpp:240-241
     vu = fma(qm, r2, vu);
-    const bool moves = valid && newA != homeA;
     __syncwarp();
 
-    // ---- deposition: one pass per cell present in the batch ---------------------------------------
+    // ---- deposition: one pass per cell of the batch ----------------------------------------------
     // lane (tu, sub) accumulates the NW1 x NWP points of its u-column over particles sub, sub+NSUB, ...
-    const int gend = gbase + nvalid;
-    for (unsigned hm = heads; hm;) {
-      const int lo = __ffs(hm) - 1;
-      hm &= hm - 1;
-      const int hi = hm ? __ffs(hm) - 1 : nvalid;
-      const int X = __shfl_sync(kFull, mc, lo);
-      const bool complete = S.pre[X + 1] <= gend;  // all particles of X have been seen
+#pragma unroll 1
+    for (int pass = 0; pass < 2; ++pass) {
+      const int lo = pass ? b.n0 : 0, hi = pass ? nvalid : b.n0;
+      if (hi <= lo) break;
+      const int X = pass ? b.c1 : b.c0;
+      const bool complete = pass ? b.done1 : b.done0;
+      const bool resume = pass == 0 && b.off0 != 0;  // accumulators of c0 were parked by the previous batch
       double acc[NW1][NWP];
-      const bool resume = X == carry_cell;
 #pragma unroll
       for (int k = 0; k < NW1; ++k)
 #pragma unroll
@@ -508,15 +549,14 @@ __global__ void __launch_bounds__(kThreads, 2)
         double a[NW1], In[NWP];
         lds_row<NW1>(w, a);
         lds_row<NWP>(w + 2 * NW1, In);
-        const double b = inr ? w[NW1 + tuB] : 0.0;
+        const double bw = inr ? w[NW1 + tuB] : 0.0;
 #pragma unroll
         for (int t = 0; t < NWP; ++t) {
-          const double bI = b * In[t];
+          const double bI = bw * In[t];
 #pragma unroll
           for (int k = 0; k < NW1; ++k) acc[k][t] = fma(a[k], bI, acc[k][t]);
         }
       }
-      __syncwarp();
 #pragma unroll
       for (int k = 0; k < NW1; ++k)
 #pragma unroll
@@ -533,10 +573,7 @@ __global__ void __launch_bounds__(kThreads, 2)
           for (int sb = 0; sb < NSUB; ++sb) sum += sAcc[kt * RS + tu + NW1 * sb];
           atomicAdd(&Ea[bX + tu * stU + (kt / NWP) * stL + (kt % NWP) * stA], sum);
         }
-        carry_cell = -1;
         __syncwarp();
-      } else {
-        carry_cell = X;  // continues in the next batch (always as its first cell)
       }
     }
 
@@ -544,16 +581,10 @@ __global__ void __launch_bounds__(kThreads, 2)
     const bool stay = valid && !moves;
     const unsigned stay_mask = __ballot_sync(kFull, stay);
     const unsigned move_mask = __ballot_sync(kFull, moves);
-    // my cell's lanes in this batch: [lo_my, hi_my)
-    const int lo_my = 31 - __clz(heads & lanes_le);
-    const unsigned later = heads & ~lanes_le;
-    const int hi_my = later ? __ffs(later) - 1 : nvalid;
-    const unsigned group = (hi_my >= 32 ? 0xffffffffu : (1u << hi_my) - 1u) & ~((1u << lo_my) - 1u);
-    const int wbase = mc == wp_cell ? wp_carry : 0;
-    const int stayers = wbase + __popc(stay_mask & group);  // live particles of my cell so far
-    const bool complete_my = S.pre[mc + 1] <= gend;
+    const unsigned m0 = b.n0 >= 32 ? 0xffffffffu : (1u << b.n0) - 1u;  // lanes of c0
+    const int stay0 = wp0 + __popc(stay_mask & m0), stay1 = __popc(stay_mask & ~m0);
     if (stay) {
-      const long dst = T.start[mc] + wbase + __popc(stay_mask & group & lanes_lt);
+      const long dst = T.start[mc] + (second ? __popc(stay_mask & ~m0 & lanes_lt) : wp0 + __popc(stay_mask & lanes_lt));
       if (dst == idx) {  // nothing ahead of us left: only the changed components move
         p.x[A][dst] = xa_new;
         p.v[U][dst] = vu;
@@ -568,7 +599,10 @@ __global__ void __launch_bounds__(kThreads, 2)
         p.v[L][dst] = vl;
       }
     }
-    if (valid && lane == lo_my && complete_my) count[cbeg_blk + mc] = stayers;
+    if (lane == 0) {
+      if (b.done0) count[cbeg_blk + b.c0] = stay0;
+      if (b.n1 > 0 && b.done1) count[cbeg_blk + b.c1] = stay1;
+    }
     if (move_mask) {
       unsigned basei = 0;
       const int leader = __ffs(move_mask) - 1;
@@ -577,15 +611,6 @@ __global__ void __launch_bounds__(kThreads, 2)
       if (moves) {
         const unsigned m = basei + __popc(move_mask & lanes_lt);
         if (m < mv.cap) {
-          const long cell = cbeg_blk + mc;
-          int dest;
-          if (A == 2) {
-            const int knew = newA - g.z0;
-            dest = knew < 0 ? -1
-                            : (knew >= g.n[2] ? -2 : (int)(cell + (long)(knew - T.cc[mc][2]) * g.n[0] * g.n[1]));
-          } else {
-            dest = (int)(cell + (long)(newA - homeA) * (A == 0 ? 1 : g.n[0]));
-          }
           mv.x[A][m] = xa_new;
           mv.x[U][m] = xu;
           mv.x[L][m] = xl;
@@ -598,20 +623,10 @@ __global__ void __launch_bounds__(kThreads, 2)
         }
       }
     }
-    {  // the last cell of the batch may continue: carry its compaction pointer
-      const int last = nvalid - 1;
-      const int l_mc = __shfl_sync(kFull, mc, last);
-      const int l_stayers = __shfl_sync(kFull, stayers, last);
-      const bool l_complete = __shfl_sync(kFull, (int)complete_my, last) != 0;
-      wp_cell = l_complete ? -1 : l_mc;
-      wp_carry = l_stayers;
-    }
+    // compaction pointer of the next batch's first cell
+    wp0 = b.n1 > 0 ? (b.done1 ? 0 : stay1) : (b.done0 ? 0 : stay0);
     __syncwarp();  // every lane is done with this batch's buffers before they are refilled
-    gbase = n_gbase;
-    mc = n_mc;
-    valid = n_valid;
-    nvalid = n_nvalid;
-    heads = n_heads;
+    b.unpack(nb_w, nb_off);
     pb ^= 1;
   }
   cp_async_wait<0>();
