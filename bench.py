@@ -254,9 +254,13 @@ def ours_main(a):
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 
-    def barrier():
-        if dist is not None:
-            dist.barrier()
+    def _noop():
+        pass
+
+    def _barrier():
+        dist.barrier()
+
+    barrier = _noop if dist is None else _barrier
 
     def allmax(x):
         if dist is None:
@@ -325,7 +329,7 @@ def ours_main(a):
     f_pv = FLOP_PUSHVE if a.interp == "p8r2" else FLOP_PUSHVE_PWL
     achieved = BYTES_PER_SUBFLOW * npart_local / (ax_avg * 1e-3) / 1e9 if ax_n else 0.0
     traffic = ncu_traffic()
-    roofline = {"kernel": "k_theta_axis_binned", "bound": "hbm", "achieved": achieved, "peak": peaks["hbm_gbs"],
+    roofline = {"kernel": "k_theta_axis_v2" if a.ppc >= 40 else "k_theta_axis_v3", "bound": "hbm", "achieved": achieved, "peak": peaks["hbm_gbs"],
                 "unit": "GB/s", "frac": achieved / peaks["hbm_gbs"],
                 "traffic": traffic["theta_axis_bytes_per_launch"] if traffic else None,
                 "peak_source": peak_src, "avg_launch_ms": ax_avg, "launches_timed": ax_n,
@@ -334,7 +338,7 @@ def ours_main(a):
                 "note": "W8 is FP64-pipe bound (10 flop/B > ridge 5.8): see roofline_fp64 for the binding roof"}
     ach_tf = f_axis * npart_local / (ax_avg * 1e-3) / 1e12 if ax_n else 0.0
     step_tf = (18 * f_axis + 6 * f_pv) * npart_local * a.steps / (ms * 1e-3) / 1e12 if a.order == 4 else None
-    roofline_fp64 = {"kernel": "k_theta_axis_binned", "bound": "fp64", "achieved": ach_tf, "peak": fp64_peak,
+    roofline_fp64 = {"kernel": "k_theta_axis_v2" if a.ppc >= 40 else "k_theta_axis_v3", "bound": "fp64", "achieved": ach_tf, "peak": fp64_peak,
                      "unit": "TFLOP/s", "frac": ach_tf / fp64_peak if fp64_peak else None,
                      "peak_source": "measured here: spic_probe_fp64_tflops (dependent-free DFMA chains, all SMs)",
                      "algorithmic_flop_per_particle": f_axis,
@@ -389,13 +393,18 @@ def run_e2e(a, sim, spic, np, torch, npart_local, npart, barrier, allmax):
     if avail and need * 1.3 > avail:
         return {"value": None, "unit": UNIT, "skipped": "host RAM: need %.0f GB pinned, %.0f GB available"
                 % (need / 1e9, avail / 1e9)}
-    host_p = [torch.empty(npart_local, dtype=torch.float64, pin_memory=True).numpy() for _ in range(6)]
+    # with N > 1 particles migrate between slabs, so the per-rank count changes from step to step:
+    # pinned buffers carry 2 % slack and every transfer uses the live count
+    cap = int(npart_local * 1.02) + 4096 if barrier.__name__ != "_noop" else npart_local
+    pinned = [torch.empty(cap, dtype=torch.float64, pin_memory=True).numpy() for _ in range(6)]
     host_f = [torch.empty((3, a.n, a.n, a.n), dtype=torch.float64, pin_memory=True).numpy() for _ in range(2)]
-    sim.get_particles(0, out=host_p)
+    n_live = sim.num_particles()
+    sim.get_particles(0, out=[t[:n_live] for t in pinned])
     sim.get_field(spic.FIELD_E, out=host_f[0])
     sim.get_field(spic.FIELD_B, out=host_f[1])
     sim.sync()
-    h2d = d2h = sum(t.nbytes for t in host_p) + sum(t.nbytes for t in host_f)
+    fbytes = sum(t.nbytes for t in host_f)
+    h2d = d2h = 0
     times = []
     for s in range(1 + a.e2e_steps):
         torch.cuda.synchronize()
@@ -403,19 +412,25 @@ def run_e2e(a, sim, spic, np, torch, npart_local, npart, barrier, allmax):
         t0 = time.perf_counter()
         sim.set_field(spic.FIELD_E, host_f[0])
         sim.set_field(spic.FIELD_B, host_f[1])
-        sim.set_particles(0, *host_p)
+        sim.set_particles(0, *[t[:n_live] for t in pinned])
+        up = 48 * n_live + fbytes
         sim.map(a.order, 0.5)
         sim.get_field(spic.FIELD_E, out=host_f[0])
         sim.get_field(spic.FIELD_B, out=host_f[1])
-        sim.get_particles(0, out=host_p)
+        n_live = sim.num_particles()
+        if n_live > cap:
+            raise RuntimeError("e2e: pinned particle buffer too small after migration")
+        sim.get_particles(0, out=[t[:n_live] for t in pinned])
         sim.sync()
         torch.cuda.synchronize()
         dt = time.perf_counter() - t0
         barrier()
         if s >= 1:
             times.append(allmax(dt))
+            h2d, d2h = up, 48 * n_live + fbytes
     t = sum(times) / len(times)
     return {"value": npart / t, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+            "bytes_are": "per rank",
             "ms_per_step": 1e3 * t, "steps": a.e2e_steps,
             "path": "spic_set_field x2 + spic_set_particles (pinned host -> HBM, re-binned) + spic_map + "
                     "spic_get_field x2 + spic_get_particles (HBM -> pinned host), wall clock, max over ranks"}

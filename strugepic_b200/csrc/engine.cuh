@@ -21,8 +21,10 @@ struct EngineState {
   int cells_per_block = 64;
   // particle-kernel generation: 1 warp-per-cell (k_*_binned), 2 cp.async pipelined warp-per-cell
   // (k_*_v2), 3 particle-stream batches that span cells (k_*_v3, particles_stream.cu)
-  int axis_kernel = 3;
-  int pushve_kernel = 3;
+  // 0 = automatic: theta_axis uses v3 below ~40 particles per cell (batches would be mostly padding
+  // with one warp per cell) and v2 above (its per-batch bookkeeping is cheaper); push_V_E uses v3.
+  int axis_kernel = 0;
+  int pushve_kernel = 0;
   unsigned long long* d_scalar = nullptr;  // small device scratch (8 words)
 };
 EngineState* eng(Ctx* c);

@@ -1346,10 +1346,12 @@ int engine_theta_axis(Ctx* c, Species& s, int comp, double dt) {
   EngineState* e = eng(c);
   {
     KernelTimer t(c, KT_AXIS);
-    if (e->axis_kernel == 3) {
+    int variant = e->axis_kernel;
+    if (variant == 0) variant = s.n_total < 40 * c->g.cells() ? 3 : 2;
+    if (variant == 3) {
       const int rc = stream_theta_axis(c, s, comp, dt);
       if (rc) return rc;
-    } else if (e->axis_kernel == 1) {
+    } else if (variant == 1) {
       if (c->cfg.interp == SPIC_INTERP_P8R2)
         theta_axis_binned_dispatch<InterpP8R2>(c, s, comp, dt);
       else
@@ -1397,7 +1399,7 @@ int engine_push_v_e(Ctx* c, Species& s, double dt) {
   const double coef = dt * s.q / s.m;  // hpp:267
   {
     KernelTimer t(c, KT_PUSHVE);
-    if (e->pushve_kernel == 3) {
+    if (e->pushve_kernel == 3 || e->pushve_kernel == 0) {
       const int rc = stream_push_v_e(c, s, dt);
       if (rc) return rc;
       c->launches--;  // counted below
