@@ -346,12 +346,44 @@ def ours_main(a):
                      "push_V_E_avg_ms": pv_ms / max(pv_n, 1),
                      "push_V_E_tflops": f_pv * npart_local / (pv_ms / max(pv_n, 1) * 1e-3) / 1e12 if pv_n else None}
 
+    energy = sim.get_total_energy()
     # ---- e2e: the same step through the C ABI with HOST buffers ------------------------------
     e2e = None
     if not a.no_e2e:
-        e2e = run_e2e(a, sim, spic, np, torch, npart_local, npart, barrier, allmax)
+        # pinned host memory for every local rank's brick must fit the host; otherwise the e2e leg
+        # runs on a smaller brick per GPU (and says so)
+        avail = 0
+        try:
+            for ln in open("/proc/meminfo"):
+                if ln.startswith("MemAvailable"):
+                    avail = int(ln.split()[1]) * 1024
+        except OSError:
+            pass
+        e2e_n = a.n
+        while avail and e2e_n > 32 and (48 * a.ppc + 48) * e2e_n ** 3 * world * 1.4 > avail:
+            e2e_n //= 2
+        e2e_n = int(-allmax(-float(e2e_n)))  # every rank must take the same decision
+        if e2e_n != a.n:
+            sim.close()
+            sim = spic.Simulation((e2e_n, e2e_n, e2e_n * world), interp=interp, device=local, nranks=world, rank=rank)
+            if world > 1:
+                uid2 = torch.zeros(128, dtype=torch.uint8, device="cuda")
+                if rank == 0:
+                    uid2 = torch.tensor(list(spic.comm_unique_id()), dtype=torch.uint8, device="cuda")
+                dist.broadcast(uid2, 0)
+                sim.comm_init(bytes(uid2.cpu().tolist()))
+            sim.set_uniform_field(spic.FIELD_E, [0.0, 0.0, 0.0])
+            sim.set_uniform_field(spic.FIELD_B, [0.0, 0.0, 1.0])
+            sim.add_particle_density_uniform(a.ppc, 100.0, -1.0, 0.01, seed=12345)
+            sim.map(a.order, 0.5)
+            sim.sync()
+        n_loc = sim.num_particles()
+        e2e = run_e2e(a, sim, spic, np, torch, n_loc, int(allsum(float(n_loc))), barrier, allmax, e2e_n)
+        if e2e_n != a.n:
+            e2e["workload"] = ("%dx%dx%d cells x %d ppc (per-GPU brick reduced from %d^3: pinned host buffers for "
+                               "%d ranks would not fit %.0f GB of host RAM)" %
+                               (e2e_n, e2e_n, e2e_n * world, a.ppc, a.n, world, avail / 1e9))
 
-    energy = sim.get_total_energy()
     sim.close()
     if rank == 0:
         line = {
@@ -380,24 +412,13 @@ def ours_main(a):
     return 0
 
 
-def run_e2e(a, sim, spic, np, torch, npart_local, npart, barrier, allmax):
+def run_e2e(a, sim, spic, np, torch, npart_local, npart, barrier, allmax, cells):
     """Upload (pinned host -> device, re-bin), one Theta_map, read back: all timed."""
-    avail = 0
-    try:
-        for ln in open("/proc/meminfo"):
-            if ln.startswith("MemAvailable"):
-                avail = int(ln.split()[1]) * 1024
-    except OSError:
-        pass
-    need = 48 * npart_local + 2 * 24 * a.n ** 3
-    if avail and need * 1.3 > avail:
-        return {"value": None, "unit": UNIT, "skipped": "host RAM: need %.0f GB pinned, %.0f GB available"
-                % (need / 1e9, avail / 1e9)}
     # with N > 1 particles migrate between slabs, so the per-rank count changes from step to step:
     # pinned buffers carry 2 % slack and every transfer uses the live count
     cap = int(npart_local * 1.02) + 4096 if barrier.__name__ != "_noop" else npart_local
     pinned = [torch.empty(cap, dtype=torch.float64, pin_memory=True).numpy() for _ in range(6)]
-    host_f = [torch.empty((3, a.n, a.n, a.n), dtype=torch.float64, pin_memory=True).numpy() for _ in range(2)]
+    host_f = [torch.empty((3, cells, cells, cells), dtype=torch.float64, pin_memory=True).numpy() for _ in range(2)]
     n_live = sim.num_particles()
     sim.get_particles(0, out=[t[:n_live] for t in pinned])
     sim.get_field(spic.FIELD_E, out=host_f[0])
