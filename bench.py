@@ -331,7 +331,8 @@ def ours_main(a):
     traffic = ncu_traffic()
     roofline = {"kernel": "k_theta_axis_v2" if a.ppc >= 40 else "k_theta_axis_v3", "bound": "hbm", "achieved": achieved, "peak": peaks["hbm_gbs"],
                 "unit": "GB/s", "frac": achieved / peaks["hbm_gbs"],
-                "traffic": traffic["theta_axis_bytes_per_launch"] if traffic else None,
+                "traffic": traffic["theta_axis_dram_bytes_per_particle"] * npart_local if traffic else None,
+                "traffic_source": (traffic["capture"] + "; DRAM read+write bytes per particle x the particles of one launch here") if traffic else None,
                 "peak_source": peak_src, "avg_launch_ms": ax_avg, "launches_timed": ax_n,
                 "algorithmic_bytes_per_launch": BYTES_PER_SUBFLOW * npart_local,
                 "share_of_step": ax_ms / ms if ms else None,
