@@ -59,6 +59,7 @@ def parse():
     ap.add_argument("--interp", default="p8r2", choices=["p8r2", "pwl"])
     ap.add_argument("--order", type=int, default=4, choices=[1, 2, 4])
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-fuse", action="store_true", help="reference launch-per-sub-flow schedule (A/B against the fused axis block)")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--e2e-steps", type=int, default=2)
     ap.add_argument("--cpu-steps", type=int, default=3)
@@ -293,6 +294,8 @@ def ours_main(a):
     npart = int(allsum(float(npart_local)))
     fp64_peak = spic.probe_fp64_tflops(local, 0.5)
 
+    if a.no_fuse:
+        sim.set_option("fuse", 0)
     stream = torch.cuda.ExternalStream(sim.stream())
     for _ in range(a.warmup):
         sim.map(a.order, 0.5)
@@ -320,31 +323,46 @@ def ours_main(a):
     sim.set_option("time_kernels", 0)
     value = npart * a.steps / (ms * 1e-3)
 
-    # ---- roofline of the dominant kernel (theta_axis) ----------------------------------------
+    # ---- roofline of the dominant kernel ---------------------------------------------------------
+    # fused schedule (default on periodic single-rank boxes): k_axis_block = the six Theta of one map2 in one
+    # launch; otherwise k_theta_axis_* = one Theta per launch.  Algorithmic work is counted on the REFERENCE
+    # schedule either way (72 B and 718 flop per particle and reference sub-flow), so fusion shows
+    # up as time saved, not as work invented; the fused lower bound (96 B per particle and block) is given too.
     peaks, peak_src = measured_peaks()
-    ax_ms, ax_n = kt["theta_axis"]
+    fused = kt["axis_block"][1] > 0
+    ax_ms, ax_n = kt["axis_block"] if fused else kt["theta_axis"]
+    sub_per_launch = 6 if fused else 1
     pv_ms, pv_n = kt["push_V_E"]
     ax_avg = ax_ms / max(ax_n, 1)
     f_axis = FLOP_AXIS if a.interp == "p8r2" else FLOP_AXIS_PWL
     f_pv = FLOP_PUSHVE if a.interp == "p8r2" else FLOP_PUSHVE_PWL
-    achieved = BYTES_PER_SUBFLOW * npart_local / (ax_avg * 1e-3) / 1e9 if ax_n else 0.0
+    kname = "k_axis_block" if fused else ("k_theta_axis_v2" if a.ppc >= 40 else "k_theta_axis_v3")
+    alg_bytes = BYTES_PER_SUBFLOW * sub_per_launch * npart_local
+    achieved = alg_bytes / (ax_avg * 1e-3) / 1e9 if ax_n else 0.0
     traffic = ncu_traffic()
-    roofline = {"kernel": "k_theta_axis_v2" if a.ppc >= 40 else "k_theta_axis_v3", "bound": "hbm", "achieved": achieved, "peak": peaks["hbm_gbs"],
+    tkey = "axis_block_dram_bytes_per_particle" if fused else "theta_axis_dram_bytes_per_particle"
+    roofline = {"kernel": kname, "bound": "hbm", "achieved": achieved, "peak": peaks["hbm_gbs"],
                 "unit": "GB/s", "frac": achieved / peaks["hbm_gbs"],
-                "traffic": traffic["theta_axis_dram_bytes_per_particle"] * npart_local if traffic else None,
-                "traffic_source": (traffic["capture"] + "; DRAM read+write bytes per particle x the particles of one launch here") if traffic else None,
+                "traffic": traffic[tkey] * npart_local if traffic and tkey in traffic else None,
+                "traffic_source": (traffic["capture"] + "; DRAM read+write bytes per particle x the particles of one launch here")
+                if traffic and tkey in traffic else None,
                 "peak_source": peak_src, "avg_launch_ms": ax_avg, "launches_timed": ax_n,
-                "algorithmic_bytes_per_launch": BYTES_PER_SUBFLOW * npart_local,
+                "reference_subflows_per_launch": sub_per_launch,
+                "algorithmic_bytes_per_launch": alg_bytes,
+                "fused_lower_bound_bytes_per_launch": 96.0 * npart_local if fused else None,
                 "share_of_step": ax_ms / ms if ms else None,
                 "note": "W8 is FP64-pipe bound (10 flop/B > ridge 5.8): see roofline_fp64 for the binding roof"}
-    ach_tf = f_axis * npart_local / (ax_avg * 1e-3) / 1e12 if ax_n else 0.0
+    ach_tf = f_axis * sub_per_launch * npart_local / (ax_avg * 1e-3) / 1e12 if ax_n else 0.0
     step_tf = (18 * f_axis + 6 * f_pv) * npart_local * a.steps / (ms * 1e-3) / 1e12 if a.order == 4 else None
-    roofline_fp64 = {"kernel": "k_theta_axis_v2" if a.ppc >= 40 else "k_theta_axis_v3", "bound": "fp64", "achieved": ach_tf, "peak": fp64_peak,
+    roofline_fp64 = {"kernel": kname, "bound": "fp64", "achieved": ach_tf, "peak": fp64_peak,
                      "unit": "TFLOP/s", "frac": ach_tf / fp64_peak if fp64_peak else None,
                      "peak_source": "measured here: spic_probe_fp64_tflops (dependent-free DFMA chains, all SMs)",
-                     "algorithmic_flop_per_particle": f_axis,
+                     "algorithmic_flop_per_particle": f_axis * sub_per_launch,
+                     "flop_accounting": "reference schedule: 18 Theta x 718 + 6 Theta_E x 842 flop per particle-step "
+                                        "(SURVEY 8d); the fused schedule executes fewer (shared weight evaluations, "
+                                        "merged Theta_z and Theta_E halves)",
                      "whole_step_tflops": step_tf, "whole_step_frac": step_tf / fp64_peak if step_tf else None,
-                     "push_V_E_avg_ms": pv_ms / max(pv_n, 1),
+                     "push_V_E_avg_ms": pv_ms / max(pv_n, 1), "push_V_E_launches_per_step": pv_n / max(a.steps, 1),
                      "push_V_E_tflops": f_pv * npart_local / (pv_ms / max(pv_n, 1) * 1e-3) / 1e12 if pv_n else None}
 
     energy = sim.get_total_energy()
@@ -395,6 +413,8 @@ def ours_main(a):
                        "parallelism": "z-slab x%d" % world,
                        "l2": "inputs (%.1f GB of particle state per GPU) exceed the 126 MB L2; no flush needed"
                              % (48e-9 * npart_local)},
+            "schedule": ("fused: per map2 one axis-block launch (x y z z y x) + Theta_B, adjacent Theta_E halves merged"
+                         if fused else "reference: one launch per sub-flow"),
             "clocks": clocks, "e2e": e2e, "gpu_launches": launches,
             "roofline": roofline, "roofline_fp64": roofline_fp64,
             "cell_updates_per_s": a.n ** 3 * world * a.steps / (ms * 1e-3),

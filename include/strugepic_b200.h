@@ -154,10 +154,12 @@ int64_t spic_launch_count(const spic_ctx* ctx); /* kernels launched so far */
 /* CUDA-event time (ms) accumulated inside the particle kernels since the last reset */
 int spic_kernel_time_ms(spic_ctx* ctx, int reset, double* particle_ms, int64_t* particle_launches);
 /* Same, per kernel kind: [0] theta_axis (Theta, hpp:80-244), [1] push_V_E (hpp:247-344),
- * [2] curl sweeps (cpp:71-91), [3] other timed launches (overflow-tail kernels).
+ * [2] curl sweeps (cpp:71-91), [3] other timed launches (overflow-tail and continuation kernels),
+ * [4] fused axis block (the six Theta of one Theta_map2, hpp:562-569, in one launch).
  * With option "time_kernels" = 1 every such launch is bracketed by a CUDA-event pair on
  * the context's stream (no synchronisation); this call synchronises and sums them. */
-int spic_kernel_times(spic_ctx* ctx, int reset, double ms[4], int64_t launches[4]);
+#define SPIC_KERNEL_KINDS 5
+int spic_kernel_times(spic_ctx* ctx, int reset, double ms[SPIC_KERNEL_KINDS], int64_t launches[SPIC_KERNEL_KINDS]);
 int spic_set_option(spic_ctx* ctx, const char* name, double value);
 void* spic_stream(spic_ctx* ctx); /* cudaStream_t */
 /* FP64 FMA micro-benchmark for the roofline denominator: returns TFLOP/s */

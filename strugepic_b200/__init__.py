@@ -252,10 +252,10 @@ class Simulation:
         return int(self.lib.spic_launch_count(self.h))
 
     def kernel_times(self, reset=False):
-        """{kind: (ms, launches)} for theta_axis / push_V_E / curl / other (CUDA events, own stream)."""
-        ms, n = (C.c_double * 4)(), (C.c_int64 * 4)()
+        """{kind: (ms, launches)} for theta_axis / push_V_E / curl / other / axis_block (CUDA events, own stream)."""
+        ms, n = (C.c_double * 5)(), (C.c_int64 * 5)()
         self._ck(self.lib.spic_kernel_times(self.h, int(reset), C.byref(ms), C.byref(n)))
-        return {k: (ms[i], n[i]) for i, k in enumerate(("theta_axis", "push_V_E", "curl", "other"))}
+        return {k: (ms[i], n[i]) for i, k in enumerate(("theta_axis", "push_V_E", "curl", "other", "axis_block"))}
 
     def stream(self):
         return self.lib.spic_stream(self.h)

@@ -55,7 +55,7 @@ SIGNATURES = {
     "spic_tap_IWp": (dbl, [i32, i32, dbl, dbl, i32]),
     "spic_launch_count": (i64, [vp]),
     "spic_kernel_time_ms": (i32, [vp, i32, _dp, C.POINTER(i64)]),
-    "spic_kernel_times": (i32, [vp, i32, C.POINTER(C.c_double * 4), C.POINTER(C.c_int64 * 4)]),
+    "spic_kernel_times": (i32, [vp, i32, C.POINTER(C.c_double * 5), C.POINTER(C.c_int64 * 5)]),
     "spic_set_option": (i32, [vp, C.c_char_p, dbl]),
     "spic_stream": (vp, [vp]),
     "spic_probe_fp64_tflops": (i32, [i32, dbl, _dp]),

@@ -428,6 +428,34 @@ static int map2(spic_ctx* c, double dt) {  // hpp:559-572
   return spic_theta_E(c, dt / 2);
 }
 
+// The axis block of one Theta_map2(dt): Theta_B(dt), then x(h) y(h) z(h) z(h) y(h) x(h) with h = dt/2 as one
+// fused pass per species.  Theta_B only adds dt * curl B into E and the axis sub-flows only add their
+// currents into E and read B, which neither changes (hpp:562-569, cpp:102-113): the order is free.
+static int axis_block(spic_ctx* c, double dt) {
+  int rc = spic_theta_B(c, dt);  // fills the guards of B (cpp:104): B does not change until the next Theta_E
+  if (rc) return rc;
+  launch_zero_guards(c, c->E);  // E.setBndry(0), hpp:351-352: the guards collect this block's currents
+  for (auto& s : c->sp)
+    if ((rc = engine_axis_block(c, s, dt / 2))) return rc;
+  for (int comp = 0; comp < 3; ++comp)
+    if ((rc = halo_sum(c, c->E, comp))) return rc;  // E.SumBoundary, hpp:367
+  return SPIC_OK;
+}
+
+// Theta_map2(d_0) o ... o Theta_map2(d_{n-1}) with fused axis blocks; adjacent Theta_E halves are merged:
+// Theta_E(s) o Theta_E(t) = Theta_E(s + t) exactly, because Theta_E changes neither E nor the positions
+// (hpp:52-71, 339-341; cpp:93-95).
+static int fused_maps(spic_ctx* c, const double* d, int n) {
+  int rc;
+  if ((rc = spic_theta_E(c, d[0] / 2))) return rc;
+  for (int i = 0; i < n; ++i) {
+    if ((rc = axis_block(c, d[i]))) return rc;
+    const double next = i + 1 < n ? d[i + 1] : 0.0;
+    if ((rc = spic_theta_E(c, d[i] / 2 + next / 2))) return rc;
+  }
+  return SPIC_OK;
+}
+
 static int map_body(spic_ctx* c, int order, double dt);
 int spic_map(spic_ctx* c, int order, double dt) {
   if (!c) return SPIC_EINVAL;
@@ -445,13 +473,16 @@ static int map_body(spic_ctx* c, int order, double dt) {
     if ((rc = spic_theta_axis(c, 1, dt))) return rc;
     return spic_theta_axis(c, 0, dt);
   }
-  if (order == 2) return map2(c, dt);
+  const bool fuse = engine_can_fuse(c);
+  if (order == 2) return fuse ? fused_maps(c, &dt, 1) : map2(c, dt);
   if (order == 4) {  // hpp:574-583; alpha = 1, beta = -1 in the reference (integer division at :578)
     const double alpha = c->cfg.map4_mode == SPIC_MAP4_YOSHIDA ? 1.0 / (2.0 - cbrt(2.0)) : 1.0;
     const double beta = 1 - 2 * alpha;
-    if ((rc = map2(c, alpha * dt))) return rc;
-    if ((rc = map2(c, beta * dt))) return rc;
-    return map2(c, alpha * dt);
+    const double d[3] = {alpha * dt, beta * dt, alpha * dt};
+    if (fuse) return fused_maps(c, d, 3);
+    if ((rc = map2(c, d[0]))) return rc;
+    if ((rc = map2(c, d[1]))) return rc;
+    return map2(c, d[2]);
   }
   return fail(c, SPIC_EINVAL, "order must be 1, 2 or 4");
 }
@@ -727,7 +758,7 @@ double spic_tap_IWp(int interp, int tap, double s, double e, int cell) {
 
 // ---- introspection ------------------------------------------------------------------------
 int64_t spic_launch_count(const spic_ctx* c) { return c ? c->launches : 0; }
-int spic_kernel_times(spic_ctx* c, int reset, double ms[4], int64_t launches[4]) {
+int spic_kernel_times(spic_ctx* c, int reset, double ms[SPIC_KERNEL_KINDS], int64_t launches[SPIC_KERNEL_KINDS]) {
   if (!c) return SPIC_EINVAL;
   cudaSetDevice(c->cfg.device);
   collect_timed(c);
@@ -742,12 +773,12 @@ int spic_kernel_times(spic_ctx* c, int reset, double ms[4], int64_t launches[4])
   return SPIC_OK;
 }
 int spic_kernel_time_ms(spic_ctx* c, int reset, double* particle_ms, int64_t* particle_launches) {
-  double ms[4];
-  int64_t n[4];
+  double ms[SPIC_KERNEL_KINDS];
+  int64_t n[SPIC_KERNEL_KINDS];
   int rc = spic_kernel_times(c, reset, ms, n);
   if (rc) return rc;
-  if (particle_ms) *particle_ms = ms[KT_AXIS] + ms[KT_PUSHVE];
-  if (particle_launches) *particle_launches = n[KT_AXIS] + n[KT_PUSHVE];
+  if (particle_ms) *particle_ms = ms[KT_AXIS] + ms[KT_PUSHVE] + ms[KT_BLOCK];
+  if (particle_launches) *particle_launches = n[KT_AXIS] + n[KT_PUSHVE] + n[KT_BLOCK];
   return SPIC_OK;
 }
 int spic_set_option(spic_ctx* c, const char* name, double value) {

@@ -25,6 +25,9 @@ struct EngineState {
   // with one warp per cell) and v2 above (its per-batch bookkeeping is cheaper); push_V_E uses v3.
   int axis_kernel = 0;
   int pushve_kernel = 0;
+  // 1: Theta_map2 / Theta_map4 run the six position sub-flows of every map2 as one fused axis block
+  // (particles_fused.cu) and merge adjacent Theta_E; 0: the reference's launch-per-sub-flow schedule
+  int fuse = 1;
   unsigned long long* d_scalar = nullptr;  // small device scratch (8 words)
 };
 EngineState* eng(Ctx* c);
@@ -55,6 +58,11 @@ __device__ __forceinline__ void lds_row(const double* src, double (&out)[N]) {
 int stream_theta_axis(Ctx* c, Species& s, int comp, double dt);
 int stream_push_v_e(Ctx* c, Species& s, double dt);
 
+// ---- fused axis block (particles_fused.cu) ------------------------------------------------
+bool fused_block_supported(const Ctx* c);                 // fully periodic box on one rank
+int fused_axis_block(Ctx* c, Species& s, double h);       // x(h) y(h) z(2h) y(h) x(h) over the bins
+int fused_axis_continue(Ctx* c, Species& s, double h);    // finishes the particles the block ejected
+
 // ---- cell-binned engine ------------------------------------------------------------
 int engine_ingest(Ctx* c, Species& s);  // move s.d (direct list) into cell bins (no-op for ENGINE_DIRECT)
 void engine_free_species(Ctx* c, Species& s);
@@ -63,6 +71,8 @@ int engine_count(Ctx* c, Species& s, long* nb);
 int engine_gather(Ctx* c, Species& s, double* hx[3], double* hv[3], long* nb);
 int engine_theta_axis(Ctx* c, Species& s, int comp, double dt);
 int engine_push_v_e(Ctx* c, Species& s, double dt);
+bool engine_can_fuse(Ctx* c);                      // option "fuse" on, box supported, every species binned
+int engine_axis_block(Ctx* c, Species& s, double h);  // the six Theta of a map2 (step h each) for one species
 int engine_kinetic(Ctx* c, Species& s, double* acc);
 int engine_deposit_rho(Ctx* c, Species& s, double* out);
 int engine_number_density(Ctx* c, Species& s, double* nd);  // nd: one guarded component

@@ -56,6 +56,81 @@ SPIC_DI double wrap_periodic(double x, int n, int per, int* flags) {
   return x;
 }
 
+// One position sub-flow Theta<comp = A> for one particle held in registers, any position
+// (include/strugepic_propagators.hpp:80-244): weights from global coordinates, <= 2 segments,
+// B gathered through L1/L2, deposition with native FP64 global reductions (RED.E.ADD.F64),
+// reflection (util.hpp:172-186), periodic wrap (Redistribute, hpp:368).  Used by the
+// thread-per-particle kernels and by the continuation of particles that left their cell
+// inside a fused axis block.  The triple sums are factorised (push axis innermost, then u, then l).
+template <class I, int A>
+SPIC_DI void theta_axis_one(const Grid& g, double (&x)[3], double (&v)[3], double* __restrict__ E,
+                            const double* __restrict__ B, double q, double qm, double dt, int* __restrict__ flags) {
+  constexpr int U = (A + 1) % 3, L = (A + 2) % 3;  // hpp:90-91
+  const long st[3] = {1, g.pj, g.pk};
+  double xa = x[A];
+  const double xu = x[U], xl = x[L];
+  double va = v[A];
+  int cell[3];
+  cell[A] = (int)floor(xa);
+  cell[U] = (int)floor(xu);
+  cell[L] = (int)floor(xl);
+
+  double uW1[I::NW1], lW1[I::NW1], uWp[I::NWP], lWp[I::NWP];
+  eval_w1<I>(xl, cell[L], lW1);
+  eval_wp<I>(xl, cell[L], lWp);
+  eval_w1<I>(xu, cell[U], uW1);
+  eval_wp<I>(xu, cell[U], uWp);
+
+  Segments sg = make_segments<I, A>(g, xa, xa + dt * va, flags);
+
+  cell[2] -= g.z0;  // local k
+  double r1 = 0, r2 = 0;
+  const double nq = -q;  // -E_coef, hpp:114,215 (Ics = Cs = 1)
+  double* Ea = E + (long)A * g.pc;
+  const double* Bu = B + (long)U * g.pc;
+  const double* Bl = B + (long)L * g.pc;
+  for (int s = 0; s < sg.n; ++s) {
+    const int ca = sg.cell[s];
+    double Iw[I::NWP];
+    eval_iwp<I>(sg.pt[s], sg.pt[s + 1], ca, Iw);
+    int cc[3] = {cell[0], cell[1], cell[2]};
+    cc[A] = ca - (A == 2 ? g.z0 : 0);
+    const long base = g.at(cc[0], cc[1], cc[2]) + (1 - I::W) * (st[A] + st[U] + st[L]);
+#pragma unroll
+    for (int tl = 0; tl < I::NW1; ++tl) {
+      double a1 = 0, a2 = 0;
+#pragma unroll
+      for (int tu = 0; tu < I::NW1; ++tu) {
+        const long row = base + tl * st[L] + tu * st[U];
+        const double mul = nq * (lW1[tl] * uW1[tu]);
+        double s1 = 0, s2 = 0;
+#pragma unroll
+        for (int tc = 0; tc < I::NWP; ++tc) {
+          const long idx = row + tc * st[A];
+          atomicAdd(&Ea[idx], mul * Iw[tc]);  // hpp:215
+          s1 = fma(__ldg(&Bu[idx]), Iw[tc], s1);
+          s2 = fma(__ldg(&Bl[idx]), Iw[tc], s2);
+        }
+        a1 = fma(uW1[tu], s1, a1);
+        if (tu < I::NWP) a2 = fma(uWp[tu], s2, a2);
+      }
+      if (tl < I::NWP) r1 = fma(lWp[tl], a1, r1);  // hpp:216
+      r2 = fma(-lW1[tl], a2, r2);                  // hpp:217
+    }
+  }
+
+  if (sg.reflected) {  // particle_reflect, util.hpp:182-186
+    xa = sg.pt[2];
+    va = -va;
+    v[A] = va;
+  } else {
+    xa = xa + dt * va;  // hpp:237
+  }
+  x[A] = wrap_periodic(xa, g.gn[A], g.per[A], flags);
+  v[L] += qm * r1;  // hpp:240
+  v[U] += qm * r2;  // hpp:241
+}
+
 // push_V_E gather (include/strugepic_propagators.hpp:322-338), factorised:
 //   dv_x = sum_k W1z sum_j W1y sum_i E_x Wpx   etc.
 // `E0` points at the (-W+1,-W+1,-W+1) corner of the stencil of component 0.

@@ -1376,6 +1376,32 @@ int engine_theta_axis(Ctx* c, Species& s, int comp, double dt) {
   return SPIC_OK;
 }
 
+bool engine_can_fuse(Ctx* c) {
+  if (!c->engine || !eng(c)->fuse || !fused_block_supported(c)) return false;
+  for (auto& s : c->sp)
+    if (!s.binned) return false;
+  return true;
+}
+
+// Theta_x(h) Theta_y(h) Theta_z(h) Theta_z(h) Theta_y(h) Theta_x(h) for one species
+// (include/strugepic_propagators.hpp:562-569 without the Theta_B in the middle, which commutes)
+int engine_axis_block(Ctx* c, Species& s, double h) {
+  if (!s.binned) return SPIC_OK;
+  EngineState* e = eng(c);
+  int rc;
+  if ((rc = fused_axis_block(c, s, h))) return rc;
+  // the overflow tail runs through the thread-per-particle kernels BEFORE new overflow can join it
+  static const int prog[6] = {0, 1, 2, 2, 1, 0};
+  for (int k = 0; k < 6; ++k) launch_theta_axis_direct(c, s.d, s.capd, s.d_nd, s.q, s.m, prog[k], h);
+  if ((rc = fused_axis_continue(c, s, h))) return rc;
+  int nb = (int)((e->mv.cap + 255) / 256);
+  if (nb > c->sm_count * 8) nb = c->sm_count * 8;
+  k_insert_movers<<<nb, 256, 0, c->stream>>>(e->mv, s.b, s.start, s.count, s.d, s.d_nd, s.capd, c->d_flags);
+  c->launches++;
+  SPIC_CUDA_CHECK(c, cudaMemsetAsync(e->mv.n, 0, sizeof(unsigned), c->stream));
+  return SPIC_OK;
+}
+
 int engine_insert_list(Ctx* c, Species& s, double* const x[3], double* const v[3], long n) {
   if (n <= 0) return SPIC_OK;
   if (!s.binned) {
@@ -1514,6 +1540,10 @@ int engine_set_option(Ctx* c, const char* name, double value) {
   }
   if (!strcmp(name, "pushve_kernel")) {
     e->pushve_kernel = (int)value;
+    return SPIC_OK;
+  }
+  if (!strcmp(name, "fuse")) {
+    e->fuse = value != 0;
     return SPIC_OK;
   }
   if (!strcmp(name, "cells_per_block")) {

@@ -28,70 +28,12 @@ __global__ void __launch_bounds__(kBlock)
   const long i = blockIdx.x * (long)blockDim.x + threadIdx.x;
   if (n_dev) n = (long)*n_dev;
   if (i >= n) return;
-  const long st[3] = {1, g.pj, g.pk};
-
-  double xa = p.x[A][i];
-  const double xu = p.x[U][i], xl = p.x[L][i];
-  double va = p.v[A][i];
-  int cell[3];
-  cell[A] = (int)floor(xa);
-  cell[U] = (int)floor(xu);
-  cell[L] = (int)floor(xl);
-
-  double uW1[I::NW1], lW1[I::NW1], uWp[I::NWP], lWp[I::NWP];
-  eval_w1<I>(xl, cell[L], lW1);
-  eval_wp<I>(xl, cell[L], lWp);
-  eval_w1<I>(xu, cell[U], uW1);
-  eval_wp<I>(xu, cell[U], uWp);
-
-  Segments sg = make_segments<I, A>(g, xa, xa + dt * va, flags);
-
-  cell[2] -= g.z0;  // local k
-  double r1 = 0, r2 = 0;
-  const double nq = -q;  // -E_coef, hpp:114,215 (Ics = Cs = 1)
-  double* Ea = E + (long)A * g.pc;
-  const double* Bu = B + (long)U * g.pc;
-  const double* Bl = B + (long)L * g.pc;
-  for (int s = 0; s < sg.n; ++s) {
-    const int ca = sg.cell[s];
-    double Iw[I::NWP];
-    eval_iwp<I>(sg.pt[s], sg.pt[s + 1], ca, Iw);
-    int cc[3] = {cell[0], cell[1], cell[2]};
-    cc[A] = ca - (A == 2 ? g.z0 : 0);
-    const long base = g.at(cc[0], cc[1], cc[2]) + (1 - I::W) * (st[A] + st[U] + st[L]);
-#pragma unroll
-    for (int tl = 0; tl < I::NW1; ++tl) {
-      double a1 = 0, a2 = 0;
-#pragma unroll
-      for (int tu = 0; tu < I::NW1; ++tu) {
-        const long row = base + tl * st[L] + tu * st[U];
-        const double mul = nq * (lW1[tl] * uW1[tu]);
-        double s1 = 0, s2 = 0;
-#pragma unroll
-        for (int tc = 0; tc < I::NWP; ++tc) {
-          const long idx = row + tc * st[A];
-          atomicAdd(&Ea[idx], mul * Iw[tc]);  // hpp:215
-          s1 = fma(__ldg(&Bu[idx]), Iw[tc], s1);
-          s2 = fma(__ldg(&Bl[idx]), Iw[tc], s2);
-        }
-        a1 = fma(uW1[tu], s1, a1);
-        if (tu < I::NWP) a2 = fma(uWp[tu], s2, a2);
-      }
-      if (tl < I::NWP) r1 = fma(lWp[tl], a1, r1);  // hpp:216
-      r2 = fma(-lW1[tl], a2, r2);                  // hpp:217
-    }
-  }
-
-  if (sg.reflected) {  // particle_reflect, util.hpp:182-186
-    xa = sg.pt[2];
-    va = -va;
-    p.v[A][i] = va;
-  } else {
-    xa = xa + dt * va;  // hpp:237
-  }
-  p.x[A][i] = wrap_periodic(xa, g.gn[A], g.per[A], flags);
-  p.v[L][i] += qm * r1;  // hpp:240
-  p.v[U][i] += qm * r2;  // hpp:241
+  double x[3] = {p.x[0][i], p.x[1][i], p.x[2][i]}, v[3] = {p.v[0][i], p.v[1][i], p.v[2][i]};
+  theta_axis_one<I, A>(g, x, v, E, B, q, qm, dt, flags);
+  p.x[A][i] = x[A];
+  p.v[L][i] = v[L];
+  p.v[U][i] = v[U];
+  if (!g.per[A]) p.v[A][i] = v[A];  // only a reflection changes it
 }
 
 template <class I>

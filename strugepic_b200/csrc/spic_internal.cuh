@@ -107,8 +107,8 @@ struct Ctx {
   };
   std::vector<TimedLaunch> timed;       // event pairs recorded since the last reset
   std::vector<cudaEvent_t> event_pool;  // recycled events
-  double kind_ms[4] = {0, 0, 0, 0};
-  int64_t kind_launches[4] = {0, 0, 0, 0};
+  double kind_ms[SPIC_KERNEL_KINDS] = {0, 0, 0, 0, 0};
+  int64_t kind_launches[SPIC_KERNEL_KINDS] = {0, 0, 0, 0, 0};
   void* engine = nullptr;  // EngineState (particles_binned.cu)
   void* comm = nullptr;    // CommState (comm.cu)
   std::string err;
@@ -118,8 +118,8 @@ struct Ctx {
 // Brackets one hot-kernel launch: counts it and, when the "time_kernels" option is on,
 // records a CUDA-event pair around it on the context's stream WITHOUT synchronising, so
 // the timed region of bench.py is not perturbed; spic_kernel_times() reads the pairs
-// back after the region.  kind: 0 theta_axis, 1 push_V_E, 2 curl sweeps, 3 other.
-enum { KT_AXIS = 0, KT_PUSHVE = 1, KT_CURL = 2, KT_OTHER = 3, KT_KINDS = 4 };
+// back after the region.  kind: 0 theta_axis, 1 push_V_E, 2 curl sweeps, 3 other, 4 fused axis block.
+enum { KT_AXIS = 0, KT_PUSHVE = 1, KT_CURL = 2, KT_OTHER = 3, KT_BLOCK = 4, KT_KINDS = SPIC_KERNEL_KINDS };
 struct KernelTimer {
   Ctx* c;
   int kind;

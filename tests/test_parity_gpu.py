@@ -273,6 +273,40 @@ def test_kernel_variants_agree_with_oracle(variant):
         util.compare_states(util.state_of(o), util.state_of(s), 2 * TOL_STEP, 2 * TOL_STEP, box=n_cell)
 
 
+@pytest.mark.parametrize("interp", [0, 1])
+@pytest.mark.parametrize("fuse", [0, 1])
+@pytest.mark.parametrize("mode", [0, 1])
+def test_fused_axis_block_and_reference_schedule(fuse, interp, mode):
+    """Theta_map2/4 with the six position sub-flows of every map2 fused into one pass (option fuse = 1, the
+    default on periodic boxes) and with the reference's launch-per-sub-flow schedule (fuse = 0) against the
+    oracle; 40 ppc => cells with two batches, v_th = 0.08 => ~10 % of the particles leave their cell inside a
+    block and finish it in the continuation kernel; both Theta_map4 coefficient modes."""
+    n_cell = (12, 10, 7)
+    E, B = util.rng_fields(n_cell, 77, 0.3)
+    parts = util.plasma(n_cell, 40, 0.08, 77)
+    q, m = -1.0 / 40, 100.0 / 40
+    dt = 0.5 if mode == 0 else 0.3  # Yoshida: |beta| dt must stay below the vacuum CFL limit (SURVEY 0.1)
+    # (the reference's own Theta_map4 only knows alpha = 1, beta = -1: Yoshida is checked against the C port)
+    o = ora.best_oracle(n_cell, interp=interp) if mode == 0 else util.make_oracle("port", n_cell, (1, 1, 1), interp)
+    s = spic().Simulation(n_cell, interp=interp, map4_mode=mode)
+    s.set_option("fuse", fuse)
+    s.set_option("time_kernels", 1)
+    for t in (o, s):
+        util.load_state(t, E, B, parts, q, m)
+    for _ in range(2):
+        o.map(4, dt, yoshida=mode == 1)
+        s.map(4, dt)
+    for _ in range(2):
+        o.map(2, dt)
+        s.map(2, dt)
+    errs = util.compare_states(util.state_of(o), util.state_of(s), TOL_STEP * 8, TOL_STEP * 8, box=n_cell)
+    kt = s.kernel_times()
+    assert kt["axis_block"][1] == (8 if fuse else 0), kt
+    assert kt["theta_axis"][1] == (0 if fuse else 48), kt
+    assert s.num_particles() == len(parts[0])
+    print(fuse, interp, mode, errs, kt)
+
+
 def test_errors_are_reported():
     sp = spic()
     with pytest.raises(sp.SpicError):
