@@ -32,7 +32,8 @@ for variant in (1, 2, 3):
               (variant, cpb, ax[0] / ax[1], 718 * npart / (ax[0] / ax[1] * 1e-3) / 1e12 if interp == 0 else 0,
                pv[0] / pv[1], 842 * npart / (pv[0] / pv[1] * 1e-3) / 1e12 if interp == 0 else 0))
 s.set_option("fuse", 1)
-for cpb in (32, 64):
+for bk, cpb in ((1, 64), (2, 64)):
+    s.set_option("block_kernel", bk)
     s.set_option("cells_per_block", cpb)
     for _ in range(2):
         s.Theta_map2(0.5)
@@ -41,7 +42,7 @@ for cpb in (32, 64):
         s.Theta_map2(0.5)
     kt = s.kernel_times(reset=True)
     ab, pv, ot = kt["axis_block"], kt["push_V_E"], kt["other"]
-    print("fused     cpb %3d: axis_block %.3f ms/launch = %.3f ms per reference sub-flow (%.2f TF)  push_V_E %.3f ms/launch x %d  other %.3f ms x %d" %
-          (cpb, ab[0] / ab[1], ab[0] / ab[1] / 6, 6 * 718 * npart / (ab[0] / ab[1] * 1e-3) / 1e12 if interp == 0 else 0,
+    print("fused bk=%d cpb %3d: axis_block %.3f ms/launch = %.3f ms per reference sub-flow (%.2f TF)  push_V_E %.3f ms/launch x %d  other %.3f ms x %d" %
+          (bk, cpb, ab[0] / ab[1], ab[0] / ab[1] / 6, 6 * 718 * npart / (ab[0] / ab[1] * 1e-3) / 1e12 if interp == 0 else 0,
            pv[0] / pv[1], pv[1], ot[0] / max(ot[1], 1), ot[1]))
 print("energy", s.get_total_energy())

@@ -12,13 +12,14 @@ import strugepic_b200 as spic  # noqa: E402
 import util  # noqa: E402
 
 
-def case(n_cell, ppc, vth, interp, order, steps, fuse, dt=0.5):
+def case(n_cell, ppc, vth, interp, order, steps, fuse, dt=0.5, bk=2):
     E, B = util.rng_fields(n_cell, 5, 0.3)
     parts = util.plasma(n_cell, ppc, vth, 5)
     q, m = -1.0 / ppc, 100.0 / ppc
     o = ora.best_oracle(n_cell, interp=interp)
     s = spic.Simulation(n_cell, interp=interp)
     s.set_option("fuse", fuse)
+    s.set_option("block_kernel", bk)
     s.set_option("time_kernels", 1)
     for t in (o, s):
         util.load_state(t, E, B, parts, q, m)
@@ -45,6 +46,8 @@ if __name__ == "__main__":
     case((8, 8, 8), 4, 0.01, 0, 2, 2, 1)       # a few leave
     case((8, 8, 8), 40, 0.01, 0, 2, 2, 1)      # two batches per cell
     case((12, 10, 7), 40, 0.08, 0, 4, 2, 1)    # many leave
-    case((12, 10, 7), 40, 0.08, 0, 4, 2, 0)
+    case((12, 10, 7), 40, 0.08, 0, 4, 2, 1, bk=1)
+    case((12, 10, 7), 40, 0.3, 0, 4, 2, 1)     # queue overflow into the mover list
+    case((3, 3, 3), 1, 0.01, 0, 4, 2, 1)       # fewer chunks than warps, sparse cells
     case((12, 10, 7), 40, 0.08, 1, 4, 2, 1)    # PWL
     case((4, 4, 1), 5, 0.2, 0, 2, 3, 1)

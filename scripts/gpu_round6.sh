@@ -7,6 +7,7 @@ timeout 600 compute-sanitizer --tool memcheck --error-exitcode 9 python -c "
 import sys; sys.path[:0]=['.','oracle','tests']
 import scripts.debug_fused as d
 d.case((6,5,4), 40, 0.08, 0, 4, 1, 1)
+d.case((6,5,4), 40, 0.3, 0, 4, 1, 1)
 d.case((6,5,4), 40, 0.08, 1, 2, 1, 1)
 " 2>&1 | tail -25 | tee gpurun_out/sanitizer.log
 ( time timeout 900 python -m pytest tests -m gpu -x -q ) 2>&1 | tail -25 | tee gpurun_out/pytest_gpu.log

@@ -28,6 +28,10 @@ struct EngineState {
   // 1: Theta_map2 / Theta_map4 run the six position sub-flows of every map2 as one fused axis block
   // (particles_fused.cu) and merge adjacent Theta_E; 0: the reference's launch-per-sub-flow schedule
   int fuse = 1;
+  // fused axis block: 2 = persistent warps with in-kernel continuation (default), 1 = block per cell range
+  int block_kernel = 2;
+  unsigned* block_work = nullptr;   // chunk counter of the persistent kernel
+  double* block_queues = nullptr;   // per-warp queues of ejected particles
   unsigned long long* d_scalar = nullptr;  // small device scratch (8 words)
 };
 EngineState* eng(Ctx* c);

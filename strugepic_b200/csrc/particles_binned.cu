@@ -1278,6 +1278,8 @@ void engine_destroy(Ctx* c) {
   if (e->mv.n) cudaFree(e->mv.n);
   if (e->cub_tmp) cudaFree(e->cub_tmp);
   if (e->d_scalar) cudaFree(e->d_scalar);
+  if (e->block_work) cudaFree(e->block_work);
+  if (e->block_queues) cudaFree(e->block_queues);
   delete e;
   c->engine = nullptr;
 }
@@ -1544,6 +1546,11 @@ int engine_set_option(Ctx* c, const char* name, double value) {
   }
   if (!strcmp(name, "fuse")) {
     e->fuse = value != 0;
+    return SPIC_OK;
+  }
+  if (!strcmp(name, "block_kernel")) {
+    if (value != 1 && value != 2) return SPIC_EINVAL;
+    e->block_kernel = (int)value;
     return SPIC_OK;
   }
   if (!strcmp(name, "cells_per_block")) {

@@ -400,6 +400,453 @@ __global__ void __launch_bounds__(kThreads, 2)
   cp_async_wait<0>();
 }
 
+// ------------------------------------------------------------------------------------------------
+// Persistent variant (default).  Same batch arithmetic (block_subflow), different control:
+//   * every WARP is its own worker: it draws chunks of kChunk consecutive cells from a global counter
+//     until none are left, so no warp idles behind a slower sibling (ncu of the block-per-64-cells
+//     kernels: 13.5 of 16 resident warps active on average);
+//   * the chunk tables (bin counts and starts) are staged with cp.async one chunk ahead, like the
+//     particle batches and the stencils, so the pipeline never drains between chunks;
+//   * ejected particles go to a small per-warp queue in global memory (L1/L2 resident); whenever 32 of
+//     them wait, the warp finishes them itself, one lane per particle (finish_ejected); the currents of
+//     those sub-flows are spread over the whole launch instead of being squeezed into a separate
+//     kernel that is bound by the L2's FP64 reduction rate (k_axis_continue: 11 % of the block's time
+//     for 1 % of its sub-flows).  A full queue overflows into the mover list with a continuation code,
+//     which k_axis_continue still serves.
+// ------------------------------------------------------------------------------------------------
+constexpr int kChunk = 8;    // cells per work unit
+constexpr int kQueueCap = 64;  // queued ejected particles per warp (8 doubles each)
+constexpr int kTableDoubles = 3 * kChunk + 4;  // per-warp chunk tables + the current cell's coordinates
+
+SPIC_DI double* warp_queue(double* queues) {
+  return queues + ((long)blockIdx.x * kWarps + (threadIdx.x >> 5)) * (kQueueCap * 8);
+}
+
+// Appends the lanes with `go` to the warp's queue (or, when it is full, to the mover list with the
+// continuation code); those lanes become resting padding.
+SPIC_DI void eject_queue(bool go, int resume, double (&x)[3], double (&v)[3], const double (&hc)[3], bool& alive,
+                         double* __restrict__ queues, int& qn, const MoverList& mv, int* __restrict__ flags, int lane) {
+  const unsigned m = __ballot_sync(kFull, go);
+  if (m == 0) return;
+  double* queue = warp_queue(queues);
+  const int slot = qn + __popc(m & ((1u << lane) - 1u));
+  const bool over = go && slot >= kQueueCap;
+  if (go && !over) {
+    double* e = queue + slot * 8;
+    reinterpret_cast<double2*>(e)[0] = make_double2(x[0], x[1]);
+    reinterpret_cast<double2*>(e)[1] = make_double2(x[2], v[0]);
+    reinterpret_cast<double2*>(e)[2] = make_double2(v[1], v[2]);
+    e[6] = (double)resume;
+  }
+  const unsigned mo = __ballot_sync(kFull, over);
+  if (mo) {
+    unsigned base = 0;
+    const int leader = __ffs(mo) - 1;
+    if (lane == leader) base = atomicAdd(mv.n, (unsigned)__popc(mo));
+    base = __shfl_sync(kFull, base, leader);
+    if (over) {
+      const unsigned ms = base + __popc(mo & ((1u << lane) - 1u));
+      if (ms < mv.cap) {
+#pragma unroll
+        for (int d = 0; d < 3; ++d) {
+          mv.x[d][ms] = x[d];
+          mv.v[d][ms] = v[d];
+        }
+        mv.dest[ms] = kContBase - resume;
+      } else {
+        atomicOr(&flags[1], 1);
+      }
+    }
+  }
+  qn = min(kQueueCap, qn + __popc(m));
+  if (go) {
+#pragma unroll
+    for (int d = 0; d < 3; ++d) {
+      x[d] = hc[d] + 0.5;
+      v[d] = 0.0;
+    }
+    alive = false;
+  }
+}
+
+// The local cell that holds a (wrapped) position: Redistribute, hpp:368
+SPIC_DI int dest_cell(const Grid& g, const double (&x)[3]) {
+  int i = (int)floor(x[0]), j = (int)floor(x[1]), k = (int)floor(x[2]) - g.z0;
+  i = min(max(i, 0), g.n[0] - 1);
+  j = min(max(j, 0), g.n[1] - 1);
+  k = min(max(k, 0), g.n[2] - 1);
+  return (int)(((long)k * g.n[1] + j) * g.n[0] + i);
+}
+
+// Sub-flows resume..5 of the program x y z z y x (step h each) for one particle, general code.
+template <class I>
+SPIC_DI void finish_program(const Grid& g, int resume, double (&x)[3], double (&v)[3], double* __restrict__ E,
+                            const double* __restrict__ B, double q, double qm, double h, int* __restrict__ flags) {
+#pragma unroll 1
+  for (int k = resume; k < 6; ++k) {
+    const int axis = k < 3 ? k : 5 - k;
+    if (axis == 0) theta_axis_one<I, 0>(g, x, v, E, B, q, qm, h, flags);
+    else if (axis == 1) theta_axis_one<I, 1>(g, x, v, E, B, q, qm, h, flags);
+    else theta_axis_one<I, 2>(g, x, v, E, B, q, qm, h, flags);
+  }
+}
+
+// One lane per queued particle: finish its sub-flows and hand it to the mover list with its destination
+// cell.  Kept out of line: it is the rare path and must not cost the batch loop registers.
+template <class I>
+__device__ __noinline__ void finish_ejected(const Grid* gp, const MoverList* mvp, const double* entry, bool active,
+                                            double* E, const double* B, double q, double qm, double h, int* flags) {
+  const Grid& g = *gp;
+  const MoverList& mv = *mvp;
+  const int lane = threadIdx.x & 31;
+  double x[3] = {0, 0, 0}, v[3] = {0, 0, 0};
+  if (active) {
+    // (written by other lanes of this warp: read through L2)
+    const double2 a = __ldcg(reinterpret_cast<const double2*>(entry)), b = __ldcg(reinterpret_cast<const double2*>(entry) + 1),
+                  c = __ldcg(reinterpret_cast<const double2*>(entry) + 2);
+    x[0] = a.x;
+    x[1] = a.y;
+    x[2] = b.x;
+    v[0] = b.y;
+    v[1] = c.x;
+    v[2] = c.y;
+    finish_program<I>(g, (int)__ldcg(entry + 6), x, v, E, B, q, qm, h, flags);
+  }
+  const unsigned m = __ballot_sync(kFull, active);
+  unsigned base = 0;
+  const int leader = __ffs(m) - 1;
+  if (lane == leader) base = atomicAdd(mv.n, (unsigned)__popc(m));
+  base = __shfl_sync(kFull, base, leader);
+  if (active) {
+    const unsigned slot = base + __popc(m & ((1u << lane) - 1u));
+    if (slot < mv.cap) {
+#pragma unroll
+      for (int d = 0; d < 3; ++d) {
+        mv.x[d][slot] = x[d];
+        mv.v[d][slot] = v[d];
+      }
+      mv.dest[slot] = dest_cell(g, x);
+    } else {
+      atomicOr(&flags[1], 1);
+    }
+  }
+}
+
+// The axis-specific part of one in-cell sub-flow along A (the rest is shared by the three axes so that the
+// batch loop stays inside the instruction cache): deposition record, the two B gathers, velocity and
+// position update.  Same arithmetic as block_subflow.
+template <class I, int A>
+SPIC_DI void axis_part(double (&x)[3], double (&v)[3], double x1, const double (&I0)[I::NWP],
+                       const double (&uW1)[I::NW1], const double (&uWp)[I::NWP], const double (&lW1)[I::NW1],
+                       const double (&lWp)[I::NWP], const double* sB, double* sW, double nq, double qm, int lane) {
+  constexpr int U = (A + 1) % 3, L = (A + 2) % 3;  // hpp:90-91
+  constexpr int NW1 = I::NW1, NWP = I::NWP;
+  using Lay = BlockLayout<I>;
+  constexpr int NS = Lay::NS, SW = Lay::SW;
+  {  // deposition record of this particle: -q W1_l, W1_u, I   (hpp:194,215)
+    double2* w = reinterpret_cast<double2*>(sW + lane * SW);
+#pragma unroll
+    for (int t = 0; t < NW1 / 2; ++t) w[t] = make_double2(nq * lW1[2 * t], nq * lW1[2 * t + 1]);
+#pragma unroll
+    for (int t = 0; t < NW1 / 2; ++t) w[NW1 / 2 + t] = make_double2(uW1[2 * t], uW1[2 * t + 1]);
+    if (NWP == 3) {
+      w[NW1] = make_double2(I0[0], I0[NWP > 1 ? 1 : 0]);
+      sW[lane * SW + 2 * NW1 + 2] = I0[NWP - 1];
+    } else {
+      sW[lane * SW + 2 * NW1] = I0[0];
+    }
+  }
+  // B gathers (hpp:216-217), factorised; direction 0 (x) is the contiguous one of the staged block
+  double s1, s2;
+  const double* bU = sB + U * NS;
+  const double* bL = sB + L * NS;
+  if (A == 0) {  // U = y, L = z
+    s1 = gather_block<NW1>(bU, I0, uW1, lWp);
+    s2 = gather_block<NW1>(bL, I0, uWp, lW1);
+  } else if (A == 1) {  // U = z, L = x
+    s1 = gather_block<NW1>(bU, lWp, I0, uW1);
+    s2 = gather_block<NW1>(bL, lW1, I0, uWp);
+  } else {  // U = x, L = y
+    s1 = gather_block<NW1>(bU, uW1, lWp, I0);
+    s2 = gather_block<NW1>(bL, uWp, lW1, I0);
+  }
+  v[L] = fma(qm, s1, v[L]);   // hpp:240
+  v[U] = fma(-qm, s2, v[U]);  // hpp:241 (res_c2 carries the minus sign of hpp:217)
+  x[A] = x1;
+}
+
+// Cell-centric deposition of the records in sW into the parked accumulators sAccA (see block_subflow).
+template <class I>
+SPIC_DI void deposit_records(const double* sW, double* sAccA, bool fresh, int nit, int lane) {
+  constexpr int NW1 = I::NW1, NWP = I::NWP;
+  using Lay = BlockLayout<I>;
+  constexpr int SW = Lay::SW, TH = Lay::TH, LPP = Lay::LPP, NSUB = Lay::NSUB;
+  const int tu = lane % NW1, th = (lane / NW1) % TH, sub = lane / LPP;
+  double acc[2][NWP];
+#pragma unroll
+  for (int j = 0; j < 2; ++j)
+#pragma unroll
+    for (int t = 0; t < NWP; ++t) acc[j][t] = fresh ? 0.0 : sAccA[(j * NWP + t) * 32 + lane];
+#pragma unroll 2
+  for (int it = 0; it < nit; ++it) {
+    const double* w = sW + (it * NSUB + sub) * SW;
+    const double2 a = *reinterpret_cast<const double2*>(w + 2 * th);
+    const double b = w[NW1 + tu];
+    double In[NWP];
+    lds_row<NWP>(w + 2 * NW1, In);
+#pragma unroll
+    for (int t = 0; t < NWP; ++t) {
+      const double bI = b * In[t];
+      acc[0][t] = fma(a.x, bI, acc[0][t]);
+      acc[1][t] = fma(a.y, bI, acc[1][t]);
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < 2; ++j)
+#pragma unroll
+    for (int t = 0; t < NWP; ++t) sAccA[(j * NWP + t) * 32 + lane] = acc[j][t];
+}
+
+template <class I>
+__global__ void __launch_bounds__(kThreads, 2)
+    k_axis_block_persistent(const __grid_constant__ Grid g, ParticleSoA p, const long* __restrict__ start,
+                            int* __restrict__ count, double* __restrict__ E, const double* __restrict__ B, double q,
+                            double qm, double h, const __grid_constant__ MoverList mv, int* __restrict__ flags,
+                            long ncell, unsigned* __restrict__ work, double* __restrict__ queues) {
+  constexpr int NW1 = I::NW1, NWP = I::NWP;
+  using Lay = BlockLayout<I>;
+  constexpr int NS = Lay::NS, SB = Lay::SB, SP = Lay::SP, SW = Lay::SW, NACC = Lay::NACC, NSUB = Lay::NSUB;
+  constexpr int ST = kTableDoubles;  // start[2][kChunk] (long), cnt[2][kChunk] (int), cell corner as doubles [4]
+  extern __shared__ __align__(16) double smem[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  double* sWarp = smem + warp * (Lay::PER_WARP + ST);
+  long* tStart = reinterpret_cast<long*>(sWarp);               // [2][kChunk]
+  int* tCnt = reinterpret_cast<int*>(sWarp + 2 * kChunk);       // [2][kChunk]
+  double* sH = sWarp + 3 * kChunk;                              // [3] (+ pad): the cell's global coordinates
+  double* sPart = sWarp + ST;                                   // [6][32]
+  double* sBst = sPart + SP;                                    // [2][3][NW1][NW1][NW1]
+  double* sW = sBst + 2 * SB;                                   // [32][SW]
+  double* sAcc = sW + 32 * SW;                                  // [3][NACC][32]
+  const long st[3] = {1, g.pj, g.pk};
+  const double nq = -q;  // -E_coef (hpp:114; Ics = Cs = 1)
+  const unsigned nchunk = (unsigned)((ncell + kChunk - 1) / kChunk);
+
+  // draws the next chunk; the value is broadcast only where it is used, so the reduction's latency hides
+  auto grab = [&]() -> unsigned {
+    unsigned c = 0;
+    if (lane == 0) c = atomicAdd(work, 1u);
+    return c;
+  };
+  // bin counts / starts of chunk `chunk` -> table buffer tb (cp.async: lands with the next waited group)
+  auto load_table = [&](unsigned chunk, int tb) {
+    if (lane < kChunk) {
+      const long cell = (long)chunk * kChunk + lane;
+      if (cell < ncell) {
+        const unsigned d4 = (unsigned)__cvta_generic_to_shared(tCnt + tb * kChunk + lane);
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 4;\n" ::"r"(d4), "l"(count + cell) : "memory");
+        cp_async8(reinterpret_cast<double*>(tStart + tb * kChunk + lane), reinterpret_cast<const double*>(start + cell));
+      } else {
+        tCnt[tb * kChunk + lane] = 0;
+        tStart[tb * kChunk + lane] = 0;
+      }
+    }
+  };
+  auto corner_of = [&](unsigned cell, int (&cc)[3]) -> long {  // stencil corner (-W+1 in every direction)
+    const unsigned row = cell / (unsigned)g.n[0];                 // (32-bit: a brick has < 2^31 cells)
+    cc[0] = (int)(cell - row * (unsigned)g.n[0]);
+    cc[2] = (int)(row / (unsigned)g.n[1]);
+    cc[1] = (int)(row - (unsigned)cc[2] * (unsigned)g.n[1]);
+    return g.at(cc[0], cc[1], cc[2]) + (1 - I::W) * (1 + g.pj + g.pk);
+  };
+  // stage batch `off` of cell (chunk, tb, ci); with off == 0 also the cell's stencil into buffer bb
+  auto stage = [&](unsigned chunk, int tb, int ci, int off, int bb) {
+    const int n = tCnt[tb * kChunk + ci];
+    if (off + lane < n) {
+      const long src = tStart[tb * kChunk + ci] + off + lane;
+      double* d = sPart + lane;
+      cp_async8(d + 0 * 32, p.x[0] + src);
+      cp_async8(d + 1 * 32, p.x[1] + src);
+      cp_async8(d + 2 * 32, p.x[2] + src);
+      cp_async8(d + 3 * 32, p.v[0] + src);
+      cp_async8(d + 4 * 32, p.v[1] + src);
+      cp_async8(d + 5 * 32, p.v[2] + src);
+    }
+    if (off == 0 && n > 0) {
+      int cc[3];
+      const double* src = B + corner_of(chunk * kChunk + ci, cc);
+      double* d = sBst + bb * SB;
+#pragma unroll
+      for (int s = lane; s < SB; s += 32) {
+        const int comp = s / NS, r = s % NS;
+        const int ti = r % NW1, tj = (r / NW1) % NW1, tk = r / (NW1 * NW1);
+        cp_async8(d + s, src + (long)comp * g.pc + ti + tj * g.pj + tk * g.pk);
+      }
+    }
+  };
+
+  // ---- prologue: first chunk's table, then the second chunk's table and the first batch ------------
+  unsigned chunk = __shfl_sync(kFull, grab(), 0);
+  if (chunk >= nchunk) return;
+  load_table(chunk, 0);
+  cp_async_commit();
+  unsigned pending = grab();  // lane 0 holds the id of the chunk after next
+  cp_async_wait<0>();
+  __syncwarp();
+  unsigned chunk_next = __shfl_sync(kFull, pending, 0);
+  if (chunk_next < nchunk) load_table(chunk_next, 1);
+  pending = grab();
+  int tb = 0, ci = 0, off = 0, bb = 0, qn = 0;
+  stage(chunk, 0, 0, 0, 0);
+  cp_async_commit();
+
+  int wp = 0, cnt = 0;
+  long s0 = 0, base = 0;
+  bool more = true;
+
+  while (more) {
+    cp_async_wait<0>();  // this batch (at a new cell its stencil, at a new chunk the next table) has landed
+    __syncwarp();
+    if (off == 0) {  // new cell
+      int cc[3];
+      cnt = tCnt[tb * kChunk + ci];
+      s0 = tStart[tb * kChunk + ci];
+      base = corner_of(chunk * kChunk + ci, cc);
+      if (lane < 3) sH[lane] = (double)(cc[lane] + (lane == 2 ? g.z0 : 0));
+      wp = 0;
+      __syncwarp();
+    }
+    const double hc[3] = {sH[0], sH[1], sH[2]};
+    const int nvalid = cnt - off < 32 ? cnt - off : 32;  // <= 0: empty cell
+    const bool valid = lane < nvalid;
+    // (padding lanes carry a resting particle at the cell centre: v = 0 makes every I exactly 0)
+    double x[3] = {hc[0] + 0.5, hc[1] + 0.5, hc[2] + 0.5}, v[3] = {0.0, 0.0, 0.0};
+    if (valid) {
+      const double* sP = sPart + lane;
+      x[0] = sP[0 * 32];
+      x[1] = sP[1 * 32];
+      x[2] = sP[2 * 32];
+      v[0] = sP[3 * 32];
+      v[1] = sP[4 * 32];
+      v[2] = sP[5 * 32];
+    }
+    __syncwarp();  // the staging buffer has been consumed: refill it while this batch computes
+
+    // ---- the next batch: same cell, next cell of the chunk, or first cell of the next chunk ----------
+    unsigned nchunk_id = chunk;
+    int ntb = tb, nci = ci, noff = off + 32;
+    if (noff >= cnt) {
+      noff = 0;
+      nci = ci + 1;
+      if (nci == kChunk) {
+        nci = 0;
+        ntb = tb ^ 1;
+        nchunk_id = chunk_next;
+        more = chunk_next < nchunk;
+      }
+    }
+    const bool last_of_cell = noff == 0;
+    if (more) stage(nchunk_id, ntb, nci, noff, last_of_cell ? bb ^ 1 : bb);
+    cp_async_commit();
+
+    if (nvalid > 0) {
+      const double* sB = sBst + bb * SB;
+      const int nit = (nvalid + NSUB - 1) / NSUB;
+      const bool first = off == 0;
+      bool alive = valid;
+      double* sAx = sAcc;
+      double* sAy = sAcc + NACC * 32;
+      double* sAz = sAcc + 2 * NACC * 32;
+
+      // x(h) y(h) z(2h) y(h) x(h) as a LOOP over the sub-flows (steps -2, -1 only evaluate the y and z
+      // weights): one copy of the shared code and one of each axis-specific part, instead of five inlined
+      // sub-flows (ncu of the unrolled kernel: 20 % of the stall samples were instruction fetch).  The weights
+      // of a direction are re-evaluated only after the sub-flow that moved it; every array index is static.
+      double xW1[NW1] = {}, xWp[NWP] = {}, yW1[NW1] = {}, yWp[NWP] = {}, zW1[NW1] = {}, zWp[NWP] = {};
+#pragma unroll 1
+      for (int step = -2; step < 5; ++step) {
+        const int A = step < 0 ? step + 3 : (step < 3 ? step : 4 - step);
+        double x1 = 0.0;
+        double I0[NWP] = {};
+        if (step >= 0) {
+          const double xa = A == 0 ? x[0] : (A == 1 ? x[1] : x[2]);
+          const double va = A == 0 ? v[0] : (A == 1 ? v[1] : v[2]);
+          const double hA = A == 0 ? hc[0] : (A == 1 ? hc[1] : hc[2]);
+          x1 = xa + (step == 2 ? 2.0 * h : h) * va;  // hpp:237
+          // construct_segments (util.cpp:160-174): one segment  <=>  floor(x1) == cell  <=>  hA <= x1 < hA + 1
+          const bool leaves = alive && !(x1 >= hA && x1 < hA + 1.0);
+          eject_queue(leaves, step < 3 ? step : step + 1, x, v, hc, alive, queues, qn, mv, flags, lane);
+          const double xs = leaves ? hA + 0.5 : xa;  // an ejected lane is a resting padding particle from here on
+          if (leaves) x1 = xs;
+          eval_iwp_in<I>(xs, x1, hA, I0);  // hpp:178-186
+        }
+        switch (A) {  // f = x - cell is exact: the particle lies inside its bin cell
+          case 0:
+            if (step >= 0) axis_part<I, 0>(x, v, x1, I0, yW1, yWp, zW1, zWp, sB, sW, nq, qm, lane);
+            if (step != 4) {
+              eval_w1_in<I>(x[0] - hc[0], xW1);
+              eval_wp_in<I>(x[0] - hc[0], xWp);
+            }
+            break;
+          case 1:
+            if (step >= 0) axis_part<I, 1>(x, v, x1, I0, zW1, zWp, xW1, xWp, sB, sW, nq, qm, lane);
+            eval_w1_in<I>(x[1] - hc[1], yW1);
+            eval_wp_in<I>(x[1] - hc[1], yWp);
+            break;
+          default:
+            if (step >= 0) axis_part<I, 2>(x, v, x1, I0, xW1, xWp, yW1, yWp, sB, sW, nq, qm, lane);
+            eval_w1_in<I>(x[2] - hc[2], zW1);
+            eval_wp_in<I>(x[2] - hc[2], zWp);
+            break;
+        }
+        if (step >= 0) {
+          __syncwarp();
+          deposit_records<I>(sW, sAcc + A * (NACC * 32), first && step < 3, nit, lane);
+          __syncwarp();  // the record area is free again
+        }
+      }
+
+      // ---- re-file: the particles still in the cell are compacted in place ---------------------------
+      const bool stays = valid && alive;
+      const unsigned stay_mask = __ballot_sync(kFull, stays);
+      if (stays) {
+        const long dst = s0 + wp + __popc(stay_mask & ((1u << lane) - 1u));
+#pragma unroll
+        for (int d = 0; d < 3; ++d) {
+          p.x[d][dst] = x[d];
+          p.v[d][dst] = v[d];
+        }
+      }
+      wp += __popc(stay_mask);
+
+      if (last_of_cell) {
+        flush_component<I, 0>(sAx, E, base, st, g.pc, lane);
+        flush_component<I, 1>(sAy, E, base, st, g.pc, lane);
+        flush_component<I, 2>(sAz, E, base, st, g.pc, lane);
+        if (lane == 0) count[(long)chunk * kChunk + ci] = wp;
+        if (qn >= 32) {  // a full warp of ejected particles waits: finish them now, one lane each
+          __syncwarp();
+          qn -= 32;
+          finish_ejected<I>(&g, &mv, warp_queue(queues) + (qn + lane) * 8, true, E, B, q, qm, h, flags);
+        }
+      }
+    }
+    __syncwarp();
+    if (last_of_cell) bb ^= 1;
+    if (ntb != tb && more) {  // entered a new chunk: its predecessor's table buffer is free for the chunk after
+      chunk = chunk_next;
+      chunk_next = __shfl_sync(kFull, pending, 0);
+      if (chunk_next < nchunk) load_table(chunk_next, tb);
+      pending = grab();
+    }
+    tb = ntb;
+    ci = nci;
+    off = noff;
+  }
+  cp_async_wait<0>();
+  __syncwarp();
+  if (qn > 0) finish_ejected<I>(&g, &mv, warp_queue(queues) + (lane < qn ? lane : 0) * 8, lane < qn, E, B, q, qm, h, flags);
+}
+
 // Finishes the sub-flows of the ejected particles (mover-list entries with a continuation code), one
 // thread per particle with the general code, and replaces the code by the particle's destination cell.
 // Program: x y z z y x with step h each (the merged z(2h) of the block is undone here so that the
@@ -414,24 +861,13 @@ __global__ void __launch_bounds__(128)
     if (code > kContBase) continue;
     const int resume = kContBase - code;
     double x[3] = {mv.x[0][m], mv.x[1][m], mv.x[2][m]}, v[3] = {mv.v[0][m], mv.v[1][m], mv.v[2][m]};
-#pragma unroll 1
-    for (int k = resume; k < 6; ++k) {
-      const int axis = k < 3 ? k : 5 - k;
-      if (axis == 0) theta_axis_one<I, 0>(g, x, v, E, B, q, qm, h, flags);
-      else if (axis == 1) theta_axis_one<I, 1>(g, x, v, E, B, q, qm, h, flags);
-      else theta_axis_one<I, 2>(g, x, v, E, B, q, qm, h, flags);
-    }
+    finish_program<I>(g, resume, x, v, E, B, q, qm, h, flags);
 #pragma unroll
     for (int d = 0; d < 3; ++d) {
       mv.x[d][m] = x[d];
       mv.v[d][m] = v[d];
     }
-    // positions are wrapped into the box (Redistribute, hpp:368): the destination is the cell that holds it
-    int i = (int)floor(x[0]), j = (int)floor(x[1]), k = (int)floor(x[2]) - g.z0;
-    i = min(max(i, 0), g.n[0] - 1);
-    j = min(max(j, 0), g.n[1] - 1);
-    k = min(max(k, 0), g.n[2] - 1);
-    mv.dest[m] = (int)(((long)k * g.n[1] + j) * g.n[0] + i);
+    mv.dest[m] = dest_cell(g, x);  // positions are wrapped into the box (Redistribute, hpp:368)
   }
 }
 
@@ -439,16 +875,39 @@ template <class I>
 int launch_block(Ctx* c, Species& s, double h) {
   EngineState* e = eng(c);
   const long ncell = c->g.cells();
-  const int cpb = e->cells_per_block;
-  const int grid = (int)((ncell + cpb - 1) / cpb);
-  const size_t smem = sizeof(double) * kWarps * BlockLayout<I>::PER_WARP;
+  if (e->block_kernel == 1) {  // one thread block per cells_per_block cells, continuation in a second kernel
+    const int cpb = e->cells_per_block;
+    const int grid = (int)((ncell + cpb - 1) / cpb);
+    const size_t smem = sizeof(double) * kWarps * BlockLayout<I>::PER_WARP;
+    static bool attr = false;
+    if (!attr) {
+      SPIC_CUDA_CHECK(c, cudaFuncSetAttribute(k_axis_block<I>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      attr = true;
+    }
+    k_axis_block<I><<<grid, kThreads, smem, c->stream>>>(c->g, s.b, s.start, s.count, c->E, c->B, s.q, s.q / s.m, h,
+                                                         e->mv, c->d_flags, ncell, cpb);
+    c->launches++;
+    return SPIC_OK;
+  }
+  // persistent: two blocks per SM, every warp draws chunks of kChunk cells from a counter
+  const long nchunk = (ncell + kChunk - 1) / kChunk;
+  long want = (nchunk + kWarps - 1) / kWarps;
+  if (want > 2L * c->sm_count) want = 2L * c->sm_count;
+  const int grid = (int)want;
+  const size_t qbytes = sizeof(double) * 8 * kQueueCap * kWarps * (size_t)(2 * c->sm_count);
+  if (!e->block_work) SPIC_CUDA_CHECK(c, cudaMalloc(&e->block_work, sizeof(unsigned)));
+  if (!e->block_queues) SPIC_CUDA_CHECK(c, cudaMalloc(&e->block_queues, qbytes));
+  SPIC_CUDA_CHECK(c, cudaMemsetAsync(e->block_work, 0, sizeof(unsigned), c->stream));
+  const size_t smem = sizeof(double) * kWarps * (BlockLayout<I>::PER_WARP + kTableDoubles);
   static bool attr = false;
   if (!attr) {
-    SPIC_CUDA_CHECK(c, cudaFuncSetAttribute(k_axis_block<I>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    SPIC_CUDA_CHECK(c, cudaFuncSetAttribute(k_axis_block_persistent<I>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                            (int)smem));
     attr = true;
   }
-  k_axis_block<I><<<grid, kThreads, smem, c->stream>>>(c->g, s.b, s.start, s.count, c->E, c->B, s.q, s.q / s.m, h,
-                                                       e->mv, c->d_flags, ncell, cpb);
+  k_axis_block_persistent<I><<<grid, kThreads, smem, c->stream>>>(c->g, s.b, s.start, s.count, c->E, c->B, s.q,
+                                                                  s.q / s.m, h, e->mv, c->d_flags, ncell,
+                                                                  e->block_work, e->block_queues);
   c->launches++;
   return SPIC_OK;
 }
