@@ -336,7 +336,7 @@ def ours_main(a):
     ax_avg = ax_ms / max(ax_n, 1)
     f_axis = FLOP_AXIS if a.interp == "p8r2" else FLOP_AXIS_PWL
     f_pv = FLOP_PUSHVE if a.interp == "p8r2" else FLOP_PUSHVE_PWL
-    kname = "k_axis_block_persistent" if fused else ("k_theta_axis_v2" if a.ppc >= 40 else "k_theta_axis_v3")
+    kname = "k_axis_block" if fused else ("k_theta_axis_v2" if a.ppc >= 40 else "k_theta_axis_v3")
     alg_bytes = BYTES_PER_SUBFLOW * sub_per_launch * npart_local
     achieved = alg_bytes / (ax_avg * 1e-3) / 1e9 if ax_n else 0.0
     traffic = ncu_traffic()

@@ -16,7 +16,7 @@ npart = s.num_particles()
 print("fp64 probe TFLOP/s:", spic.probe_fp64_tflops(0, 0.5), "particles", npart)
 s.set_option("time_kernels", 1)
 s.set_option("fuse", 0)
-for variant in (1, 2, 3):
+for variant in (() if 'fusedonly' in sys.argv else (1, 2, 3)):
     s.set_option("axis_kernel", variant)
     s.set_option("pushve_kernel", variant)
     for cpb in ((64,) if variant == 1 else (32, 64)):
@@ -32,9 +32,7 @@ for variant in (1, 2, 3):
               (variant, cpb, ax[0] / ax[1], 718 * npart / (ax[0] / ax[1] * 1e-3) / 1e12 if interp == 0 else 0,
                pv[0] / pv[1], 842 * npart / (pv[0] / pv[1] * 1e-3) / 1e12 if interp == 0 else 0))
 s.set_option("fuse", 1)
-for bk, cpb in ((1, 64), (2, 64)):
-    s.set_option("block_kernel", bk)
-    s.set_option("cells_per_block", cpb)
+for bk, cpb in ((2, 64),):
     for _ in range(2):
         s.Theta_map2(0.5)
     s.kernel_times(reset=True)

@@ -19,7 +19,6 @@ def case(n_cell, ppc, vth, interp, order, steps, fuse, dt=0.5, bk=2):
     o = ora.best_oracle(n_cell, interp=interp)
     s = spic.Simulation(n_cell, interp=interp)
     s.set_option("fuse", fuse)
-    s.set_option("block_kernel", bk)
     s.set_option("time_kernels", 1)
     for t in (o, s):
         util.load_state(t, E, B, parts, q, m)
@@ -46,7 +45,6 @@ if __name__ == "__main__":
     case((8, 8, 8), 4, 0.01, 0, 2, 2, 1)       # a few leave
     case((8, 8, 8), 40, 0.01, 0, 2, 2, 1)      # two batches per cell
     case((12, 10, 7), 40, 0.08, 0, 4, 2, 1)    # many leave
-    case((12, 10, 7), 40, 0.08, 0, 4, 2, 1, bk=1)
     case((12, 10, 7), 40, 0.3, 0, 4, 2, 1)     # queue overflow into the mover list
     case((3, 3, 3), 1, 0.01, 0, 4, 2, 1)       # fewer chunks than warps, sparse cells
     case((12, 10, 7), 40, 0.08, 1, 4, 2, 1)    # PWL

@@ -122,9 +122,12 @@ int spic_create(const spic_config* cfg, spic_ctx** out) {
   if (cfg->interp != SPIC_INTERP_P8R2 && cfg->interp != SPIC_INTERP_PWL)
     return fail(nullptr, SPIC_EINVAL, "interp must be SPIC_INTERP_P8R2 or SPIC_INTERP_PWL");
   const int W = cfg->interp == SPIC_INTERP_P8R2 ? 2 : 1;
-  const int ng = cfg->ng == 0 ? W : cfg->ng;
-  if (ng < W) return fail(nullptr, SPIC_EINVAL, "ng must be >= the interpolation range");
   const int nranks = cfg->nranks <= 0 ? 1 : cfg->nranks;
+  // default guard width: the interpolation range; one more with z slabs on a periodic box, so that the fused axis
+  // block can let a particle finish its sub-flows one cell outside the slab before it migrates
+  const bool all_periodic = cfg->periodic[0] && cfg->periodic[1] && cfg->periodic[2];
+  const int ng = cfg->ng == 0 ? (nranks > 1 && all_periodic && cfg->n_cell[2] / nranks >= W + 1 ? W + 1 : W) : cfg->ng;
+  if (ng < W) return fail(nullptr, SPIC_EINVAL, "ng must be >= the interpolation range");
   for (int d = 0; d < 3; ++d)
     if (cfg->n_cell[d] < 1) return fail(nullptr, SPIC_EINVAL, "n_cell must be >= 1");
   if (cfg->rank < 0 || cfg->rank >= nranks) return fail(nullptr, SPIC_EINVAL, "rank out of range");
@@ -439,7 +442,8 @@ static int axis_block(spic_ctx* c, double dt) {
     if ((rc = engine_axis_block(c, s, dt / 2))) return rc;
   for (int comp = 0; comp < 3; ++comp)
     if ((rc = halo_sum(c, c->E, comp))) return rc;  // E.SumBoundary, hpp:367
-  return SPIC_OK;
+  if (c->cfg.nranks > 1) rc = comm_migrate(c);       // P.Redistribute across slabs, hpp:368 (once per block)
+  return rc;
 }
 
 // Theta_map2(d_0) o ... o Theta_map2(d_{n-1}) with fused axis blocks; adjacent Theta_E halves are merged:

@@ -28,10 +28,7 @@ struct EngineState {
   // 1: Theta_map2 / Theta_map4 run the six position sub-flows of every map2 as one fused axis block
   // (particles_fused.cu) and merge adjacent Theta_E; 0: the reference's launch-per-sub-flow schedule
   int fuse = 1;
-  // fused axis block: 2 = persistent warps with in-kernel continuation (default), 1 = block per cell range
-  int block_kernel = 2;
-  unsigned* block_work = nullptr;   // chunk counter of the persistent kernel
-  double* block_queues = nullptr;   // per-warp queues of ejected particles
+  unsigned* block_work = nullptr;   // chunk counter of the fused axis-block kernel
   unsigned long long* d_scalar = nullptr;  // small device scratch (8 words)
 };
 EngineState* eng(Ctx* c);
@@ -63,9 +60,10 @@ int stream_theta_axis(Ctx* c, Species& s, int comp, double dt);
 int stream_push_v_e(Ctx* c, Species& s, double dt);
 
 // ---- fused axis block (particles_fused.cu) ------------------------------------------------
-bool fused_block_supported(const Ctx* c);                 // fully periodic box on one rank
+bool fused_block_supported(const Ctx* c);                 // fully periodic box (guard width W + 1 with z slabs)
 int fused_axis_block(Ctx* c, Species& s, double h);       // x(h) y(h) z(2h) y(h) x(h) over the bins
 int fused_axis_continue(Ctx* c, Species& s, double h);    // finishes the particles the block ejected
+int fused_axis_tail(Ctx* c, Species& s, double h);        // the same six sub-flows for the overflow tail
 
 // ---- cell-binned engine ------------------------------------------------------------
 int engine_ingest(Ctx* c, Species& s);  // move s.d (direct list) into cell bins (no-op for ENGINE_DIRECT)

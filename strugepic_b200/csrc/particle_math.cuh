@@ -56,15 +56,30 @@ SPIC_DI double wrap_periodic(double x, int n, int per, int* flags) {
   return x;
 }
 
+// Destination of a binned particle that moved along z from global plane `home` to the (globally wrapped)
+// plane `now`, |move| <= 1 cell: its new local cell, or -1 / -2 when it left this rank's slab through the low /
+// high face.  The SIDE follows the direction of the move, not the wrapped coordinate: a particle leaving the top
+// of the last slab re-appears at z ~ 0 and still belongs to the NEXT rank of the periodic ring.
+SPIC_DI int z_dest(const Grid& g, long cell, int home, int now) {
+  const long plane = (long)g.n[0] * g.n[1];
+  if (g.zlocal) return (int)(cell + (long)(now - home) * plane);
+  int du = now - home;
+  if (du > 1) du -= g.gn[2];
+  if (du < -1) du += g.gn[2];
+  const int ku = home - g.z0 + du;
+  return ku < 0 ? -1 : (ku >= g.n[2] ? -2 : (int)(cell + (long)du * plane));
+}
+
 // One position sub-flow Theta<comp = A> for one particle held in registers, any position
 // (include/strugepic_propagators.hpp:80-244): weights from global coordinates, <= 2 segments,
 // B gathered through L1/L2, deposition with native FP64 global reductions (RED.E.ADD.F64),
-// reflection (util.hpp:172-186), periodic wrap (Redistribute, hpp:368).  Used by the
+// reflection (util.hpp:172-186), periodic wrap (Redistribute, hpp:368; optional).  Used by the
 // thread-per-particle kernels and by the continuation of particles that left their cell
 // inside a fused axis block.  The triple sums are factorised (push axis innermost, then u, then l).
 template <class I, int A>
 SPIC_DI void theta_axis_one(const Grid& g, double (&x)[3], double (&v)[3], double* __restrict__ E,
-                            const double* __restrict__ B, double q, double qm, double dt, int* __restrict__ flags) {
+                            const double* __restrict__ B, double q, double qm, double dt, int* __restrict__ flags,
+                            bool wrap = true) {
   constexpr int U = (A + 1) % 3, L = (A + 2) % 3;  // hpp:90-91
   const long st[3] = {1, g.pj, g.pk};
   double xa = x[A];
@@ -126,7 +141,7 @@ SPIC_DI void theta_axis_one(const Grid& g, double (&x)[3], double (&v)[3], doubl
   } else {
     xa = xa + dt * va;  // hpp:237
   }
-  x[A] = wrap_periodic(xa, g.gn[A], g.per[A], flags);
+  x[A] = wrap ? wrap_periodic(xa, g.gn[A], g.per[A], flags) : xa;  // (no wrap: the caller keeps slab coordinates)
   v[L] += qm * r1;  // hpp:240
   v[U] += qm * r2;  // hpp:241
 }

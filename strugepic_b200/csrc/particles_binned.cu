@@ -238,8 +238,7 @@ __global__ void __launch_bounds__(kThreads, 2)
           if (m < mv.cap) {
             int dest;
             if (A == 2) {
-              const int knew = newA - g.z0;
-              dest = knew < 0 ? -1 : (knew >= g.n[2] ? -2 : (int)(cell + (long)(knew - cc[2]) * cstride[2]));
+              dest = z_dest(g, cell, homeA, newA);
             } else {
               dest = (int)(cell + (long)(newA - homeA) * cstride[A]);
             }
@@ -596,9 +595,7 @@ __global__ void __launch_bounds__(kThreads, 2)
           const long cell = cbeg + ci;
           int dest;
           if (A == 2) {
-            const int knew = newA - g.z0;
-            dest = knew < 0 ? -1
-                            : (knew >= g.n[2] ? -2 : (int)(cell + (long)(knew - s_cc[ci][2]) * g.n[0] * g.n[1]));
+            dest = z_dest(g, cell, homeA, newA);
           } else {
             dest = (int)(cell + (long)(newA - homeA) * (A == 0 ? 1 : g.n[0]));
           }
@@ -1279,7 +1276,6 @@ void engine_destroy(Ctx* c) {
   if (e->cub_tmp) cudaFree(e->cub_tmp);
   if (e->d_scalar) cudaFree(e->d_scalar);
   if (e->block_work) cudaFree(e->block_work);
-  if (e->block_queues) cudaFree(e->block_queues);
   delete e;
   c->engine = nullptr;
 }
@@ -1392,14 +1388,17 @@ int engine_axis_block(Ctx* c, Species& s, double h) {
   EngineState* e = eng(c);
   int rc;
   if ((rc = fused_axis_block(c, s, h))) return rc;
-  // the overflow tail runs through the thread-per-particle kernels BEFORE new overflow can join it
-  static const int prog[6] = {0, 1, 2, 2, 1, 0};
-  for (int k = 0; k < 6; ++k) launch_theta_axis_direct(c, s.d, s.capd, s.d_nd, s.q, s.m, prog[k], h);
+  // the overflow tail takes the general per-particle code BEFORE new overflow can join it
+  if ((rc = fused_axis_tail(c, s, h))) return rc;
   if ((rc = fused_axis_continue(c, s, h))) return rc;
   int nb = (int)((e->mv.cap + 255) / 256);
   if (nb > c->sm_count * 8) nb = c->sm_count * 8;
   k_insert_movers<<<nb, 256, 0, c->stream>>>(e->mv, s.b, s.start, s.count, s.d, s.d_nd, s.capd, c->d_flags);
   c->launches++;
+  if (c->cfg.nranks > 1) {  // movers that left the slab (dest -1 / -2) -> the send buffers of the migration step
+    rc = comm_collect_leavers(c, s, e->mv.x, e->mv.v, e->mv.dest, e->mv.n, e->mv.cap);
+    if (rc) return rc;
+  }
   SPIC_CUDA_CHECK(c, cudaMemsetAsync(e->mv.n, 0, sizeof(unsigned), c->stream));
   return SPIC_OK;
 }
@@ -1546,11 +1545,6 @@ int engine_set_option(Ctx* c, const char* name, double value) {
   }
   if (!strcmp(name, "fuse")) {
     e->fuse = value != 0;
-    return SPIC_OK;
-  }
-  if (!strcmp(name, "block_kernel")) {
-    if (value != 1 && value != 2) return SPIC_EINVAL;
-    e->block_kernel = (int)value;
     return SPIC_OK;
   }
   if (!strcmp(name, "cells_per_block")) {

@@ -471,8 +471,7 @@ __global__ void __launch_bounds__(kThreads, 2)
       if (moves) {  // destination bin (or -1 / -2: leaves through the low / high z face of the slab)
         const long cell = cbeg_blk + mc;
         if (A == 2) {
-          const int knew = newA - g.z0, kold = homeA - g.z0;
-          dest = knew < 0 ? -1 : (knew >= g.n[2] ? -2 : (int)(cell + (long)(knew - kold) * g.n[0] * g.n[1]));
+          dest = z_dest(g, cell, homeA, newA);
         } else {
           dest = (int)(cell + (long)(newA - homeA) * (A == 0 ? 1 : g.n[0]));
         }

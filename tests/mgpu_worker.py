@@ -29,6 +29,7 @@ def main():
     case = sys.argv[1] if len(sys.argv) > 1 else "p8"
     interp = 0 if case.startswith("p8") else 1
     nz = 4 * world if case.endswith("thin") else 6 * world
+    fuse = 0 if case.endswith("nofuse") else 1  # fused axis blocks (guard width W + 1) / launch per sub-flow
     n_cell = (12, 10, nz)
     ppc, vth = 6, 0.25
     E, B = util.rng_fields(n_cell, 77, 0.3)
@@ -39,6 +40,7 @@ def main():
     ids = [spic.comm_unique_id() if rank == 0 else None]
     dist.broadcast_object_list(ids, src=0)
     s.comm_init(ids[0])
+    s.set_option("fuse", fuse)
     k0, k1 = s.lo[2], s.lo[2] + s.n[2]
     assert s.n[2] == nz // world
     s.set_field(0, E[:, k0:k1])

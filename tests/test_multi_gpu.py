@@ -14,7 +14,7 @@ def _ngpu():
     return torch.cuda.device_count()
 
 
-@pytest.mark.parametrize("case", ["p8", "pwl", "p8_thin"])
+@pytest.mark.parametrize("case", ["p8", "pwl", "p8_thin", "p8_nofuse"])
 @pytest.mark.parametrize("world", [2, 4])
 def test_slab_decomposition_matches_oracle(world, case):
     if _ngpu() < world:

@@ -274,14 +274,13 @@ def test_kernel_variants_agree_with_oracle(variant):
 
 
 @pytest.mark.parametrize("interp", [0, 1])
-@pytest.mark.parametrize("fuse", [0, 1, 2])
+@pytest.mark.parametrize("fuse", [0, 1])
 @pytest.mark.parametrize("mode", [0, 1])
 def test_fused_axis_block_and_reference_schedule(fuse, interp, mode):
     """Theta_map2/4 with the six position sub-flows of every map2 fused into one pass (option fuse = 1, the
     default on periodic boxes) and with the reference's launch-per-sub-flow schedule (fuse = 0) against the
     oracle; 40 ppc => cells with two batches, v_th = 0.08 => ~10 % of the particles leave their cell inside a
-    block and are finished by the general per-particle code (fuse = 1: block-per-cell-range kernel + continuation
-    kernel; fuse = 2: persistent kernel with in-kernel continuation, the default); both Theta_map4 modes."""
+    block and are finished by the general per-particle code (k_axis_continue); both Theta_map4 coefficient modes."""
     n_cell = (12, 10, 7)
     E, B = util.rng_fields(n_cell, 77, 0.3)
     parts = util.plasma(n_cell, 40, 0.08, 77)
@@ -290,9 +289,7 @@ def test_fused_axis_block_and_reference_schedule(fuse, interp, mode):
     # (the reference's own Theta_map4 only knows alpha = 1, beta = -1: Yoshida is checked against the C port)
     o = ora.best_oracle(n_cell, interp=interp) if mode == 0 else util.make_oracle("port", n_cell, (1, 1, 1), interp)
     s = spic().Simulation(n_cell, interp=interp, map4_mode=mode)
-    s.set_option("fuse", 1 if fuse else 0)
-    if fuse:
-        s.set_option("block_kernel", fuse)
+    s.set_option("fuse", fuse)
     s.set_option("time_kernels", 1)
     for t in (o, s):
         util.load_state(t, E, B, parts, q, m)
