@@ -344,7 +344,8 @@ def ours_main(a):
     roofline = {"kernel": kname, "bound": "hbm", "achieved": achieved, "peak": peaks["hbm_gbs"],
                 "unit": "GB/s", "frac": achieved / peaks["hbm_gbs"],
                 "traffic": traffic[tkey] * npart_local if traffic and tkey in traffic else None,
-                "traffic_source": (traffic["capture"] + "; DRAM read+write bytes per particle x the particles of one launch here")
+                "traffic_source": (traffic["axis_block_capture" if fused else "capture"] +
+                                   "; DRAM read+write bytes per particle x the particles of one launch here")
                 if traffic and tkey in traffic else None,
                 "peak_source": peak_src, "avg_launch_ms": ax_avg, "launches_timed": ax_n,
                 "reference_subflows_per_launch": sub_per_launch,

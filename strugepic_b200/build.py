@@ -22,7 +22,7 @@ LIB = os.path.join(LIBDIR, "libstrugepic_b200.so")
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 FLAGS = ["-std=c++17", "-O3", "-lineinfo", "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr",
-         "--expt-extended-lambda", "-Xptxas", "-v"]
+         "--expt-extended-lambda", "-Xptxas", "-v"] + os.environ.get("SPIC_EXTRA_NVCC_FLAGS", "").split()
 
 
 def _sources():

@@ -122,7 +122,9 @@ SPIC_DI void theta_axis_one(const Grid& g, double (&x)[3], double (&v)[3], doubl
 #pragma unroll
         for (int tc = 0; tc < I::NWP; ++tc) {
           const long idx = row + tc * st[A];
+#ifndef SPIC_EXPERIMENT_NO_GENERAL_RED  // (timing experiment only: how much of the general code is the reductions)
           atomicAdd(&Ea[idx], mul * Iw[tc]);  // hpp:215
+#endif
           s1 = fma(__ldg(&Bu[idx]), Iw[tc], s1);
           s2 = fma(__ldg(&Bl[idx]), Iw[tc], s2);
         }

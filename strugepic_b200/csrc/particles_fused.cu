@@ -364,13 +364,16 @@ __global__ void __launch_bounds__(kThreads, 2)
       const bool first = off == 0;
       bool alive = valid;
 
-      // x(h) y(h) z(2h) y(h) x(h) as a LOOP over the sub-flows.  Only TWO weight sets are alive at a time:
-      // sub-flow A reads the sets of U = (A+1)%3 and L = (A+2)%3, then the set of A is evaluated at the new
-      // position and takes the place of the one the next sub-flow does not need.  The sets are rotated so that
-      // P is always U and Q always L (every array index is static):
-      //   step   -2   -1 |  0    1    2    3    4
-      //   axis    z    y |  x    y    z    y    x        (steps -2, -1 only evaluate)
-      //   P,Q    z,-  y,z| z,x  x,y  z,x  y,z            (after the step = at the start of the next one)
+      // x(h) y(h) z(2h) y(h) x(h) as a LOOP over the sub-flows.  Only TWO weight sets are alive at a time, in the
+      // register slots P and Q: sub-flow A reads the sets of U = (A+1)%3 and L = (A+2)%3, then the set of A is
+      // evaluated at the new position INTO THE SLOT OF THE SET THE NEXT SUB-FLOW DOES NOT NEED -- no set is ever
+      // moved.  Which slot holds U and which L depends on the axis alone, so each axis-specific part exists once
+      // and every array index is static:
+      //   step        -2   -1 |  0     1     2     3     4
+      //   axis         z    y |  x     y     z     y     x      (steps -2, -1 only evaluate)
+      //   reads (U,L)         | P,Q   Q,P   P,Q   Q,P   P,Q
+      //   new set ->   Q    P |  P     Q     Q     P     -
+      //   P,Q after   -,z  y,z| x,z   x,y   x,z   y,z
       double P1[NW1] = {}, Pp[NWP] = {}, Q1[NW1] = {}, Qp[NWP] = {};
 #pragma unroll 1
       for (int step = -2; step < 5; ++step) {
@@ -387,9 +390,9 @@ __global__ void __launch_bounds__(kThreads, 2)
           if (leaves) x1 = xs;
           double I0[NWP];
           eval_iwp_in<I>(xs, x1, hA, I0);  // hpp:178-186
-          if (A == 0) axis_part<I, 0>(x, v, x1, I0, P1, Pp, Q1, Qp, sB, sW, nq, qm, lane);
-          else if (A == 1) axis_part<I, 1>(x, v, x1, I0, P1, Pp, Q1, Qp, sB, sW, nq, qm, lane);
-          else axis_part<I, 2>(x, v, x1, I0, P1, Pp, Q1, Qp, sB, sW, nq, qm, lane);
+          if (A == 0) axis_part<I, 0>(x, v, x1, I0, P1, Pp, Q1, Qp, sB, sW, nq, qm, lane);       // U = y in P, L = z in Q
+          else if (A == 1) axis_part<I, 1>(x, v, x1, I0, Q1, Qp, P1, Pp, sB, sW, nq, qm, lane);  // U = z in Q, L = x in P
+          else axis_part<I, 2>(x, v, x1, I0, P1, Pp, Q1, Qp, sB, sW, nq, qm, lane);              // U = x in P, L = y in Q
           __syncwarp();
           deposit_records<I>(sW, sAcc + A * (NACC * 32), first && step < 3, nit, lane);
           __syncwarp();  // the record area is free again
@@ -397,21 +400,12 @@ __global__ void __launch_bounds__(kThreads, 2)
         if (step < 4) {
           // f = x - cell is exact: the particle lies inside its bin cell
           const double f = (A == 0 ? x[0] : (A == 1 ? x[1] : x[2])) - sH[A];
-          double N1[NW1], Np[NWP];
-          eval_w1_in<I>(f, N1);
-          eval_wp_in<I>(f, Np);
-          const bool keepQ = step == 0 || step == 1;  // the next sub-flow reads (old Q, new) : (new, old P)
-#pragma unroll
-          for (int t = 0; t < NW1; ++t) {
-            const double pv = P1[t], qv = Q1[t];
-            P1[t] = keepQ ? qv : N1[t];
-            Q1[t] = keepQ ? N1[t] : pv;
-          }
-#pragma unroll
-          for (int t = 0; t < NWP; ++t) {
-            const double pv = Pp[t], qv = Qp[t];
-            Pp[t] = keepQ ? qv : Np[t];
-            Qp[t] = keepQ ? Np[t] : pv;
+          if (step == -1 || step == 0 || step == 3) {
+            eval_w1_in<I>(f, P1);
+            eval_wp_in<I>(f, Pp);
+          } else {
+            eval_w1_in<I>(f, Q1);
+            eval_wp_in<I>(f, Qp);
           }
         }
       }
