@@ -455,17 +455,26 @@ def run_e2e(a, sim, spic, np, torch, npart_local, npart, barrier, allmax, cells)
         t0 = time.perf_counter()
         sim.set_field(spic.FIELD_E, host_f[0])
         sim.set_field(spic.FIELD_B, host_f[1])
+        t1 = time.perf_counter()
         sim.set_particles(0, *[t[:n_live] for t in pinned])
+        sim.sync()
+        t2 = time.perf_counter()
         up = 48 * n_live + fbytes
         sim.map(a.order, 0.5)
+        sim.sync()
+        t3 = time.perf_counter()
         sim.get_field(spic.FIELD_E, out=host_f[0])
         sim.get_field(spic.FIELD_B, out=host_f[1])
+        sim.sync()
+        t4 = time.perf_counter()
         n_live = sim.num_particles()
         if n_live > cap:
             raise RuntimeError("e2e: pinned particle buffer too small after migration")
         sim.get_particles(0, out=[t[:n_live] for t in pinned])
         sim.sync()
         torch.cuda.synchronize()
+        phases = {"set_fields": t1 - t0, "set_particles": t2 - t1, "map": t3 - t2, "get_fields": t4 - t3,
+                  "get_particles": time.perf_counter() - t4}
         dt = time.perf_counter() - t0
         barrier()
         if s >= 1:
@@ -475,6 +484,7 @@ def run_e2e(a, sim, spic, np, torch, npart_local, npart, barrier, allmax, cells)
     return {"value": npart / t, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
             "bytes_are": "per rank",
             "ms_per_step": 1e3 * t, "steps": a.e2e_steps,
+            "phase_ms_last_step_rank0": {k: round(1e3 * v, 1) for k, v in phases.items()},
             "path": "spic_set_field x2 + spic_set_particles (pinned host -> HBM, re-binned) + spic_map + "
                     "spic_get_field x2 + spic_get_particles (HBM -> pinned host), wall clock, max over ranks"}
 
