@@ -29,6 +29,15 @@ struct EngineState {
   // (particles_fused.cu) and merge adjacent Theta_E; 0: the reference's launch-per-sub-flow schedule
   int fuse = 1;
   unsigned* block_work = nullptr;   // chunk counter of the fused axis-block kernel
+  // continuation of the ejected particles: sort key (home cell) per mover-list entry + radix-sort buffers
+  unsigned* cont_key = nullptr;
+  unsigned cont_key_cap = 0;
+  unsigned* cont_key2 = nullptr;
+  unsigned* cont_idx = nullptr;
+  unsigned* cont_perm = nullptr;
+  unsigned cont_sort_cap = 0;
+  void* cont_tmp = nullptr;
+  size_t cont_tmp_bytes = 0;
   unsigned long long* d_scalar = nullptr;  // small device scratch (8 words)
 };
 EngineState* eng(Ctx* c);

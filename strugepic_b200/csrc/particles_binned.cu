@@ -1276,6 +1276,8 @@ void engine_destroy(Ctx* c) {
   if (e->cub_tmp) cudaFree(e->cub_tmp);
   if (e->d_scalar) cudaFree(e->d_scalar);
   if (e->block_work) cudaFree(e->block_work);
+  for (void* p : {(void*)e->cont_key, (void*)e->cont_key2, (void*)e->cont_idx, (void*)e->cont_perm, e->cont_tmp})
+    if (p) cudaFree(p);
   delete e;
   c->engine = nullptr;
 }

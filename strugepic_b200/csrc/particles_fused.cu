@@ -40,6 +40,8 @@
 // Only for fully periodic boxes (walls need the reference's order around MABC, hpp:516).  With z slabs over
 // several ranks the guard width must be W + 1: a particle that left the slab in Theta_z finishes its
 // Theta_y, Theta_x one cell outside before it migrates (Redistribute once per block, hpp:368).
+#include <cub/device/device_radix_sort.cuh>
+
 #include "engine.cuh"
 #include "particle_math.cuh"
 
@@ -96,9 +98,10 @@ SPIC_DI double gather_block(const double* blk, const double (&w0)[N0], const dou
   return a2;
 }
 
-// Appends the lanes with `go` to the mover list with code `code`; those lanes become resting padding.
-SPIC_DI void eject(bool go, int code, double (&x)[3], double (&v)[3], const double* hc, bool& alive,
-                   const MoverList& mv, int* __restrict__ flags, int lane) {
+// Appends the lanes with `go` to the mover list with code `code` (and their home cell to `ekey`, the sort key of
+// the continuation); those lanes become resting padding.
+SPIC_DI void eject(bool go, int code, unsigned cell, unsigned* __restrict__ ekey, double (&x)[3], double (&v)[3],
+                   const double* hc, bool& alive, const MoverList& mv, int* __restrict__ flags, int lane) {
   const unsigned m = __ballot_sync(kFull, go);
   if (m == 0) return;
   unsigned base = 0;
@@ -114,6 +117,7 @@ SPIC_DI void eject(bool go, int code, double (&x)[3], double (&v)[3], const doub
         mv.v[d][slot] = v[d];
       }
       mv.dest[slot] = code;
+      ekey[slot] = cell;
     } else {
       atomicOr(&flags[1], 1);
     }
@@ -231,7 +235,7 @@ template <class I>
 __global__ void __launch_bounds__(kThreads, 2)
     k_axis_block(Grid g, ParticleSoA p, const long* __restrict__ start, int* __restrict__ count,
                  double* __restrict__ E, const double* __restrict__ B, double q, double qm, double h, MoverList mv,
-                 int* __restrict__ flags, long ncell, unsigned* __restrict__ work) {
+                 int* __restrict__ flags, long ncell, unsigned* __restrict__ work, unsigned* __restrict__ ekey) {
   constexpr int NW1 = I::NW1, NWP = I::NWP;
   using Lay = BlockLayout<I>;
   constexpr int NS = Lay::NS, SB = Lay::SB, SP = Lay::SP, SW = Lay::SW, NACC = Lay::NACC, NSUB = Lay::NSUB;
@@ -385,7 +389,8 @@ __global__ void __launch_bounds__(kThreads, 2)
           double x1 = xa + (step == 2 ? 2.0 * h : h) * va;  // hpp:237
           // construct_segments (util.cpp:160-174): one segment  <=>  floor(x1) == cell  <=>  hA <= x1 < hA + 1
           const bool leaves = alive && !(x1 >= hA && x1 < hA + 1.0);
-          eject(leaves, kContBase - (step < 3 ? step : step + 1), x, v, sH, alive, mv, flags, lane);
+          eject(leaves, kContBase - (step < 3 ? step : step + 1), chunk * kChunk + ci, ekey, x, v, sH, alive, mv, flags,
+                lane);
           const double xs = leaves ? hA + 0.5 : xa;  // an ejected lane is a resting padding particle from here on
           if (leaves) x1 = xs;
           double I0[NWP];
@@ -462,8 +467,12 @@ __global__ void __launch_bounds__(kThreads, 2)
 template <class I>
 SPIC_DI void finish_program(const Grid& g, int resume, double (&x)[3], double (&v)[3], double* __restrict__ E,
                             const double* __restrict__ B, double q, double qm, double h, int* __restrict__ flags) {
+  // Every thread walks the whole program and skips the sub-flows it has behind it, so that the lanes of a
+  // warp run the SAME sub-flow at the same time: with the list sorted by cell their gathers and reductions then
+  // fall into shared 32-byte sectors (this code is bound by L1/L2 sector operations, not by issue slots).
 #pragma unroll 1
-  for (int k = resume; k < 6; ++k) {
+  for (int k = 0; k < 6; ++k) {
+    if (k < resume) continue;
     const int axis = k < 3 ? k : 5 - k;
     if (axis == 0) theta_axis_one<I, 0>(g, x, v, E, B, q, qm, h, flags);
     else if (axis == 1) theta_axis_one<I, 1>(g, x, v, E, B, q, qm, h, flags);
@@ -473,7 +482,7 @@ SPIC_DI void finish_program(const Grid& g, int resume, double (&x)[3], double (&
         const int kk = (int)floor(x[2]) - g.z0;
         if (kk < -1 || kk > g.n[2]) {  // more than one cell outside the slab: the stencil would leave the guards
           atomicOr(&flags[0], 1);
-          return;
+          resume = 6;
         }
       }
     }
@@ -497,13 +506,15 @@ SPIC_DI int finish_dest(const Grid& g, double (&x)[3], int* __restrict__ flags) 
 }
 
 // Finishes the sub-flows of the ejected particles (mover-list entries with a continuation code), one thread per
-// particle, and replaces the code by the particle's destination.
+// particle, and replaces the code by the particle's destination.  `perm` (optional) lists the entries sorted by
+// home cell: neighbouring lanes then work on neighbouring stencils.
 template <class I>
 __global__ void __launch_bounds__(128)
-    k_axis_continue(Grid g, MoverList mv, double* __restrict__ E, const double* __restrict__ B, double q, double qm,
-                    double h, int* __restrict__ flags) {
+    k_axis_continue(Grid g, MoverList mv, const unsigned* __restrict__ perm, double* __restrict__ E,
+                    const double* __restrict__ B, double q, double qm, double h, int* __restrict__ flags) {
   const unsigned n = min(*mv.n, mv.cap);
-  for (unsigned m = blockIdx.x * blockDim.x + threadIdx.x; m < n; m += gridDim.x * blockDim.x) {
+  for (unsigned t = blockIdx.x * blockDim.x + threadIdx.x; t < n; t += gridDim.x * blockDim.x) {
+    const unsigned m = perm ? perm[t] : t;
     const int code = mv.dest[m];
     if (code > kContBase) continue;
     double x[3] = {mv.x[0][m], mv.x[1][m], mv.x[2][m]}, v[3] = {mv.v[0][m], mv.v[1][m], mv.v[2][m]};
@@ -516,6 +527,10 @@ __global__ void __launch_bounds__(128)
     }
     mv.dest[m] = dest;
   }
+}
+
+__global__ void k_iota(unsigned* __restrict__ a, unsigned n) {
+  for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) a[i] = i;
 }
 
 // The overflow tail of the bins (particles that did not fit their bin at the last re-file): the whole block
@@ -548,6 +563,12 @@ int launch_block(Ctx* c, Species& s, double h) {
   long want = (nchunk + kWarps - 1) / kWarps;
   if (want > 2L * c->sm_count) want = 2L * c->sm_count;
   if (!e->block_work) SPIC_CUDA_CHECK(c, cudaMalloc(&e->block_work, sizeof(unsigned)));
+  if (e->cont_key_cap < e->mv.cap) {  // home cell of every ejected particle: the sort key of the continuation
+    if (e->cont_key) cudaFree(e->cont_key);
+    e->cont_key = nullptr;
+    SPIC_CUDA_CHECK(c, cudaMalloc(&e->cont_key, sizeof(unsigned) * (size_t)e->mv.cap));
+    e->cont_key_cap = e->mv.cap;
+  }
   SPIC_CUDA_CHECK(c, cudaMemsetAsync(e->block_work, 0, sizeof(unsigned), c->stream));
   const size_t smem = sizeof(double) * kWarps * BlockLayout<I>::PER_WARP;
   static bool attr = false;
@@ -556,7 +577,7 @@ int launch_block(Ctx* c, Species& s, double h) {
     attr = true;
   }
   k_axis_block<I><<<(int)want, kThreads, smem, c->stream>>>(c->g, s.b, s.start, s.count, c->E, c->B, s.q, s.q / s.m,
-                                                            h, e->mv, c->d_flags, ncell, e->block_work);
+                                                            h, e->mv, c->d_flags, ncell, e->block_work, e->cont_key);
   c->launches++;
   return SPIC_OK;
 }
@@ -575,13 +596,49 @@ int fused_axis_block(Ctx* c, Species& s, double h) {
 
 int fused_axis_continue(Ctx* c, Species& s, double h) {
   EngineState* e = eng(c);
+  // how many were ejected?  (one small read-back per block; the host only runs ahead of the stream anyway)
+  unsigned n = 0;
+  SPIC_CUDA_CHECK(c, cudaMemcpyAsync(&n, e->mv.n, sizeof(unsigned), cudaMemcpyDeviceToHost, c->stream));
+  SPIC_CUDA_CHECK(c, cudaStreamSynchronize(c->stream));
+  if (n > e->mv.cap) n = e->mv.cap;
+  if (n == 0) return SPIC_OK;
+  const unsigned* perm = nullptr;
+  if (n >= 4096) {  // sort the entries by home cell (radix sort of (cell, index) pairs)
+    if (e->cont_sort_cap < n) {
+      const unsigned want = n + n / 4 + 4096;
+      for (unsigned** p : {&e->cont_key2, &e->cont_idx, &e->cont_perm}) {
+        if (*p) cudaFree(*p);
+        *p = nullptr;
+        SPIC_CUDA_CHECK(c, cudaMalloc(p, sizeof(unsigned) * (size_t)want));
+      }
+      e->cont_sort_cap = want;
+      k_iota<<<c->sm_count * 4, 256, 0, c->stream>>>(e->cont_idx, want);
+      c->launches++;
+    }
+    int bits = 1;
+    while ((1L << bits) < c->g.cells() && bits < 32) ++bits;
+    size_t bytes = 0;
+    cub::DeviceRadixSort::SortPairs(nullptr, bytes, e->cont_key, e->cont_key2, e->cont_idx, e->cont_perm, (int)n, 0,
+                                    bits, c->stream);
+    if (bytes > e->cont_tmp_bytes) {
+      if (e->cont_tmp) cudaFree(e->cont_tmp);
+      e->cont_tmp = nullptr;
+      SPIC_CUDA_CHECK(c, cudaMalloc(&e->cont_tmp, bytes));
+      e->cont_tmp_bytes = bytes;
+    }
+    SPIC_CUDA_CHECK(c, cub::DeviceRadixSort::SortPairs(e->cont_tmp, bytes, e->cont_key, e->cont_key2, e->cont_idx,
+                                                       e->cont_perm, (int)n, 0, bits, c->stream));
+    c->launches += 3;
+    perm = e->cont_perm;
+  }
   KernelTimer t(c, KT_OTHER);
-  const int grid = c->sm_count * 16;
+  long nb = ((long)n + 127) / 128;
+  if (nb > (long)c->sm_count * 16) nb = (long)c->sm_count * 16;
   const double qm = s.q / s.m;
   if (c->cfg.interp == SPIC_INTERP_P8R2)
-    k_axis_continue<InterpP8R2><<<grid, 128, 0, c->stream>>>(c->g, e->mv, c->E, c->B, s.q, qm, h, c->d_flags);
+    k_axis_continue<InterpP8R2><<<(int)nb, 128, 0, c->stream>>>(c->g, e->mv, perm, c->E, c->B, s.q, qm, h, c->d_flags);
   else
-    k_axis_continue<InterpPWL><<<grid, 128, 0, c->stream>>>(c->g, e->mv, c->E, c->B, s.q, qm, h, c->d_flags);
+    k_axis_continue<InterpPWL><<<(int)nb, 128, 0, c->stream>>>(c->g, e->mv, perm, c->E, c->B, s.q, qm, h, c->d_flags);
   c->launches++;
   return SPIC_OK;
 }
