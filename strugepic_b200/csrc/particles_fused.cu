@@ -509,7 +509,7 @@ SPIC_DI int finish_dest(const Grid& g, double (&x)[3], int* __restrict__ flags) 
 // particle, and replaces the code by the particle's destination.  `perm` (optional) lists the entries sorted by
 // home cell: neighbouring lanes then work on neighbouring stencils.
 template <class I>
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(128, 4)
     k_axis_continue(Grid g, MoverList mv, const unsigned* __restrict__ perm, double* __restrict__ E,
                     const double* __restrict__ B, double q, double qm, double h, int* __restrict__ flags) {
   const unsigned n = min(*mv.n, mv.cap);
