@@ -112,6 +112,8 @@ int halo_sum(Ctx* c, double* F, int comp) {
 }
 }  // namespace
 
+static int flush_pending(spic_ctx* c);  // applies the deferred trailing Theta_E of the last fused map (below)
+
 extern "C" {
 
 const char* spic_last_error(const spic_ctx* ctx) { return ctx ? ctx->err.c_str() : g_create_error.c_str(); }
@@ -216,6 +218,7 @@ int spic_destroy(spic_ctx* c) {
 int spic_sync(spic_ctx* c) {
   if (!c) return SPIC_EINVAL;
   cudaSetDevice(c->cfg.device);
+  if (int frc = flush_pending(c)) return frc;
   return check_flags(c);
 }
 
@@ -231,6 +234,7 @@ int spic_local_box(const spic_ctx* c, int32_t lo[3], int32_t n[3]) {
 int spic_set_uniform_field(spic_ctx* c, int which, const double val[3]) {
   if (!c || (which != SPIC_FIELD_E && which != SPIC_FIELD_B)) return SPIC_EINVAL;
   cudaSetDevice(c->cfg.device);
+  if (int frc = flush_pending(c)) return frc;
   double* F = which == SPIC_FIELD_E ? c->E : c->B;
   launch_set_uniform(c, F, val);
   return halo_fill(c, F);
@@ -238,6 +242,7 @@ int spic_set_uniform_field(spic_ctx* c, int which, const double val[3]) {
 int spic_set_field(spic_ctx* c, int which, const double* host) {
   if (!c || !host || (which != SPIC_FIELD_E && which != SPIC_FIELD_B)) return SPIC_EINVAL;
   cudaSetDevice(c->cfg.device);
+  if (int frc = flush_pending(c)) return frc;
   double* F = which == SPIC_FIELD_E ? c->E : c->B;
   const size_t bytes = sizeof(double) * 3 * (size_t)c->g.cells();
   SPIC_CUDA_CHECK(c, cudaMemcpyAsync(c->scratch, host, bytes, cudaMemcpyHostToDevice, c->stream));
@@ -250,6 +255,7 @@ int spic_set_field(spic_ctx* c, int which, const double* host) {
 int spic_get_field(spic_ctx* c, int which, double* host) {
   if (!c || !host || (which != SPIC_FIELD_E && which != SPIC_FIELD_B)) return SPIC_EINVAL;
   cudaSetDevice(c->cfg.device);
+  if (int frc = flush_pending(c)) return frc;
   const double* F = which == SPIC_FIELD_E ? c->E : c->B;
   const size_t bytes = sizeof(double) * 3 * (size_t)c->g.cells();
   launch_pack_field(c, F, c->scratch);
@@ -280,6 +286,7 @@ int spic_add_species(spic_ctx* c, double q, double m, int64_t n, const double* x
   if (!c || n < 0 || m == 0.0) return SPIC_EINVAL;
   if (n > 0 && (!x || !y || !z || !vx || !vy || !vz)) return fail(c, SPIC_EINVAL, "null particle array");
   cudaSetDevice(c->cfg.device);
+  if (int frc = flush_pending(c)) return frc;
   Species s;
   s.q = q;
   s.m = m;
@@ -297,6 +304,7 @@ int spic_set_particles(spic_ctx* c, int species, int64_t n, const double* x, con
                        const double* vx, const double* vy, const double* vz) {
   if (!c || species < 0 || species >= (int)c->sp.size() || n < 0) return SPIC_EINVAL;
   cudaSetDevice(c->cfg.device);
+  if (int frc = flush_pending(c)) return frc;
   Species& s = c->sp[species];
   if (n > 0 && (!x || !y || !z || !vx || !vy || !vz)) return fail(c, SPIC_EINVAL, "null particle array");
   const double* hx[3] = {x, y, z};
@@ -326,6 +334,7 @@ int spic_set_particles(spic_ctx* c, int species, int64_t n, const double* x, con
 int spic_load_uniform_plasma(spic_ctx* c, double q, double m, int32_t ppc, double v_th, uint64_t seed) {
   if (!c || ppc < 1 || m == 0.0) return SPIC_EINVAL;
   cudaSetDevice(c->cfg.device);
+  if (int frc = flush_pending(c)) return frc;
   Species s;
   s.q = q / ppc;  // q_c, m_c: src/strugepic_util.cpp:273-274
   s.m = m / ppc;
@@ -353,6 +362,7 @@ int spic_num_particles(spic_ctx* c, int species, int64_t* n) {
 int spic_get_particles(spic_ctx* c, int species, double* x, double* y, double* z, double* vx, double* vy, double* vz) {
   if (!c || species < 0 || species >= (int)c->sp.size()) return SPIC_EINVAL;
   cudaSetDevice(c->cfg.device);
+  if (int frc = flush_pending(c)) return frc;
   Species& s = c->sp[species];
   double* hx[3] = {x, y, z};
   double* hv[3] = {vx, vy, vz};
@@ -367,9 +377,9 @@ int spic_get_particles(spic_ctx* c, int species, double* x, double* y, double* z
 }
 
 // ---- sub-flows ------------------------------------------------------------------------
-int spic_theta_axis(spic_ctx* c, int comp, double dt) {
-  if (!c || comp < 0 || comp > 2) return SPIC_EINVAL;
-  cudaSetDevice(c->cfg.device);
+}  // extern "C"
+
+static int theta_axis_impl(spic_ctx* c, int comp, double dt) {
   int rc = halo_fill(c, c->B);  // B.FillBoundary            hpp:350
   if (rc) return rc;
   launch_zero_guards(c, c->E);  // E.setBndry(0)             hpp:351-352
@@ -386,9 +396,7 @@ int spic_theta_axis(spic_ctx* c, int comp, double dt) {
   return rc;
 }
 
-int spic_theta_E(spic_ctx* c, double dt) {
-  if (!c) return SPIC_EINVAL;
-  cudaSetDevice(c->cfg.device);
+static int theta_E_impl(spic_ctx* c, double dt) {
   int rc = halo_fill(c, c->E);  // E.FillBoundary  hpp:56
   if (rc) return rc;
   for (auto& s : c->sp) {       // push_V_E        hpp:57-62
@@ -402,40 +410,39 @@ int spic_theta_E(spic_ctx* c, double dt) {
   return SPIC_OK;
 }
 
-int spic_theta_B(spic_ctx* c, double dt) {
-  if (!c) return SPIC_EINVAL;
-  cudaSetDevice(c->cfg.device);
+static int theta_B_impl(spic_ctx* c, double dt) {
   int rc = halo_fill(c, c->B);  // cpp:104
   if (rc) return rc;
   launch_curl_B_into_E(c, dt);  // cpp:105-110
   return SPIC_OK;
 }
 
-int spic_source(spic_ctx* c, int pos, int comp, double E0, double omega, double dt, double t) {
-  if (!c || comp < 0 || comp > 2) return SPIC_EINVAL;
-  cudaSetDevice(c->cfg.device);
-  if (pos >= 0 && pos < c->g.n[0]) launch_source(c, pos, comp, 2 * E0 * sin(omega * t) * dt);  // cpp:32-36
-  return halo_fill(c, c->E);                                                                   // cpp:40
+// Applies the deferred trailing Theta_E of the last fused map (see Ctx::pending_E).
+static int flush_pending(spic_ctx* c) {
+  if (c->pending_E == 0.0) return SPIC_OK;
+  const double d = c->pending_E;
+  c->pending_E = 0.0;
+  return theta_E_impl(c, d);
 }
 
 static int map2(spic_ctx* c, double dt) {  // hpp:559-572
   int rc;
-  if ((rc = spic_theta_E(c, dt / 2))) return rc;
-  if ((rc = spic_theta_axis(c, 0, dt / 2))) return rc;
-  if ((rc = spic_theta_axis(c, 1, dt / 2))) return rc;
-  if ((rc = spic_theta_axis(c, 2, dt / 2))) return rc;
-  if ((rc = spic_theta_B(c, dt))) return rc;
-  if ((rc = spic_theta_axis(c, 2, dt / 2))) return rc;
-  if ((rc = spic_theta_axis(c, 1, dt / 2))) return rc;
-  if ((rc = spic_theta_axis(c, 0, dt / 2))) return rc;
-  return spic_theta_E(c, dt / 2);
+  if ((rc = theta_E_impl(c, dt / 2))) return rc;
+  if ((rc = theta_axis_impl(c, 0, dt / 2))) return rc;
+  if ((rc = theta_axis_impl(c, 1, dt / 2))) return rc;
+  if ((rc = theta_axis_impl(c, 2, dt / 2))) return rc;
+  if ((rc = theta_B_impl(c, dt))) return rc;
+  if ((rc = theta_axis_impl(c, 2, dt / 2))) return rc;
+  if ((rc = theta_axis_impl(c, 1, dt / 2))) return rc;
+  if ((rc = theta_axis_impl(c, 0, dt / 2))) return rc;
+  return theta_E_impl(c, dt / 2);
 }
 
 // The axis block of one Theta_map2(dt): Theta_B(dt), then x(h) y(h) z(h) z(h) y(h) x(h) with h = dt/2 as one
 // fused pass per species.  Theta_B only adds dt * curl B into E and the axis sub-flows only add their
 // currents into E and read B, which neither changes (hpp:562-569, cpp:102-113): the order is free.
 static int axis_block(spic_ctx* c, double dt) {
-  int rc = spic_theta_B(c, dt);  // fills the guards of B (cpp:104): B does not change until the next Theta_E
+  int rc = theta_B_impl(c, dt);  // fills the guards of B (cpp:104): B does not change until the next Theta_E
   if (rc) return rc;
   launch_zero_guards(c, c->E);  // E.setBndry(0), hpp:351-352: the guards collect this block's currents
   for (auto& s : c->sp)
@@ -448,36 +455,37 @@ static int axis_block(spic_ctx* c, double dt) {
 
 // Theta_map2(d_0) o ... o Theta_map2(d_{n-1}) with fused axis blocks; adjacent Theta_E halves are merged:
 // Theta_E(s) o Theta_E(t) = Theta_E(s + t) exactly, because Theta_E changes neither E nor the positions
-// (hpp:52-71, 339-341; cpp:93-95).
+// (hpp:52-71, 339-341; cpp:93-95).  That includes the half kick a previous call left pending; the last half kick
+// of this call is left pending in turn (option "defer_kick") and applied by whatever entry point runs next.
 static int fused_maps(spic_ctx* c, const double* d, int n) {
   int rc;
-  if ((rc = spic_theta_E(c, d[0] / 2))) return rc;
+  const double lead = d[0] / 2 + c->pending_E;
+  c->pending_E = 0.0;
+  if ((rc = theta_E_impl(c, lead))) return rc;
   for (int i = 0; i < n; ++i) {
     if ((rc = axis_block(c, d[i]))) return rc;
-    const double next = i + 1 < n ? d[i + 1] : 0.0;
-    if ((rc = spic_theta_E(c, d[i] / 2 + next / 2))) return rc;
+    if (i + 1 < n) {
+      if ((rc = theta_E_impl(c, d[i] / 2 + d[i + 1] / 2))) return rc;
+    } else if (c->defer_kick) {
+      c->pending_E = d[i] / 2;
+    } else if ((rc = theta_E_impl(c, d[i] / 2))) {
+      return rc;
+    }
   }
   return SPIC_OK;
 }
 
-static int map_body(spic_ctx* c, int order, double dt);
-int spic_map(spic_ctx* c, int order, double dt) {
-  if (!c) return SPIC_EINVAL;
-  cudaSetDevice(c->cfg.device);
-  int rc = map_body(c, order, dt);
-  if (rc) return rc;
-  return engine_maintain(c);  // re-bin when the overflow tail has grown
-}
 static int map_body(spic_ctx* c, int order, double dt) {
   int rc;
+  const bool fuse = (order == 2 || order == 4) && engine_can_fuse(c);
+  if (!fuse && (rc = flush_pending(c))) return rc;
   if (order == 1) {  // hpp:548-557
-    if ((rc = spic_theta_B(c, dt))) return rc;
-    if ((rc = spic_theta_E(c, dt))) return rc;
-    if ((rc = spic_theta_axis(c, 2, dt))) return rc;
-    if ((rc = spic_theta_axis(c, 1, dt))) return rc;
-    return spic_theta_axis(c, 0, dt);
+    if ((rc = theta_B_impl(c, dt))) return rc;
+    if ((rc = theta_E_impl(c, dt))) return rc;
+    if ((rc = theta_axis_impl(c, 2, dt))) return rc;
+    if ((rc = theta_axis_impl(c, 1, dt))) return rc;
+    return theta_axis_impl(c, 0, dt);
   }
-  const bool fuse = engine_can_fuse(c);
   if (order == 2) return fuse ? fused_maps(c, &dt, 1) : map2(c, dt);
   if (order == 4) {  // hpp:574-583; alpha = 1, beta = -1 in the reference (integer division at :578)
     const double alpha = c->cfg.map4_mode == SPIC_MAP4_YOSHIDA ? 1.0 / (2.0 - cbrt(2.0)) : 1.0;
@@ -489,6 +497,46 @@ static int map_body(spic_ctx* c, int order, double dt) {
     return map2(c, d[2]);
   }
   return fail(c, SPIC_EINVAL, "order must be 1, 2 or 4");
+}
+
+extern "C" {
+
+int spic_theta_axis(spic_ctx* c, int comp, double dt) {
+  if (!c || comp < 0 || comp > 2) return SPIC_EINVAL;
+  cudaSetDevice(c->cfg.device);
+  int rc = flush_pending(c);
+  return rc ? rc : theta_axis_impl(c, comp, dt);
+}
+
+int spic_theta_E(spic_ctx* c, double dt) {
+  if (!c) return SPIC_EINVAL;
+  cudaSetDevice(c->cfg.device);
+  int rc = flush_pending(c);
+  return rc ? rc : theta_E_impl(c, dt);
+}
+
+int spic_theta_B(spic_ctx* c, double dt) {
+  if (!c) return SPIC_EINVAL;
+  cudaSetDevice(c->cfg.device);
+  int rc = flush_pending(c);
+  return rc ? rc : theta_B_impl(c, dt);
+}
+
+int spic_source(spic_ctx* c, int pos, int comp, double E0, double omega, double dt, double t) {
+  if (!c || comp < 0 || comp > 2) return SPIC_EINVAL;
+  cudaSetDevice(c->cfg.device);
+  int rc = flush_pending(c);
+  if (rc) return rc;
+  if (pos >= 0 && pos < c->g.n[0]) launch_source(c, pos, comp, 2 * E0 * sin(omega * t) * dt);  // cpp:32-36
+  return halo_fill(c, c->E);                                                                   // cpp:40
+}
+
+int spic_map(spic_ctx* c, int order, double dt) {
+  if (!c) return SPIC_EINVAL;
+  cudaSetDevice(c->cfg.device);
+  int rc = map_body(c, order, dt);
+  if (rc) return rc;
+  return engine_maintain(c);  // re-bin when the overflow tail has grown
 }
 
 int spic_field_only_step(spic_ctx* c, int pos, int comp, double E0, double omega, double dt, int step) {
@@ -503,6 +551,7 @@ int spic_field_only_step(spic_ctx* c, int pos, int comp, double E0, double omega
 int spic_energy(spic_ctx* c, double out[2]) {
   if (!c || !out) return SPIC_EINVAL;
   cudaSetDevice(c->cfg.device);
+  if (int frc = flush_pending(c)) return frc;
   double ss[6];
   field_energy(c, ss);
   double* acc = c->scratch + 1024 * 3 + 8;
@@ -530,6 +579,7 @@ int spic_gauss_residual(spic_ctx* c, double* host) {
   if (!c || !host) return SPIC_EINVAL;
   if (c->cfg.nranks > 1) return fail(c, SPIC_EINVAL, "gauss residual is a single-rank diagnostic");
   cudaSetDevice(c->cfg.device);
+  if (int frc = flush_pending(c)) return frc;
   int rc = halo_fill(c, c->E);
   if (rc) return rc;
   double* out = c->scratch;
@@ -551,6 +601,7 @@ int spic_gauss_residual(spic_ctx* c, double* host) {
 int spic_number_density(spic_ctx* c, double* host) {
   if (!c || !host) return SPIC_EINVAL;
   cudaSetDevice(c->cfg.device);
+  if (int frc = flush_pending(c)) return frc;
   double* nd = nullptr;
   const size_t gbytes = sizeof(double) * (size_t)c->g.pc;
   SPIC_CUDA_CHECK(c, cudaMalloc(&nd, gbytes));
@@ -582,6 +633,7 @@ struct PlotHeader {
 int spic_plot_write(spic_ctx* c, const char* path) {
   if (!c || !path) return SPIC_EINVAL;
   cudaSetDevice(c->cfg.device);
+  if (int frc = flush_pending(c)) return frc;
   const size_t cells = (size_t)c->g.cells();
   std::vector<double> buf(7 * cells);
   int rc;
@@ -618,6 +670,7 @@ struct CkptHeader {
 int spic_checkpoint_write(spic_ctx* c, const char* path) {
   if (!c || !path) return SPIC_EINVAL;
   cudaSetDevice(c->cfg.device);
+  if (int frc = flush_pending(c)) return frc;
   FILE* f = fopen(path, "wb");
   if (!f) return fail(c, SPIC_EIO, std::string("cannot open ") + path);
   CkptHeader h{};
@@ -665,6 +718,7 @@ int spic_checkpoint_write(spic_ctx* c, const char* path) {
 int spic_checkpoint_read(spic_ctx* c, const char* path) {
   if (!c || !path) return SPIC_EINVAL;
   cudaSetDevice(c->cfg.device);
+  if (int frc = flush_pending(c)) return frc;
   FILE* f = fopen(path, "rb");
   if (!f) return fail(c, SPIC_EIO, std::string("cannot open ") + path);
   CkptHeader h{};
@@ -789,6 +843,12 @@ int spic_set_option(spic_ctx* c, const char* name, double value) {
   if (!c || !name) return SPIC_EINVAL;
   if (!strcmp(name, "time_kernels")) {
     c->time_kernels = value != 0;
+    return SPIC_OK;
+  }
+  cudaSetDevice(c->cfg.device);
+  if (int frc = flush_pending(c)) return frc;  // (options may change the schedule)
+  if (!strcmp(name, "defer_kick")) {
+    c->defer_kick = value != 0;
     return SPIC_OK;
   }
   return engine_set_option(c, name, value);

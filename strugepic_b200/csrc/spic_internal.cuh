@@ -101,6 +101,12 @@ struct Ctx {
   int sm_count = 148;
   int64_t launches = 0;
   bool time_kernels = false;
+  // Deferred trailing Theta_E of the last fused Theta_map2/4 (0 = none).  Theta_E(s) o Theta_E(t) = Theta_E(s + t),
+  // so the last half kick of one step and the first of the next run as one launch; every other entry point
+  // (getters, setters, single sub-flows, diagnostics, IO, sync) applies it first: the state a caller can observe
+  // is always the fully stepped one.  Option "defer_kick" = 0 turns it off.
+  double pending_E = 0.0;
+  bool defer_kick = true;
   struct TimedLaunch {
     cudaEvent_t e0, e1;
     int kind;

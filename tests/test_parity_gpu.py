@@ -307,6 +307,35 @@ def test_fused_axis_block_and_reference_schedule(fuse, interp, mode):
     print(fuse, interp, mode, errs, kt)
 
 
+def test_deferred_half_kick_is_invisible():
+    """The last Theta_E half of a fused map is deferred and merged with the first half of the next one
+    (Theta_E(s) o Theta_E(t) = Theta_E(s + t)); any observation applies it first.  Three chained Theta_map4 with
+    and without deferral, and with an observation between the steps, against the oracle."""
+    n_cell = (10, 9, 8)
+    E, B = util.rng_fields(n_cell, 91, 0.3)
+    parts = util.plasma(n_cell, 12, 0.05, 91)
+    q, m = -1.0 / 12, 100.0 / 12
+    o = ora.best_oracle(n_cell, interp=0)
+    util.load_state(o, E, B, parts, q, m)
+    for _ in range(3):
+        o.map(4, 0.5)
+    ref = util.state_of(o)
+    launches = {}
+    for mode in ("deferred", "observed", "immediate"):
+        s = spic().Simulation(n_cell, interp=0)
+        s.set_option("defer_kick", 0 if mode == "immediate" else 1)
+        s.set_option("time_kernels", 1)
+        util.load_state(s, E, B, parts, q, m)
+        for _ in range(3):
+            s.map(4, 0.5)
+            if mode == "observed":
+                s.get_total_energy()
+        util.compare_states(ref, util.state_of(s), 3 * TOL_STEP, 3 * TOL_STEP, box=n_cell)
+        launches[mode] = s.kernel_times()["push_V_E"][1]
+        s.close()
+    assert launches == {"deferred": 10, "observed": 12, "immediate": 12}, launches
+
+
 def test_errors_are_reported():
     sp = spic()
     with pytest.raises(sp.SpicError):
