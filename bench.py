@@ -407,7 +407,8 @@ def ours_main(a):
     sim.close()
     if rank == 0:
         line = {
-            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
+            "metric": METRIC if a.interp == "p8r2" and a.order == 4 else METRIC.replace("W8", "PWL" if a.interp == "pwl" else "W8").replace("4th-order split", "Theta_map%d" % a.order if a.order != 4 else "4th-order split"),
+            "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
             "ms_per_step": ms / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic",
             "config": {"workload": workload_name(a, world), "particles": npart, "cells": a.n ** 3 * world,
