@@ -98,6 +98,13 @@ int spic_add_species(spic_ctx* ctx, double q, double m, int64_t n, const double*
  * generated on the device from a counter-based RNG (strugepic_b200/synthetic.py is the
  * host twin); per-particle charge q/ppc and mass m/ppc as in the reference. */
 int spic_load_uniform_plasma(spic_ctx* ctx, double q, double m, int32_t ppc, double v_th, uint64_t seed);
+/* add_particle_density(geom, P, dist_func, ppc_max, m, q, v) with an arbitrary density profile
+ * (src/strugepic_util.cpp:267-311; bernstein_density :181-200, simple_line_density :206-208): the caller
+ * evaluates `int(dist_func(geom,i,j,k) * ppc_max)` on the host into count[k][j][i] over this rank's brick;
+ * particles are generated on the device like spic_load_uniform_plasma (identical when every count ==
+ * ppc_max).  rng_stride >= max(count) over the GLOBAL domain keys the counter-based RNG (0: ppc_max). */
+int spic_load_density_plasma(spic_ctx* ctx, double q, double m, int32_t ppc_max, int32_t rng_stride, double v_th,
+                             uint64_t seed, const int32_t* count);
 int spic_num_species(const spic_ctx* ctx);
 int spic_num_particles(spic_ctx* ctx, int species, int64_t* n);
 int spic_get_particles(spic_ctx* ctx, int species, double* x, double* y, double* z, double* vx,

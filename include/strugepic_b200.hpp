@@ -25,11 +25,22 @@
 #define STRUGEPIC_B200_HPP
 
 #include <array>
+#include <chrono>
+#include <cmath>
 #include <cstdint>
+#include <cstdio>
+#include <cstdlib>
+#include <fstream>
+#include <iostream>
+#include <sstream>
 #include <stdexcept>
 #include <string>
+#include <thread>
 #include <utility>
 #include <vector>
+
+#include <sys/stat.h>
+#include <sys/types.h>
 
 #include "strugepic_b200.h"
 
@@ -46,6 +57,52 @@ class Error : public std::runtime_error {
   int code_;
 };
 
+// ---- process environment (amrex::Initialize / ParallelDescriptor / amrex::Print) ------------------------
+// One process per GPU.  Rank and size come from the launcher's environment (RANK / WORLD_SIZE / LOCAL_RANK as
+// torchrun sets them, or OMPI_COMM_WORLD_* / PMI_* under an MPI launcher); a single process is rank 0 of 1.
+namespace ParallelDescriptor {
+namespace detail {
+inline int env_int(const char* const* names, int dflt) {
+  for (; *names; ++names)
+    if (const char* v = std::getenv(*names)) return std::atoi(v);
+  return dflt;
+}
+}  // namespace detail
+inline int MyProc() {
+  static const char* const n[] = {"RANK", "OMPI_COMM_WORLD_RANK", "PMI_RANK", "SLURM_PROCID", nullptr};
+  return detail::env_int(n, 0);
+}
+inline int NProcs() {
+  static const char* const n[] = {"WORLD_SIZE", "OMPI_COMM_WORLD_SIZE", "PMI_SIZE", "SLURM_NTASKS", nullptr};
+  return detail::env_int(n, 1);
+}
+inline int LocalRank() {
+  static const char* const n[] = {"LOCAL_RANK", "OMPI_COMM_WORLD_LOCAL_RANK", "SLURM_LOCALID", nullptr};
+  return detail::env_int(n, MyProc());
+}
+inline bool IOProcessor() { return MyProc() == 0; }
+}  // namespace ParallelDescriptor
+
+// amrex::Print(): a stream that only the IO rank writes
+class Print {
+ public:
+  ~Print() {
+    if (ParallelDescriptor::IOProcessor()) std::cout << ss_.str() << std::flush;
+  }
+  template <class T>
+  Print& operator<<(const T& v) {
+    ss_ << v;
+    return *this;
+  }
+  Print& operator<<(std::ostream& (*f)(std::ostream&)) {
+    f(ss_);
+    return *this;
+  }
+
+ private:
+  std::ostringstream ss_;
+};
+
 // amrex::Geometry for the only configuration the reference is self-consistent in
 // (ProbLo = 0, dx = dy = dz = 1)
 struct Geometry {
@@ -53,6 +110,10 @@ struct Geometry {
   std::array<int, 3> is_periodic;
   Geometry(std::array<int, 3> n, std::array<int, 3> per = {1, 1, 1}) : n_cell(n), is_periodic(per) {}
   bool isPeriodic(int d) const { return is_periodic[d] != 0; }
+  int lo(int) const { return 0; }                   // amrex::lbound(geom.Domain())
+  int hi(int d) const { return n_cell[d] - 1; }     // amrex::ubound(geom.Domain())
+  double ProbLo(int) const { return 0.0; }
+  double CellSize(int) const { return 1.0; }
   bool isAllPeriodic() const { return is_periodic[0] && is_periodic[1] && is_periodic[2]; }
 };
 
@@ -108,7 +169,8 @@ class Simulation {
   // W_range selects the interpolation compiled into the kernels (the reference picks it at link time)
   Simulation(const Geometry& geom, int W_range, int ng = 0, int device = 0, int map4_mode = SPIC_MAP4_REFERENCE,
              int nranks = 1, int rank = 0)
-      : geom_(geom), W_(W_range), E_(this, SPIC_FIELD_E), B_(this, SPIC_FIELD_B), P_(this) {
+      : geom_(geom), W_(W_range), nranks_(nranks), rank_(rank), E_(this, SPIC_FIELD_E), B_(this, SPIC_FIELD_B),
+        P_(this) {
     spic_config cfg{};
     for (int d = 0; d < 3; ++d) {
       cfg.n_cell[d] = geom.n_cell[d];
@@ -139,10 +201,52 @@ class Simulation {
   }
   void sync() const { check(spic_sync(ctx_)); }
   void comm_init(const void* nccl_unique_id_128) { check(spic_comm_init(ctx_, nccl_unique_id_128)); }
+  // Rendezvous without MPI: rank 0 creates the ncclUniqueId and publishes it through a file every rank of the
+  // node can read (`path`; default $SPIC_ID_FILE or /tmp/spic_nccl_id.$MASTER_PORT), the others poll for it.
+  void comm_bootstrap(std::string path = std::string(), double timeout_s = 120.0) {
+    if (nranks_ <= 1) return;
+    if (path.empty()) {
+      if (const char* e = std::getenv("SPIC_ID_FILE")) path = e;
+      else {
+        const char* port = std::getenv("MASTER_PORT");
+        path = std::string("/tmp/spic_nccl_id.") + (port ? port : "0");
+      }
+    }
+    char id[128];
+    if (rank_ == 0) {
+      check(spic_comm_unique_id(id));
+      const std::string tmp = path + ".tmp";
+      {
+        std::ofstream f(tmp, std::ios::binary | std::ios::trunc);
+        f.write(id, sizeof id);
+      }
+      if (std::rename(tmp.c_str(), path.c_str()) != 0) throw Error(SPIC_EIO, "cannot publish " + path);
+    } else {
+      const auto t0 = std::chrono::steady_clock::now();
+      for (;;) {
+        std::ifstream f(path, std::ios::binary);
+        if (f && f.read(id, sizeof id) && f.gcount() == (std::streamsize)sizeof id) break;
+        if (std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count() > timeout_s)
+          throw Error(SPIC_ENCCL, "timed out waiting for " + path);
+        std::this_thread::sleep_for(std::chrono::milliseconds(20));
+      }
+    }
+    comm_init(id);  // collective: returns once every rank has joined
+    if (rank_ == 0) std::remove(path.c_str());
+  }
+  int nranks() const { return nranks_; }
+  int rank() const { return rank_; }
+  // this rank's brick (z slab) in global cell indices
+  void local_box(std::array<int, 3>& lo, std::array<int, 3>& n) const {
+    std::int32_t l[3], m[3];
+    check(spic_local_box(ctx_, l, m));
+    for (int d = 0; d < 3; ++d) lo[d] = l[d], n[d] = m[d];
+  }
 
  private:
   Geometry geom_;
   int W_;
+  int nranks_, rank_;
   spic_ctx* ctx_ = nullptr;
   MultiFab E_, B_;
   CParticleContainer P_;
@@ -243,6 +347,71 @@ inline void add_particle_density_uniform(const Geometry&, CParticleContainer& P,
   Simulation& s = P.sim();
   s.check(spic_load_uniform_plasma(s.ctx(), q, m, ppc, v_th, seed));
 }
+// Density profiles of util.cpp:181-208.  A profile returns the fraction of ppc_max a cell receives.
+typedef double (*density_func)(const Geometry, int, int, int);
+inline double uniform_density(const Geometry, int, int, int) { return 1; }                    // util.cpp:202-204
+inline double simple_line_density(const Geometry, int i, int, int) { return 1.0 * i / 20; }   // util.cpp:206-208
+inline double bernstein_density(const Geometry geom, int i, int, int) {                       // util.cpp:181-200
+  const int nr = 380, ramp_end = nr + 320, fall_start = 1300;
+  if (i <= geom.lo(X) + 3 || i >= geom.hi(X) - 3) return 0;  // nothing near the x walls (reflect cells)
+  if (i < ramp_end) {
+    const int d = i - ramp_end;
+    return std::exp(-(d * d) / (2 * (nr / 3.5) * (nr / 3.5)));
+  }
+  if (i >= fall_start) {
+    const int d = i - fall_start;
+    return std::exp(-(d * d) / 26122.0);
+  }
+  return 1;
+}
+// add_particle_density(geom, P, dist_func, ppc_max, m, q, v) -- util.cpp:267-311.  The profile is evaluated on the
+// host (one int per cell), the particles are generated on the device.  The reference seeds std::mt19937 from
+// std::random_device (util.cpp:269-270: not reproducible); here the draw is a pure function of (seed, cell, p).
+inline void add_particle_density(const Geometry geom, CParticleContainer& P, density_func dist_func, int ppc_max,
+                                 double m, double q, double v, std::uint64_t seed = 12345) {
+  Simulation& s = P.sim();
+  std::array<int, 3> lo, n;
+  s.local_box(lo, n);
+  long stride = ppc_max;  // RNG key stride: the largest per-cell count of the GLOBAL box
+  for (int k = 0; k < geom.n_cell[2]; ++k)
+    for (int j = 0; j < geom.n_cell[1]; ++j)
+      for (int i = 0; i < geom.n_cell[0]; ++i) {
+        const long c = (long)(int)(dist_func(geom, i, j, k) * ppc_max);  // util.cpp:304
+        if (c > stride) stride = c;
+      }
+  std::vector<std::int32_t> count((std::size_t)n[0] * n[1] * n[2]);
+  std::size_t t = 0;
+  for (int k = lo[2]; k < lo[2] + n[2]; ++k)
+    for (int j = lo[1]; j < lo[1] + n[1]; ++j)
+      for (int i = lo[0]; i < lo[0] + n[0]; ++i) {
+        const int c = (int)(dist_func(geom, i, j, k) * ppc_max);
+        count[t++] = c > 0 ? c : 0;
+      }
+  s.check(spic_load_density_plasma(s.ctx(), q, m, ppc_max, (std::int32_t)stride, v, seed, count.data()));
+}
+// add_particle_n_per_cell(geom, P, m, q, v, n) -- util.cpp:314-348
+inline void add_particle_n_per_cell(const Geometry geom, CParticleContainer& P, double m, double q, double v, int n,
+                                    std::uint64_t seed = 12345) {
+  add_particle_density(geom, P, uniform_density, n, m, q, v, seed);
+}
+// print_Particle_info(geom, P) -- util.cpp:351-362: the POS / VEL lines test/particle_data.sh greps for
+inline void print_Particle_info(const Geometry&, CParticleContainer& P) {
+  Simulation& s = P.sim();
+  const int ns = spic_num_species(s.ctx());
+  for (int sp = 0; sp < ns; ++sp) {
+    const std::int64_t n = P.TotalNumberOfParticles(sp);
+    if (n == 0) continue;
+    std::vector<double> a[6];
+    for (auto& t : a) t.resize((std::size_t)n);
+    s.check(spic_get_particles(s.ctx(), sp, a[0].data(), a[1].data(), a[2].data(), a[3].data(), a[4].data(),
+                               a[5].data()));
+    for (std::int64_t p = 0; p < n; ++p) {
+      std::cout << "(" << sp << "," << p << "," << s.rank() << ")" << std::endl;
+      std::cout << "POS: [" << a[0][p] << "," << a[1][p] << "," << a[2][p] << "]" << std::endl;
+      std::cout << "VEL: [" << a[3][p] << "," << a[4][p] << "," << a[5][p] << "]" << std::endl;
+    }
+  }
+}
 // util.cpp:364-394: (field energy, kinetic energy)
 inline std::pair<double, double> get_total_energy(const Geometry&, CParticleContainer& P, MultiFab&, MultiFab&) {
   Simulation& s = P.sim();
@@ -259,16 +428,29 @@ class SimulationIO {
   template <int W_range>
   void write(int step, bool checkpoint = false, bool particles = false) {
     (void)particles;  // "not implemented" in the reference as well (util.hpp:144-146)
+    make_folder();
     if (checkpoint) sim_.check(spic_checkpoint_write(sim_.ctx(), path(step).c_str()));
     else sim_.check(spic_plot_write(sim_.ctx(), plot_path(step).c_str()));
   }
   void read(int step) { sim_.check(spic_checkpoint_read(sim_.ctx(), path(step).c_str())); }
-  std::string path(int step) const { return folder_ + "/CP" + pad(step) + ".spic"; }
-  std::string plot_path(int step) const { return folder_ + "/plt" + pad(step) + ".spic"; }
+  std::string path(int step) const { return folder_ + "/CP" + pad(step) + rank_tag() + ".spic"; }
+  std::string plot_path(int step) const { return folder_ + "/plt" + pad(step) + rank_tag() + ".spic"; }
 
  private:
   static std::string pad(int step) {  // amrex::Concatenate(name, step, 0)
     return std::to_string(step);
+  }
+  std::string rank_tag() const {  // one file per rank (z slab)
+    return sim_.nranks() > 1 ? ".r" + std::to_string(sim_.rank()) : std::string();
+  }
+  void make_folder() const {  // the plotfile writers of the reference create their directories
+    std::string cur;
+    for (std::size_t p = 0; p <= folder_.size(); ++p) {
+      if (p == folder_.size() || folder_[p] == '/') {
+        if (!cur.empty()) ::mkdir(cur.c_str(), 0777);  // EEXIST is fine; a real failure shows up in fopen
+      }
+      if (p < folder_.size()) cur.push_back(folder_[p]);
+    }
   }
   Simulation& sim_;
   std::string folder_;

@@ -19,7 +19,7 @@ import ctypes as C
 
 import numpy as np
 
-from . import _lib
+from . import _lib, synthetic
 from ._lib import SpicConfig
 
 P8R2, PWL = 0, 1
@@ -175,6 +175,16 @@ class Simulation:
     def add_particle_density_uniform(self, ppc, m, q, v_th, seed=12345):
         """add_particle_density(geom, P, uniform_density, ppc, m, q, v) -- util.cpp:267-311."""
         return self._ck(self.lib.spic_load_uniform_plasma(self.h, q, m, ppc, v_th, seed))
+
+    def add_particle_density(self, dist_func, ppc_max, m, q, v_th, seed=12345):
+        """add_particle_density(geom, P, dist_func, ppc_max, m, q, v) -- util.cpp:267-311 -- with any density
+        profile `dist_func(i, j, k)` over GLOBAL cell indices (bernstein_density util.cpp:181-200, ...):
+        cell (i,j,k) receives int(dist_func * ppc_max) particles of charge q/ppc_max and mass m/ppc_max."""
+        count, stride = synthetic.density_counts(self.n_global, dist_func, ppc_max)
+        k0 = self.lo[2]
+        local = np.ascontiguousarray(count[k0:k0 + self.n[2]], dtype=np.int32)
+        return self._ck(self.lib.spic_load_density_plasma(
+            self.h, q, m, ppc_max, stride, v_th, seed, local.ctypes.data_as(C.POINTER(C.c_int32))))
 
     def num_species(self):
         return self.lib.spic_num_species(self.h)

@@ -29,6 +29,7 @@ SIGNATURES = {
     "spic_get_field": (i32, [vp, i32, _dp]),
     "spic_add_species": (i32, [vp, dbl, dbl, i64] + [_dp] * 6),
     "spic_load_uniform_plasma": (i32, [vp, dbl, dbl, C.c_int32, dbl, u64]),
+    "spic_load_density_plasma": (i32, [vp, dbl, dbl, C.c_int32, C.c_int32, dbl, u64, C.POINTER(C.c_int32)]),
     "spic_num_species": (i32, [vp]),
     "spic_num_particles": (i32, [vp, i32, C.POINTER(i64)]),
     "spic_get_particles": (i32, [vp, i32] + [_dp] * 6),

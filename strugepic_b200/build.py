@@ -77,5 +77,33 @@ def build(force=False, verbose=False):
     return LIB
 
 
+DRIVERS = os.path.join(HERE, "..", "drivers")
+DRIVER_BIN = os.path.join(DRIVERS, "bin")
+CXX = os.environ.get("CXX", "g++")
+
+
+def build_drivers(names=None):
+    """The re-created reference drivers (drivers/*.cpp: plain C++14 over include/strugepic_b200.hpp, linked
+    against the in-tree library with an rpath relative to the binary)."""
+    os.makedirs(DRIVER_BIN, exist_ok=True)
+    inc = os.path.join(HERE, "..", "include")
+    deps = [os.path.join(inc, f) for f in os.listdir(inc)] + [os.path.join(DRIVERS, "common.hpp")]
+    out = []
+    for f in sorted(os.listdir(DRIVERS)):
+        if not f.endswith(".cpp") or (names and f[:-4] not in names):
+            continue
+        exe = os.path.join(DRIVER_BIN, f[:-4])
+        src = os.path.join(DRIVERS, f)
+        if _stale(exe, [src, LIB] + deps):
+            cmd = [CXX, "-std=c++14", "-O2", "-Wall", "-Werror", "-I", inc, src, "-o", exe, "-L", LIBDIR,
+                   "-lstrugepic_b200", "-Wl,-rpath,$ORIGIN/../../strugepic_b200/lib", "-pthread"]
+            r = subprocess.run(cmd, capture_output=True, text=True)
+            if r.returncode != 0:
+                raise RuntimeError("driver build failed for %s:\n%s" % (f, r.stderr[-4000:]))
+        out.append(exe)
+    return out
+
+
 if __name__ == "__main__":
     print(build(force="--force" in sys.argv, verbose="--verbose" in sys.argv))
+    print("\n".join(build_drivers()))

@@ -349,6 +349,38 @@ int spic_load_uniform_plasma(spic_ctx* c, double q, double m, int32_t ppc, doubl
   return (int)c->sp.size() - 1;
 }
 
+int spic_load_density_plasma(spic_ctx* c, double q, double m, int32_t ppc_max, int32_t rng_stride, double v_th,
+                             uint64_t seed, const int32_t* count) {
+  if (!c || ppc_max < 1 || m == 0.0 || !count || rng_stride < 0) return SPIC_EINVAL;
+  cudaSetDevice(c->cfg.device);
+  if (int frc = flush_pending(c)) return frc;
+  const long ncell = c->g.cells();
+  const int stride = rng_stride ? rng_stride : ppc_max;
+  std::vector<long> start((size_t)ncell + 1);
+  start[0] = 0;
+  for (long i = 0; i < ncell; ++i) {
+    if (count[i] < 0 || count[i] > stride) return fail(c, SPIC_EINVAL, "per-cell count outside [0, rng_stride]");
+    start[i + 1] = start[i] + count[i];
+  }
+  const long n = start[ncell];
+  Species s;
+  s.q = q / ppc_max;  // q_c, m_c: src/strugepic_util.cpp:273-274
+  s.m = m / ppc_max;
+  int rc = alloc_soa(c, s.d, n);
+  if (rc) return rc;
+  s.nd = s.capd = n;
+  long* d_start = nullptr;
+  SPIC_CUDA_CHECK(c, cudaMalloc(&d_start, sizeof(long) * start.size()));
+  SPIC_CUDA_CHECK(c, cudaMemcpyAsync(d_start, start.data(), sizeof(long) * start.size(), cudaMemcpyHostToDevice, c->stream));
+  launch_load_counts(c, s.d, d_start, ncell, stride, v_th, seed);
+  SPIC_CUDA_CHECK(c, cudaStreamSynchronize(c->stream));
+  cudaFree(d_start);
+  c->sp.push_back(s);
+  rc = engine_ingest(c, c->sp.back());
+  if (rc) return rc;
+  return (int)c->sp.size() - 1;
+}
+
 int spic_num_particles(spic_ctx* c, int species, int64_t* n) {
   if (!c || !n || species < 0 || species >= (int)c->sp.size()) return SPIC_EINVAL;
   cudaSetDevice(c->cfg.device);

@@ -139,6 +139,36 @@ __global__ void __launch_bounds__(256)
   }
 }
 
+// add_particle_density with a density profile (src/strugepic_util.cpp:267-311): cell c of this brick
+// receives count = start[c+1] - start[c] particles (the host evaluated `dist_func(geom,i,j,k)*ppc_max`);
+// one warp per cell, particle p of global cell gc draws from the counter gc * stride + p, so the result
+// does not depend on the decomposition and equals k_load_uniform when every count == stride.
+__global__ void __launch_bounds__(256)
+    k_load_counts(Grid g, ParticleSoA p, const long* __restrict__ start, long ncell, int stride, double vth,
+                  uint64_t seed) {
+  const int lane = threadIdx.x & 31;
+  const long warps = ((long)gridDim.x * blockDim.x) >> 5;
+  for (long cell = ((long)blockIdx.x * blockDim.x + threadIdx.x) >> 5; cell < ncell; cell += warps) {
+    const long s0 = start[cell];
+    const int cnt = (int)(start[cell + 1] - s0);
+    const int i = (int)(cell % g.n[0]);
+    const int j = (int)((cell / g.n[0]) % g.n[1]);
+    const int k = (int)(cell / ((long)g.n[0] * g.n[1])) + g.z0;
+    const uint64_t gcell = ((uint64_t)k * g.gn[1] + j) * g.gn[0] + i;
+    for (int q = lane; q < cnt; q += 32) {
+      double xyz[3], vel[3];
+      synth_particle(seed, gcell * (uint64_t)stride + (uint64_t)q, vth, xyz, vel);
+      const long t = s0 + q;
+      p.x[0][t] = (double)i + xyz[0];
+      p.x[1][t] = (double)j + xyz[1];
+      p.x[2][t] = (double)k + xyz[2];
+      p.v[0][t] = vel[0];
+      p.v[1][t] = vel[1];
+      p.v[2][t] = vel[2];
+    }
+  }
+}
+
 template <class I>
 void theta_axis_dispatch(Ctx* c, const ParticleSoA& p, long n, const unsigned long long* n_dev, double q, double m,
                          int comp, double dt) {
@@ -212,6 +242,15 @@ void launch_load_uniform(Ctx* c, const ParticleSoA& p, long n, int ppc, double v
   long b = (n + 255) / 256;
   if (b > (long)c->sm_count * 16) b = (long)c->sm_count * 16;
   k_load_uniform<<<(int)b, 256, 0, c->stream>>>(c->g, p, n, ppc, vth, seed);
+  c->launches++;
+}
+
+void launch_load_counts(Ctx* c, const ParticleSoA& p, const long* start, long ncell, int stride, double vth,
+                        uint64_t seed) {
+  if (ncell <= 0) return;
+  long b = (ncell + 7) / 8;
+  if (b > (long)c->sm_count * 16) b = (long)c->sm_count * 16;
+  k_load_counts<<<(int)b, 256, 0, c->stream>>>(c->g, p, start, ncell, stride, vth, seed);
   c->launches++;
 }
 

@@ -83,6 +83,9 @@ void launch_kinetic_energy(Ctx* c, const ParticleSoA& p, long n, const unsigned 
                            double* accum);
 void launch_deposit_rho(Ctx* c, const ParticleSoA& p, long n, const unsigned long long* n_dev, double q, double* out);
 void launch_load_uniform(Ctx* c, const ParticleSoA& p, long n, int ppc, double vth, uint64_t seed);
+// density-profile loader: start = exclusive prefix of the per-cell counts (device, ncell + 1 entries)
+void launch_load_counts(Ctx* c, const ParticleSoA& p, const long* start, long ncell, int stride, double vth,
+                        uint64_t seed);
 // get_particle_number_density (include/strugepic_util.hpp:30-85): nd is ONE guarded component
 void launch_number_density(Ctx* c, const ParticleSoA& p, long n, const unsigned long long* n_dev, double* nd);
 
