@@ -43,6 +43,11 @@ extern "C" {
 /* interpolation variants: src/interpolation/interpolation.cpp:19-84 and 87-157 */
 #define SPIC_INTERP_P8R2 0 /* 8th-order piecewise polynomial on [-2,2], W_range 2 */
 #define SPIC_INTERP_PWL 1  /* piecewise linear on [-1,1], W_range 1               */
+/* The user's own W1 / Wp / I_W1 / I_Wp / interpolation_range, linked into the library the way the
+ * reference lets a user override its weak defaults (include/strugepic_w.hpp:12-16;
+ * src/interpolation/interpolation.cpp:10,14,20,89): see include/strugepic_user_w.h.  The stock
+ * library carries the cubic B-spline pair in this slot.  One GPU, thread-per-particle engine. */
+#define SPIC_INTERP_USER 2
 
 #define SPIC_FIELD_E 0
 #define SPIC_FIELD_B 1

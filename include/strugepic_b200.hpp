@@ -168,7 +168,7 @@ class Simulation {
  public:
   // W_range selects the interpolation compiled into the kernels (the reference picks it at link time)
   Simulation(const Geometry& geom, int W_range, int ng = 0, int device = 0, int map4_mode = SPIC_MAP4_REFERENCE,
-             int nranks = 1, int rank = 0)
+             int nranks = 1, int rank = 0, int interp = -1)
       : geom_(geom), W_(W_range), nranks_(nranks), rank_(rank), E_(this, SPIC_FIELD_E), B_(this, SPIC_FIELD_B),
         P_(this) {
     spic_config cfg{};
@@ -177,7 +177,11 @@ class Simulation {
       cfg.periodic[d] = geom.is_periodic[d];
     }
     cfg.ng = ng;
-    cfg.interp = W_range == 2 ? SPIC_INTERP_P8R2 : SPIC_INTERP_PWL;
+    // interp = SPIC_INTERP_USER selects the user-supplied W linked into the library (strugepic_user_w.h), the
+    // GPU form of overriding the reference's weak W symbols; W_range must then equal its interpolation_range
+    cfg.interp = interp >= 0 ? interp : (W_range == 2 ? SPIC_INTERP_P8R2 : SPIC_INTERP_PWL);
+    if (spic_interpolation_range(cfg.interp) != W_range)
+      throw Error(SPIC_EINVAL, "W_range does not match the interpolation_range of the selected interp");
     cfg.map4_mode = map4_mode;
     cfg.engine = SPIC_ENGINE_BINNED;
     cfg.device = device;

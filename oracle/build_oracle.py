@@ -81,7 +81,33 @@ def build_ref(force=False):
     return outs
 
 
+DEFAULT_USER_W = os.path.join(HERE, "..", "strugepic_b200", "csrc", "user_w_default.cu")
+
+
+def build_ref_user(user_src=DEFAULT_USER_W, wrange=2, tag="user", force=False):
+    """The reference with a USER-supplied W linked over its weak defaults (the reference's own override
+    mechanism, include/strugepic_w.hpp:7-8): reference sources unmodified + oracle/user_w_adapter.cpp + the
+    user's file compiled as plain C++.  -> oracle/_ref/liboracle_ref_<tag>.so; [] without /root/reference."""
+    if not reference_present():
+        return []
+    os.makedirs(REFOUT, exist_ok=True)
+    srcs = [
+        os.path.join(REF, "src", "strugepic_propagators.cpp"),
+        os.path.join(REF, "src", "strugepic_util.cpp"),
+        os.path.join(HERE, "ref_driver.cpp"),
+        os.path.join(HERE, "user_w_adapter.cpp"),
+    ]
+    deps = srcs + [user_src, os.path.join(HERE, "amrex_shim", "amrex_standin.H")]
+    inc = ["-I" + os.path.join(HERE, "amrex_shim"), "-I" + os.path.join(REF, "include"),
+           "-I" + os.path.join(HERE, "..", "include")]
+    out = os.path.join(REFOUT, "liboracle_ref_%s.so" % tag)
+    if force or not _newer(out, deps):
+        _run(["g++", "-std=c++14", "-fPIC", "-shared", "-w"] + PARITY + ["-DWRANGE=%d" % wrange] + inc + srcs +
+             ["-x", "c++", user_src, "-o", out])
+    return [out]
+
+
 if __name__ == "__main__":
     force = "--force" in sys.argv
-    for o in build_port(force) + build_ref(force):
+    for o in build_port(force) + build_ref(force) + build_ref_user(force=force):
         print("built", os.path.relpath(o, HERE))

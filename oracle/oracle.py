@@ -37,7 +37,12 @@ def port_lib_path(fast=False):
     return os.path.join(HERE, "_build", "liboracle_port%s.so" % ("_fast" if fast else ""))
 
 
+USER = 2  # SPIC_INTERP_USER: the reference with a user-supplied W linked in (build_oracle.build_ref_user)
+
+
 def ref_lib_path(interp, fast=False):
+    if interp == USER:
+        return os.path.join(HERE, "_ref", "liboracle_ref_user.so")
     return os.path.join(HERE, "_ref", "liboracle_ref_%s%s.so" % ("p8" if interp == P8R2 else "pwl",
                                                                   "_fast" if fast else ""))
 
@@ -54,6 +59,7 @@ def ensure_built():
         import build_oracle
         build_oracle.build_port()
         build_oracle.build_ref()
+        build_oracle.build_ref_user()
     finally:
         sys.path.pop(0)
 
@@ -208,8 +214,9 @@ class RefOracle(_Base):
         self.lib = C.CDLL(path)
         self.interp = interp
         self.n = tuple(int(t) for t in n_cell)
-        self.W = 2 if interp == P8R2 else 1
-        assert self._f("wrange", C.c_int, [])() == self.W
+        self.W = self._f("wrange", C.c_int, [])()
+        assert self.W == (2 if interp == P8R2 else 1) or interp == USER
+        assert self._f("interpolation_range", C.c_int, [])() == self.W
         self.ng = self.W + 1 if ng is None else ng
         self._bind_common()
         create = self._f("create", C.c_void_p, [C.c_int * 3, C.c_int * 3, C.c_int])

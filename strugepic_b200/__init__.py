@@ -22,7 +22,7 @@ import numpy as np
 from . import _lib, synthetic
 from ._lib import SpicConfig
 
-P8R2, PWL = 0, 1
+P8R2, PWL, USER = 0, 1, 2  # USER: the user-supplied W slot (include/strugepic_user_w.h)
 FIELD_E, FIELD_B = 0, 1
 MAP4_REFERENCE, MAP4_YOSHIDA = 0, 1
 ENGINE_BINNED, ENGINE_DIRECT = 0, 1
@@ -43,8 +43,8 @@ def _p(a):
 
 
 def interpolation_range(interp):
-    """`interpolation_range` of include/strugepic_w.hpp:16 for the two shipped variants."""
-    return 2 if interp == P8R2 else 1
+    """`interpolation_range` of include/strugepic_w.hpp:16 (USER: what the linked-in user file defines)."""
+    return _lib.load().spic_interpolation_range(interp)
 
 
 def W1(x, interp=P8R2):

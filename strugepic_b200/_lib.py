@@ -3,7 +3,9 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "lib", "libstrugepic_b200.so")
+# SPIC_B200_LIBRARY selects another build of the same library, e.g. one made with
+# `python -m strugepic_b200.build --user-w my_w.cu` (include/strugepic_user_w.h)
+LIB_PATH = os.environ.get("SPIC_B200_LIBRARY") or os.path.join(HERE, "lib", "libstrugepic_b200.so")
 
 _dp = C.POINTER(C.c_double)
 

@@ -42,12 +42,20 @@ def _stale(out, deps):
     return any(os.path.getmtime(d) > t for d in deps)
 
 
-def _compile(src, verbose):
-    obj = os.path.join(OBJ, src[:-3] + ".o")
-    path = os.path.join(CSRC, src)
+# the user-W slot (include/strugepic_user_w.h): these two translation units are relocatable device code, device-
+# linked with each other at the final link; USER_W_DEFAULT is replaced by the user's file with --user-w
+RDC = {"user_w.cu", "user_w_default.cu"}
+USER_W_DEFAULT = "user_w_default.cu"
+
+
+def _compile(src, verbose, path=None, obj=None):
+    rdc = src in RDC or path is not None
+    obj = obj or os.path.join(OBJ, src[:-3] + ".o")
+    path = path or os.path.join(CSRC, src)
     if not _stale(obj, [path] + _headers()):
         return obj, ""
-    cmd = [NVCC] + ARCH + FLAGS + ["-c", path, "-o", obj]
+    cmd = [NVCC] + ARCH + FLAGS + (["-rdc=true", "-I", os.path.join(HERE, "..", "include")] if rdc else []) + [
+        "-x", "cu", "-c", path, "-o", obj]
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:
         raise RuntimeError("nvcc failed for %s:\n%s" % (src, r.stderr[-6000:]))
@@ -57,24 +65,35 @@ def _compile(src, verbose):
     return obj, (r.stderr if verbose else "")
 
 
-def build(force=False, verbose=False):
+def build(force=False, verbose=False, user_w=None, out=None):
+    """Builds the library.  user_w = path of a source file defining the five symbols of
+    include/strugepic_user_w.h: it takes the place of csrc/user_w_default.cu and the result goes to `out`
+    (default lib/libstrugepic_b200_userw.so), leaving the stock library untouched."""
     os.makedirs(OBJ, exist_ok=True)
     os.makedirs(LIBDIR, exist_ok=True)
     if force:
         for f in os.listdir(OBJ):
             os.remove(os.path.join(OBJ, f))
+    srcs = [s for s in _sources() if not (user_w and s == USER_W_DEFAULT)]
     with ThreadPoolExecutor(max_workers=8) as ex:
-        res = list(ex.map(lambda s: _compile(s, verbose), _sources()))
+        res = list(ex.map(lambda s: _compile(s, verbose), srcs))
+    lib = LIB
+    if user_w:
+        lib = out or os.path.join(LIBDIR, "libstrugepic_b200_userw.so")
+        tag = os.path.splitext(os.path.basename(lib))[0]
+        res.append(_compile(os.path.basename(user_w), verbose, path=os.path.abspath(user_w),
+                            obj=os.path.join(OBJ, "userw_%s.o" % tag)))
     objs = [o for o, _ in res]
     for _, log in res:
         if log:
             print(log)
-    if force or _stale(LIB, objs):
-        cmd = [NVCC] + ARCH + ["-shared", "-o", LIB] + objs + ["-ldl"]
+    if force or _stale(lib, objs):
+        # nvcc device-links the relocatable objects (user_w.o + the W definitions) on the way
+        cmd = [NVCC] + ARCH + ["-shared", "-o", lib] + objs + ["-ldl"]
         r = subprocess.run(cmd, capture_output=True, text=True)
         if r.returncode != 0:
             raise RuntimeError("link failed:\n" + r.stderr[-4000:])
-    return LIB
+    return lib
 
 
 DRIVERS = os.path.join(HERE, "..", "drivers")
@@ -105,5 +124,10 @@ def build_drivers(names=None):
 
 
 if __name__ == "__main__":
-    print(build(force="--force" in sys.argv, verbose="--verbose" in sys.argv))
-    print("\n".join(build_drivers()))
+    def _opt(name):
+        return sys.argv[sys.argv.index(name) + 1] if name in sys.argv else None
+
+    print(build(force="--force" in sys.argv, verbose="--verbose" in sys.argv, user_w=_opt("--user-w"),
+                out=_opt("--out")))
+    if not _opt("--user-w"):
+        print("\n".join(build_drivers()))

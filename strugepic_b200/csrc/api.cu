@@ -112,6 +112,16 @@ int halo_sum(Ctx* c, double* F, int comp) {
 }
 }  // namespace
 
+extern "C" {  // host side of the user-W slot (user_w.cu)
+double spic_user_host_W1(double x);
+double spic_user_host_Wp(double x);
+double spic_user_host_I_W1(double a, double b);
+double spic_user_host_I_Wp(double a, double b);
+}
+namespace spic {
+int user_w_range();
+}
+
 static int flush_pending(spic_ctx* c);  // applies the deferred trailing Theta_E of the last fused map (below)
 
 extern "C" {
@@ -121,10 +131,13 @@ const char* spic_last_error(const spic_ctx* ctx) { return ctx ? ctx->err.c_str()
 int spic_create(const spic_config* cfg, spic_ctx** out) {
   if (!cfg || !out) return fail(nullptr, SPIC_EINVAL, "null argument");
   *out = nullptr;
-  if (cfg->interp != SPIC_INTERP_P8R2 && cfg->interp != SPIC_INTERP_PWL)
-    return fail(nullptr, SPIC_EINVAL, "interp must be SPIC_INTERP_P8R2 or SPIC_INTERP_PWL");
-  const int W = cfg->interp == SPIC_INTERP_P8R2 ? 2 : 1;
+  if (cfg->interp != SPIC_INTERP_P8R2 && cfg->interp != SPIC_INTERP_PWL && cfg->interp != SPIC_INTERP_USER)
+    return fail(nullptr, SPIC_EINVAL, "interp must be SPIC_INTERP_P8R2, SPIC_INTERP_PWL or SPIC_INTERP_USER");
+  const int W = spic_interpolation_range(cfg->interp);
+  if (W != 1 && W != 2) return fail(nullptr, SPIC_EINVAL, "spic_user_interpolation_range must be 1 or 2");
   const int nranks = cfg->nranks <= 0 ? 1 : cfg->nranks;
+  if (cfg->interp == SPIC_INTERP_USER && nranks > 1)
+    return fail(nullptr, SPIC_EINVAL, "SPIC_INTERP_USER runs on one GPU (thread-per-particle engine)");
   // default guard width: the interpolation range; one more with z slabs on a periodic box, so that the fused axis
   // block can let a particle finish its sub-flows one cell outside the slab before it migrates
   const bool all_periodic = cfg->periodic[0] && cfg->periodic[1] && cfg->periodic[2];
@@ -151,6 +164,8 @@ int spic_create(const spic_config* cfg, spic_ctx** out) {
   c->cfg = *cfg;
   c->cfg.ng = ng;
   c->cfg.nranks = nranks;
+  // the warp-per-cell kernels are specialised per tap for the two shipped variants; a user W runs thread per particle
+  if (cfg->interp == SPIC_INTERP_USER) c->cfg.engine = SPIC_ENGINE_DIRECT;
   c->W = W;
   c->sm_count = prop.multiProcessorCount;
   Grid& g = c->g;
@@ -804,15 +819,26 @@ int spic_checkpoint_read(spic_ctx* c, const char* path) {
 
 // ---- interpolation interface (include/strugepic_w.hpp:12-16), host evaluation of the very
 //      same code the kernels inline (csrc/interp.cuh) ------------------------------------------
-double spic_W1(int interp, double x) { return interp == SPIC_INTERP_PWL ? InterpPWL::W1(x) : InterpP8R2::W1(x); }
-double spic_Wp(int interp, double x) { return interp == SPIC_INTERP_PWL ? InterpPWL::Wp(x) : InterpP8R2::Wp(x); }
+double spic_W1(int interp, double x) {
+  if (interp == SPIC_INTERP_USER) return spic_user_host_W1(x);
+  return interp == SPIC_INTERP_PWL ? InterpPWL::W1(x) : InterpP8R2::W1(x);
+}
+double spic_Wp(int interp, double x) {
+  if (interp == SPIC_INTERP_USER) return spic_user_host_Wp(x);
+  return interp == SPIC_INTERP_PWL ? InterpPWL::Wp(x) : InterpP8R2::Wp(x);
+}
 double spic_I_W1(int interp, double a, double b) {
+  if (interp == SPIC_INTERP_USER) return spic_user_host_I_W1(a, b);
   return interp == SPIC_INTERP_PWL ? InterpPWL::I_W1(a, b) : InterpP8R2::I_W1(a, b);
 }
 double spic_I_Wp(int interp, double a, double b) {
+  if (interp == SPIC_INTERP_USER) return spic_user_host_I_Wp(a, b);
   return interp == SPIC_INTERP_PWL ? InterpPWL::I_Wp(a, b) : InterpP8R2::I_Wp(a, b);
 }
-int spic_interpolation_range(int interp) { return interp == SPIC_INTERP_PWL ? InterpPWL::W : InterpP8R2::W; }
+int spic_interpolation_range(int interp) {
+  if (interp == SPIC_INTERP_USER) return user_w_range();
+  return interp == SPIC_INTERP_PWL ? InterpPWL::W : InterpP8R2::W;
+}
 // The in-cell tap forms used by the binned kernels (f = x - cell in [0,1), tap t): exposed so that
 // the CPU test-suite can pin them bit for bit against the general forms.
 double spic_tap_W1(int interp, int tap, double f) {

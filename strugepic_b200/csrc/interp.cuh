@@ -105,6 +105,10 @@ struct InterpP8R2 {
     return a >= 2.0 ? 1.0 : (a < -1.0 ? 0.0 : v);
   }
 
+  // I_Wp(a, b) for the tap's node (propagators.hpp:178-186): difference of the running integral
+  template <int T>
+  static SPIC_HDI double iwp_seg(double a, double b) { return iwp_tap<T>(b) - iwp_tap<T>(a); }
+
   // In-cell tap forms (the binned kernels): the argument is KNOWN to lie in the closed range of
   // the tap's piece (particle inside its bin cell, segment inside its cell), so the support tests
   // of poly_util.hpp:32,42-47 can only fire at a piece end point -- and there every piece
@@ -182,6 +186,8 @@ struct InterpPWL {
   template <int T>
   static SPIC_HDI double iwp_tap(double a) { return IWp_cdf(a); }
   template <int T>
+  static SPIC_HDI double iwp_seg(double a, double b) { return IWp_cdf(b) - IWp_cdf(a); }
+  template <int T>
   static SPIC_HDI double w1_in(double a) { return W1(a); }
   template <int T>
   static SPIC_HDI double wp_in(double a) { return Wp(a); }
@@ -231,12 +237,12 @@ SPIC_HDI void eval_iwp(double s, double e, int cell, double (&out)[I::NWP]) {
   if (I::NWP == 3) {
     const double c0 = (double)(cell + 0 - I::W + 1), c1 = (double)(cell + 1 - I::W + 1),
                  c2 = (double)(cell + 2 - I::W + 1);
-    out[0] = I::template iwp_tap<0>(e - c0) - I::template iwp_tap<0>(s - c0);
-    out[I::NWP > 1 ? 1 : 0] = I::template iwp_tap<1>(e - c1) - I::template iwp_tap<1>(s - c1);
-    out[I::NWP > 2 ? 2 : 0] = I::template iwp_tap<2>(e - c2) - I::template iwp_tap<2>(s - c2);
+    out[0] = I::template iwp_seg<0>(s - c0, e - c0);
+    out[I::NWP > 1 ? 1 : 0] = I::template iwp_seg<1>(s - c1, e - c1);
+    out[I::NWP > 2 ? 2 : 0] = I::template iwp_seg<2>(s - c2, e - c2);
   } else {
     const double c0 = (double)(cell + 0 - I::W + 1);
-    out[0] = I::template iwp_tap<0>(e - c0) - I::template iwp_tap<0>(s - c0);
+    out[0] = I::template iwp_seg<0>(s - c0, e - c0);
   }
 }
 

@@ -11,55 +11,10 @@
 //   get_total_energy (kinetic)   src/strugepic_util.cpp:364-380
 // The triple sums are factorised (sum over the push axis innermost, then u, then
 // l); this changes rounding by O(1e-16) relative, see DESIGN.md "parity budget".
-#include "particle_math.cuh"
-#include "spic_internal.cuh"
+#include "particles_direct.cuh"
 
 namespace spic {
 namespace {
-
-constexpr int kBlock = 128;
-
-template <class I, int A>
-__global__ void __launch_bounds__(kBlock)
-    k_theta_axis_direct(Grid g, ParticleSoA p, long n, const unsigned long long* __restrict__ n_dev,
-                        double* __restrict__ E, const double* __restrict__ B, double q, double qm, double dt,
-                        int* __restrict__ flags) {
-  constexpr int U = (A + 1) % 3, L = (A + 2) % 3;  // hpp:90-91
-  const long i = blockIdx.x * (long)blockDim.x + threadIdx.x;
-  if (n_dev) n = (long)*n_dev;
-  if (i >= n) return;
-  double x[3] = {p.x[0][i], p.x[1][i], p.x[2][i]}, v[3] = {p.v[0][i], p.v[1][i], p.v[2][i]};
-  theta_axis_one<I, A>(g, x, v, E, B, q, qm, dt, flags);
-  p.x[A][i] = x[A];
-  p.v[L][i] = v[L];
-  p.v[U][i] = v[U];
-  if (!g.per[A]) p.v[A][i] = v[A];  // only a reflection changes it
-}
-
-template <class I>
-__global__ void __launch_bounds__(kBlock)
-    k_push_v_e_direct(Grid g, ParticleSoA p, long n, const unsigned long long* __restrict__ n_dev,
-                      const double* __restrict__ E, double coef) {
-  const long i = blockIdx.x * (long)blockDim.x + threadIdx.x;
-  if (n_dev) n = (long)*n_dev;
-  if (i >= n) return;
-  const double x = p.x[0][i], y = p.x[1][i], z = p.x[2][i];
-  const int cx = (int)floor(x), cy = (int)floor(y), cz = (int)floor(z);
-  double w1x[I::NW1], w1y[I::NW1], w1z[I::NW1], wpx[I::NWP], wpy[I::NWP], wpz[I::NWP];
-  eval_w1<I>(x, cx, w1x);
-  eval_w1<I>(y, cy, w1y);
-  eval_w1<I>(z, cz, w1z);
-  eval_wp<I>(x, cx, wpx);
-  eval_wp<I>(y, cy, wpy);
-  eval_wp<I>(z, cz, wpz);
-  const long base = g.at(cx, cy, cz - g.z0) + (1 - I::W) * (1 + g.pj + g.pk);
-  double dv[3];
-  gather_E<I>(E + base, g.pj, g.pk, g.pc, w1x, w1y, w1z, wpx, wpy, wpz, dv,
-              [](const double* ptr) { return __ldg(ptr); });
-  p.v[0][i] = fma(dv[0], coef, p.v[0][i]);  // hpp:339-341
-  p.v[1][i] = fma(dv[1], coef, p.v[1][i]);
-  p.v[2][i] = fma(dv[2], coef, p.v[2][i]);
-}
 
 __global__ void __launch_bounds__(256) k_kinetic(ParticleSoA p, long n, const unsigned long long* __restrict__ n_dev,
                                                  double half_m, double* __restrict__ accum) {
@@ -78,45 +33,6 @@ __global__ void __launch_bounds__(256) k_kinetic(ParticleSoA p, long n, const un
     for (int w = 0; w < 8; ++w) t += sh[w];
     atomicAdd(accum, t);
   }
-}
-
-// rho deposit for the Gauss diagnostic: out[cell] -= q W1 W1 W1 (periodic images folded)
-template <class I>
-__global__ void __launch_bounds__(kBlock) k_deposit_rho(Grid g, ParticleSoA p, long n,
-                                                        const unsigned long long* __restrict__ n_dev, double q,
-                                                        double* __restrict__ out) {
-  const long i = blockIdx.x * (long)blockDim.x + threadIdx.x;
-  if (n_dev) n = (long)*n_dev;
-  if (i >= n) return;
-  const double x = p.x[0][i], y = p.x[1][i], z = p.x[2][i];
-  const int cx = (int)floor(x), cy = (int)floor(y), cz = (int)floor(z);
-  double w1x[I::NW1], w1y[I::NW1], w1z[I::NW1];
-  eval_w1<I>(x, cx, w1x);
-  eval_w1<I>(y, cy, w1y);
-  eval_w1<I>(z, cz, w1z);
-#pragma unroll
-  for (int tk = 0; tk < I::NW1; ++tk)
-#pragma unroll
-    for (int tj = 0; tj < I::NW1; ++tj)
-#pragma unroll
-      for (int ti = 0; ti < I::NW1; ++ti) {
-        int ii = cx + ti + 1 - I::W, jj = cy + tj + 1 - I::W, kk = cz + tk + 1 - I::W;
-        if (g.per[0]) ii = (ii % g.gn[0] + g.gn[0]) % g.gn[0];
-        if (g.per[1]) jj = (jj % g.gn[1] + g.gn[1]) % g.gn[1];
-        if (g.per[2]) kk = (kk % g.gn[2] + g.gn[2]) % g.gn[2];
-        if (ii < 0 || ii >= g.gn[0] || jj < 0 || jj >= g.gn[1] || kk < 0 || kk >= g.gn[2]) continue;
-        atomicAdd(&out[((long)kk * g.gn[1] + jj) * g.gn[0] + ii], -q * w1x[ti] * w1y[tj] * w1z[tk]);
-      }
-}
-
-template <class I>
-__global__ void __launch_bounds__(kBlock) k_number_density(Grid g, ParticleSoA p, long n,
-                                                           const unsigned long long* __restrict__ n_dev,
-                                                           double* __restrict__ nd) {
-  const long i = blockIdx.x * (long)blockDim.x + threadIdx.x;
-  if (n_dev) n = (long)*n_dev;
-  if (i >= n) return;
-  deposit_number_density<I>(g, p.x[0][i], p.x[1][i], p.x[2][i], nd);
 }
 
 __global__ void __launch_bounds__(256)
@@ -169,19 +85,6 @@ __global__ void __launch_bounds__(256)
   }
 }
 
-template <class I>
-void theta_axis_dispatch(Ctx* c, const ParticleSoA& p, long n, const unsigned long long* n_dev, double q, double m,
-                         int comp, double dt) {
-  const int grid = (int)((n + kBlock - 1) / kBlock);
-  const double qm = q / m;  // B_coef, hpp:113
-  if (comp == 0)
-    k_theta_axis_direct<I, 0><<<grid, kBlock, 0, c->stream>>>(c->g, p, n, n_dev, c->E, c->B, q, qm, dt, c->d_flags);
-  else if (comp == 1)
-    k_theta_axis_direct<I, 1><<<grid, kBlock, 0, c->stream>>>(c->g, p, n, n_dev, c->E, c->B, q, qm, dt, c->d_flags);
-  else
-    k_theta_axis_direct<I, 2><<<grid, kBlock, 0, c->stream>>>(c->g, p, n, n_dev, c->E, c->B, q, qm, dt, c->d_flags);
-}
-
 }  // namespace
 
 void launch_theta_axis_direct(Ctx* c, const ParticleSoA& p, long n, const unsigned long long* n_dev, double q,
@@ -189,9 +92,11 @@ void launch_theta_axis_direct(Ctx* c, const ParticleSoA& p, long n, const unsign
   if (n <= 0) return;
   KernelTimer t(c, n_dev ? KT_OTHER : KT_AXIS);  // n_dev: the (small) overflow tail of the binned engine
   if (c->cfg.interp == SPIC_INTERP_P8R2)
-    theta_axis_dispatch<InterpP8R2>(c, p, n, n_dev, q, m, comp, dt);
+    direct::theta_axis_launch<InterpP8R2>(c, p, n, n_dev, q, m, comp, dt);
+  else if (c->cfg.interp == SPIC_INTERP_PWL)
+    direct::theta_axis_launch<InterpPWL>(c, p, n, n_dev, q, m, comp, dt);
   else
-    theta_axis_dispatch<InterpPWL>(c, p, n, n_dev, q, m, comp, dt);
+    user_theta_axis(c, p, n, n_dev, q, m, comp, dt);
   c->launches++;
 }
 
@@ -199,12 +104,13 @@ void launch_push_v_e_direct(Ctx* c, const ParticleSoA& p, long n, const unsigned
                             double dt) {
   if (n <= 0) return;
   KernelTimer t(c, n_dev ? KT_OTHER : KT_PUSHVE);
-  const int grid = (int)((n + kBlock - 1) / kBlock);
   const double coef = dt * q / m;  // hpp:267
   if (c->cfg.interp == SPIC_INTERP_P8R2)
-    k_push_v_e_direct<InterpP8R2><<<grid, kBlock, 0, c->stream>>>(c->g, p, n, n_dev, c->E, coef);
+    direct::push_v_e_launch<InterpP8R2>(c, p, n, n_dev, coef);
+  else if (c->cfg.interp == SPIC_INTERP_PWL)
+    direct::push_v_e_launch<InterpPWL>(c, p, n, n_dev, coef);
   else
-    k_push_v_e_direct<InterpPWL><<<grid, kBlock, 0, c->stream>>>(c->g, p, n, n_dev, c->E, coef);
+    user_push_v_e(c, p, n, n_dev, coef);
   c->launches++;
 }
 
@@ -219,21 +125,23 @@ void launch_kinetic_energy(Ctx* c, const ParticleSoA& p, long n, const unsigned 
 
 void launch_deposit_rho(Ctx* c, const ParticleSoA& p, long n, const unsigned long long* n_dev, double q, double* out) {
   if (n <= 0) return;
-  const int grid = (int)((n + kBlock - 1) / kBlock);
   if (c->cfg.interp == SPIC_INTERP_P8R2)
-    k_deposit_rho<InterpP8R2><<<grid, kBlock, 0, c->stream>>>(c->g, p, n, n_dev, q, out);
+    direct::deposit_rho_launch<InterpP8R2>(c, p, n, n_dev, q, out);
+  else if (c->cfg.interp == SPIC_INTERP_PWL)
+    direct::deposit_rho_launch<InterpPWL>(c, p, n, n_dev, q, out);
   else
-    k_deposit_rho<InterpPWL><<<grid, kBlock, 0, c->stream>>>(c->g, p, n, n_dev, q, out);
+    user_deposit_rho(c, p, n, n_dev, q, out);
   c->launches++;
 }
 
 void launch_number_density(Ctx* c, const ParticleSoA& p, long n, const unsigned long long* n_dev, double* nd) {
   if (n <= 0) return;
-  const int grid = (int)((n + kBlock - 1) / kBlock);
   if (c->cfg.interp == SPIC_INTERP_P8R2)
-    k_number_density<InterpP8R2><<<grid, kBlock, 0, c->stream>>>(c->g, p, n, n_dev, nd);
+    direct::number_density_launch<InterpP8R2>(c, p, n, n_dev, nd);
+  else if (c->cfg.interp == SPIC_INTERP_PWL)
+    direct::number_density_launch<InterpPWL>(c, p, n, n_dev, nd);
   else
-    k_number_density<InterpPWL><<<grid, kBlock, 0, c->stream>>>(c->g, p, n, n_dev, nd);
+    user_number_density(c, p, n, n_dev, nd);
   c->launches++;
 }
 

@@ -38,9 +38,20 @@ CASES = {
 }
 
 
+# the user-W slot (SPIC_INTERP_USER = 2) with the default file csrc/user_w_default.cu (cubic B-spline, range 2),
+# generated from the reference with that file linked over its weak W symbols (oracle/_ref/liboracle_ref_user.so)
+USER_CASES = {
+    "user_subflows": ((8, 6, 5), (1, 1, 1), 2, 2, 0.2, 31, -1.0 / 2, 100.0 / 2,
+                      [("E", 0.25), ("axis", 0, 0.25), ("axis", 1, 0.25), ("axis", 2, 0.25), ("B", 0.5)]),
+    "user_map2x3": ((7, 8, 6), (1, 1, 1), 2, 3, 0.15, 32, -1.0 / 3, 100.0 / 3, [("map", 2, DT)] * 3),
+    "user_wall_map4x2": ((16, 5, 4), (0, 1, 1), 2, 2, 0.3, 33, -1.0 / 2, 100.0 / 2, [("map", 4, DT)] * 2),
+}
+W_OF = {0: 2, 1: 1, 2: 2}
+
+
 def build_case(name):
-    n_cell, periodic, interp, ppc, v_th, seed, q, m, schedule = CASES[name]
-    W = 2 if interp == 0 else 1
+    n_cell, periodic, interp, ppc, v_th, seed, q, m, schedule = (CASES.get(name) or USER_CASES[name])
+    W = W_OF[interp]
     E, B = util.rng_fields(n_cell, seed, amp=0.5)
     parts = util.plasma(n_cell, ppc, v_th, seed, periodic, W)
     return dict(n_cell=n_cell, periodic=periodic, interp=interp, q=q, m=m, schedule=schedule,
@@ -49,7 +60,7 @@ def build_case(name):
 
 def main():
     ora.ensure_built()
-    for name in CASES:
+    for name in list(CASES) + list(USER_CASES):
         c = build_case(name)
         o = ora.RefOracle(c["n_cell"], periodic=c["periodic"], interp=c["interp"])
         util.load_state(o, c["E"], c["B"], c["parts"], c["q"], c["m"])
@@ -62,7 +73,7 @@ def main():
     # W-function table on a fixed argument grid (both variants)
     xs = np.linspace(-2.5, 2.5, 201)
     tab = {}
-    for interp, tag in ((0, "p8"), (1, "pwl")):
+    for interp, tag in ((0, "p8"), (1, "pwl"), (2, "user")):
         o = ora.RefOracle((4, 4, 4), interp=interp)
         tab[tag + "_W1"] = np.array([o.W1(x) for x in xs])
         tab[tag + "_Wp"] = np.array([o.Wp(x) for x in xs])
