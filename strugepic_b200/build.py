@@ -15,9 +15,12 @@ from concurrent.futures import ThreadPoolExecutor
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
-OBJ = os.path.join(HERE, "build")
+# SPIC_BUILD_TAG=<tag> builds a side-by-side variant (objects in build_<tag>/, lib/libstrugepic_b200_<tag>.so) for
+# A/B timing; select it at run time with SPIC_B200_LIBRARY
+_TAG = os.environ.get("SPIC_BUILD_TAG", "")
+OBJ = os.path.join(HERE, "build" + ("_" + _TAG if _TAG else ""))
 LIBDIR = os.path.join(HERE, "lib")
-LIB = os.path.join(LIBDIR, "libstrugepic_b200.so")
+LIB = os.path.join(LIBDIR, "libstrugepic_b200%s.so" % ("_" + _TAG if _TAG else ""))
 
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]

@@ -62,13 +62,32 @@ struct BlockLayout {
   static constexpr int NS = NW1 * NW1 * NW1;            // stencil points per B component
   static constexpr int SB = 3 * NS;                     // one stencil buffer [comp][k][j][i]
   static constexpr int SP = 6 * 32;                     // one particle batch
-  static constexpr int SW = NW1 == 4 ? 14 : 6;          // deposition record: a[NW1] b[NW1] I[NWP] pad
+  // deposition record a[NW1] b[NW1] I[NWP] (+ pad).  W8: 12 doubles = 24 banks, and every group of four records
+  // is followed by 2 pad doubles (rec()): the four records read together in one deposition iteration (one per
+  // particle subset) then sit in disjoint banks for every field -- a[2th..], b[tu], I[0..2] -- so no read is
+  // replayed, and the 32 records written at once still cover all banks evenly (group g starts 4 g banks later).
+  // ncu on the 14-double record: every b read replayed, 8 wavefronts per sub-flow and batch, on a kernel whose
+  // shared-memory pipe is ~80 % busy.
+#ifdef SPIC_RECORD_14  // (A/B only: the previous 14-double record)
+  static constexpr int SW = NW1 == 4 ? 14 : 6;
+  static constexpr int SWZ = 0;
+#else
+  static constexpr int SW = NW1 == 4 ? 12 : 6;
+  static constexpr int SWZ = NW1 == 4 ? 2 : 0;          // pad after every group of four records
+#endif
+  static SPIC_HDI int rec(int p) { return p * SW + SWZ * (p >> 2); }
+  static_assert(SWZ == 0 || 32 / (NW1 * (NW1 / 2)) == 4, "the pad follows every group of NSUB = 4 records");
   static constexpr int TH = NW1 / 2;                    // lanes along l (each owns two l taps)
   static constexpr int LPP = NW1 * TH;                  // lanes per particle in the deposition phase
   static constexpr int NSUB = 32 / LPP;                 // particle subsets
   static constexpr int NACC = 2 * NWP;                  // accumulators per lane and E component
   static constexpr int SA = 3 * NACC * 32;              // parked accumulators
-  static constexpr int PER_WARP = kTableDoubles + SP + 2 * SB + 32 * SW + SA;
+  static constexpr int SWA = 32 * SW + 8 * SWZ;         // record area
+#ifndef SPIC_WARP_ALIGN
+#define SPIC_WARP_ALIGN 16  // doubles: every warp's buffer starts on a 128-byte boundary
+#endif
+  static constexpr int PER_WARP =
+      (kTableDoubles + SP + 2 * SB + SWA + SA + SPIC_WARP_ALIGN - 1) / SPIC_WARP_ALIGN * SPIC_WARP_ALIGN;
   static_assert(SB % 2 == 0 && SW % 2 == 0 && NW1 % 2 == 0 && kTableDoubles % 2 == 0,
                 "16-byte alignment of the sub-buffers");
 };
@@ -144,16 +163,17 @@ SPIC_DI void axis_part(double (&x)[3], double (&v)[3], double x1, const double (
   using Lay = BlockLayout<I>;
   constexpr int NS = Lay::NS, SW = Lay::SW;
   {  // deposition record of this particle: -q W1_l, W1_u, I   (hpp:194,215)
-    double2* w = reinterpret_cast<double2*>(sW + lane * SW);
+    double* wr = sW + Lay::rec(lane);
+    double2* w = reinterpret_cast<double2*>(wr);
 #pragma unroll
     for (int t = 0; t < NW1 / 2; ++t) w[t] = make_double2(nq * lW1[2 * t], nq * lW1[2 * t + 1]);
 #pragma unroll
     for (int t = 0; t < NW1 / 2; ++t) w[NW1 / 2 + t] = make_double2(uW1[2 * t], uW1[2 * t + 1]);
     if (NWP == 3) {
       w[NW1] = make_double2(I0[0], I0[NWP > 1 ? 1 : 0]);
-      sW[lane * SW + 2 * NW1 + 2] = I0[NWP - 1];
+      wr[2 * NW1 + 2] = I0[NWP - 1];
     } else {
-      sW[lane * SW + 2 * NW1] = I0[0];
+      wr[2 * NW1] = I0[0];
     }
   }
   // B gathers (hpp:216-217), factorised; direction 0 (x) is the contiguous one of the staged block
@@ -192,7 +212,8 @@ SPIC_DI void deposit_records(const double* sW, double* sAccA, bool fresh, int ni
     for (int t = 0; t < NWP; ++t) acc[j][t] = fresh ? 0.0 : sAccA[(j * NWP + t) * 32 + lane];
 #pragma unroll 2
   for (int it = 0; it < nit; ++it) {
-    const double* w = sW + (it * NSUB + sub) * SW;
+    // = sW + rec(it * NSUB + sub); written out so that the per-lane part stays a loop invariant
+    const double* w = sW + sub * SW + it * (NSUB * SW + Lay::SWZ * (NSUB / 4));
     const double2 a = *reinterpret_cast<const double2*>(w + 2 * th);
     const double b = w[NW1 + tu];
     double In[NWP];
@@ -248,7 +269,7 @@ __global__ void __launch_bounds__(kThreads, 2)
   double* sPart = sWarp + kTableDoubles;                    // [6][32]
   double* sBst = sPart + SP;                                // [2][3][NW1][NW1][NW1]
   double* sW = sBst + 2 * SB;                               // [32][SW]
-  double* sAcc = sW + 32 * SW;                              // [3][NACC][32]
+  double* sAcc = sW + Lay::SWA;                             // [3][NACC][32]
   const long st[3] = {1, g.pj, g.pk};
   const double nq = -q;  // -E_coef (hpp:114; Ics = Cs = 1)
   const unsigned nchunk = (unsigned)((ncell + kChunk - 1) / kChunk);
