@@ -53,7 +53,10 @@ constexpr int kWarps = 8;
 constexpr int kThreads = kWarps * 32;
 constexpr unsigned kFull = 0xffffffffu;
 constexpr int kContBase = -100;  // mover-list code of an ejected particle: kContBase - first sub-flow still to do
-constexpr int kChunk = 8;        // cells per work unit
+#ifndef SPIC_CHUNK
+#define SPIC_CHUNK 8
+#endif
+constexpr int kChunk = SPIC_CHUNK;        // cells per work unit
 constexpr int kTableDoubles = 3 * kChunk + 4;  // per-warp chunk tables + the current cell's coordinates
 
 template <class I>
@@ -112,7 +115,9 @@ SPIC_DI double gather_block(const double* blk, const double (&w0)[N0], const dou
       a1 = j == 0 ? w1[0] * s : fma(w1[j], s, a1);
     }
     a2 = k == 0 ? w2[0] * a1 : fma(w2[k], a1, a2);
+#ifndef SPIC_GATHER_NO_BARRIER
     asm volatile("" ::: "memory");  // bound load hoisting (register pressure)
+#endif
   }
   return a2;
 }
@@ -161,7 +166,7 @@ SPIC_DI void axis_part(double (&x)[3], double (&v)[3], double x1, const double (
   constexpr int U = (A + 1) % 3, L = (A + 2) % 3;  // hpp:90-91
   constexpr int NW1 = I::NW1, NWP = I::NWP;
   using Lay = BlockLayout<I>;
-  constexpr int NS = Lay::NS, SW = Lay::SW;
+  constexpr int NS = Lay::NS;
   {  // deposition record of this particle: -q W1_l, W1_u, I   (hpp:194,215)
     double* wr = sW + Lay::rec(lane);
     double2* w = reinterpret_cast<double2*>(wr);
@@ -210,7 +215,11 @@ SPIC_DI void deposit_records(const double* sW, double* sAccA, bool fresh, int ni
   for (int j = 0; j < 2; ++j)
 #pragma unroll
     for (int t = 0; t < NWP; ++t) acc[j][t] = fresh ? 0.0 : sAccA[(j * NWP + t) * 32 + lane];
-#pragma unroll 2
+#ifndef SPIC_DEPOSIT_UNROLL
+#define SPIC_DEPOSIT_UNROLL 8
+#endif
+  constexpr int kUnroll = SPIC_DEPOSIT_UNROLL;
+#pragma unroll kUnroll
   for (int it = 0; it < nit; ++it) {
     // = sW + rec(it * NSUB + sub); written out so that the per-lane part stays a loop invariant
     const double* w = sW + sub * SW + it * (NSUB * SW + Lay::SWZ * (NSUB / 4));
@@ -259,7 +268,7 @@ __global__ void __launch_bounds__(kThreads, 2)
                  int* __restrict__ flags, long ncell, unsigned* __restrict__ work, unsigned* __restrict__ ekey) {
   constexpr int NW1 = I::NW1, NWP = I::NWP;
   using Lay = BlockLayout<I>;
-  constexpr int NS = Lay::NS, SB = Lay::SB, SP = Lay::SP, SW = Lay::SW, NACC = Lay::NACC, NSUB = Lay::NSUB;
+  constexpr int NS = Lay::NS, SB = Lay::SB, SP = Lay::SP, NACC = Lay::NACC, NSUB = Lay::NSUB;
   extern __shared__ __align__(16) double smem[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   double* sWarp = smem + warp * Lay::PER_WARP;
