@@ -140,8 +140,15 @@ struct PushLayout {
   static constexpr int NW1 = I::NW1;
   static constexpr int NS = NW1 * NW1 * NW1;  // stencil points per component
   static constexpr int SE = 3 * NS;           // one stencil
+#ifdef SPIC_PUSH_NO_SLOT_PAD
+  static constexpr int SES = SE;
+#else
+  // slot stride: 16 bytes more than the stencil, so that the lanes of a batch that spans two cells read their
+  // two stencil rows (same row offset, different slots) from different banks instead of replaying the LDS.128
+  static constexpr int SES = SE + 2;
+#endif
   static constexpr int SP = 6 * 32;           // one particle batch
-  static constexpr int PER_WARP = 2 * SP + kRing * SE;
+  static constexpr int PER_WARP = 2 * SP + kRing * SES;
 };
 
 template <class I>
@@ -150,7 +157,7 @@ __global__ void __launch_bounds__(kThreads, 2)
                   const double* __restrict__ E, double coef, long ncell, int cells_per_block) {
   constexpr int NW1 = I::NW1, NWP = I::NWP;
   using Lay = PushLayout<I>;
-  constexpr int NS = Lay::NS, SE = Lay::SE, SP = Lay::SP;
+  constexpr int NS = Lay::NS, SE = Lay::SE, SES = Lay::SES, SP = Lay::SP;
   extern __shared__ __align__(16) double smem[];
   __shared__ BlockTables T;
   __shared__ long s_soff[SE];
@@ -173,7 +180,7 @@ __global__ void __launch_bounds__(kThreads, 2)
 
   auto stage = [&](int X, int sl) {
     const double* src = E + T.base[X];
-    double* d = sEst + sl * SE;
+    double* d = sEst + sl * SES;
 #pragma unroll
     for (int s = lane; s < SE; s += 32) cp_async8(d + s, src + s_soff[s]);
   };
@@ -217,7 +224,7 @@ __global__ void __launch_bounds__(kThreads, 2)
     if (lane < b.n()) {
       const long idx = my_index(b);
       const double* sP = sPart + pb * SP + lane;
-      const double* sE = sEst + (lane < b.n0 ? b.slot0 : b.slot1) * SE;
+      const double* sE = sEst + (lane < b.n0 ? b.slot0 : b.slot1) * SES;
       // the particle lies inside its bin cell: x - floor(x) is the exact in-cell coordinate
       const double x = sP[0], y = sP[32], z = sP[64];
       const double fx = x - floor(x), fy = y - floor(y), fz = z - floor(z);
