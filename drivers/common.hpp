@@ -59,8 +59,10 @@ struct Common {
 // one Simulation per process: device = local rank, z slabs over the launcher's ranks
 inline Simulation* make_simulation(const Common& c, int nghost) {
   const int nranks = ParallelDescriptor::NProcs(), rank = ParallelDescriptor::MyProc();
-  Simulation* s = new Simulation(c.geometry(), c.wrange, nghost, ParallelDescriptor::LocalRank(), c.map4_mode,
-                                 nranks, rank);
+  // guard cells are internal to the library (fields travel as valid cells): across ranks it picks the width
+  // itself (interpolation range + 1 on periodic boxes, which the fused schedule needs over z slabs)
+  Simulation* s = new Simulation(c.geometry(), c.wrange, nranks > 1 ? 0 : nghost, ParallelDescriptor::LocalRank(),
+                                 c.map4_mode, nranks, rank);
   s->comm_bootstrap();
   return s;
 }

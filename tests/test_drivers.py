@@ -200,3 +200,27 @@ def test_bernstein_driver_tracks_the_oracle(drivers, tmp_path):
     got = energies(r.stdout)
     assert got.shape == ref.shape
     assert np.max(np.abs(got - ref) / np.abs(ref)) < 1e-11 * nsteps
+
+
+@pytest.mark.gpu
+def test_langmuir_driver_on_two_gpus_matches_one(drivers, tmp_path):
+    """One process per GPU, z slabs, NCCL id exchanged through a file (Simulation::comm_bootstrap): the ENERGY
+    lines of a 2-rank run equal those of the 1-rank run of the same deck (fused and reference schedules)."""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    args = ["n_cell=8 8 16", "ppc=6", "nsteps=6", "precision=17", "seed=5", "order=2", "output_interval=-1",
+            "checkpoint_interval=-1", "data_folder_name=%s" % (tmp_path / "mg")]
+    one = run_driver(drivers["langmuir"], "langmuir", *args)
+    assert one.returncode == 0, one.stderr
+    procs = []
+    for rank in range(2):
+        env = dict(os.environ, RANK=str(rank), WORLD_SIZE="2", LOCAL_RANK=str(rank), MASTER_PORT="29517",
+                   SPIC_ID_FILE=str(tmp_path / "nccl_id"))
+        procs.append(subprocess.Popen([drivers["langmuir"], os.path.join(DECKS, "langmuir.input")] + args, env=env,
+                                      stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True))
+    outs = [p.communicate(timeout=300) for p in procs]
+    assert all(p.returncode == 0 for p in procs), [o[1] for o in outs]
+    e1, e2 = energies(one.stdout), energies(outs[0][0])
+    assert e1.shape == e2.shape == (6, 2) and energies(outs[1][0]).size == 0  # only the IO rank prints
+    assert np.max(np.abs(e2 - e1) / np.abs(e1)) < 1e-11
