@@ -59,6 +59,8 @@ def parse():
     ap.add_argument("--interp", default="p8r2", choices=["p8r2", "pwl"])
     ap.add_argument("--order", type=int, default=4, choices=[1, 2, 4])
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--clock-period-ms", type=int, default=200,
+                    help="nvidia-smi sampling period during the timed region (0: no sampler; diagnosis only)")
     ap.add_argument("--no-fuse", action="store_true", help="reference launch-per-sub-flow schedule (A/B against the fused axis block)")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--e2e-steps", type=int, default=2)
@@ -175,11 +177,14 @@ class ClockSampler:
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
 
-    def __init__(self, device):
+    def __init__(self, device, period_ms=200):
         self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        self.p = None
+        if period_ms <= 0:
+            return
         try:
             self.p = subprocess.Popen(["nvidia-smi", "-i", str(device), "--query-gpu=" + self.Q,
-                                       "--format=csv,noheader,nounits", "-lms", "200"],
+                                       "--format=csv,noheader,nounits", "-lms", str(period_ms)],
                                       stdout=self.f, stderr=subprocess.DEVNULL)
         except OSError:
             self.p = None
@@ -306,7 +311,7 @@ def ours_main(a):
     sim.kernel_times(reset=True)
     l0 = sim.launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    sampler = ClockSampler(local)
+    sampler = ClockSampler(local, a.clock_period_ms)
     torch.cuda.synchronize()
     barrier()
     e0.record(stream)

@@ -1249,6 +1249,14 @@ int engine_ingest(Ctx* c, Species& s) {
 }
 
 void engine_free_species(Ctx*, Species& s) {
+  if (s.tail_ev) {
+    if (s.tail_pending) cudaEventSynchronize(s.tail_ev);
+    cudaEventDestroy(s.tail_ev);
+  }
+  if (s.h_tail) cudaFreeHost(s.h_tail);
+  s.tail_ev = nullptr;
+  s.h_tail = nullptr;
+  s.tail_pending = false;
   free_soa_local(s.b);
   if (s.start) cudaFree(s.start);
   if (s.count) cudaFree(s.count);
@@ -1509,15 +1517,29 @@ int engine_number_density(Ctx* c, Species& s, double* nd) {
 }
 
 int engine_maintain(Ctx* c) {
-  // rebin a species whose overflow tail has grown past ~0.4 % of its particles
+  // Rebin a species whose overflow tail has grown past ~0.4 % of its particles.  The tail length is read back
+  // WITHOUT stalling the stream: every call enqueues a copy into a pinned slot and looks at the value of the
+  // previous call once its event has completed -- the decision lags by one step, the step path has no host sync
+  // (each one idled the GPU for a host round trip; on a busy host that was 5-20 % of the step).
   for (auto& s : c->sp) {
-    if (!s.binned) continue;
-    long tail = 0;
-    int rc = tail_count(c, s, &tail);
-    if (rc) return rc;
-    if (tail > s.n_total / 256 + 1024 || tail >= s.capd) {
-      if ((rc = rebin(c, s, tail))) return rc;
+    if (!s.binned || !s.d_nd) continue;
+    if (!s.h_tail) {
+      SPIC_CUDA_CHECK(c, cudaMallocHost(&s.h_tail, sizeof(unsigned long long)));
+      SPIC_CUDA_CHECK(c, cudaEventCreateWithFlags(&s.tail_ev, cudaEventDisableTiming));
+      *s.h_tail = 0;
     }
+    if (s.tail_pending) {
+      if (cudaEventQuery(s.tail_ev) != cudaSuccess) continue;  // still in flight: look again next step
+      s.tail_pending = false;
+      const long tail = (long)*s.h_tail < s.capd ? (long)*s.h_tail : s.capd;
+      if (tail > s.n_total / 256 + 1024 || tail >= s.capd) {
+        int rc = rebin(c, s, -1);  // (re-reads the exact count itself)
+        if (rc) return rc;
+      }
+    }
+    SPIC_CUDA_CHECK(c, cudaMemcpyAsync(s.h_tail, s.d_nd, sizeof(unsigned long long), cudaMemcpyDeviceToHost, c->stream));
+    SPIC_CUDA_CHECK(c, cudaEventRecord(s.tail_ev, c->stream));
+    s.tail_pending = true;
   }
   return SPIC_OK;
 }

@@ -600,6 +600,8 @@ int launch_block(Ctx* c, Species& s, double h) {
     e->cont_key_cap = e->mv.cap;
   }
   SPIC_CUDA_CHECK(c, cudaMemsetAsync(e->block_work, 0, sizeof(unsigned), c->stream));
+  // unused sort keys = all ones: they sort behind every cell index (fused_axis_continue)
+  SPIC_CUDA_CHECK(c, cudaMemsetAsync(e->cont_key, 0xff, sizeof(unsigned) * (size_t)e->mv.cap, c->stream));
   const size_t smem = sizeof(double) * kWarps * BlockLayout<I>::PER_WARP;
   static bool attr = false;
   if (!attr) {
@@ -626,49 +628,50 @@ int fused_axis_block(Ctx* c, Species& s, double h) {
 
 int fused_axis_continue(Ctx* c, Species& s, double h) {
   EngineState* e = eng(c);
-  // how many were ejected?  (one small read-back per block; the host only runs ahead of the stream anyway)
-  unsigned n = 0;
-  SPIC_CUDA_CHECK(c, cudaMemcpyAsync(&n, e->mv.n, sizeof(unsigned), cudaMemcpyDeviceToHost, c->stream));
-  SPIC_CUDA_CHECK(c, cudaStreamSynchronize(c->stream));
-  if (n > e->mv.cap) n = e->mv.cap;
-  if (n == 0) return SPIC_OK;
-  const unsigned* perm = nullptr;
-  if (n >= 4096) {  // sort the entries by home cell (radix sort of (cell, index) pairs)
-    if (e->cont_sort_cap < n) {
-      const unsigned want = n + n / 4 + 4096;
-      for (unsigned** p : {&e->cont_key2, &e->cont_idx, &e->cont_perm}) {
-        if (*p) cudaFree(*p);
-        *p = nullptr;
-        SPIC_CUDA_CHECK(c, cudaMalloc(p, sizeof(unsigned) * (size_t)want));
-      }
-      e->cont_sort_cap = want;
-      k_iota<<<c->sm_count * 4, 256, 0, c->stream>>>(e->cont_idx, want);
-      c->launches++;
-    }
-    int bits = 1;
-    while ((1L << bits) < c->g.cells() && bits < 32) ++bits;
-    size_t bytes = 0;
-    cub::DeviceRadixSort::SortPairs(nullptr, bytes, e->cont_key, e->cont_key2, e->cont_idx, e->cont_perm, (int)n, 0,
-                                    bits, c->stream);
-    if (bytes > e->cont_tmp_bytes) {
-      if (e->cont_tmp) cudaFree(e->cont_tmp);
-      e->cont_tmp = nullptr;
-      SPIC_CUDA_CHECK(c, cudaMalloc(&e->cont_tmp, bytes));
-      e->cont_tmp_bytes = bytes;
-    }
-    SPIC_CUDA_CHECK(c, cub::DeviceRadixSort::SortPairs(e->cont_tmp, bytes, e->cont_key, e->cont_key2, e->cont_idx,
-                                                       e->cont_perm, (int)n, 0, bits, c->stream));
-    c->launches += 3;
-    perm = e->cont_perm;
+  // No read-back of the ejected count: the whole mover list (capacity entries) is sorted by home cell, the unused
+  // entries carry the key 0xffffffff (set before the block ran) and sort behind the real ones; k_axis_continue
+  // reads the count on the device.  One host round trip per block idled the GPU for longer than the extra sort.
+  const unsigned cap = e->mv.cap;
+  if (cap == 0) return SPIC_OK;
+  if (cap > 0x7fffffffu) {
+    c->err = "mover list too long for one radix sort (lower option mover_frac)";
+    return SPIC_ECAPACITY;
   }
+  if (e->cont_sort_cap < cap) {
+    for (unsigned** p : {&e->cont_key2, &e->cont_idx, &e->cont_perm}) {
+      if (*p) cudaFree(*p);
+      *p = nullptr;
+      SPIC_CUDA_CHECK(c, cudaMalloc(p, sizeof(unsigned) * (size_t)cap));
+    }
+    e->cont_sort_cap = cap;
+    k_iota<<<c->sm_count * 4, 256, 0, c->stream>>>(e->cont_idx, cap);
+    c->launches++;
+  }
+  int bits = 1;
+  while ((1L << bits) < c->g.cells() && bits < 31) ++bits;
+  ++bits;  // the bit that tells an unused entry (all ones) from a cell index
+  size_t bytes = 0;
+  cub::DeviceRadixSort::SortPairs(nullptr, bytes, e->cont_key, e->cont_key2, e->cont_idx, e->cont_perm, (int)cap, 0, bits,
+                                  c->stream);
+  if (bytes > e->cont_tmp_bytes) {
+    if (e->cont_tmp) cudaFree(e->cont_tmp);
+    e->cont_tmp = nullptr;
+    SPIC_CUDA_CHECK(c, cudaMalloc(&e->cont_tmp, bytes));
+    e->cont_tmp_bytes = bytes;
+  }
+  SPIC_CUDA_CHECK(c, cub::DeviceRadixSort::SortPairs(e->cont_tmp, bytes, e->cont_key, e->cont_key2, e->cont_idx,
+                                                     e->cont_perm, (int)cap, 0, bits, c->stream));
+  c->launches += 3;
   KernelTimer t(c, KT_OTHER);
-  long nb = ((long)n + 127) / 128;
+  long nb = ((long)cap + 127) / 128;
   if (nb > (long)c->sm_count * 16) nb = (long)c->sm_count * 16;
   const double qm = s.q / s.m;
   if (c->cfg.interp == SPIC_INTERP_P8R2)
-    k_axis_continue<InterpP8R2><<<(int)nb, 128, 0, c->stream>>>(c->g, e->mv, perm, c->E, c->B, s.q, qm, h, c->d_flags);
+    k_axis_continue<InterpP8R2><<<(int)nb, 128, 0, c->stream>>>(c->g, e->mv, e->cont_perm, c->E, c->B, s.q, qm, h,
+                                                              c->d_flags);
   else
-    k_axis_continue<InterpPWL><<<(int)nb, 128, 0, c->stream>>>(c->g, e->mv, perm, c->E, c->B, s.q, qm, h, c->d_flags);
+    k_axis_continue<InterpPWL><<<(int)nb, 128, 0, c->stream>>>(c->g, e->mv, e->cont_perm, c->E, c->B, s.q, qm, h,
+                                                             c->d_flags);
   c->launches++;
   return SPIC_OK;
 }

@@ -55,6 +55,10 @@ struct Species {
   int* count = nullptr;   // [cells]
   long n_total = 0;       // particles of this species on this rank at the last rebin
   bool binned = false;
+  // tail length as last read back WITHOUT synchronising (engine_maintain): pinned slot + the event after the copy
+  unsigned long long* h_tail = nullptr;
+  cudaEvent_t tail_ev = nullptr;
+  bool tail_pending = false;
 };
 
 struct Ctx;
