@@ -198,6 +198,34 @@ def test_device_loader_is_the_numpy_twin(engine):
 
 
 @pytest.mark.parametrize("engine", ENGINES)
+def test_density_profile_loader_is_the_numpy_twin(engine):
+    """spic_load_density_plasma (add_particle_density with a profile, util.cpp:267-311): counts per cell =
+    int(profile * ppc_max), including profiles above 1 (simple_line_density) and empty cells; bit-identical
+    to synthetic.density_plasma, and equal to the uniform loader when the profile is 1."""
+    from strugepic_b200 import synthetic
+    n_cell = (48, 3, 4)
+    for prof, ppc in ((synthetic.simple_line_density, 5), (lambda n, i, j, k: np.exp(-((i - 24.0) / 8) ** 2) + 0.0 * (j + k), 7),
+                      (lambda n, i, j, k: 0.5 + 0.25 * ((i + j + k) % 3), 6)):
+        s = spic().Simulation(n_cell, interp=0, engine=engine)
+        s.add_particle_density(prof, ppc, 100.0, -1.0, 0.02, seed=99)
+        want = np.stack(synthetic.density_plasma(n_cell, prof, ppc, 0.02, 99))
+        got = np.stack(s.get_particles())
+        assert got.shape == want.shape and want.shape[1] > 0
+        got = got[:, util.match_particles(want, got)]
+        assert np.array_equal(got, want)
+        counts, _ = synthetic.density_counts(n_cell, prof, ppc)
+        cell = (np.floor(got[2]).astype(int) * n_cell[1] + np.floor(got[1]).astype(int)) * n_cell[0] + \
+            np.floor(got[0]).astype(int)
+        assert np.array_equal(np.bincount(cell, minlength=counts.size), counts.ravel())
+        s.close()
+    s = spic().Simulation(n_cell, interp=0, engine=engine)
+    s.add_particle_density(synthetic.uniform_density, 4, 100.0, -1.0, 0.01, seed=777)
+    want = np.stack(synthetic.uniform_plasma(n_cell, 4, 0.01, 777))
+    got = np.stack(s.get_particles())
+    assert np.array_equal(got[:, util.match_particles(want, got)], want)
+
+
+@pytest.mark.parametrize("engine", ENGINES)
 def test_energy_tracks_oracle(engine):
     n_cell = (16, 16, 16)
     parts = util.plasma(n_cell, 8, 0.01, 12345)
