@@ -298,6 +298,7 @@ def ours_main(a):
     npart_local = sim.num_particles()
     npart = int(allsum(float(npart_local)))
     fp64_peak = spic.probe_fp64_tflops(local, 0.5)
+    fp64_peak3 = spic.probe_fp64_tflops(local, 0.25, three_operands=True)
 
     if a.no_fuse:
         sim.set_option("fuse", 0)
@@ -363,6 +364,10 @@ def ours_main(a):
     roofline_fp64 = {"kernel": kname, "bound": "fp64", "achieved": ach_tf, "peak": fp64_peak,
                      "unit": "TFLOP/s", "frac": ach_tf / fp64_peak if fp64_peak else None,
                      "peak_source": "measured here: spic_probe_fp64_tflops (dependent-free DFMA chains, all SMs)",
+                     "three_register_operand_dfma_tflops": fp64_peak3,
+                     "three_register_operand_note": "DFMA with three distinct register operands (gathers, deposition: "
+                                                    "~2/3 of this kernel's FP64 instructions) issues every 3 cycles "
+                                                    "instead of 2: the register file, not the pipe, bounds it",
                      "algorithmic_flop_per_particle": f_axis * sub_per_launch,
                      "flop_accounting": "reference schedule: 18 Theta x 718 + 6 Theta_E x 842 flop per particle-step "
                                         "(SURVEY 8d); the fused schedule executes fewer (shared weight evaluations, "

@@ -176,6 +176,9 @@ int spic_set_option(spic_ctx* ctx, const char* name, double value);
 void* spic_stream(spic_ctx* ctx); /* cudaStream_t */
 /* FP64 FMA micro-benchmark for the roofline denominator: returns TFLOP/s */
 int spic_probe_fp64_tflops(int device, double seconds, double* tflops);
+/* the same chains with three distinct register operands per DFMA (what gathers and deposition issue): the
+ * register file sustains ~2/3 of the rate above; reported beside the roofline, not used as its denominator */
+int spic_probe_fp64_three_operand_tflops(int device, double seconds, double* tflops);
 
 #ifdef __cplusplus
 }

@@ -64,9 +64,13 @@ def I_Wp(a, b, interp=P8R2):
     return _lib.load().spic_I_Wp(interp, a, b)
 
 
-def probe_fp64_tflops(device=0, seconds=1.0):
+def probe_fp64_tflops(device=0, seconds=1.0, three_operands=False):
+    """Measured DFMA rate (TFLOP/s): chains with two loop-constant operands, or with three distinct register
+    operands per instruction (what the gathers and the deposition issue; the register file sustains ~2/3)."""
     out = C.c_double(0)
-    rc = _lib.load().spic_probe_fp64_tflops(device, seconds, C.byref(out))
+    lib = _lib.load()
+    fn = lib.spic_probe_fp64_three_operand_tflops if three_operands else lib.spic_probe_fp64_tflops
+    rc = fn(device, seconds, C.byref(out))
     if rc:
         raise SpicError(rc, "fp64 probe failed")
     return out.value

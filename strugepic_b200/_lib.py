@@ -62,6 +62,7 @@ SIGNATURES = {
     "spic_set_option": (i32, [vp, C.c_char_p, dbl]),
     "spic_stream": (vp, [vp]),
     "spic_probe_fp64_tflops": (i32, [i32, dbl, _dp]),
+    "spic_probe_fp64_three_operand_tflops": (i32, [i32, dbl, _dp]),
 }
 
 _lib = None

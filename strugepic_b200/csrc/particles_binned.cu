@@ -1436,7 +1436,7 @@ int engine_push_v_e(Ctx* c, Species& s, double dt) {
   const double coef = dt * s.q / s.m;  // hpp:267
   {
     KernelTimer t(c, KT_PUSHVE);
-    if (e->pushve_kernel == 3 || e->pushve_kernel == 0) {
+    if (e->pushve_kernel == 3 || e->pushve_kernel == 4 || e->pushve_kernel == 0) {
       const int rc = stream_push_v_e(c, s, dt);
       if (rc) return rc;
       c->launches--;  // counted below

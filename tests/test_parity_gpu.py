@@ -282,16 +282,17 @@ def test_number_density_and_plot_file(tmp_path, interp, periodic, engine):
     assert np.allclose(plt["n_density"], got, rtol=1e-13, atol=0)  # atomics: the order of additions varies
 
 
-@pytest.mark.parametrize("variant", [1, 2, 3])
+@pytest.mark.parametrize("variant", [1, 2, 3, 4])
 def test_kernel_variants_agree_with_oracle(variant):
-    """Both generations of the binned particle kernels stay covered (option axis_kernel / pushve_kernel)."""
+    """Every generation of the binned particle kernels stays covered (option axis_kernel / pushve_kernel;
+    4 = the pair-blocked push_V_E, with the v3 theta_axis)."""
     n_cell = (16, 12, 8)
     E, B = util.rng_fields(n_cell, 71, 0.3)
     parts = util.plasma(n_cell, 40, 0.15, 71)   # > 32 per cell: several batches per bin
     for interp in (0, 1):
         o = ora.best_oracle(n_cell, interp=interp)
         s = spic().Simulation(n_cell, interp=interp)
-        s.set_option("axis_kernel", variant)
+        s.set_option("axis_kernel", min(variant, 3))
         s.set_option("pushve_kernel", variant)
         for t in (o, s):
             util.load_state(t, E, B, parts, -1.0 / 40, 100.0 / 40)
@@ -382,3 +383,5 @@ def test_errors_are_reported():
 def test_fp64_probe_runs():
     tf = spic().probe_fp64_tflops(0, 0.2)
     assert 5.0 < tf < 80.0, tf
+    tf3 = spic().probe_fp64_tflops(0, 0.2, three_operands=True)  # register-file bound: ~2/3 of the above
+    assert 5.0 < tf3 <= tf * 1.02, (tf3, tf)
