@@ -23,6 +23,7 @@ struct EngineState {
   // (k_*_v2), 3 particle-stream batches that span cells (k_*_v3, particles_stream.cu)
   // 0 = automatic: theta_axis uses v3 below ~40 particles per cell (batches would be mostly padding
   // with one warp per cell) and v2 above (its per-batch bookkeeping is cheaper); push_V_E uses v3.
+  // pushve_kernel = 4: the v3 stream with two particles per lane (k_push_v_e_v4), opt-in.
   int axis_kernel = 0;
   int pushve_kernel = 0;
   // 1: Theta_map2 / Theta_map4 run the six position sub-flows of every map2 as one fused axis block
@@ -41,6 +42,15 @@ struct EngineState {
   unsigned long long* d_scalar = nullptr;  // small device scratch (8 words)
 };
 EngineState* eng(Ctx* c);
+
+// cudaFuncSetAttribute(MaxDynamicSharedMemorySize) is per DEVICE: each launch site keeps one mask per kernel with a
+// bit per device ordinal (a process may hold contexts on several GPUs).
+inline bool smem_attr_needed(unsigned long long& mask, int device) {
+  const unsigned long long bit = 1ull << (device & 63);
+  if (mask & bit) return false;
+  mask |= bit;
+  return true;
+}
 
 // ---- shared-memory pipeline helpers (cp.async = LDGSTS) --------------------------------
 __device__ __forceinline__ void cp_async8(double* smem_dst, const double* gsrc) {

@@ -1199,13 +1199,12 @@ int theta_axis_v2_dispatch(Ctx* c, Species& s, int comp, double dt) {
   const int grid = (int)((ncell + cpb - 1) / cpb);
   const size_t smem = sizeof(double) * kWarps * AxisV2Layout<I>::PER_WARP;
   const double qm = s.q / s.m;
-  static bool attr_set[3] = {false, false, false};
+  static unsigned long long attr_set[3] = {0, 0, 0};
 #define SPIC_LAUNCH_V2(AX)                                                                                        \
   do {                                                                                                            \
-    if (!attr_set[AX]) {                                                                                          \
+    if (smem_attr_needed(attr_set[AX], c->cfg.device)) {                                                          \
       SPIC_CUDA_CHECK(c, cudaFuncSetAttribute(k_theta_axis_v2<I, AX>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
                                               (int)smem));                                                        \
-      attr_set[AX] = true;                                                                                        \
     }                                                                                                             \
     k_theta_axis_v2<I, AX><<<grid, kThreads, smem, c->stream>>>(c->g, s.b, s.start, s.count, c->E, c->B, s.q, qm, dt, \
                                                                 e->mv, c->d_flags, ncell, cpb);                   \
@@ -1443,12 +1442,10 @@ int engine_push_v_e(Ctx* c, Species& s, double dt) {
     } else if (e->pushve_kernel != 1) {
       if (c->cfg.interp == SPIC_INTERP_P8R2) {
         const size_t smem = sizeof(double) * kWarps * PushV2Layout<InterpP8R2>::PER_WARP;
-        static bool attr = false;
-        if (!attr) {
+        static unsigned long long attr = 0;
+        if (smem_attr_needed(attr, c->cfg.device))
           SPIC_CUDA_CHECK(c, cudaFuncSetAttribute(k_push_v_e_v2<InterpP8R2>,
                                                   cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-          attr = true;
-        }
         k_push_v_e_v2<InterpP8R2><<<grid, kThreads, smem, c->stream>>>(c->g, s.b, s.start, s.count, c->E, coef, ncell, cpb);
       } else {
         const size_t smem = sizeof(double) * kWarps * PushV2Layout<InterpPWL>::PER_WARP;

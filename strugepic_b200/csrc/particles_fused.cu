@@ -603,11 +603,9 @@ int launch_block(Ctx* c, Species& s, double h) {
   // unused sort keys = all ones: they sort behind every cell index (fused_axis_continue)
   SPIC_CUDA_CHECK(c, cudaMemsetAsync(e->cont_key, 0xff, sizeof(unsigned) * (size_t)e->mv.cap, c->stream));
   const size_t smem = sizeof(double) * kWarps * BlockLayout<I>::PER_WARP;
-  static bool attr = false;
-  if (!attr) {
+  static unsigned long long attr = 0;
+  if (smem_attr_needed(attr, c->cfg.device))
     SPIC_CUDA_CHECK(c, cudaFuncSetAttribute(k_axis_block<I>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attr = true;
-  }
   k_axis_block<I><<<(int)want, kThreads, smem, c->stream>>>(c->g, s.b, s.start, s.count, c->E, c->B, s.q, s.q / s.m,
                                                             h, e->mv, c->d_flags, ncell, e->block_work, e->cont_key);
   c->launches++;

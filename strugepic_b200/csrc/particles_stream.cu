@@ -839,11 +839,9 @@ __global__ void __launch_bounds__(kThreads, 2)
 }
 
 template <class K>
-int set_smem(Ctx* c, K kernel, size_t smem, bool& done) {
-  if (!done) {
+int set_smem(Ctx* c, K kernel, size_t smem, unsigned long long& done) {
+  if (smem_attr_needed(done, c->cfg.device))
     SPIC_CUDA_CHECK(c, cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    done = true;
-  }
   return SPIC_OK;
 }
 
@@ -863,7 +861,7 @@ int axis_dispatch(Ctx* c, Species& s, int comp, double dt) {
   const int grid = (int)((ncell + cpb - 1) / cpb);
   const size_t smem = sizeof(double) * kWarps * AxisLayout<I>::PER_WARP;
   const double qm = s.q / s.m;
-  static bool attr[3] = {false, false, false};
+  static unsigned long long attr[3] = {0, 0, 0};
   int rc;
 #define SPIC_LAUNCH_AXIS(AX)                                                                                       \
   do {                                                                                                             \
@@ -888,14 +886,14 @@ int push_dispatch(Ctx* c, Species& s, double dt) {
   int rc;
   if (eng(c)->pushve_kernel == 4) {  // two particles per lane (opt-in: option pushve_kernel = 4)
     const size_t smem4 = sizeof(double) * kWarps * PushLayout4<I>::PER_WARP;
-    static bool attr4 = false;
+    static unsigned long long attr4 = 0;
     if ((rc = set_smem(c, k_push_v_e_v4<I>, smem4, attr4))) return rc;
     k_push_v_e_v4<I><<<grid, kThreads, smem4, c->stream>>>(c->g, s.b, s.start, s.count, c->E, coef, ncell, cpb);
     c->launches++;
     return SPIC_OK;
   }
   const size_t smem = sizeof(double) * kWarps * PushLayout<I>::PER_WARP;
-  static bool attr = false;
+  static unsigned long long attr = 0;
   if ((rc = set_smem(c, k_push_v_e_v3<I>, smem, attr))) return rc;
   k_push_v_e_v3<I><<<grid, kThreads, smem, c->stream>>>(c->g, s.b, s.start, s.count, c->E, coef, ncell, cpb);
   c->launches++;
