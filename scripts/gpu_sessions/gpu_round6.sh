@@ -2,10 +2,10 @@
 # first run of the fused axis block: debug cases, sanitizer, parity tests, A/B timing, bench
 set -x
 mkdir -p gpurun_out
-timeout 300 python scripts/debug_fused.py 2>&1 | tee gpurun_out/debug_fused.log | tail -60
+timeout 300 python tests/tools/debug_fused.py 2>&1 | tee gpurun_out/debug_fused.log | tail -60
 timeout 600 compute-sanitizer --tool memcheck --error-exitcode 9 python -c "
 import sys; sys.path[:0]=['.','oracle','tests']
-import scripts.debug_fused as d
+import sys; sys.path.insert(0, "tests/tools"); import debug_fused as d
 d.case((6,5,4), 40, 0.08, 0, 4, 1, 1)
 d.case((6,5,4), 40, 0.3, 0, 4, 1, 1)
 d.case((6,5,4), 40, 0.08, 1, 2, 1, 1)

@@ -1,10 +1,10 @@
-"""Pair-blocked push_V_E (option pushve_kernel = 4) against the oracle and against v3, then its time at 128^3 x 64 ppc."""
+"""(test infrastructure: uses the oracle)  Pair-blocked push_V_E (option pushve_kernel = 4) against the oracle and against v3, then its time at 128^3 x 64 ppc."""
 import os
 import sys
 
 import numpy as np
 
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 for p in (ROOT, os.path.join(ROOT, "oracle"), os.path.join(ROOT, "tests")):
     sys.path.insert(0, p)
 import oracle as ora  # noqa: E402

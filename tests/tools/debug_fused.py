@@ -1,10 +1,10 @@
-"""Development aid: fused axis block vs the oracle on small boxes, errors printed without asserting."""
+"""(test infrastructure: uses the oracle)  Development aid: fused axis block vs the oracle on small boxes, errors printed without asserting."""
 import os
 import sys
 
 import numpy as np
 
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 for p in (ROOT, os.path.join(ROOT, "oracle"), os.path.join(ROOT, "tests")):
     sys.path.insert(0, p)
 import oracle as ora  # noqa: E402
