@@ -66,3 +66,21 @@ def test_synthetic_generator_statistics():
     # slab generation is a slice of the global generation
     xs = synthetic.uniform_plasma((6, 5, 4), 16, 0.01, 12345, z_range=(2, 4))
     assert np.array_equal(xs[0], x[len(x) // 2:]) and np.array_equal(xs[5], vz[len(x) // 2:])
+
+
+def test_density_profile_twin_is_decomposition_independent():
+    """synthetic.density_plasma (the numpy twin of spic_load_density_plasma): the z slabs of a decomposed box
+    concatenate to the undecomposed draw, a profile of 1 reproduces uniform_plasma, counts follow int(profile * ppc)."""
+    import numpy as np
+    from strugepic_b200 import synthetic
+    n_cell = (9, 4, 6)
+    prof = lambda n, i, j, k: 0.25 + 0.125 * ((i + 2 * j + 3 * k) % 7)  # noqa: E731  (up to 1.0)
+    whole = np.stack(synthetic.density_plasma(n_cell, prof, 8, 0.05, 42))
+    parts = [np.stack(synthetic.density_plasma(n_cell, prof, 8, 0.05, 42, z_range=(k0, k0 + 2))) for k0 in (0, 2, 4)]
+    assert np.array_equal(np.concatenate(parts, axis=1), whole)
+    counts, stride = synthetic.density_counts(n_cell, prof, 8)
+    assert stride == 8 and whole.shape[1] == counts.sum() and counts.min() == 2 and counts.max() == 8
+    uni = np.stack(synthetic.density_plasma(n_cell, synthetic.uniform_density, 5, 0.05, 42))
+    assert np.array_equal(uni, np.stack(synthetic.uniform_plasma(n_cell, 5, 0.05, 42)))
+    over, stride2 = synthetic.density_counts((40, 1, 1), synthetic.simple_line_density, 10)
+    assert stride2 == 19 and over[0, 0, 39] == 19  # a profile above 1 widens the RNG key stride
