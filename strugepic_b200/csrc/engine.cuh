@@ -29,6 +29,8 @@ struct EngineState {
   // 1: Theta_map2 / Theta_map4 run the six position sub-flows of every map2 as one fused axis block
   // (particles_fused.cu) and merge adjacent Theta_E; 0: the reference's launch-per-sub-flow schedule
   int fuse = 1;
+  // 1: the fused axis block cuts batches that may span two cells (k_axis_block_s); opt-in, see particles_fused.cu
+  int block_stream = 0;
   unsigned* block_work = nullptr;   // chunk counter of the fused axis-block kernel
   // continuation of the ejected particles: sort key (home cell) per mover-list entry + radix-sort buffers
   unsigned* cont_key = nullptr;

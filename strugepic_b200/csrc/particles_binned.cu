@@ -1564,6 +1564,10 @@ int engine_set_option(Ctx* c, const char* name, double value) {
     e->pushve_kernel = (int)value;
     return SPIC_OK;
   }
+  if (!strcmp(name, "block_stream")) {
+    e->block_stream = value != 0;
+    return SPIC_OK;
+  }
   if (!strcmp(name, "fuse")) {
     e->fuse = value != 0;
     return SPIC_OK;

@@ -43,6 +43,7 @@
 #include <cub/device/device_radix_sort.cuh>
 
 #include "engine.cuh"
+#include "fused_cut.cuh"
 #include "particle_math.cuh"
 
 namespace spic {
@@ -91,6 +92,9 @@ struct BlockLayout {
 #endif
   static constexpr int PER_WARP =
       (kTableDoubles + SP + 2 * SB + SWA + SA + SPIC_WARP_ALIGN - 1) / SPIC_WARP_ALIGN * SPIC_WARP_ALIGN;
+  // the cell-spanning variant: coordinates of two cells, stencil buffers with a 2-double pad each
+  static constexpr int PER_WARP_S = (kTableDoubles + 4 + SP + 2 * (SB + 2) + SWA + SA + SPIC_WARP_ALIGN - 1) /
+                                    SPIC_WARP_ALIGN * SPIC_WARP_ALIGN;
   static_assert(SB % 2 == 0 && SW % 2 == 0 && NW1 % 2 == 0 && kTableDoubles % 2 == 0,
                 "16-byte alignment of the sub-buffers");
 };
@@ -490,6 +494,334 @@ __global__ void __launch_bounds__(kThreads, 2)
   cp_async_wait<0>();
 }
 
+// ------------------------------------------------------------------------------------------------------------------
+// k_axis_block_s: the same block with batches that may span two cells (option "block_stream" = 1; NOT the default
+// until it has been verified on the GPU -- see DESIGN.md "what comes next").
+//
+// k_axis_block hands out the particles cell by cell, so a cell of 65 particles costs three batches: 2.3-2.5 batches
+// per cell at 64 ppc against 2.0 ideal, i.e. 15-20 % of the FP64 issue slots go to padding lanes.  Here the last,
+// short batch of a cell A is topped up with the first particles of the next cell B (fused_cut.cuh; 2.08 batches per
+// cell on the same distribution).  What changes in a mixed batch:
+//   * cell data is per lane: coordinates sH[buf][.] and the staged stencil sBst[buf] with buf = bb for the lanes
+//     of A and bb ^ 1 for those of B (B's stencil is the one that is prefetched anyway);
+//   * deposition runs in two parts over the same records: the part of A adds to A's parked accumulators and goes
+//     straight to memory (A ends here: one RED per stencil point and sub-flow), which frees the parked slot for
+//     the part of B, which starts from zero like any first batch.  One set of parked accumulators stays enough;
+//   * stayers are compacted per cell, A's count is final after the batch.
+// ------------------------------------------------------------------------------------------------------------------
+template <class I>
+SPIC_DI void acc_load(const double* sAccA, double (&acc)[2][I::NWP], bool zero, int lane) {
+#pragma unroll
+  for (int j = 0; j < 2; ++j)
+#pragma unroll
+    for (int t = 0; t < I::NWP; ++t) acc[j][t] = zero ? 0.0 : sAccA[(j * I::NWP + t) * 32 + lane];
+}
+template <class I>
+SPIC_DI void acc_store(double* sAccA, const double (&acc)[2][I::NWP], int lane) {
+#pragma unroll
+  for (int j = 0; j < 2; ++j)
+#pragma unroll
+    for (int t = 0; t < I::NWP; ++t) sAccA[(j * I::NWP + t) * 32 + lane] = acc[j][t];
+}
+// records of the iterations [it0, it1), particles p in [lo, hi) only, added to acc (same arithmetic as deposit_records)
+template <class I>
+SPIC_DI void deposit_range(const double* sW, double (&acc)[2][I::NWP], int it0, int it1, int lo, int hi, int lane) {
+  constexpr int NW1 = I::NW1, NWP = I::NWP;
+  using Lay = BlockLayout<I>;
+  constexpr int SW = Lay::SW, TH = Lay::TH, LPP = Lay::LPP, NSUB = Lay::NSUB;
+  const int tu = lane % NW1, th = (lane / NW1) % TH, sub = lane / LPP;
+#pragma unroll 4
+  for (int it = it0; it < it1; ++it) {
+    const int p = it * NSUB + sub;
+    const double* w = sW + sub * SW + it * (NSUB * SW + Lay::SWZ * (NSUB / 4));
+    const double2 a = *reinterpret_cast<const double2*>(w + 2 * th);
+    const double b = w[NW1 + tu];
+    double In[NWP];
+    lds_row<NWP>(w + 2 * NW1, In);
+    if (p >= lo && p < hi) {
+#pragma unroll
+      for (int t = 0; t < NWP; ++t) {
+        const double bI = b * In[t];
+        acc[0][t] = fma(a.x, bI, acc[0][t]);
+        acc[1][t] = fma(a.y, bI, acc[1][t]);
+      }
+    }
+  }
+}
+// sums acc over the particle subsets and issues one RED per stencil point; Ea = this lane's first point of the
+// component, sL / sA = the strides along l and along the push axis (hpp:215)
+template <class I>
+SPIC_DI void flush_regs(const double (&acc)[2][I::NWP], double* __restrict__ Ea, long sL, long sA, int lane) {
+  using Lay = BlockLayout<I>;
+  const int sub = lane / Lay::LPP;
+#pragma unroll
+  for (int j = 0; j < 2; ++j)
+#pragma unroll
+    for (int t = 0; t < I::NWP; ++t) {
+      double a = acc[j][t];
+#pragma unroll
+      for (int m = Lay::LPP; m < 32; m <<= 1) a += __shfl_xor_sync(kFull, a, m);
+      if (sub == 0) atomicAdd(Ea + j * sL + t * sA, a);
+    }
+}
+
+template <class I>
+__global__ void __launch_bounds__(kThreads, 2)
+    k_axis_block_s(Grid g, ParticleSoA p, const long* __restrict__ start, int* __restrict__ count,
+                   double* __restrict__ E, const double* __restrict__ B, double q, double qm, double h, MoverList mv,
+                   int* __restrict__ flags, long ncell, unsigned* __restrict__ work, unsigned* __restrict__ ekey) {
+  constexpr int NW1 = I::NW1, NWP = I::NWP;
+  using Lay = BlockLayout<I>;
+  constexpr int NS = Lay::NS, SB = Lay::SB, SP = Lay::SP, NACC = Lay::NACC, NSUB = Lay::NSUB;
+  constexpr int SBP = SB + 2;  // stencil buffers 16 bytes apart in bank space: lanes of A and of B read both at once
+  extern __shared__ __align__(16) double smem[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  double* sWarp = smem + warp * Lay::PER_WARP_S;
+  long* tStart = reinterpret_cast<long*>(sWarp);           // [2][kChunk]  bin starts of two chunks
+  int* tCnt = reinterpret_cast<int*>(sWarp + 2 * kChunk);   // [2][kChunk]  bin counts
+  double* sH = sWarp + 3 * kChunk;                          // [2][4]  global coordinates of the cells in the two buffers
+  double* sPart = sWarp + kTableDoubles + 4;                // [6][32]
+  double* sBst = sPart + SP;                                // [2][SBP]
+  double* sW = sBst + 2 * SBP;                              // records
+  double* sAcc = sW + Lay::SWA;                             // [3][NACC][32]
+  const long st[3] = {1, g.pj, g.pk};
+  const double nq = -q;
+  const unsigned nchunk = (unsigned)((ncell + kChunk - 1) / kChunk);
+
+  auto grab = [&]() -> unsigned {
+    unsigned c = 0;
+    if (lane == 0) c = atomicAdd(work, 1u);
+    return c;
+  };
+  auto load_table = [&](unsigned chunk, int tb) {
+    if (lane < kChunk) {
+      const long cell = (long)chunk * kChunk + lane;
+      if (cell < ncell) {
+        const unsigned d4 = (unsigned)__cvta_generic_to_shared(tCnt + tb * kChunk + lane);
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 4;\n" ::"r"(d4), "l"(count + cell) : "memory");
+        cp_async8(reinterpret_cast<double*>(tStart + tb * kChunk + lane), reinterpret_cast<const double*>(start + cell));
+      } else {
+        tCnt[tb * kChunk + lane] = 0;
+        tStart[tb * kChunk + lane] = 0;
+      }
+    }
+  };
+  auto corner_of = [&](unsigned cell, int (&cc)[3]) -> long {
+    const unsigned row = cell / (unsigned)g.n[0];
+    cc[0] = (int)(cell - row * (unsigned)g.n[0]);
+    cc[2] = (int)(row / (unsigned)g.n[1]);
+    cc[1] = (int)(row - (unsigned)cc[2] * (unsigned)g.n[1]);
+    return g.at(cc[0], cc[1], cc[2]) + (1 - I::W) * (1 + g.pj + g.pk);
+  };
+  auto stage_stencil = [&](unsigned cell, int buf) {
+    int cc[3];
+    const double* src = B + corner_of(cell, cc);
+    double* d = sBst + buf * SBP;
+#pragma unroll
+    for (int s = lane; s < SB; s += 32) {
+      const int comp = s / NS, r = s % NS;
+      const int ti = r % NW1, tj = (r / NW1) % NW1, tk = r / (NW1 * NW1);
+      cp_async8(d + s, src + (long)comp * g.pc + ti + tj * g.pj + tk * g.pk);
+    }
+  };
+  // stage batch b of chunk `chunk` (tables in buffer tb); bufA = the stencil buffer of its cell A
+  auto stage = [&](unsigned chunk, int tb, const CutBatch& b, int bufA) {
+    const int n = b.nA + b.nB;
+    if (lane < n) {
+      const long src = lane < b.nA ? tStart[tb * kChunk + b.ci] + b.off + lane
+                                   : tStart[tb * kChunk + b.ci + 1] + (lane - b.nA);
+      double* d = sPart + lane;
+      cp_async8(d + 0 * 32, p.x[0] + src);
+      cp_async8(d + 1 * 32, p.x[1] + src);
+      cp_async8(d + 2 * 32, p.x[2] + src);
+      cp_async8(d + 3 * 32, p.v[0] + src);
+      cp_async8(d + 4 * 32, p.v[1] + src);
+      cp_async8(d + 5 * 32, p.v[2] + src);
+    }
+    if (b.off == 0 && b.nA > 0) stage_stencil(chunk * kChunk + b.ci, bufA);
+    if (b.nB > 0) stage_stencil(chunk * kChunk + b.ci + 1, bufA ^ 1);
+  };
+
+  // ---- prologue ----------------------------------------------------------------------------------------
+  unsigned chunk = __shfl_sync(kFull, grab(), 0);
+  if (chunk >= nchunk) return;
+  load_table(chunk, 0);
+  cp_async_commit();
+  unsigned pending = grab();
+  cp_async_wait<0>();
+  __syncwarp();
+  unsigned chunk_next = __shfl_sync(kFull, pending, 0);
+  if (chunk_next < nchunk) load_table(chunk_next, 1);
+  pending = grab();
+  int tb = 0, ci = 0, off = 0, bb = 0;
+  bool pmix = false;
+  stage(chunk, 0, cut_batch<kChunk>(tCnt, 0, 0, false), 0);
+  cp_async_commit();
+
+  int wp = 0;
+  bool more = true;
+
+  while (more) {
+    cp_async_wait<0>();
+    __syncwarp();
+    const CutBatch b = cut_batch<kChunk>(tCnt + tb * kChunk, ci, off, pmix);
+    const bool mixed = b.nB > 0;
+    if (b.off == 0 || mixed) {  // coordinates of a cell touched for the first time, in the slot of its stencil buffer
+      int cc[3];
+      if (b.off == 0) {
+        corner_of(chunk * kChunk + ci, cc);
+        if (lane < 3) sH[bb * 4 + lane] = (double)(cc[lane] + (lane == 2 ? g.z0 : 0));
+        wp = 0;
+      }
+      if (mixed) {
+        corner_of(chunk * kChunk + ci + 1, cc);
+        if (lane < 3) sH[(bb ^ 1) * 4 + lane] = (double)(cc[lane] + (lane == 2 ? g.z0 : 0));
+      }
+      __syncwarp();
+    }
+    const int nvalid = b.nA + b.nB;
+    const bool valid = lane < nvalid;
+    const bool isB = lane >= b.nA && mixed;            // lanes past the particles (padding) count as A
+    const double* sHl = sH + (isB ? (bb ^ 1) : bb) * 4;  // this lane's cell
+    double x[3] = {sHl[0] + 0.5, sHl[1] + 0.5, sHl[2] + 0.5}, v[3] = {0.0, 0.0, 0.0};
+    if (valid) {
+      const double* sP = sPart + lane;
+      x[0] = sP[0 * 32];
+      x[1] = sP[1 * 32];
+      x[2] = sP[2 * 32];
+      v[0] = sP[3 * 32];
+      v[1] = sP[4 * 32];
+      v[2] = sP[5 * 32];
+    }
+    __syncwarp();  // the staging buffer has been consumed: refill it while this batch computes
+
+    // ---- the next batch ----------------------------------------------------------------------------------
+    int nci = ci, noff = off;
+    bool npmix = pmix;
+    const bool in_chunk = cut_advance<kChunk>(b, nci, noff, npmix);
+    const bool new_cell = nci != ci;  // the next batch's cell A lives in the other stencil buffer
+    if (in_chunk) {
+      stage(chunk, tb, cut_batch<kChunk>(tCnt + tb * kChunk, nci, noff, npmix), new_cell ? bb ^ 1 : bb);
+    } else if (chunk_next < nchunk) {
+      stage(chunk_next, tb ^ 1, cut_batch<kChunk>(tCnt + (tb ^ 1) * kChunk, 0, 0, false), bb ^ 1);
+    }
+    cp_async_commit();
+
+    if (nvalid > 0) {
+      const double* sB = sBst + (isB ? (bb ^ 1) : bb) * SBP;
+      const int nit = (nvalid + NSUB - 1) / NSUB;
+      const int itA = (b.nA + NSUB - 1) / NSUB;  // iterations that hold particles of A
+      const int itB = b.nA / NSUB;               // first iteration that holds a particle of B
+      const bool first = b.off == 0;
+      bool alive = valid;
+      const unsigned my_cell = chunk * kChunk + ci + (isB ? 1 : 0);
+      // this lane's first stencil point of each E component (deposition lanes: tu, th as in deposit_records)
+      int ccA[3];
+      const long baseA = corner_of(chunk * kChunk + ci, ccA);  // (B's points are flushed at B's own end)
+
+      double P1[NW1] = {}, Pp[NWP] = {}, Q1[NW1] = {}, Qp[NWP] = {};
+#pragma unroll 1
+      for (int step = -2; step < 5; ++step) {
+        const int A = step < 0 ? -step : (step < 3 ? step : 4 - step);
+        if (step >= 0) {
+          const double xa = A == 0 ? x[0] : (A == 1 ? x[1] : x[2]);
+          const double va = A == 0 ? v[0] : (A == 1 ? v[1] : v[2]);
+          const double hA = sHl[A];
+          double x1 = xa + (step == 2 ? 2.0 * h : h) * va;  // hpp:237
+          const bool leaves = alive && !(x1 >= hA && x1 < hA + 1.0);
+          eject(leaves, kContBase - (step < 3 ? step : step + 1), my_cell, ekey, x, v, sHl, alive, mv, flags, lane);
+          const double xs = leaves ? hA + 0.5 : xa;
+          if (leaves) x1 = xs;
+          double I0[NWP];
+          eval_iwp_in<I>(xs, x1, hA, I0);  // hpp:178-186
+          if (A == 0) axis_part<I, 0>(x, v, x1, I0, P1, Pp, Q1, Qp, sB, sW, nq, qm, lane);
+          else if (A == 1) axis_part<I, 1>(x, v, x1, I0, Q1, Qp, P1, Pp, sB, sW, nq, qm, lane);
+          else axis_part<I, 2>(x, v, x1, I0, P1, Pp, Q1, Qp, sB, sW, nq, qm, lane);
+          __syncwarp();
+          double* sAccA = sAcc + A * (NACC * 32);
+          if (!mixed) {
+            deposit_records<I>(sW, sAccA, first && step < 3, nit, lane);
+          } else {
+            // lane-to-stencil-point map of the deposition (as in flush_component)
+            const int tu = lane % NW1, th = (lane / NW1) % Lay::TH;
+            // strides along A, U = (A+1)%3, L = (A+2)%3 without indexing a local array by a run-time value
+            const long sA = A == 0 ? 1 : (A == 1 ? g.pj : g.pk);
+            const long sU = A == 0 ? g.pj : (A == 1 ? g.pk : 1);
+            const long sL = A == 0 ? g.pk : (A == 1 ? 1 : g.pj);
+            double acc[2][NWP];
+            // part of A: with what A parked in its earlier batches (first visit) or from zero (already flushed)
+            acc_load<I>(sAccA, acc, step >= 3, lane);
+            deposit_range<I>(sW, acc, 0, itA, 0, b.nA, lane);
+            flush_regs<I>(acc, E + (long)A * g.pc + baseA + tu * sU + (2 * th) * sL, sL, sA, lane);
+            // part of B: B starts here (first visit: zero) and parks like any first batch
+            acc_load<I>(sAccA, acc, step < 3, lane);
+            deposit_range<I>(sW, acc, itB, nit, b.nA, nvalid, lane);
+            acc_store<I>(sAccA, acc, lane);
+          }
+          __syncwarp();  // the record area is free again
+        }
+        if (step < 4) {
+          const double f = (A == 0 ? x[0] : (A == 1 ? x[1] : x[2])) - sHl[A];
+          if (step == -1 || step == 0 || step == 3) {
+            eval_w1_in<I>(f, P1);
+            eval_wp_in<I>(f, Pp);
+          } else {
+            eval_w1_in<I>(f, Q1);
+            eval_wp_in<I>(f, Qp);
+          }
+        }
+      }
+
+      // ---- re-file: stayers are compacted in place, per cell -------------------------------------------------
+      const bool stays = valid && alive;
+      const unsigned stayA = __ballot_sync(kFull, stays && !isB), stayB = __ballot_sync(kFull, stays && isB);
+      if (stays) {
+        const unsigned below = (1u << lane) - 1u;
+        const long dst = isB ? tStart[tb * kChunk + ci + 1] + __popc(stayB & below)
+                             : tStart[tb * kChunk + ci] + wp + __popc(stayA & below);
+#pragma unroll
+        for (int d = 0; d < 3; ++d) {
+          p.x[d][dst] = x[d];
+          p.v[d][dst] = v[d];
+        }
+      }
+      wp += __popc(stayA);
+
+      if (b.lastA) {
+        if (!mixed) {  // (a mixed batch has flushed A's accumulators sub-flow by sub-flow)
+          flush_component<I, 0>(sAcc, E, baseA, st, g.pc, lane);
+          flush_component<I, 1>(sAcc + NACC * 32, E, baseA, st, g.pc, lane);
+          flush_component<I, 2>(sAcc + 2 * NACC * 32, E, baseA, st, g.pc, lane);
+        }
+        if (lane == 0) count[(long)chunk * kChunk + ci] = wp;
+      }
+      if (mixed) wp = __popc(stayB);  // B is the current cell from here on
+    }
+    __syncwarp();
+    // ---- advance -----------------------------------------------------------------------------------------------
+    if (in_chunk) {
+      if (new_cell) bb ^= 1;
+      ci = nci;
+      off = noff;
+      pmix = npmix;
+    } else {
+      ci = 0;
+      off = 0;
+      pmix = false;
+      bb ^= 1;
+      more = chunk_next < nchunk;
+      if (more) {
+        chunk = chunk_next;
+        chunk_next = __shfl_sync(kFull, pending, 0);
+        if (chunk_next < nchunk) load_table(chunk_next, tb);
+        pending = grab();
+        tb ^= 1;
+      }
+    }
+  }
+  cp_async_wait<0>();
+}
+
 // Sub-flows resume..5 of the program x y z z y x (step h each; the merged z(2h) of the block is undone here so
 // that the CFL limit of the reference, |v h| < 1 cell, is the one that applies) for one particle, general code.
 // With z slabs over several ranks z is NOT wrapped between the sub-flows: the particle keeps its coordinate
@@ -602,6 +934,18 @@ int launch_block(Ctx* c, Species& s, double h) {
   SPIC_CUDA_CHECK(c, cudaMemsetAsync(e->block_work, 0, sizeof(unsigned), c->stream));
   // unused sort keys = all ones: they sort behind every cell index (fused_axis_continue)
   SPIC_CUDA_CHECK(c, cudaMemsetAsync(e->cont_key, 0xff, sizeof(unsigned) * (size_t)e->mv.cap, c->stream));
+  if (e->block_stream) {  // batches that may span two cells (opt-in until verified on the GPU)
+    const size_t smem_s = sizeof(double) * kWarps * BlockLayout<I>::PER_WARP_S;
+    static unsigned long long attr_s = 0;
+    if (smem_attr_needed(attr_s, c->cfg.device))
+      SPIC_CUDA_CHECK(c, cudaFuncSetAttribute(k_axis_block_s<I>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                              (int)smem_s));
+    k_axis_block_s<I><<<(int)want, kThreads, smem_s, c->stream>>>(c->g, s.b, s.start, s.count, c->E, c->B, s.q,
+                                                                  s.q / s.m, h, e->mv, c->d_flags, ncell,
+                                                                  e->block_work, e->cont_key);
+    c->launches++;
+    return SPIC_OK;
+  }
   const size_t smem = sizeof(double) * kWarps * BlockLayout<I>::PER_WARP;
   static unsigned long long attr = 0;
   if (smem_attr_needed(attr, c->cfg.device))
