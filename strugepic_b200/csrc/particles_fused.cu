@@ -681,7 +681,7 @@ __global__ void __launch_bounds__(kThreads, 2)
     }
     const int nvalid = b.nA + b.nB;
     const bool valid = lane < nvalid;
-    const bool isB = lane >= b.nA && mixed;            // lanes past the particles (padding) count as A
+    const bool isB = lane >= b.nA && mixed;            // (a mixed batch is always full: no padding lanes there)
     const double* sHl = sH + (isB ? (bb ^ 1) : bb) * 4;  // this lane's cell
     double x[3] = {sHl[0] + 0.5, sHl[1] + 0.5, sHl[2] + 0.5}, v[3] = {0.0, 0.0, 0.0};
     if (valid) {
