@@ -63,6 +63,8 @@ def parse():
                     help="nvidia-smi sampling period during the timed region (0: no sampler; diagnosis only)")
     ap.add_argument("--no-fuse", action="store_true", help="reference launch-per-sub-flow schedule (A/B against the fused axis block)")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--opt", action="append", default=[], metavar="NAME=VALUE",
+                    help="library option for A/B runs (spic_set_option), e.g. --opt block_stream=1")
     ap.add_argument("--e2e-steps", type=int, default=2)
     ap.add_argument("--cpu-steps", type=int, default=3)
     ap.add_argument("--cores", type=int, default=0, help="reference arm: worker processes (0 = all)")
@@ -302,6 +304,9 @@ def ours_main(a):
 
     if a.no_fuse:
         sim.set_option("fuse", 0)
+    for kv in a.opt:
+        k, v = kv.split("=")
+        sim.set_option(k, float(v))
     stream = torch.cuda.ExternalStream(sim.stream())
     for _ in range(a.warmup):
         sim.map(a.order, 0.5)

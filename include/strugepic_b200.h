@@ -134,7 +134,8 @@ int spic_field_only_step(spic_ctx* ctx, int pos, int comp, double E0, double ome
 /* ---- diagnostics ------------------------------------------------------------- */
 /* get_total_energy: src/strugepic_util.cpp:364-394; out = {field, kinetic}, summed over ranks */
 int spic_energy(spic_ctx* ctx, double out[2]);
-/* discrete Gauss residual G = div- E - rho, [k][j][i] over valid cells */
+/* discrete Gauss residual G = div- E - rho, [k][j][i] over this rank's valid cells
+ * (collective when nranks > 1: guards of E and of rho are exchanged with the neighbour slabs) */
 int spic_gauss_residual(spic_ctx* ctx, double* host);
 
 /* get_particle_number_density<W>: include/strugepic_util.hpp:30-85; [k][j][i] over valid cells */

@@ -31,6 +31,9 @@ struct EngineState {
   int fuse = 1;
   // 1: the fused axis block cuts batches that may span two cells (k_axis_block_s); opt-in, see particles_fused.cu
   int block_stream = 0;
+  // nranks > 1: 1 = the slab-face cells of an axis block run first and their halo sums / migration travel on a side
+  // stream while the interior cells compute; 0 = every exchange in stream order behind the whole block
+  int overlap = 1;
   unsigned* block_work = nullptr;   // chunk counter of the fused axis-block kernel
   // continuation of the ejected particles: sort key (home cell) per mover-list entry + radix-sort buffers
   unsigned* cont_key = nullptr;

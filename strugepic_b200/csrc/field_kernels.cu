@@ -244,14 +244,16 @@ __global__ void k_final_sum(const double* __restrict__ part, int nblocks, int wi
   }
 }
 
-__global__ void k_gauss_div(Grid g, const double* __restrict__ E, double* __restrict__ out) {
+// out[valid cell] = rho (one guarded component, already folded) + div- E
+__global__ void k_gauss_div(Grid g, const double* __restrict__ E, const double* __restrict__ rho,
+                            double* __restrict__ out) {
   const long total = g.cells();
   for (long t = blockIdx.x * (long)blockDim.x + threadIdx.x; t < total; t += (long)gridDim.x * blockDim.x) {
     const int i = (int)(t % g.n[0]);
     const int j = (int)((t / g.n[0]) % g.n[1]);
     const int k = (int)(t / ((long)g.n[0] * g.n[1]));
     const long o = g.at(i, j, k);
-    out[t] += (E[o] - E[o - 1]) + (E[o + g.pc] - E[o + g.pc - g.pj]) + (E[o + 2 * g.pc] - E[o + 2 * g.pc - g.pk]);
+    out[t] = rho[o] + ((E[o] - E[o - 1]) + (E[o + g.pc] - E[o + g.pc - g.pj]) + (E[o + 2 * g.pc] - E[o + 2 * g.pc - g.pk]));
   }
 }
 
@@ -361,8 +363,8 @@ void field_energy(Ctx* c, double* out6) {
   cudaMemcpyAsync(out6, res, 6 * sizeof(double), cudaMemcpyDeviceToHost, c->stream);
   cudaStreamSynchronize(c->stream);
 }
-void launch_gauss_div(Ctx* c, double* out) {
-  k_gauss_div<<<grid_for(c, c->g.cells()), kBlock, 0, c->stream>>>(c->g, c->E, out);
+void launch_gauss_div(Ctx* c, const double* rho, double* out) {
+  k_gauss_div<<<grid_for(c, c->g.cells()), kBlock, 0, c->stream>>>(c->g, c->E, rho, out);
   c->launches++;
 }
 

@@ -950,6 +950,62 @@ __global__ void __launch_bounds__(256)
   }
 }
 
+// rho(cell + o) += nq W1 W1 W1 for the particles of every bin: the weights of a batch go through shared memory,
+// lane s (and s + 32) owns stencil point s of the cell's (2W)^3 block and sums it over the cell's particles, then
+// ONE reduction per stencil point and cell (Gauss diagnostic; guards are folded by the caller)
+template <class I>
+__global__ void __launch_bounds__(256)
+    k_rho_binned(Grid g, ParticleSoA p, const long* __restrict__ start, const int* __restrict__ count, long ncell,
+                 double nq, double* __restrict__ rho) {
+  constexpr int N = I::NW1, NS = N * N * N, R = (NS + 31) / 32;
+  __shared__ double sw[8][32][3 * N];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const long wid = (blockIdx.x * (long)blockDim.x + threadIdx.x) >> 5, nw = ((long)gridDim.x * blockDim.x) >> 5;
+  for (long cell = wid; cell < ncell; cell += nw) {
+    const int cnt = count[cell];
+    if (cnt == 0) continue;
+    const long s0 = start[cell];
+    const int ci = (int)(cell % g.n[0]), cj = (int)((cell / g.n[0]) % g.n[1]), ck = (int)(cell / ((long)g.n[0] * g.n[1]));
+    double acc[R];
+#pragma unroll
+    for (int r = 0; r < R; ++r) acc[r] = 0.0;
+    for (int off = 0; off < cnt; off += 32) {
+      const int n = cnt - off < 32 ? cnt - off : 32;
+      if (lane < n) {
+        double w[N];
+        eval_w1<I>(p.x[0][s0 + off + lane], ci, w);
+#pragma unroll
+        for (int t = 0; t < N; ++t) sw[warp][lane][t] = w[t];
+        eval_w1<I>(p.x[1][s0 + off + lane], cj, w);
+#pragma unroll
+        for (int t = 0; t < N; ++t) sw[warp][lane][N + t] = w[t];
+        eval_w1<I>(p.x[2][s0 + off + lane], ck + g.z0, w);
+#pragma unroll
+        for (int t = 0; t < N; ++t) sw[warp][lane][2 * N + t] = w[t];
+      }
+      __syncwarp();
+#pragma unroll
+      for (int r = 0; r < R; ++r) {
+        const int sidx = lane + 32 * r;
+        if (sidx < NS) {
+          const int ti = sidx % N, tj = (sidx / N) % N, tk = sidx / (N * N);
+          for (int q = 0; q < n; ++q) acc[r] = fma(sw[warp][q][ti] * sw[warp][q][N + tj], sw[warp][q][2 * N + tk], acc[r]);
+        }
+      }
+      __syncwarp();
+    }
+    const long base = g.at(ci + 1 - I::W, cj + 1 - I::W, ck + 1 - I::W);
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+      const int sidx = lane + 32 * r;
+      if (sidx < NS) {
+        const int ti = sidx % N, tj = (sidx / N) % N, tk = sidx / (N * N);
+        atomicAdd(&rho[base + ti + tj * g.pj + tk * g.pk], nq * acc[r]);
+      }
+    }
+  }
+}
+
 // packed[prefix[cell] + i] = arr[start[cell] + i]
 __global__ void __launch_bounds__(256)
     k_pack_bins(const double* __restrict__ arr, const long* __restrict__ start, const int* __restrict__ count,
@@ -1303,7 +1359,8 @@ int engine_count(Ctx* c, Species& s, long* nb) {
   const long ncell = c->g.cells();
   cub::TransformInputIterator<long, ToLong, const int*> it(s.count, ToLong());
   size_t bytes = 0;
-  long* d_sum = reinterpret_cast<long*>(c->scratch);
+  // (its own device scalar: c->scratch may hold a caller's data, e.g. a field being packed)
+  long* d_sum = reinterpret_cast<long*>(eng(c)->d_scalar + 4);
   cub::DeviceReduce::Sum(nullptr, bytes, it, d_sum, (int)ncell, c->stream);
   int rc = ensure_cub(c, bytes);
   if (rc) return rc;
@@ -1473,31 +1530,17 @@ int engine_kinetic(Ctx* c, Species& s, double* acc) {
   return SPIC_OK;
 }
 
-// Gauss diagnostic: pack each bin array and reuse the thread-per-particle rho deposit
-int engine_deposit_rho(Ctx* c, Species& s, double* out) {
+// Gauss diagnostic: rho of the binned particles, cell-centric (one reduction per stencil point and cell); the tail
+// takes the thread-per-particle kernel.  rho = one guarded component.
+int engine_deposit_rho(Ctx* c, Species& s, double* rho) {
   if (!s.binned) return SPIC_OK;
   const long ncell = c->g.cells();
-  long live = 0;
-  int rc = engine_count(c, s, &live);
-  if (rc) return rc;
-  long* prefix = nullptr;
-  SPIC_CUDA_CHECK(c, cudaMalloc(&prefix, sizeof(long) * (ncell + 1)));
-  cub::TransformInputIterator<long, ToLong, const int*> it(s.count, ToLong());
-  size_t bytes = 0;
-  cub::DeviceScan::ExclusiveSum(nullptr, bytes, it, prefix, (int)ncell, c->stream);
-  if ((rc = ensure_cub(c, bytes))) return rc;
-  cub::DeviceScan::ExclusiveSum(eng(c)->cub_tmp, bytes, it, prefix, (int)ncell, c->stream);
-  ParticleSoA tmp{};
-  for (int d = 0; d < 3; ++d) {
-    SPIC_CUDA_CHECK(c, cudaMalloc(&tmp.x[d], sizeof(double) * (size_t)(live + 1)));
-    k_pack_bins<<<grid_warps(c, ncell), 256, 0, c->stream>>>(s.b.x[d], s.start, s.count, prefix, ncell, tmp.x[d]);
-    c->launches++;
-  }
-  launch_deposit_rho(c, tmp, live, nullptr, s.q, out);
-  launch_deposit_rho(c, s.d, s.capd, s.d_nd, s.q, out);
-  SPIC_CUDA_CHECK(c, cudaStreamSynchronize(c->stream));
-  for (int d = 0; d < 3; ++d) cudaFree(tmp.x[d]);
-  cudaFree(prefix);
+  if (c->cfg.interp == SPIC_INTERP_P8R2)
+    k_rho_binned<InterpP8R2><<<grid_warps(c, ncell), 256, 0, c->stream>>>(c->g, s.b, s.start, s.count, ncell, -s.q, rho);
+  else
+    k_rho_binned<InterpPWL><<<grid_warps(c, ncell), 256, 0, c->stream>>>(c->g, s.b, s.start, s.count, ncell, -s.q, rho);
+  c->launches++;
+  launch_deposit_rho(c, s.d, s.capd, s.d_nd, s.q, rho);
   return SPIC_OK;
 }
 
@@ -1566,6 +1609,10 @@ int engine_set_option(Ctx* c, const char* name, double value) {
   }
   if (!strcmp(name, "block_stream")) {
     e->block_stream = value != 0;
+    return SPIC_OK;
+  }
+  if (!strcmp(name, "overlap")) {
+    e->overlap = value != 0;
     return SPIC_OK;
   }
   if (!strcmp(name, "fuse")) {

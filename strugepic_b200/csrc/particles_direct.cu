@@ -19,7 +19,7 @@ namespace {
 __global__ void __launch_bounds__(256) k_kinetic(ParticleSoA p, long n, const unsigned long long* __restrict__ n_dev,
                                                  double half_m, double* __restrict__ accum) {
   double a = 0;
-  if (n_dev) n = (long)*n_dev;
+  if (n_dev) n = min((long)*n_dev, n);
   for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x) {
     const double vx = p.v[0][i], vy = p.v[1][i], vz = p.v[2][i];
     a += half_m * (vx * vx + vy * vy + vz * vz);

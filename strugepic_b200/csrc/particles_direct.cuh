@@ -17,7 +17,7 @@ __global__ void __launch_bounds__(kBlock)
                         int* __restrict__ flags) {
   constexpr int U = (A + 1) % 3, L = (A + 2) % 3;  // hpp:90-91
   const long i = blockIdx.x * (long)blockDim.x + threadIdx.x;
-  if (n_dev) n = (long)*n_dev;
+  if (n_dev) n = min((long)*n_dev, n);  // (n = the list's capacity: an overflowed count must not run past it)
   if (i >= n) return;
   double x[3] = {p.x[0][i], p.x[1][i], p.x[2][i]}, v[3] = {p.v[0][i], p.v[1][i], p.v[2][i]};
   theta_axis_one<I, A>(g, x, v, E, B, q, qm, dt, flags);
@@ -32,7 +32,7 @@ __global__ void __launch_bounds__(kBlock)
     k_push_v_e_direct(Grid g, ParticleSoA p, long n, const unsigned long long* __restrict__ n_dev,
                       const double* __restrict__ E, double coef) {
   const long i = blockIdx.x * (long)blockDim.x + threadIdx.x;
-  if (n_dev) n = (long)*n_dev;
+  if (n_dev) n = min((long)*n_dev, n);  // (n = the list's capacity: an overflowed count must not run past it)
   if (i >= n) return;
   const double x = p.x[0][i], y = p.x[1][i], z = p.x[2][i];
   const int cx = (int)floor(x), cy = (int)floor(y), cz = (int)floor(z);
@@ -52,13 +52,14 @@ __global__ void __launch_bounds__(kBlock)
   p.v[2][i] = fma(dv[2], coef, p.v[2][i]);
 }
 
-// rho deposit for the Gauss diagnostic: out[cell] -= q W1 W1 W1 (periodic images folded)
+// rho deposit for the Gauss diagnostic: rho(cell + o) -= q W1 W1 W1 over the (2W)^3 W1 taps; `rho` is ONE guarded
+// component (the caller folds the guards like a deposited current: SumBoundary semantics, across slabs too)
 template <class I>
 __global__ void __launch_bounds__(kBlock) k_deposit_rho(Grid g, ParticleSoA p, long n,
                                                         const unsigned long long* __restrict__ n_dev, double q,
-                                                        double* __restrict__ out) {
+                                                        double* __restrict__ rho) {
   const long i = blockIdx.x * (long)blockDim.x + threadIdx.x;
-  if (n_dev) n = (long)*n_dev;
+  if (n_dev) n = min((long)*n_dev, n);  // (n = the list's capacity: an overflowed count must not run past it)
   if (i >= n) return;
   const double x = p.x[0][i], y = p.x[1][i], z = p.x[2][i];
   const int cx = (int)floor(x), cy = (int)floor(y), cz = (int)floor(z);
@@ -66,19 +67,14 @@ __global__ void __launch_bounds__(kBlock) k_deposit_rho(Grid g, ParticleSoA p, l
   eval_w1<I>(x, cx, w1x);
   eval_w1<I>(y, cy, w1y);
   eval_w1<I>(z, cz, w1z);
+  const long base = g.at(cx + 1 - I::W, cy + 1 - I::W, cz - g.z0 + 1 - I::W);
 #pragma unroll
   for (int tk = 0; tk < I::NW1; ++tk)
 #pragma unroll
     for (int tj = 0; tj < I::NW1; ++tj)
 #pragma unroll
-      for (int ti = 0; ti < I::NW1; ++ti) {
-        int ii = cx + ti + 1 - I::W, jj = cy + tj + 1 - I::W, kk = cz + tk + 1 - I::W;
-        if (g.per[0]) ii = (ii % g.gn[0] + g.gn[0]) % g.gn[0];
-        if (g.per[1]) jj = (jj % g.gn[1] + g.gn[1]) % g.gn[1];
-        if (g.per[2]) kk = (kk % g.gn[2] + g.gn[2]) % g.gn[2];
-        if (ii < 0 || ii >= g.gn[0] || jj < 0 || jj >= g.gn[1] || kk < 0 || kk >= g.gn[2]) continue;
-        atomicAdd(&out[((long)kk * g.gn[1] + jj) * g.gn[0] + ii], -q * w1x[ti] * w1y[tj] * w1z[tk]);
-      }
+      for (int ti = 0; ti < I::NW1; ++ti)
+        atomicAdd(&rho[base + ti + tj * g.pj + tk * g.pk], -q * w1x[ti] * w1y[tj] * w1z[tk]);
 }
 
 template <class I>
@@ -86,7 +82,7 @@ __global__ void __launch_bounds__(kBlock) k_number_density(Grid g, ParticleSoA p
                                                            const unsigned long long* __restrict__ n_dev,
                                                            double* __restrict__ nd) {
   const long i = blockIdx.x * (long)blockDim.x + threadIdx.x;
-  if (n_dev) n = (long)*n_dev;
+  if (n_dev) n = min((long)*n_dev, n);  // (n = the list's capacity: an overflowed count must not run past it)
   if (i >= n) return;
   deposit_number_density<I>(g, p.x[0][i], p.x[1][i], p.x[2][i], nd);
 }

@@ -843,7 +843,7 @@ SPIC_DI void finish_program(const Grid& g, int resume, double (&x)[3], double (&
       if (!g.zlocal) {
         const int kk = (int)floor(x[2]) - g.z0;
         if (kk < -1 || kk > g.n[2]) {  // more than one cell outside the slab: the stencil would leave the guards
-          atomicOr(&flags[0], 1);
+          atomicOr(&flags[0], 4);  // (its own bit: this is the slab limit, not the reference's CFL limit)
           resume = 6;
         }
       }

@@ -74,7 +74,7 @@ void launch_set_uniform(Ctx* c, double* F, const double v[3]);
 void field_energy(Ctx* c, double* out_sumsq6);  // sum of squares of the 6 components (valid cells)
 void launch_pack_field(Ctx* c, const double* F, double* packed);    // guarded -> [c][k][j][i] valid
 void launch_unpack_field(Ctx* c, double* F, const double* packed);  // valid -> guarded
-void launch_gauss_div(Ctx* c, double* out);                          // out += div- E
+void launch_gauss_div(Ctx* c, const double* rho, double* out);       // out = rho (guarded, folded) + div- E
 void launch_pack_scalar(Ctx* c, const double* F, double* packed);   // one guarded component -> valid cells
 
 // ---- particle kernels, thread per particle (particles_direct.cu) ----------------

@@ -28,8 +28,9 @@ def main():
     torch.cuda.set_device(local)
     case = sys.argv[1] if len(sys.argv) > 1 else "p8"
     interp = 0 if case.startswith("p8") else 1
-    nz = 4 * world if case.endswith("thin") else 6 * world
-    fuse = 0 if case.endswith("nofuse") else 1  # fused axis blocks (guard width W + 1) / launch per sub-flow
+    opts = case.split("_")[1:]
+    nz = 4 * world if "thin" in opts else 6 * world
+    fuse = 0 if "nofuse" in opts else 1  # fused axis blocks (guard width W + 1) / launch per sub-flow
     n_cell = (12, 10, nz)
     ppc, vth = 6, 0.25
     E, B = util.rng_fields(n_cell, 77, 0.3)
@@ -41,6 +42,9 @@ def main():
     dist.broadcast_object_list(ids, src=0)
     s.comm_init(ids[0])
     s.set_option("fuse", fuse)
+    s.set_option("block_stream", 1 if "stream" in opts else 0)  # batches that span two cells (k_axis_block_s)
+    if "serial" in opts:
+        s.set_option("overlap", 0)  # exchanges in stream order behind the whole axis block
     k0, k1 = s.lo[2], s.lo[2] + s.n[2]
     assert s.n[2] == nz // world
     s.set_field(0, E[:, k0:k1])
@@ -53,10 +57,11 @@ def main():
     util.run(s, schedule)
     s.sync()
     en = s.get_total_energy()
+    gauss = s.gauss_residual()  # collective: rho and E guards cross the slab faces
     Es, Bs, Ps = util.state_of(s)
     assert np.all((Ps[2] >= k0) & (Ps[2] < k1)), "a particle sits outside its rank's slab"
     gathered = [None] * world
-    dist.gather_object((Es, Bs, Ps, en), gathered if rank == 0 else None, dst=0)
+    dist.gather_object((Es, Bs, Ps, en, gauss), gathered if rank == 0 else None, dst=0)
     ok = True
     if rank == 0:
         Eg = np.concatenate([g[0] for g in gathered], axis=1)
@@ -72,6 +77,15 @@ def main():
             eo = o.energy()
             for g in gathered:  # every rank holds the allreduced energy
                 assert np.allclose(g[3], eo, rtol=1e-10), (g[3], eo)
+            # discrete Gauss residual of the decomposed run == the C port's on the oracle's final state
+            po = ora.PortOracle(n_cell, interp=interp)
+            Eo, Bo, Po = util.state_of(o)
+            util.load_state(po, Eo, Bo, list(Po), q, m)
+            go = po.gauss()
+            gg = np.concatenate([g[4] for g in gathered], axis=0)
+            gerr = float(np.max(np.abs(gg - go)) / np.max(np.abs(go)))
+            assert gerr < 1e-10, gerr
+            errs["gauss"] = gerr
             print("multi-gpu parity ok case=%s world=%d particles=%d errs=%s" % (case, world, moved, errs))
         except AssertionError as e:
             print("MULTI-GPU PARITY FAILED:", e)

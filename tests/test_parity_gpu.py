@@ -336,6 +336,78 @@ def test_fused_axis_block_and_reference_schedule(fuse, interp, mode):
     print(fuse, interp, mode, errs, kt)
 
 
+@pytest.mark.parametrize("block_stream", [0, 1])
+@pytest.mark.parametrize("ppc", [1, 7, 8, 33, 64, 65])
+def test_fused_block_batch_shapes(ppc, block_stream):
+    """The fused axis block with one warp per cell (k_axis_block) and with batches that span two cells
+    (k_axis_block_s, option block_stream = 1) over bins of 1 ... 65+ particles: empty lanes, exactly full batches,
+    a cell of 65 (32 + 32 + 1: the short batch is topped up from the next cell), both W, warm plasma so that the
+    counts drift apart and particles are ejected to the continuation; Gauss residual constant to round-off."""
+    for interp, n_cell, vth, order in ((0, (8, 6, 5), 0.1, 4), (1, (9, 7, 3), 0.15, 2), (0, (16, 2, 2), 0.05, 2)):
+        E, B = util.rng_fields(n_cell, 5, 0.3)
+        parts = util.plasma(n_cell, ppc, vth, 5)
+        o = ora.best_oracle(n_cell, interp=interp)
+        s = spic().Simulation(n_cell, interp=interp)
+        s.set_option("block_stream", block_stream)
+        s.set_option("time_kernels", 1)
+        for t in (o, s):
+            util.load_state(t, E, B, parts, -1.0 / ppc, 100.0 / ppc)
+        g0 = s.gauss_residual()
+        for _ in range(3):
+            o.map(order, 0.5)
+            s.map(order, 0.5)
+        errs = util.compare_states(util.state_of(o), util.state_of(s), 3 * TOL_STEP, 3 * TOL_STEP, box=n_cell)
+        assert s.num_particles() == len(parts[0])
+        assert s.kernel_times()["axis_block"][1] == (9 if order == 4 else 3)
+        drift = float(np.max(np.abs(s.gauss_residual() - g0)))
+        assert drift < 1e-12 * max(1.0, float(np.max(np.abs(g0)))), drift
+        print(interp, n_cell, ppc, block_stream, errs, drift)
+        s.close()
+
+
+@pytest.mark.parametrize("engine", ENGINES)
+@pytest.mark.parametrize("block_stream", [0, 1])
+def test_two_species(engine, block_stream):
+    """Electrons + ions (two (q, m) pairs: the reference carries q, m per particle, defs.hpp:22-49): the species
+    share the mover list, the continuation buffers and the field deposits.  State vs the oracle, and the Gauss
+    residual (rho of BOTH species) against the port's."""
+    n_cell = (10, 8, 6)
+    E, B = util.rng_fields(n_cell, 83, 0.3)
+    el = util.plasma(n_cell, 36, 0.1, 83)
+    io = util.plasma(n_cell, 20, 0.02, 84)
+    qe, me, qi, mi = -1.0 / 36, 100.0 / 36, 1.0 / 20, 1836.0 / 20
+    allp = [np.concatenate([a, b]) for a, b in zip(el, io)]
+    qa = np.concatenate([np.full(len(el[0]), qe), np.full(len(io[0]), qi)])
+    ma = np.concatenate([np.full(len(el[0]), me), np.full(len(io[0]), mi)])
+    o = util.make_oracle("port", n_cell, (1, 1, 1), 0)
+    o.set_field(0, E)
+    o.set_field(1, B)
+    o.set_particles(*allp, qa, ma)
+    s = spic().Simulation(n_cell, interp=0, engine=engine)
+    if engine == 0:
+        s.set_option("block_stream", block_stream)
+    s.set_field(0, E)
+    s.set_field(1, B)
+    s.add_species(qe, me, *el)
+    s.add_species(qi, mi, *io)
+    go, gs = o.gauss(), s.gauss_residual()
+    assert np.max(np.abs(gs - go)) < 1e-12 * np.max(np.abs(go))
+    for order in (2, 4, 1):
+        o.map(order, 0.5)
+        s.map(order, 0.5)
+    Eo, Bo = o.get_field(0), o.get_field(1)
+    Po = np.stack(o.get_particles())
+    Ps = np.concatenate([np.stack(s.get_particles(0)), np.stack(s.get_particles(1))], axis=1)
+    errs = util.compare_states((Eo, Bo, Po), (s.get_field(0), s.get_field(1), Ps), 3 * TOL_STEP, 3 * TOL_STEP, box=n_cell)
+    assert s.num_particles(0) == len(el[0]) and s.num_particles(1) == len(io[0])
+    go1, gs1 = o.gauss(), s.gauss_residual()
+    assert np.max(np.abs(gs1 - go1)) < 1e-11 * np.max(np.abs(go1))
+    assert np.max(np.abs(gs1 - gs)) < 1e-12 * max(1.0, float(np.max(np.abs(gs))))
+    ho, hs = sum(o.energy()), sum(s.get_total_energy())
+    assert abs(hs - ho) <= 1e-11 * abs(ho)
+    print(engine, block_stream, errs)
+
+
 def test_deferred_half_kick_is_invisible():
     """The last Theta_E half of a fused map is deferred and merged with the first half of the next one
     (Theta_E(s) o Theta_E(t) = Theta_E(s + t)); any observation applies it first.  Three chained Theta_map4 with
