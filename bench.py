@@ -64,7 +64,9 @@ def parse():
     ap.add_argument("--no-fuse", action="store_true", help="reference launch-per-sub-flow schedule (A/B against the fused axis block)")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--opt", action="append", default=[], metavar="NAME=VALUE",
-                    help="library option for A/B runs (spic_set_option), e.g. --opt block_stream=1")
+                    help="library option for A/B runs (spic_set_option), e.g. --opt fuse=0")
+    ap.add_argument("--no-secondary", action="store_true", help="skip the secondary records (low ppc, PWL, field_only)")
+    ap.add_argument("--secondary-all-ranks", action="store_true", help="run the secondary records at N > 1 too")
     ap.add_argument("--e2e-steps", type=int, default=2)
     ap.add_argument("--cpu-steps", type=int, default=3)
     ap.add_argument("--cores", type=int, default=0, help="reference arm: worker processes (0 = all)")
@@ -240,10 +242,247 @@ def ncu_traffic():
     return None
 
 
+class Env:
+    """Process-wide plumbing of our arm: torch.distributed rendezvous, reductions over ranks."""
+
+    def __init__(self):
+        import numpy as np
+        import torch
+        import strugepic_b200 as spic  # raises ImportError when the CUDA library is missing: no fallback
+        self.np, self.torch, self.spic = np, torch, spic
+        self.rank = int(os.environ.get("RANK", "0"))
+        self.world = int(os.environ.get("WORLD_SIZE", "1"))
+        self.local = int(os.environ.get("LOCAL_RANK", "0"))
+        torch.cuda.set_device(self.local)
+        self.dist = None
+        if self.world > 1:
+            import torch.distributed as dist
+            dist.init_process_group("nccl", device_id=torch.device("cuda", self.local))
+            self.dist = dist
+
+    def barrier(self):
+        if self.dist is not None:
+            self.dist.barrier()
+
+    def _red(self, x, op):
+        if self.dist is None:
+            return x
+        t = self.torch.tensor([x], dtype=self.torch.float64, device="cuda")
+        self.dist.all_reduce(t, op=op)
+        return float(t.item())
+
+    def allmax(self, x):
+        return self._red(x, self.dist.ReduceOp.MAX) if self.dist else x
+
+    def allsum(self, x):
+        return self._red(x, self.dist.ReduceOp.SUM) if self.dist else x
+
+    def make_sim(self, n, interp, ppc, periodic=(1, 1, 1), opts=()):
+        """One brick of n^3 cells per GPU (z slabs), E = 0, B = (0,0,1), uniform thermal plasma (ppc = 0: vacuum)."""
+        spic, torch = self.spic, self.torch
+        sim = spic.Simulation((n, n, n * self.world), periodic=periodic, interp=interp, device=self.local,
+                              nranks=self.world, rank=self.rank)
+        if self.world > 1:
+            uid = torch.zeros(128, dtype=torch.uint8, device="cuda")
+            if self.rank == 0:
+                uid = torch.tensor(list(spic.comm_unique_id()), dtype=torch.uint8, device="cuda")
+            self.dist.broadcast(uid, 0)
+            sim.comm_init(bytes(uid.cpu().tolist()))
+        sim.set_uniform_field(spic.FIELD_E, [0.0, 0.0, 0.0])
+        sim.set_uniform_field(spic.FIELD_B, [0.0, 0.0, 1.0] if ppc else [0.0, 0.0, 0.0])
+        if ppc:
+            sim.add_particle_density_uniform(ppc, 100.0, -1.0, 0.01, seed=12345)
+        for kv in opts:
+            k, v = kv.split("=")
+            sim.set_option(k, float(v))
+        sim.sync()
+        return sim
+
+    def invariants(self, sim):
+        """What the reader can check without an oracle: particle count, discrete Gauss residual, energy."""
+        n = int(self.allsum(float(sim.num_particles()))) if sim.num_species() else 0
+        g = sim.gauss_residual()  # collective over the slabs
+        return {"n": n, "g": g, "h": sum(sim.get_total_energy())}
+
+    def checks(self, before, after):
+        np = self.np
+        gmax = self.allmax(float(np.max(np.abs(before["g"]))))
+        drift = self.allmax(float(np.max(np.abs(after["g"] - before["g"]))))
+        return {"particles_before": before["n"], "particles_after": after["n"],
+                "particles_conserved": before["n"] == after["n"],
+                "gauss_residual_max": gmax, "gauss_drift_max": drift,
+                "gauss_ok": bool(drift < 1e-12 * max(1.0, gmax)),
+                "energy_before": before["h"], "energy_after": after["h"],
+                "energy_rel_change": (after["h"] - before["h"]) / before["h"] if before["h"] else 0.0,
+                "what": "taken outside the timed region, before and after it: global particle count, max over cells "
+                        "and ranks of |G1 - G0| with G = div E - rho (spic_gauss_residual: charge conservation of the "
+                        "deposition, north_star check 2: < 1e-12 max(1,|G|)), H = field + kinetic energy (spic_energy)"}
+
+
+def timed_steps(env, sim, step, steps, warmup, clock_period_ms=0):
+    """W untimed + K timed calls of step() on the library's stream: CUDA events, barrier + synchronize on both sides,
+    max over ranks.  The last event is recorded after spic_sync, which applies the deferred half kick of the last
+    step: every launch of the K steps is inside the clock."""
+    torch = env.torch
+    stream = torch.cuda.ExternalStream(sim.stream())
+    for _ in range(warmup):
+        step()
+    sim.sync()
+    before = env.invariants(sim)
+    sim.set_option("time_kernels", 1)
+    sim.kernel_times(reset=True)
+    l0 = sim.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    sampler = ClockSampler(env.local, clock_period_ms)
+    torch.cuda.synchronize()
+    env.barrier()
+    e0.record(stream)
+    for _ in range(steps):
+        step()
+    sim.sync()
+    e1.record(stream)
+    torch.cuda.synchronize()
+    env.barrier()
+    clocks = sampler.stop()
+    ms = env.allmax(e0.elapsed_time(e1))
+    launches = sim.launch_count() - l0
+    kt = sim.kernel_times(reset=True)
+    sim.set_option("time_kernels", 0)
+    after = env.invariants(sim)
+    return {"ms": ms, "launches": launches, "kt": kt, "clocks": clocks, "checks": env.checks(before, after)}
+
+
+def fp64_roof(env):
+    """FP64 denominator: the better of the two dependent-free DFMA probes, named."""
+    spic = env.spic
+    two = spic.probe_fp64_tflops(env.local, 0.5)
+    imm = spic.probe_fp64_tflops(env.local, 0.5, immediate=True)
+    three = spic.probe_fp64_tflops(env.local, 0.25, three_operands=True)
+    return {"peak": max(two, imm), "two_constant_operand_dfma_tflops": two, "immediate_horner_dfma_tflops": imm,
+            "three_register_operand_dfma_tflops": three, "nominal_tflops": 37.2,
+            "peak_source": "measured here, max of spic_probe_fp64_immediate_tflops (Horner steps with immediate "
+                           "coefficients) and spic_probe_fp64_tflops (two loop-constant operands): %s wins"
+                           % ("immediate" if imm >= two else "two-constant")}
+
+
+def particle_rooflines(a, env, r, npart_local, ppc, interp_name, order, steps, roof):
+    """roofline / roofline_fp64 of the dominant kernel from the event pairs recorded inside the timed region."""
+    kt, ms = r["kt"], r["ms"]
+    peaks, peak_src = measured_peaks()
+    fused = kt["axis_block"][1] > 0
+    ax_ms, ax_n = kt["axis_block"] if fused else kt["theta_axis"]
+    sub_per_launch = 6 if fused else 1
+    # one "launch" of the fused schedule = one axis block = the six Theta of a map2; with z slabs a block is two
+    # kernel launches (slab-face planes, then the interior planes): they are counted as one
+    blocks = {4: 3, 2: 1}.get(order, 1) * steps
+    n_units = blocks if fused else max(ax_n, 1)
+    pv_ms, pv_n = kt["push_V_E"]
+    ax_avg = ax_ms / max(n_units, 1)
+    f_axis = FLOP_AXIS if interp_name == "p8r2" else FLOP_AXIS_PWL
+    f_pv = FLOP_PUSHVE if interp_name == "p8r2" else FLOP_PUSHVE_PWL
+    kname = "k_axis_block" if fused else ("k_theta_axis_v2" if ppc >= 40 else "k_theta_axis_v3")
+    alg_bytes = BYTES_PER_SUBFLOW * sub_per_launch * npart_local
+    achieved = alg_bytes / (ax_avg * 1e-3) / 1e9 if ax_n else 0.0
+    traffic = ncu_traffic()
+    tkey = "axis_block_dram_bytes_per_particle" if fused else "theta_axis_dram_bytes_per_particle"
+    fused_bytes = 96.0 * npart_local if fused else None
+    roofline = {"kernel": kname, "bound": "hbm", "achieved": achieved, "peak": peaks["hbm_gbs"],
+                "unit": "GB/s", "frac": achieved / peaks["hbm_gbs"],
+                "traffic": traffic[tkey] * npart_local if traffic and tkey in traffic else None,
+                "traffic_source": (traffic["axis_block_capture" if fused else "capture"] +
+                                   "; DRAM read+write bytes per particle x the particles of one launch here")
+                if traffic and tkey in traffic else None,
+                "peak_source": peak_src, "avg_launch_ms": ax_avg, "launches_timed": ax_n,
+                "kernel_launches_per_axis_block": ax_n / max(blocks, 1) if fused else None,
+                "reference_subflows_per_launch": sub_per_launch,
+                "algorithmic_bytes_per_launch": alg_bytes,
+                "fused_lower_bound_bytes_per_launch": fused_bytes,
+                "fused_bytes_achieved_gbs": fused_bytes / (ax_avg * 1e-3) / 1e9 if fused and ax_n else None,
+                "fused_bytes_frac": fused_bytes / (ax_avg * 1e-3) / 1e9 / peaks["hbm_gbs"] if fused and ax_n else None,
+                "share_of_step": ax_ms / ms if ms else None,
+                "note": ("W8 is FP64-pipe bound (10 flop/B > ridge 5.8): see roofline_fp64 for the binding roof"
+                         if interp_name == "p8r2" else
+                         "PWL is HBM bound; `achieved` counts reference-schedule bytes (6 x 72 B per particle and "
+                         "launch) on a kernel that moves them once: the binding figure is fused_bytes_frac")}
+    ach_tf = f_axis * sub_per_launch * npart_local / (ax_avg * 1e-3) / 1e12 if ax_n else 0.0
+    step_tf = (18 * f_axis + 6 * f_pv) * npart_local * steps / (ms * 1e-3) / 1e12 if order == 4 else None
+    roofline_fp64 = {"kernel": kname, "bound": "fp64", "achieved": ach_tf, "peak": roof["peak"],
+                     "unit": "TFLOP/s", "frac": ach_tf / roof["peak"] if roof["peak"] else None,
+                     "frac_of_nominal": ach_tf / roof["nominal_tflops"],
+                     "peak_source": roof["peak_source"],
+                     "probes": {k: roof[k] for k in ("two_constant_operand_dfma_tflops", "immediate_horner_dfma_tflops",
+                                                     "three_register_operand_dfma_tflops", "nominal_tflops")},
+                     "three_register_operand_note": "DFMA with three distinct register operands (gathers, deposition: "
+                                                    "~2/3 of this kernel's FP64 instructions) issues every 3 cycles "
+                                                    "instead of 2: the register file, not the pipe, bounds it",
+                     "algorithmic_flop_per_particle": f_axis * sub_per_launch,
+                     "flop_accounting": "reference schedule: 18 Theta x 718 + 6 Theta_E x 842 flop per particle-step "
+                                        "(SURVEY 8d); the fused schedule executes fewer (shared weight evaluations, "
+                                        "merged Theta_z and Theta_E halves)",
+                     "whole_step_tflops": step_tf, "whole_step_frac": step_tf / roof["peak"] if step_tf else None,
+                     "push_V_E_avg_ms": pv_ms / max(pv_n, 1), "push_V_E_launches_per_step": pv_n / max(steps, 1),
+                     "push_V_E_tflops": f_pv * npart_local / (pv_ms / max(pv_n, 1) * 1e-3) / 1e12 if pv_n else None}
+    return fused, roofline, roofline_fp64
+
+
+def secondary_particles(a, env, roof, name, n, ppc, interp_name):
+    """A secondary particle shape (SURVEY 8d C4 / north_star): same step, same timing rules, short record."""
+    spic = env.spic
+    interp = spic.P8R2 if interp_name == "p8r2" else spic.PWL
+    sim = env.make_sim(n, interp, ppc)
+    npart_local = sim.num_particles()
+    npart = int(env.allsum(float(npart_local)))
+    steps = 2
+    r = timed_steps(env, sim, lambda: sim.map(4, 0.5), steps, 3)
+    _, rl, rl64 = particle_rooflines(a, env, r, npart_local, ppc, interp_name, 4, steps, roof)
+    sim.close()
+    keep = ("kernel", "bound", "achieved", "peak", "unit", "frac", "avg_launch_ms", "share_of_step")
+    out = {"name": name, "metric": "particle-steps/s (%s, 4th-order split)" % ("W8" if interp_name == "p8r2" else "PWL"),
+           "workload": "uniform plasma %d^3 cells x %d ppc per GPU, %s, Theta_map4, dt=0.5, v_th=0.01"
+                       % (n, ppc, "W8/P8R2" if interp_name == "p8r2" else "PWL"),
+           "value": npart * steps / (r["ms"] * 1e-3), "unit": UNIT, "particles": npart, "steps": steps, "warmup": 3,
+           "ms_per_step": r["ms"] / steps, "gpu_launches": r["launches"],
+           "kernel_ms_per_step": {k: v[0] / steps for k, v in r["kt"].items()},
+           "roofline_fp64": {k: rl64[k] for k in keep if k in rl64} | {"frac_of_nominal": rl64["frac_of_nominal"],
+                                                                        "whole_step_frac": rl64["whole_step_frac"]},
+           "roofline": {k: rl[k] for k in keep if k in rl} | {"fused_bytes_achieved_gbs": rl["fused_bytes_achieved_gbs"],
+                                                              "fused_bytes_frac": rl["fused_bytes_frac"]},
+           "checks": r["checks"]}
+    return out
+
+
+def secondary_field_only(a, env, n=256):
+    """BASELINE configs[2]: vacuum Maxwell n^3 with the soft plane-wave source and MABC in x, field sub-flows only
+    (examples/field_only/main.cpp:142-145).  Algorithmic traffic: 3 curl sweeps x 72 B per cell and step."""
+    spic = env.spic
+    sim = env.make_sim(n, spic.P8R2, 0, periodic=(0, 1, 1))
+    state = {"k": 0}
+
+    def step():
+        sim.field_only_step(n // 8, 1, 0.1, 0.3, 0.5, state["k"])
+        state["k"] += 1
+
+    steps = 200
+    r = timed_steps(env, sim, step, steps, 20)
+    sim.close()
+    peaks, peak_src = measured_peaks()
+    cells = n ** 3 * env.world
+    value = cells * steps / (r["ms"] * 1e-3)
+    gbs = 216.0 * n ** 3 * steps / (r["ms"] * 1e-3) / 1e9
+    return {"name": "field_only", "metric": "cell-updates/s (vacuum Maxwell, source + MABC-x)",
+            "workload": "%d^3 cells per GPU, x walls (MABC) + soft plane-wave source, y z periodic, dt=0.5" % n,
+            "value": value, "unit": "cell-updates/s", "steps": steps, "warmup": 20, "ms_per_step": r["ms"] / steps,
+            "gpu_launches": r["launches"], "kernel_ms_per_step": {k: v[0] / steps for k, v in r["kt"].items()},
+            "roofline": {"kernel": "field step (Theta_E/2, source, Theta_B, Theta_E/2: 3 curl sweeps)", "bound": "hbm",
+                         "achieved": gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": gbs / peaks["hbm_gbs"],
+                         "peak_source": peak_src, "algorithmic_bytes_per_cell_step": 216.0,
+                         "roof_cell_updates_per_s": peaks["hbm_gbs"] * 1e9 / 216.0},
+            "energy_after": r["checks"]["energy_after"]}
+
+
 def ours_main(a):
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
     cpu = None
     if rank == 0 and world == 1 and not a.no_cpu:
         # reference CPU code timed beside us, BEFORE CUDA is initialised (fork-safe), rank 0, N=1 only
@@ -252,136 +491,27 @@ def ours_main(a):
         except Exception as e:  # noqa: BLE001
             cpu = {"error": repr(e)}
 
-    import numpy as np
-    import torch
-    import strugepic_b200 as spic  # raises ImportError when the CUDA library is missing: no fallback
-
-    torch.cuda.set_device(local)
-    dist = None
-    if world > 1:
-        import torch.distributed as dist
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-
-    def _noop():
-        pass
-
-    def _barrier():
-        dist.barrier()
-
-    barrier = _noop if dist is None else _barrier
-
-    def allmax(x):
-        if dist is None:
-            return x
-        t = torch.tensor([x], dtype=torch.float64, device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        return float(t.item())
-
-    def allsum(x):
-        if dist is None:
-            return x
-        t = torch.tensor([x], dtype=torch.float64, device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.SUM)
-        return float(t.item())
-
+    env = Env()
+    spic, np, torch, dist, local = env.spic, env.np, env.torch, env.dist, env.local
     interp = spic.P8R2 if a.interp == "p8r2" else spic.PWL
-    n_cell = (a.n, a.n, a.n * world)
-    sim = spic.Simulation(n_cell, interp=interp, device=local, nranks=world, rank=rank)
-    if world > 1:
-        uid = torch.zeros(128, dtype=torch.uint8, device="cuda")
-        if rank == 0:
-            uid = torch.tensor(list(spic.comm_unique_id()), dtype=torch.uint8, device="cuda")
-        dist.broadcast(uid, 0)
-        sim.comm_init(bytes(uid.cpu().tolist()))
-    sim.set_uniform_field(spic.FIELD_E, [0.0, 0.0, 0.0])
-    sim.set_uniform_field(spic.FIELD_B, [0.0, 0.0, 1.0])
-    sim.add_particle_density_uniform(a.ppc, 100.0, -1.0, 0.01, seed=12345)
-    sim.sync()
+    opts = list(a.opt) + (["fuse=0"] if a.no_fuse else [])
+    sim = env.make_sim(a.n, interp, a.ppc, opts=opts)
     npart_local = sim.num_particles()
-    npart = int(allsum(float(npart_local)))
-    fp64_peak = spic.probe_fp64_tflops(local, 0.5)
-    fp64_peak3 = spic.probe_fp64_tflops(local, 0.25, three_operands=True)
-
-    if a.no_fuse:
-        sim.set_option("fuse", 0)
-    for kv in a.opt:
-        k, v = kv.split("=")
-        sim.set_option(k, float(v))
-    stream = torch.cuda.ExternalStream(sim.stream())
-    for _ in range(a.warmup):
-        sim.map(a.order, 0.5)
-    sim.sync()
+    npart = int(env.allsum(float(npart_local)))
+    roof = fp64_roof(env)
 
     # ---- timed region: K steps, state resident in HBM --------------------------------------
-    sim.set_option("time_kernels", 1)
-    sim.kernel_times(reset=True)
-    l0 = sim.launch_count()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    sampler = ClockSampler(local, a.clock_period_ms)
-    torch.cuda.synchronize()
-    barrier()
-    e0.record(stream)
-    for _ in range(a.steps):
-        sim.map(a.order, 0.5)
-    e1.record(stream)
-    sim.sync()
-    torch.cuda.synchronize()
-    barrier()
-    clocks = sampler.stop()
-    ms = allmax(e0.elapsed_time(e1))
-    launches = sim.launch_count() - l0
-    kt = sim.kernel_times(reset=True)
-    sim.set_option("time_kernels", 0)
+    r = timed_steps(env, sim, lambda: sim.map(a.order, 0.5), a.steps, a.warmup, a.clock_period_ms)
+    ms, launches, kt, clocks = r["ms"], r["launches"], r["kt"], r["clocks"]
     value = npart * a.steps / (ms * 1e-3)
 
     # ---- roofline of the dominant kernel ---------------------------------------------------------
-    # fused schedule (default on periodic single-rank boxes): k_axis_block = the six Theta of one map2 in one
-    # launch; otherwise k_theta_axis_* = one Theta per launch.  Algorithmic work is counted on the REFERENCE
-    # schedule either way (72 B and 718 flop per particle and reference sub-flow), so fusion shows
-    # up as time saved, not as work invented; the fused lower bound (96 B per particle and block) is given too.
-    peaks, peak_src = measured_peaks()
-    fused = kt["axis_block"][1] > 0
-    ax_ms, ax_n = kt["axis_block"] if fused else kt["theta_axis"]
-    sub_per_launch = 6 if fused else 1
-    pv_ms, pv_n = kt["push_V_E"]
-    ax_avg = ax_ms / max(ax_n, 1)
-    f_axis = FLOP_AXIS if a.interp == "p8r2" else FLOP_AXIS_PWL
-    f_pv = FLOP_PUSHVE if a.interp == "p8r2" else FLOP_PUSHVE_PWL
-    kname = "k_axis_block" if fused else ("k_theta_axis_v2" if a.ppc >= 40 else "k_theta_axis_v3")
-    alg_bytes = BYTES_PER_SUBFLOW * sub_per_launch * npart_local
-    achieved = alg_bytes / (ax_avg * 1e-3) / 1e9 if ax_n else 0.0
-    traffic = ncu_traffic()
-    tkey = "axis_block_dram_bytes_per_particle" if fused else "theta_axis_dram_bytes_per_particle"
-    roofline = {"kernel": kname, "bound": "hbm", "achieved": achieved, "peak": peaks["hbm_gbs"],
-                "unit": "GB/s", "frac": achieved / peaks["hbm_gbs"],
-                "traffic": traffic[tkey] * npart_local if traffic and tkey in traffic else None,
-                "traffic_source": (traffic["axis_block_capture" if fused else "capture"] +
-                                   "; DRAM read+write bytes per particle x the particles of one launch here")
-                if traffic and tkey in traffic else None,
-                "peak_source": peak_src, "avg_launch_ms": ax_avg, "launches_timed": ax_n,
-                "reference_subflows_per_launch": sub_per_launch,
-                "algorithmic_bytes_per_launch": alg_bytes,
-                "fused_lower_bound_bytes_per_launch": 96.0 * npart_local if fused else None,
-                "share_of_step": ax_ms / ms if ms else None,
-                "note": "W8 is FP64-pipe bound (10 flop/B > ridge 5.8): see roofline_fp64 for the binding roof"}
-    ach_tf = f_axis * sub_per_launch * npart_local / (ax_avg * 1e-3) / 1e12 if ax_n else 0.0
-    step_tf = (18 * f_axis + 6 * f_pv) * npart_local * a.steps / (ms * 1e-3) / 1e12 if a.order == 4 else None
-    roofline_fp64 = {"kernel": kname, "bound": "fp64", "achieved": ach_tf, "peak": fp64_peak,
-                     "unit": "TFLOP/s", "frac": ach_tf / fp64_peak if fp64_peak else None,
-                     "peak_source": "measured here: spic_probe_fp64_tflops (dependent-free DFMA chains, all SMs)",
-                     "three_register_operand_dfma_tflops": fp64_peak3,
-                     "three_register_operand_note": "DFMA with three distinct register operands (gathers, deposition: "
-                                                    "~2/3 of this kernel's FP64 instructions) issues every 3 cycles "
-                                                    "instead of 2: the register file, not the pipe, bounds it",
-                     "algorithmic_flop_per_particle": f_axis * sub_per_launch,
-                     "flop_accounting": "reference schedule: 18 Theta x 718 + 6 Theta_E x 842 flop per particle-step "
-                                        "(SURVEY 8d); the fused schedule executes fewer (shared weight evaluations, "
-                                        "merged Theta_z and Theta_E halves)",
-                     "whole_step_tflops": step_tf, "whole_step_frac": step_tf / fp64_peak if step_tf else None,
-                     "push_V_E_avg_ms": pv_ms / max(pv_n, 1), "push_V_E_launches_per_step": pv_n / max(a.steps, 1),
-                     "push_V_E_tflops": f_pv * npart_local / (pv_ms / max(pv_n, 1) * 1e-3) / 1e12 if pv_n else None}
+    # fused schedule (default on periodic boxes): k_axis_block = the six Theta of one map2 in one launch; otherwise
+    # k_theta_axis_* = one Theta per launch.  Algorithmic work is counted on the REFERENCE schedule either way (72 B
+    # and 718 flop per particle and reference sub-flow), so fusion shows up as time saved, not as work
+    # invented; the fused lower bound (96 B per particle and block) is given too.
+    fused, roofline, roofline_fp64 = particle_rooflines(a, env, r, npart_local, a.ppc, a.interp, a.order, a.steps, roof)
 
-    energy = sim.get_total_energy()
     # ---- e2e: the same step through the C ABI with HOST buffers ------------------------------
     e2e = None
     if not a.no_e2e:
@@ -397,29 +527,33 @@ def ours_main(a):
         e2e_n = a.n
         while avail and e2e_n > 32 and (48 * a.ppc + 48) * e2e_n ** 3 * world * 1.4 > avail:
             e2e_n //= 2
-        e2e_n = int(-allmax(-float(e2e_n)))  # every rank must take the same decision
+        e2e_n = int(-env.allmax(-float(e2e_n)))  # every rank must take the same decision
         if e2e_n != a.n:
             sim.close()
-            sim = spic.Simulation((e2e_n, e2e_n, e2e_n * world), interp=interp, device=local, nranks=world, rank=rank)
-            if world > 1:
-                uid2 = torch.zeros(128, dtype=torch.uint8, device="cuda")
-                if rank == 0:
-                    uid2 = torch.tensor(list(spic.comm_unique_id()), dtype=torch.uint8, device="cuda")
-                dist.broadcast(uid2, 0)
-                sim.comm_init(bytes(uid2.cpu().tolist()))
-            sim.set_uniform_field(spic.FIELD_E, [0.0, 0.0, 0.0])
-            sim.set_uniform_field(spic.FIELD_B, [0.0, 0.0, 1.0])
-            sim.add_particle_density_uniform(a.ppc, 100.0, -1.0, 0.01, seed=12345)
+            sim = env.make_sim(e2e_n, interp, a.ppc, opts=opts)
             sim.map(a.order, 0.5)
             sim.sync()
         n_loc = sim.num_particles()
-        e2e = run_e2e(a, sim, spic, np, torch, n_loc, int(allsum(float(n_loc))), barrier, allmax, e2e_n)
+        e2e = run_e2e(a, sim, spic, np, torch, n_loc, int(env.allsum(float(n_loc))), env.barrier if dist else None,
+                      env.allmax, e2e_n)
         if e2e_n != a.n:
             e2e["workload"] = ("%dx%dx%d cells x %d ppc (per-GPU brick reduced from %d^3: pinned host buffers for "
                                "%d ranks would not fit %.0f GB of host RAM)" %
                                (e2e_n, e2e_n, e2e_n * world, a.ppc, a.n, world, avail / 1e9))
-
     sim.close()
+    del sim
+
+    # ---- secondary records (after the main region): the other shapes SURVEY 8d / BASELINE configs name ------------
+    secondary = []
+    if not a.no_secondary and (world == 1 or a.secondary_all_ranks) and a.interp == "p8r2" and a.order == 4:
+        for fn in (lambda: secondary_particles(a, env, roof, "low_ppc", 2 * a.n, max(a.ppc // 8, 1), "p8r2"),
+                   lambda: secondary_particles(a, env, roof, "pwl", a.n, a.ppc, "pwl"),
+                   lambda: secondary_field_only(a, env, a.n)):
+            try:
+                secondary.append(fn())
+            except Exception as e:  # noqa: BLE001  (a secondary must not take the headline down with it)
+                secondary.append({"error": repr(e)[:300]})
+
     if rank == 0:
         line = {
             "metric": METRIC if a.interp == "p8r2" and a.order == 4 else METRIC.replace("W8", "PWL" if a.interp == "pwl" else "W8").replace("4th-order split", "Theta_map%d" % a.order if a.order != 4 else "4th-order split"),
@@ -430,13 +564,17 @@ def ours_main(a):
                        "parallelism": "z-slab x%d" % world,
                        "l2": "inputs (%.1f GB of particle state per GPU) exceed the 126 MB L2; no flush needed"
                              % (48e-9 * npart_local)},
-            "schedule": ("fused: per map2 one axis-block launch (x y z z y x) + Theta_B, adjacent Theta_E halves merged"
+            "schedule": ("fused: per map2 one axis block (x y z z y x) + Theta_B, adjacent Theta_E halves merged"
+                         + ("; z slabs: slab-face planes first, their halo sums + migration on the comm stream under "
+                            "the interior planes" if world > 1 else "")
                          if fused else "reference: one launch per sub-flow"),
             "clocks": clocks, "e2e": e2e, "gpu_launches": launches,
             "roofline": roofline, "roofline_fp64": roofline_fp64,
+            "checks": r["checks"],
             "cell_updates_per_s": a.n ** 3 * world * a.steps / (ms * 1e-3),
             "kernel_ms_per_step": {k: v[0] / a.steps for k, v in kt.items()},
-            "energy_after": energy,
+            "energy_after": r["checks"]["energy_after"],
+            "secondary": secondary,
         }
         if cpu is not None and "error" not in cpu:
             line["cpu_baseline"] = {"value": cpu["value"], "unit": UNIT, "cores": cpu["cores"], "kind": cpu["kind"],
@@ -454,7 +592,11 @@ def run_e2e(a, sim, spic, np, torch, npart_local, npart, barrier, allmax, cells)
     """Upload (pinned host -> device, re-bin), one Theta_map, read back: all timed."""
     # with N > 1 particles migrate between slabs, so the per-rank count changes from step to step:
     # pinned buffers carry 2 % slack and every transfer uses the live count
-    cap = int(npart_local * 1.02) + 4096 if barrier.__name__ != "_noop" else npart_local
+    multi = barrier is not None
+    if barrier is None:
+        def barrier():
+            pass
+    cap = int(npart_local * 1.02) + 4096 if multi else npart_local
     pinned = [torch.empty(cap, dtype=torch.float64, pin_memory=True).numpy() for _ in range(6)]
     host_f = [torch.empty((3, cells, cells, cells), dtype=torch.float64, pin_memory=True).numpy() for _ in range(2)]
     n_live = sim.num_particles()

@@ -112,6 +112,8 @@ int spic_load_density_plasma(spic_ctx* ctx, double q, double m, int32_t ppc_max,
                              uint64_t seed, const int32_t* count);
 int spic_num_species(const spic_ctx* ctx);
 int spic_num_particles(spic_ctx* ctx, int species, int64_t* n);
+/* ParticleContainer::TotalNumberOfParticles(): summed over the ranks (collective when nranks > 1) */
+int spic_num_particles_global(spic_ctx* ctx, int species, int64_t* n);
 int spic_get_particles(spic_ctx* ctx, int species, double* x, double* y, double* z, double* vx,
                        double* vy, double* vz);
 int spic_set_particles(spic_ctx* ctx, int species, int64_t n, const double* x, const double* y,
@@ -180,6 +182,9 @@ int spic_probe_fp64_tflops(int device, double seconds, double* tflops);
 /* the same chains with three distinct register operands per DFMA (what gathers and deposition issue): the
  * register file sustains ~2/3 of the rate above; reported beside the roofline, not used as its denominator */
 int spic_probe_fp64_three_operand_tflops(int device, double seconds, double* tflops);
+/* the same chains as Horner steps with immediate coefficients, x = fma(x, t, imm): the fastest DFMA form (what the W
+ * polynomial evaluations issue); bench.py reports the FP64 roof against max(this, spic_probe_fp64_tflops) */
+int spic_probe_fp64_immediate_tflops(int device, double seconds, double* tflops);
 
 #ifdef __cplusplus
 }

@@ -155,7 +155,8 @@ class MultiFab {
 // handle standing in for `CParticleContainer&`
 class CParticleContainer {
  public:
-  std::int64_t TotalNumberOfParticles(int species = 0) const;
+  std::int64_t TotalNumberOfParticles(int species = 0) const;  // global, like the reference's (collective)
+  std::int64_t LocalNumberOfParticles(int species = 0) const;  // on this rank
   Simulation& sim() const { return *sim_; }
 
  private:
@@ -265,6 +266,11 @@ inline void MultiFab::copy_from_host(const double* host) { sim_->check(spic_set_
 inline void MultiFab::copy_to_host(double* host) const { sim_->check(spic_get_field(sim_->ctx(), which_, host)); }
 inline std::int64_t CParticleContainer::TotalNumberOfParticles(int species) const {
   std::int64_t n = 0;
+  sim_->check(spic_num_particles_global(sim_->ctx(), species, &n));
+  return n;
+}
+inline std::int64_t CParticleContainer::LocalNumberOfParticles(int species) const {
+  std::int64_t n = 0;
   sim_->check(spic_num_particles(sim_->ctx(), species, &n));
   return n;
 }
@@ -342,8 +348,13 @@ inline void set_uniform_field(MultiFab& A, std::array<double, 3> vals) {  // uti
 // util.cpp:130-155
 inline void add_single_particle(CParticleContainer& P, std::array<double, 3> pos, std::array<double, 3> vel, double m,
                                 double q) {
+  // every rank adds the species (the exchanges are per species); the rank whose slab holds `pos` owns the particle --
+  // the reference adds it on grid 0 and Redistributes (util.cpp:144-155)
   Simulation& s = P.sim();
-  s.check(spic_add_species(s.ctx(), q, m, 1, &pos[0], &pos[1], &pos[2], &vel[0], &vel[1], &vel[2]));
+  std::array<int, 3> lo, n;
+  s.local_box(lo, n);
+  const bool mine = pos[2] >= lo[2] && pos[2] < lo[2] + n[2];
+  s.check(spic_add_species(s.ctx(), q, m, mine ? 1 : 0, &pos[0], &pos[1], &pos[2], &vel[0], &vel[1], &vel[2]));
 }
 // add_particle_density(geom, P, uniform_density, ppc, m, q, v) -- util.cpp:267-311; counter-based RNG on the device
 inline void add_particle_density_uniform(const Geometry&, CParticleContainer& P, int ppc, double m, double q,
@@ -403,7 +414,7 @@ inline void print_Particle_info(const Geometry&, CParticleContainer& P) {
   Simulation& s = P.sim();
   const int ns = spic_num_species(s.ctx());
   for (int sp = 0; sp < ns; ++sp) {
-    const std::int64_t n = P.TotalNumberOfParticles(sp);
+    const std::int64_t n = P.LocalNumberOfParticles(sp);
     if (n == 0) continue;
     std::vector<double> a[6];
     for (auto& t : a) t.resize((std::size_t)n);

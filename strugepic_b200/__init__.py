@@ -64,12 +64,14 @@ def I_Wp(a, b, interp=P8R2):
     return _lib.load().spic_I_Wp(interp, a, b)
 
 
-def probe_fp64_tflops(device=0, seconds=1.0, three_operands=False):
-    """Measured DFMA rate (TFLOP/s): chains with two loop-constant operands, or with three distinct register
-    operands per instruction (what the gathers and the deposition issue; the register file sustains ~2/3)."""
+def probe_fp64_tflops(device=0, seconds=1.0, three_operands=False, immediate=False):
+    """Measured DFMA rate (TFLOP/s): chains with two loop-constant operands, with three distinct register
+    operands per instruction (what the gathers and the deposition issue; the register file sustains ~2/3), or
+    Horner steps with immediate coefficients (the W polynomials: the fastest form)."""
     out = C.c_double(0)
     lib = _lib.load()
-    fn = lib.spic_probe_fp64_three_operand_tflops if three_operands else lib.spic_probe_fp64_tflops
+    fn = lib.spic_probe_fp64_three_operand_tflops if three_operands else (
+        lib.spic_probe_fp64_immediate_tflops if immediate else lib.spic_probe_fp64_tflops)
     rc = fn(device, seconds, C.byref(out))
     if rc:
         raise SpicError(rc, "fp64 probe failed")
@@ -197,6 +199,19 @@ class Simulation:
         n = C.c_int64(0)
         self._ck(self.lib.spic_num_particles(self.h, species, C.byref(n)))
         return n.value
+
+    def num_particles_global(self, species=0):
+        """TotalNumberOfParticles(): summed over the ranks (collective)."""
+        n = C.c_int64(0)
+        self._ck(self.lib.spic_num_particles_global(self.h, species, C.byref(n)))
+        return n.value
+
+    def add_single_particle(self, pos, vel, m, q):
+        """add_single_particle (util.cpp:130-155): every rank adds the species, the rank that owns `pos` holds the
+        particle (the reference adds it on grid 0 and Redistributes)."""
+        mine = self.lo[2] <= pos[2] < self.lo[2] + self.n[2]
+        a = [[t] if mine else [] for t in (*pos, *vel)]
+        return self.add_species(q, m, *a)
 
     def get_particles(self, species=0, out=None):
         n = self.num_particles(species)

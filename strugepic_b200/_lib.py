@@ -34,6 +34,7 @@ SIGNATURES = {
     "spic_load_density_plasma": (i32, [vp, dbl, dbl, C.c_int32, C.c_int32, dbl, u64, C.POINTER(C.c_int32)]),
     "spic_num_species": (i32, [vp]),
     "spic_num_particles": (i32, [vp, i32, C.POINTER(i64)]),
+    "spic_num_particles_global": (i32, [vp, i32, C.POINTER(i64)]),
     "spic_get_particles": (i32, [vp, i32] + [_dp] * 6),
     "spic_set_particles": (i32, [vp, i32, i64] + [_dp] * 6),
     "spic_theta_axis": (i32, [vp, i32, dbl]),
@@ -63,6 +64,7 @@ SIGNATURES = {
     "spic_stream": (vp, [vp]),
     "spic_probe_fp64_tflops": (i32, [i32, dbl, _dp]),
     "spic_probe_fp64_three_operand_tflops": (i32, [i32, dbl, _dp]),
+    "spic_probe_fp64_immediate_tflops": (i32, [i32, dbl, _dp]),
 }
 
 _lib = None

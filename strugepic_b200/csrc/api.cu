@@ -114,6 +114,23 @@ int halo_sum(Ctx* c, double* F, int comp) {
   if (c->cfg.nranks > 1) return comm_exchange_sum(c, F, comp);
   return SPIC_OK;
 }
+// E.SumBoundary (hpp:367) of the components in `mask` + P.Redistribute across slabs (hpp:368) after a deposition.
+// With z slabs the guard z planes travel RAW (x / y guards included) together with the packed leavers in one exchange
+// (comm_block_begin / _end), and the x / y images are folded afterwards over the owner planes: the same sums as
+// fold-then-exchange in another order.  begin_only: the caller overlaps compute and calls deposit_exchange_end.
+int deposit_exchange_begin(Ctx* c, unsigned mask, bool migrate) {
+  if (c->cfg.nranks > 1) return comm_block_begin(c, c->E, mask, migrate);
+  return SPIC_OK;
+}
+int deposit_exchange_end(Ctx* c, unsigned mask) {
+  if (c->cfg.nranks > 1) {
+    int rc = comm_block_end(c);
+    if (rc) return rc;
+  }
+  for (int comp = 0; comp < 3; ++comp)
+    if ((mask >> comp) & 1u) launch_sum_boundary(c, c->E, comp, c->g.zlocal != 0, c->g.zlocal == 0);
+  return SPIC_OK;
+}
 }  // namespace
 
 extern "C" {  // host side of the user-W slot (user_w.cu)
@@ -410,6 +427,15 @@ int spic_num_particles(spic_ctx* c, int species, int64_t* n) {
   return SPIC_OK;
 }
 
+int spic_num_particles_global(spic_ctx* c, int species, int64_t* n) {
+  int rc = spic_num_particles(c, species, n);
+  if (rc || c->cfg.nranks == 1) return rc;
+  double v = (double)*n;  // exact below 2^53
+  if ((rc = comm_allreduce_sum(c, &v, 1))) return rc;
+  *n = (int64_t)v;
+  return SPIC_OK;
+}
+
 int spic_get_particles(spic_ctx* c, int species, double* x, double* y, double* z, double* vx, double* vy, double* vz) {
   if (!c || species < 0 || species >= (int)c->sp.size()) return SPIC_EINVAL;
   cudaSetDevice(c->cfg.device);
@@ -441,10 +467,9 @@ static int theta_axis_impl(spic_ctx* c, int comp, double dt) {
       launch_theta_axis_direct(c, s.d, s.nd, nullptr, s.q, s.m, comp, dt);
     }
   }
-  rc = halo_sum(c, c->E, comp);  // E.SumBoundary             hpp:367
-  if (rc) return rc;
-  if (comp == 2 && c->cfg.nranks > 1) rc = comm_migrate(c);  // P.Redistribute across slabs, hpp:368
-  return rc;
+  // E.SumBoundary hpp:367 + P.Redistribute across slabs hpp:368 (only Theta_z moves particles across slab faces)
+  if ((rc = deposit_exchange_begin(c, 1u << comp, comp == 2))) return rc;
+  return deposit_exchange_end(c, 1u << comp);
 }
 
 static int theta_E_impl(spic_ctx* c, double dt) {
@@ -496,12 +521,20 @@ static int axis_block(spic_ctx* c, double dt) {
   int rc = theta_B_impl(c, dt);  // fills the guards of B (cpp:104): B does not change until the next Theta_E
   if (rc) return rc;
   launch_zero_guards(c, c->E);  // E.setBndry(0), hpp:351-352: the guards collect this block's currents
+  // With z slabs (option "overlap"): the cells of the W + 2 planes next to each slab face run first -- only they can
+  // deposit into the guard z planes or lose particles to a neighbour (a particle moves < 2 cells in a block, its
+  // stencil reaches W cells further) -- then ONE exchange carries the guard planes of the three components and the
+  // leavers on the comm stream while the interior planes compute.  Per block: E.SumBoundary once per component,
+  // P.Redistribute once (hpp:367-368).
+  const int nb = c->W + 2;
+  const bool split = c->cfg.nranks > 1 && engine_overlap(c) && 2 * nb < c->g.n[2];
   for (auto& s : c->sp)
-    if ((rc = engine_axis_block(c, s, dt / 2))) return rc;
-  for (int comp = 0; comp < 3; ++comp)
-    if ((rc = halo_sum(c, c->E, comp))) return rc;  // E.SumBoundary, hpp:367
-  if (c->cfg.nranks > 1) rc = comm_migrate(c);       // P.Redistribute across slabs, hpp:368 (once per block)
-  return rc;
+    if ((rc = engine_axis_block(c, s, dt / 2, split ? 1 : 0, nb))) return rc;
+  if ((rc = deposit_exchange_begin(c, 7u, true))) return rc;
+  if (split)
+    for (auto& s : c->sp)
+      if ((rc = engine_axis_block(c, s, dt / 2, 2, nb))) return rc;
+  return deposit_exchange_end(c, 7u);
 }
 
 // Theta_map2(d_0) o ... o Theta_map2(d_{n-1}) with fused axis blocks; adjacent Theta_E halves are merged:

@@ -29,8 +29,6 @@ struct EngineState {
   // 1: Theta_map2 / Theta_map4 run the six position sub-flows of every map2 as one fused axis block
   // (particles_fused.cu) and merge adjacent Theta_E; 0: the reference's launch-per-sub-flow schedule
   int fuse = 1;
-  // 1: the fused axis block cuts batches that may span two cells (k_axis_block_s); opt-in, see particles_fused.cu
-  int block_stream = 0;
   // nranks > 1: 1 = the slab-face cells of an axis block run first and their halo sums / migration travel on a side
   // stream while the interior cells compute; 0 = every exchange in stream order behind the whole block
   int overlap = 1;
@@ -85,8 +83,11 @@ int stream_push_v_e(Ctx* c, Species& s, double dt);
 
 // ---- fused axis block (particles_fused.cu) ------------------------------------------------
 bool fused_block_supported(const Ctx* c);                 // fully periodic box (guard width W + 1 with z slabs)
-int fused_axis_block(Ctx* c, Species& s, double h);       // x(h) y(h) z(2h) y(h) x(h) over the bins
-int fused_axis_continue(Ctx* c, Species& s, double h);    // finishes the particles the block ejected
+// x(h) y(h) z(2h) y(h) x(h) over the bins of: part 0 = every cell, 1 = the nb z planes next to each slab face,
+// 2 = the planes between them; list_cap = the mover-list prefix the launch may fill (fused_list_cap)
+int fused_axis_block(Ctx* c, Species& s, double h, int part, int nb, unsigned list_cap);
+unsigned fused_list_cap(Ctx* c, long cells);
+int fused_axis_continue(Ctx* c, Species& s, double h, unsigned list_cap);  // finishes the particles the block ejected
 int fused_axis_tail(Ctx* c, Species& s, double h);        // the same six sub-flows for the overflow tail
 
 // ---- cell-binned engine ------------------------------------------------------------
@@ -97,21 +98,28 @@ int engine_count(Ctx* c, Species& s, long* nb);
 int engine_gather(Ctx* c, Species& s, double* hx[3], double* hv[3], long* nb);
 int engine_theta_axis(Ctx* c, Species& s, int comp, double dt);
 int engine_push_v_e(Ctx* c, Species& s, double dt);
+bool engine_overlap(Ctx* c);                       // option "overlap"
 bool engine_can_fuse(Ctx* c);                      // option "fuse" on, box supported, every species binned
-int engine_axis_block(Ctx* c, Species& s, double h);  // the six Theta of a map2 (step h each) for one species
+// the six Theta of a map2 (step h each) for one species over part 0 / 1 / 2 of the cells (fused_axis_block); with
+// nranks > 1 parts 0 and 1 also pack the particles that left the slab into the species' migration messages
+int engine_axis_block(Ctx* c, Species& s, double h, int part = 0, int nb = 0);
 int engine_kinetic(Ctx* c, Species& s, double* acc);
 int engine_deposit_rho(Ctx* c, Species& s, double* out);
 int engine_number_density(Ctx* c, Species& s, double* nd);  // nd: one guarded component
 int engine_set_option(Ctx* c, const char* name, double value);
 int engine_maintain(Ctx* c);
-// file n particles (device arrays, positions inside this rank's slab) into their bins / the tail
-int engine_insert_list(Ctx* c, Species& s, double* const x[3], double* const v[3], long n);  // called between steps: rebin species whose overflow tail has grown
+// file particles (device arrays, positions inside this rank's slab) into their bins / the tail: n of them, or
+// min(*n_dev, n) when n_dev is given (count on the device: arrivals from a neighbour slab)
+int engine_insert_list(Ctx* c, Species& s, double* const x[3], double* const v[3], long n,
+                       const unsigned long long* n_dev = nullptr);
 
 // ---- z-slab decomposition over NCCL --------------------------------------------------
 int comm_exchange_fill(Ctx* c, double* F);           // owner planes -> neighbour guard planes
 int comm_exchange_sum(Ctx* c, double* F, int comp);  // guard planes added into the neighbour's owner planes
-int comm_migrate(Ctx* c);
-int comm_migrate_species(Ctx* c, Species& s);       // exchange the packed leavers of one species
+// one exchange = the raw guard z planes of the components in `mask` of F + (migrate) the packed leavers of every
+// species, on the comm stream; _end makes the compute stream wait, adds the planes and files the arrivals
+int comm_block_begin(Ctx* c, double* F, unsigned mask, bool migrate);
+int comm_block_end(Ctx* c);
 int comm_init(Ctx* c, const void* id128);                            // particles that crossed a slab face change rank
 // movers with dest -1 / -2 (left through the low / high z face) are copied to the send buffers
 int comm_collect_leavers(Ctx* c, Species& s, double* const mx[3], double* const mv[3], const int* dest,

@@ -82,8 +82,9 @@ __global__ void k_zero_guards(Grid g, double* __restrict__ F) {
 // Owner-centric fold: each valid cell adds up its guard images in a fixed order
 // (deterministic; no atomics).  With z_too == 0 the z images are folded by the
 // neighbour exchange instead and the x/y fold also runs over the z guard planes.
-__global__ void k_sum_boundary(Grid g, double* __restrict__ F, int comp, int z_too) {
-  const int klo = z_too ? 0 : -g.ng, khi = z_too ? g.n[2] : g.n[2] + g.ng;
+__global__ void k_sum_boundary(Grid g, double* __restrict__ F, int comp, int z_too, int owner_only) {
+  // owner_only (with z_too == 0): the z guard planes have already been handed to the neighbour slabs
+  const int klo = z_too || owner_only ? 0 : -g.ng, khi = z_too || owner_only ? g.n[2] : g.n[2] + g.ng;
   const long total = (long)g.n[0] * g.n[1] * (khi - klo);
   double* Fc = F + (long)comp * g.pc;
   for (long t = blockIdx.x * (long)blockDim.x + threadIdx.x; t < total; t += (long)gridDim.x * blockDim.x) {
@@ -300,9 +301,9 @@ void launch_zero_guards(Ctx* c, double* F) {
   k_zero_guards<<<grid_for(c, (long)gx * gy * gz), kBlock, 0, c->stream>>>(c->g, F);
   c->launches++;
 }
-void launch_sum_boundary(Ctx* c, double* F, int comp, bool z_too) {
-  const long total = (long)c->g.n[0] * c->g.n[1] * (c->g.n[2] + (z_too ? 0 : 2 * c->g.ng));
-  k_sum_boundary<<<grid_for(c, total), kBlock, 0, c->stream>>>(c->g, F, comp, z_too ? 1 : 0);
+void launch_sum_boundary(Ctx* c, double* F, int comp, bool z_too, bool owner_only) {
+  const long total = (long)c->g.n[0] * c->g.n[1] * (c->g.n[2] + (z_too || owner_only ? 0 : 2 * c->g.ng));
+  k_sum_boundary<<<grid_for(c, total), kBlock, 0, c->stream>>>(c->g, F, comp, z_too ? 1 : 0, owner_only ? 1 : 0);
   c->launches++;
 }
 void launch_curl_E_into_B(Ctx* c, double dt) {

@@ -677,9 +677,14 @@ __global__ void __launch_bounds__(256)
 __device__ __forceinline__ long cell_of(const Grid& g, double x, double y, double z);
 __global__ void __launch_bounds__(256)
     k_insert_arrivals(Grid g, const double* ax0, const double* ax1, const double* ax2, const double* av0,
-                      const double* av1, const double* av2, long n, ParticleSoA b, const long* __restrict__ start,
-                      int* __restrict__ count, ParticleSoA tail, unsigned long long* __restrict__ tail_n, long tail_cap,
-                      int* __restrict__ flags) {
+                      const double* av1, const double* av2, long n, const unsigned long long* __restrict__ n_dev,
+                      ParticleSoA b, const long* __restrict__ start, int* __restrict__ count, ParticleSoA tail,
+                      unsigned long long* __restrict__ tail_n, long tail_cap, int* __restrict__ flags) {
+  if (n_dev) {  // a neighbour's message: the count sits in its header; more than fits was flagged by the sender
+    const long nd = (long)*n_dev;
+    if (nd > n) atomicOr(&flags[1], 4);
+    else n = nd;
+  }
   for (long m = blockIdx.x * (long)blockDim.x + threadIdx.x; m < n; m += (long)gridDim.x * blockDim.x) {
     const double px[3] = {ax0[m], ax1[m], ax2[m]}, pv[3] = {av0[m], av1[m], av2[m]};
     const long dest = cell_of(g, px[0], px[1], px[2]);
@@ -1440,6 +1445,8 @@ int engine_theta_axis(Ctx* c, Species& s, int comp, double dt) {
   return SPIC_OK;
 }
 
+bool engine_overlap(Ctx* c) { return c->engine && eng(c)->overlap; }
+
 bool engine_can_fuse(Ctx* c) {
   if (!c->engine || !eng(c)->fuse || !fused_block_supported(c)) return false;
   for (auto& s : c->sp)
@@ -1449,27 +1456,37 @@ bool engine_can_fuse(Ctx* c) {
 
 // Theta_x(h) Theta_y(h) Theta_z(h) Theta_z(h) Theta_y(h) Theta_x(h) for one species
 // (include/strugepic_propagators.hpp:562-569 without the Theta_B in the middle, which commutes)
-int engine_axis_block(Ctx* c, Species& s, double h) {
+int engine_axis_block(Ctx* c, Species& s, double h, int part, int nb) {
   if (!s.binned) return SPIC_OK;
   EngineState* e = eng(c);
   int rc;
-  if ((rc = fused_axis_block(c, s, h))) return rc;
+  const long plane = (long)c->g.n[0] * c->g.n[1];
+  const bool split = part != 0 && 2 * nb < c->g.n[2];
+  if (part == 2 && !split) return SPIC_OK;  // (thin slab: part 1 covered every cell)
+  const long cells = !split ? c->g.cells() : (part == 1 ? 2 * nb * plane : c->g.cells() - 2 * nb * plane);
+  const unsigned list_cap = fused_list_cap(c, cells);
+  if ((rc = fused_axis_block(c, s, h, part, nb, list_cap))) return rc;
   // the overflow tail takes the general per-particle code BEFORE new overflow can join it
-  if ((rc = fused_axis_tail(c, s, h))) return rc;
-  if ((rc = fused_axis_continue(c, s, h))) return rc;
-  int nb = (int)((e->mv.cap + 255) / 256);
-  if (nb > c->sm_count * 8) nb = c->sm_count * 8;
-  k_insert_movers<<<nb, 256, 0, c->stream>>>(e->mv, s.b, s.start, s.count, s.d, s.d_nd, s.capd, c->d_flags);
+  if (part != 2 && (rc = fused_axis_tail(c, s, h))) return rc;
+  if ((rc = fused_axis_continue(c, s, h, list_cap))) return rc;
+  MoverList mv = e->mv;
+  mv.cap = list_cap;
+  int nbk = (int)((list_cap + 255) / 256);
+  if (nbk > c->sm_count * 8) nbk = c->sm_count * 8;
+  k_insert_movers<<<nbk, 256, 0, c->stream>>>(mv, s.b, s.start, s.count, s.d, s.d_nd, s.capd, c->d_flags);
   c->launches++;
-  if (c->cfg.nranks > 1) {  // movers that left the slab (dest -1 / -2) -> the send buffers of the migration step
-    rc = comm_collect_leavers(c, s, e->mv.x, e->mv.v, e->mv.dest, e->mv.n, e->mv.cap);
+  // movers that left the slab (dest -1 / -2) -> this species' migration messages; none can come from the interior
+  // part (a particle moves < 2 cells in a block and nb >= 2)
+  if (c->cfg.nranks > 1 && part != 2) {
+    rc = comm_collect_leavers(c, s, e->mv.x, e->mv.v, e->mv.dest, e->mv.n, list_cap);
     if (rc) return rc;
   }
   SPIC_CUDA_CHECK(c, cudaMemsetAsync(e->mv.n, 0, sizeof(unsigned), c->stream));
   return SPIC_OK;
 }
 
-int engine_insert_list(Ctx* c, Species& s, double* const x[3], double* const v[3], long n) {
+int engine_insert_list(Ctx* c, Species& s, double* const x[3], double* const v[3], long n,
+                       const unsigned long long* n_dev) {
   if (n <= 0) return SPIC_OK;
   if (!s.binned) {
     c->err = "engine_insert_list: species is not binned";
@@ -1477,8 +1494,8 @@ int engine_insert_list(Ctx* c, Species& s, double* const x[3], double* const v[3
   }
   long b = (n + 255) / 256;
   if (b > (long)c->sm_count * 8) b = (long)c->sm_count * 8;
-  k_insert_arrivals<<<(int)b, 256, 0, c->stream>>>(c->g, x[0], x[1], x[2], v[0], v[1], v[2], n, s.b, s.start, s.count,
-                                                   s.d, s.d_nd, s.capd, c->d_flags);
+  k_insert_arrivals<<<(int)b, 256, 0, c->stream>>>(c->g, x[0], x[1], x[2], v[0], v[1], v[2], n, n_dev, s.b, s.start,
+                                                   s.count, s.d, s.d_nd, s.capd, c->d_flags);
   c->launches++;
   return SPIC_OK;
 }
@@ -1605,10 +1622,6 @@ int engine_set_option(Ctx* c, const char* name, double value) {
   }
   if (!strcmp(name, "pushve_kernel")) {
     e->pushve_kernel = (int)value;
-    return SPIC_OK;
-  }
-  if (!strcmp(name, "block_stream")) {
-    e->block_stream = value != 0;
     return SPIC_OK;
   }
   if (!strcmp(name, "overlap")) {

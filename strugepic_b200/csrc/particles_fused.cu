@@ -43,7 +43,6 @@
 #include <cub/device/device_radix_sort.cuh>
 
 #include "engine.cuh"
-#include "fused_cut.cuh"
 #include "particle_math.cuh"
 
 namespace spic {
@@ -59,6 +58,14 @@ constexpr int kContBase = -100;  // mover-list code of an ejected particle: kCon
 #endif
 constexpr int kChunk = SPIC_CHUNK;        // cells per work unit
 constexpr int kTableDoubles = 3 * kChunk + 4;  // per-warp chunk tables + the current cell's coordinates
+
+// The cells one launch of the block kernel covers: up to two ranges of consecutive cells (all cells; or the z planes
+// next to the two slab faces; or the interior planes between them).  Chunks [0, nchunk0) belong to range 0.
+struct CellRanges {
+  unsigned cell0[2];  // first cell of each range (cell0[1] = 0xffffffff when there is no second range)
+  unsigned n[2];      // cells in each range
+  unsigned nchunk0;   // chunks of range 0
+};
 
 template <class I>
 struct BlockLayout {
@@ -92,9 +99,6 @@ struct BlockLayout {
 #endif
   static constexpr int PER_WARP =
       (kTableDoubles + SP + 2 * SB + SWA + SA + SPIC_WARP_ALIGN - 1) / SPIC_WARP_ALIGN * SPIC_WARP_ALIGN;
-  // the cell-spanning variant: coordinates of two cells, stencil buffers with a 2-double pad each
-  static constexpr int PER_WARP_S = (kTableDoubles + 4 + SP + 2 * (SB + 2) + SWA + SA + SPIC_WARP_ALIGN - 1) /
-                                    SPIC_WARP_ALIGN * SPIC_WARP_ALIGN;
   static_assert(SB % 2 == 0 && SW % 2 == 0 && NW1 % 2 == 0 && kTableDoubles % 2 == 0,
                 "16-byte alignment of the sub-buffers");
 };
@@ -269,10 +273,11 @@ template <class I>
 __global__ void __launch_bounds__(kThreads, 2)
     k_axis_block(Grid g, ParticleSoA p, const long* __restrict__ start, int* __restrict__ count,
                  double* __restrict__ E, const double* __restrict__ B, double q, double qm, double h, MoverList mv,
-                 int* __restrict__ flags, long ncell, unsigned* __restrict__ work, unsigned* __restrict__ ekey) {
+                 int* __restrict__ flags, CellRanges rg, unsigned* __restrict__ work, unsigned* __restrict__ ekey) {
   constexpr int NW1 = I::NW1, NWP = I::NWP;
   using Lay = BlockLayout<I>;
   constexpr int NS = Lay::NS, SB = Lay::SB, SP = Lay::SP, NACC = Lay::NACC, NSUB = Lay::NSUB;
+  constexpr unsigned kNone = 0xffffffffu;
   extern __shared__ __align__(16) double smem[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   double* sWarp = smem + warp * Lay::PER_WARP;
@@ -285,7 +290,7 @@ __global__ void __launch_bounds__(kThreads, 2)
   double* sAcc = sW + Lay::SWA;                             // [3][NACC][32]
   const long st[3] = {1, g.pj, g.pk};
   const double nq = -q;  // -E_coef (hpp:114; Ics = Cs = 1)
-  const unsigned nchunk = (unsigned)((ncell + kChunk - 1) / kChunk);
+  const unsigned nchunk = rg.nchunk0 + (rg.n[1] + kChunk - 1) / kChunk;
 
   // draws the next chunk; the value is broadcast only where it is used, so the reduction's latency hides
   auto grab = [&]() -> unsigned {
@@ -293,11 +298,18 @@ __global__ void __launch_bounds__(kThreads, 2)
     if (lane == 0) c = atomicAdd(work, 1u);
     return c;
   };
-  // bin counts / starts of chunk `chunk` -> table buffer tb (cp.async: lands with the next waited group)
-  auto load_table = [&](unsigned chunk, int tb) {
+  // chunk id -> its first cell (kNone: no chunk left).  The launch covers up to two cell ranges (CellRanges).
+  auto to_base = [&](unsigned id) -> unsigned {
+    if (id >= nchunk) return kNone;
+    return id < rg.nchunk0 ? rg.cell0[0] + id * kChunk : rg.cell0[1] + (id - rg.nchunk0) * kChunk;
+  };
+  // bin counts / starts of the chunk that starts at cell `cbase` -> table buffer tb (cp.async: lands with the next
+  // waited group); cells past the end of the chunk's range are empty
+  auto load_table = [&](unsigned cbase, int tb) {
     if (lane < kChunk) {
-      const long cell = (long)chunk * kChunk + lane;
-      if (cell < ncell) {
+      const unsigned cell = cbase + lane;
+      const unsigned end = cbase >= rg.cell0[1] ? rg.cell0[1] + rg.n[1] : rg.cell0[0] + rg.n[0];
+      if (cell < end) {
         const unsigned d4 = (unsigned)__cvta_generic_to_shared(tCnt + tb * kChunk + lane);
         asm volatile("cp.async.ca.shared.global [%0], [%1], 4;\n" ::"r"(d4), "l"(count + cell) : "memory");
         cp_async8(reinterpret_cast<double*>(tStart + tb * kChunk + lane), reinterpret_cast<const double*>(start + cell));
@@ -315,7 +327,7 @@ __global__ void __launch_bounds__(kThreads, 2)
     return g.at(cc[0], cc[1], cc[2]) + (1 - I::W) * (1 + g.pj + g.pk);
   };
   // stage batch `off` of cell (chunk, tb, ci); with off == 0 also the cell's stencil into buffer bb
-  auto stage = [&](unsigned chunk, int tb, int ci, int off, int bb) {
+  auto stage = [&](unsigned cbase, int tb, int ci, int off, int bb) {
     const int n = tCnt[tb * kChunk + ci];
     if (off + lane < n) {
       const long src = tStart[tb * kChunk + ci] + off + lane;
@@ -329,7 +341,7 @@ __global__ void __launch_bounds__(kThreads, 2)
     }
     if (off == 0 && n > 0) {
       int cc[3];
-      const double* src = B + corner_of(chunk * kChunk + ci, cc);
+      const double* src = B + corner_of(cbase + ci, cc);
       double* d = sBst + bb * SB;
 #pragma unroll
       for (int s = lane; s < SB; s += 32) {
@@ -341,18 +353,18 @@ __global__ void __launch_bounds__(kThreads, 2)
   };
 
   // ---- prologue: first chunk's table, then the second chunk's table and the first batch ------------
-  unsigned chunk = __shfl_sync(kFull, grab(), 0);
-  if (chunk >= nchunk) return;
-  load_table(chunk, 0);
+  unsigned cbase = to_base(__shfl_sync(kFull, grab(), 0));  // first cell of the current chunk
+  if (cbase == kNone) return;
+  load_table(cbase, 0);
   cp_async_commit();
   unsigned pending = grab();  // lane 0 holds the id of the chunk after next
   cp_async_wait<0>();
   __syncwarp();
-  unsigned chunk_next = __shfl_sync(kFull, pending, 0);
-  if (chunk_next < nchunk) load_table(chunk_next, 1);
+  unsigned cbase_next = to_base(__shfl_sync(kFull, pending, 0));
+  if (cbase_next != kNone) load_table(cbase_next, 1);
   pending = grab();
   int tb = 0, ci = 0, off = 0, bb = 0;
-  stage(chunk, 0, 0, 0, 0);
+  stage(cbase, 0, 0, 0, 0);
   cp_async_commit();
 
   // Little state lives across a batch (registers are what limits this kernel): the bin count / start are
@@ -365,7 +377,7 @@ __global__ void __launch_bounds__(kThreads, 2)
     __syncwarp();
     if (off == 0) {  // new cell
       int cc[3];
-      corner_of(chunk * kChunk + ci, cc);
+      corner_of(cbase + ci, cc);
       if (lane < 3) sH[lane] = (double)(cc[lane] + (lane == 2 ? g.z0 : 0));
       wp = 0;
       __syncwarp();
@@ -390,8 +402,8 @@ __global__ void __launch_bounds__(kThreads, 2)
     const bool last_of_cell = off + 32 >= cnt;
     {
       const bool new_chunk = last_of_cell && ci + 1 == kChunk;
-      if (!new_chunk || chunk_next < nchunk)
-        stage(new_chunk ? chunk_next : chunk, new_chunk ? tb ^ 1 : tb, last_of_cell ? (new_chunk ? 0 : ci + 1) : ci,
+      if (!new_chunk || cbase_next != kNone)
+        stage(new_chunk ? cbase_next : cbase, new_chunk ? tb ^ 1 : tb, last_of_cell ? (new_chunk ? 0 : ci + 1) : ci,
               last_of_cell ? 0 : off + 32, last_of_cell ? bb ^ 1 : bb);
     }
     cp_async_commit();
@@ -423,8 +435,7 @@ __global__ void __launch_bounds__(kThreads, 2)
           double x1 = xa + (step == 2 ? 2.0 * h : h) * va;  // hpp:237
           // construct_segments (util.cpp:160-174): one segment  <=>  floor(x1) == cell  <=>  hA <= x1 < hA + 1
           const bool leaves = alive && !(x1 >= hA && x1 < hA + 1.0);
-          eject(leaves, kContBase - (step < 3 ? step : step + 1), chunk * kChunk + ci, ekey, x, v, sH, alive, mv, flags,
-                lane);
+          eject(leaves, kContBase - (step < 3 ? step : step + 1), cbase + ci, ekey, x, v, sH, alive, mv, flags, lane);
           const double xs = leaves ? hA + 0.5 : xa;  // an ejected lane is a resting padding particle from here on
           if (leaves) x1 = xs;
           double I0[NWP];
@@ -464,11 +475,11 @@ __global__ void __launch_bounds__(kThreads, 2)
 
       if (last_of_cell) {
         int cc[3];
-        const long base = corner_of(chunk * kChunk + ci, cc);
+        const long base = corner_of(cbase + ci, cc);
         flush_component<I, 0>(sAcc, E, base, st, g.pc, lane);
         flush_component<I, 1>(sAcc + NACC * 32, E, base, st, g.pc, lane);
         flush_component<I, 2>(sAcc + 2 * NACC * 32, E, base, st, g.pc, lane);
-        if (lane == 0) count[(long)chunk * kChunk + ci] = wp;
+        if (lane == 0) count[cbase + ci] = wp;
       }
     }
     __syncwarp();
@@ -480,342 +491,14 @@ __global__ void __launch_bounds__(kThreads, 2)
       bb ^= 1;
       if (++ci == kChunk) {  // enter the next chunk: this chunk's table buffer is free for the chunk after it
         ci = 0;
-        more = chunk_next < nchunk;
+        more = cbase_next != kNone;
         if (more) {
-          chunk = chunk_next;
-          chunk_next = __shfl_sync(kFull, pending, 0);
-          if (chunk_next < nchunk) load_table(chunk_next, tb);
+          cbase = cbase_next;
+          cbase_next = to_base(__shfl_sync(kFull, pending, 0));
+          if (cbase_next != kNone) load_table(cbase_next, tb);
           pending = grab();
           tb ^= 1;
         }
-      }
-    }
-  }
-  cp_async_wait<0>();
-}
-
-// ------------------------------------------------------------------------------------------------------------------
-// k_axis_block_s: the same block with batches that may span two cells (option "block_stream" = 1; NOT the default
-// until it has been verified on the GPU -- see DESIGN.md "what comes next").
-//
-// k_axis_block hands out the particles cell by cell, so a cell of 65 particles costs three batches: 2.3-2.5 batches
-// per cell at 64 ppc against 2.0 ideal, i.e. 15-20 % of the FP64 issue slots go to padding lanes.  Here the last,
-// short batch of a cell A is topped up with the first particles of the next cell B (fused_cut.cuh; 2.08 batches per
-// cell on the same distribution).  What changes in a mixed batch:
-//   * cell data is per lane: coordinates sH[buf][.] and the staged stencil sBst[buf] with buf = bb for the lanes
-//     of A and bb ^ 1 for those of B (B's stencil is the one that is prefetched anyway);
-//   * deposition runs in two parts over the same records: the part of A adds to A's parked accumulators and goes
-//     straight to memory (A ends here: one RED per stencil point and sub-flow), which frees the parked slot for
-//     the part of B, which starts from zero like any first batch.  One set of parked accumulators stays enough;
-//   * stayers are compacted per cell, A's count is final after the batch.
-// ------------------------------------------------------------------------------------------------------------------
-template <class I>
-SPIC_DI void acc_load(const double* sAccA, double (&acc)[2][I::NWP], bool zero, int lane) {
-#pragma unroll
-  for (int j = 0; j < 2; ++j)
-#pragma unroll
-    for (int t = 0; t < I::NWP; ++t) acc[j][t] = zero ? 0.0 : sAccA[(j * I::NWP + t) * 32 + lane];
-}
-template <class I>
-SPIC_DI void acc_store(double* sAccA, const double (&acc)[2][I::NWP], int lane) {
-#pragma unroll
-  for (int j = 0; j < 2; ++j)
-#pragma unroll
-    for (int t = 0; t < I::NWP; ++t) sAccA[(j * I::NWP + t) * 32 + lane] = acc[j][t];
-}
-// records of the iterations [it0, it1), particles p in [lo, hi) only, added to acc (same arithmetic as deposit_records)
-template <class I>
-SPIC_DI void deposit_range(const double* sW, double (&acc)[2][I::NWP], int it0, int it1, int lo, int hi, int lane) {
-  constexpr int NW1 = I::NW1, NWP = I::NWP;
-  using Lay = BlockLayout<I>;
-  constexpr int SW = Lay::SW, TH = Lay::TH, LPP = Lay::LPP, NSUB = Lay::NSUB;
-  const int tu = lane % NW1, th = (lane / NW1) % TH, sub = lane / LPP;
-#pragma unroll 4
-  for (int it = it0; it < it1; ++it) {
-    const int p = it * NSUB + sub;
-    const double* w = sW + sub * SW + it * (NSUB * SW + Lay::SWZ * (NSUB / 4));
-    const double2 a = *reinterpret_cast<const double2*>(w + 2 * th);
-    const double b = w[NW1 + tu];
-    double In[NWP];
-    lds_row<NWP>(w + 2 * NW1, In);
-    if (p >= lo && p < hi) {
-#pragma unroll
-      for (int t = 0; t < NWP; ++t) {
-        const double bI = b * In[t];
-        acc[0][t] = fma(a.x, bI, acc[0][t]);
-        acc[1][t] = fma(a.y, bI, acc[1][t]);
-      }
-    }
-  }
-}
-// sums acc over the particle subsets and issues one RED per stencil point; Ea = this lane's first point of the
-// component, sL / sA = the strides along l and along the push axis (hpp:215)
-template <class I>
-SPIC_DI void flush_regs(const double (&acc)[2][I::NWP], double* __restrict__ Ea, long sL, long sA, int lane) {
-  using Lay = BlockLayout<I>;
-  const int sub = lane / Lay::LPP;
-#pragma unroll
-  for (int j = 0; j < 2; ++j)
-#pragma unroll
-    for (int t = 0; t < I::NWP; ++t) {
-      double a = acc[j][t];
-#pragma unroll
-      for (int m = Lay::LPP; m < 32; m <<= 1) a += __shfl_xor_sync(kFull, a, m);
-      if (sub == 0) atomicAdd(Ea + j * sL + t * sA, a);
-    }
-}
-
-template <class I>
-__global__ void __launch_bounds__(kThreads, 2)
-    k_axis_block_s(Grid g, ParticleSoA p, const long* __restrict__ start, int* __restrict__ count,
-                   double* __restrict__ E, const double* __restrict__ B, double q, double qm, double h, MoverList mv,
-                   int* __restrict__ flags, long ncell, unsigned* __restrict__ work, unsigned* __restrict__ ekey) {
-  constexpr int NW1 = I::NW1, NWP = I::NWP;
-  using Lay = BlockLayout<I>;
-  constexpr int NS = Lay::NS, SB = Lay::SB, SP = Lay::SP, NACC = Lay::NACC, NSUB = Lay::NSUB;
-  constexpr int SBP = SB + 2;  // stencil buffers 16 bytes apart in bank space: lanes of A and of B read both at once
-  extern __shared__ __align__(16) double smem[];
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  double* sWarp = smem + warp * Lay::PER_WARP_S;
-  long* tStart = reinterpret_cast<long*>(sWarp);           // [2][kChunk]  bin starts of two chunks
-  int* tCnt = reinterpret_cast<int*>(sWarp + 2 * kChunk);   // [2][kChunk]  bin counts
-  double* sH = sWarp + 3 * kChunk;                          // [2][4]  global coordinates of the cells in the two buffers
-  double* sPart = sWarp + kTableDoubles + 4;                // [6][32]
-  double* sBst = sPart + SP;                                // [2][SBP]
-  double* sW = sBst + 2 * SBP;                              // records
-  double* sAcc = sW + Lay::SWA;                             // [3][NACC][32]
-  const long st[3] = {1, g.pj, g.pk};
-  const double nq = -q;
-  const unsigned nchunk = (unsigned)((ncell + kChunk - 1) / kChunk);
-
-  auto grab = [&]() -> unsigned {
-    unsigned c = 0;
-    if (lane == 0) c = atomicAdd(work, 1u);
-    return c;
-  };
-  auto load_table = [&](unsigned chunk, int tb) {
-    if (lane < kChunk) {
-      const long cell = (long)chunk * kChunk + lane;
-      if (cell < ncell) {
-        const unsigned d4 = (unsigned)__cvta_generic_to_shared(tCnt + tb * kChunk + lane);
-        asm volatile("cp.async.ca.shared.global [%0], [%1], 4;\n" ::"r"(d4), "l"(count + cell) : "memory");
-        cp_async8(reinterpret_cast<double*>(tStart + tb * kChunk + lane), reinterpret_cast<const double*>(start + cell));
-      } else {
-        tCnt[tb * kChunk + lane] = 0;
-        tStart[tb * kChunk + lane] = 0;
-      }
-    }
-  };
-  auto corner_of = [&](unsigned cell, int (&cc)[3]) -> long {
-    const unsigned row = cell / (unsigned)g.n[0];
-    cc[0] = (int)(cell - row * (unsigned)g.n[0]);
-    cc[2] = (int)(row / (unsigned)g.n[1]);
-    cc[1] = (int)(row - (unsigned)cc[2] * (unsigned)g.n[1]);
-    return g.at(cc[0], cc[1], cc[2]) + (1 - I::W) * (1 + g.pj + g.pk);
-  };
-  auto stage_stencil = [&](unsigned cell, int buf) {
-    int cc[3];
-    const double* src = B + corner_of(cell, cc);
-    double* d = sBst + buf * SBP;
-#pragma unroll
-    for (int s = lane; s < SB; s += 32) {
-      const int comp = s / NS, r = s % NS;
-      const int ti = r % NW1, tj = (r / NW1) % NW1, tk = r / (NW1 * NW1);
-      cp_async8(d + s, src + (long)comp * g.pc + ti + tj * g.pj + tk * g.pk);
-    }
-  };
-  // stage batch b of chunk `chunk` (tables in buffer tb); bufA = the stencil buffer of its cell A
-  auto stage = [&](unsigned chunk, int tb, const CutBatch& b, int bufA) {
-    const int n = b.nA + b.nB;
-    if (lane < n) {
-      const long src = lane < b.nA ? tStart[tb * kChunk + b.ci] + b.off + lane
-                                   : tStart[tb * kChunk + b.ci + 1] + (lane - b.nA);
-      double* d = sPart + lane;
-      cp_async8(d + 0 * 32, p.x[0] + src);
-      cp_async8(d + 1 * 32, p.x[1] + src);
-      cp_async8(d + 2 * 32, p.x[2] + src);
-      cp_async8(d + 3 * 32, p.v[0] + src);
-      cp_async8(d + 4 * 32, p.v[1] + src);
-      cp_async8(d + 5 * 32, p.v[2] + src);
-    }
-    if (b.off == 0 && b.nA > 0) stage_stencil(chunk * kChunk + b.ci, bufA);
-    if (b.nB > 0) stage_stencil(chunk * kChunk + b.ci + 1, bufA ^ 1);
-  };
-
-  // ---- prologue ----------------------------------------------------------------------------------------
-  unsigned chunk = __shfl_sync(kFull, grab(), 0);
-  if (chunk >= nchunk) return;
-  load_table(chunk, 0);
-  cp_async_commit();
-  unsigned pending = grab();
-  cp_async_wait<0>();
-  __syncwarp();
-  unsigned chunk_next = __shfl_sync(kFull, pending, 0);
-  if (chunk_next < nchunk) load_table(chunk_next, 1);
-  pending = grab();
-  int tb = 0, ci = 0, off = 0, bb = 0;
-  bool pmix = false;
-  stage(chunk, 0, cut_batch<kChunk>(tCnt, 0, 0, false), 0);
-  cp_async_commit();
-
-  int wp = 0;
-  bool more = true;
-
-  while (more) {
-    cp_async_wait<0>();
-    __syncwarp();
-    const CutBatch b = cut_batch<kChunk>(tCnt + tb * kChunk, ci, off, pmix);
-    const bool mixed = b.nB > 0;
-    if (b.off == 0 || mixed) {  // coordinates of a cell touched for the first time, in the slot of its stencil buffer
-      int cc[3];
-      if (b.off == 0) {
-        corner_of(chunk * kChunk + ci, cc);
-        if (lane < 3) sH[bb * 4 + lane] = (double)(cc[lane] + (lane == 2 ? g.z0 : 0));
-        wp = 0;
-      }
-      if (mixed) {
-        corner_of(chunk * kChunk + ci + 1, cc);
-        if (lane < 3) sH[(bb ^ 1) * 4 + lane] = (double)(cc[lane] + (lane == 2 ? g.z0 : 0));
-      }
-      __syncwarp();
-    }
-    const int nvalid = b.nA + b.nB;
-    const bool valid = lane < nvalid;
-    const bool isB = lane >= b.nA && mixed;            // (a mixed batch is always full: no padding lanes there)
-    const double* sHl = sH + (isB ? (bb ^ 1) : bb) * 4;  // this lane's cell
-    double x[3] = {sHl[0] + 0.5, sHl[1] + 0.5, sHl[2] + 0.5}, v[3] = {0.0, 0.0, 0.0};
-    if (valid) {
-      const double* sP = sPart + lane;
-      x[0] = sP[0 * 32];
-      x[1] = sP[1 * 32];
-      x[2] = sP[2 * 32];
-      v[0] = sP[3 * 32];
-      v[1] = sP[4 * 32];
-      v[2] = sP[5 * 32];
-    }
-    __syncwarp();  // the staging buffer has been consumed: refill it while this batch computes
-
-    // ---- the next batch ----------------------------------------------------------------------------------
-    int nci = ci, noff = off;
-    bool npmix = pmix;
-    const bool in_chunk = cut_advance<kChunk>(b, nci, noff, npmix);
-    const bool new_cell = nci != ci;  // the next batch's cell A lives in the other stencil buffer
-    if (in_chunk) {
-      stage(chunk, tb, cut_batch<kChunk>(tCnt + tb * kChunk, nci, noff, npmix), new_cell ? bb ^ 1 : bb);
-    } else if (chunk_next < nchunk) {
-      stage(chunk_next, tb ^ 1, cut_batch<kChunk>(tCnt + (tb ^ 1) * kChunk, 0, 0, false), bb ^ 1);
-    }
-    cp_async_commit();
-
-    if (nvalid > 0) {
-      const double* sB = sBst + (isB ? (bb ^ 1) : bb) * SBP;
-      const int nit = (nvalid + NSUB - 1) / NSUB;
-      const int itA = (b.nA + NSUB - 1) / NSUB;  // iterations that hold particles of A
-      const int itB = b.nA / NSUB;               // first iteration that holds a particle of B
-      const bool first = b.off == 0;
-      bool alive = valid;
-      const unsigned my_cell = chunk * kChunk + ci + (isB ? 1 : 0);
-      // this lane's first stencil point of each E component (deposition lanes: tu, th as in deposit_records)
-      int ccA[3];
-      const long baseA = corner_of(chunk * kChunk + ci, ccA);  // (B's points are flushed at B's own end)
-
-      double P1[NW1] = {}, Pp[NWP] = {}, Q1[NW1] = {}, Qp[NWP] = {};
-#pragma unroll 1
-      for (int step = -2; step < 5; ++step) {
-        const int A = step < 0 ? -step : (step < 3 ? step : 4 - step);
-        if (step >= 0) {
-          const double xa = A == 0 ? x[0] : (A == 1 ? x[1] : x[2]);
-          const double va = A == 0 ? v[0] : (A == 1 ? v[1] : v[2]);
-          const double hA = sHl[A];
-          double x1 = xa + (step == 2 ? 2.0 * h : h) * va;  // hpp:237
-          const bool leaves = alive && !(x1 >= hA && x1 < hA + 1.0);
-          eject(leaves, kContBase - (step < 3 ? step : step + 1), my_cell, ekey, x, v, sHl, alive, mv, flags, lane);
-          const double xs = leaves ? hA + 0.5 : xa;
-          if (leaves) x1 = xs;
-          double I0[NWP];
-          eval_iwp_in<I>(xs, x1, hA, I0);  // hpp:178-186
-          if (A == 0) axis_part<I, 0>(x, v, x1, I0, P1, Pp, Q1, Qp, sB, sW, nq, qm, lane);
-          else if (A == 1) axis_part<I, 1>(x, v, x1, I0, Q1, Qp, P1, Pp, sB, sW, nq, qm, lane);
-          else axis_part<I, 2>(x, v, x1, I0, P1, Pp, Q1, Qp, sB, sW, nq, qm, lane);
-          __syncwarp();
-          double* sAccA = sAcc + A * (NACC * 32);
-          if (!mixed) {
-            deposit_records<I>(sW, sAccA, first && step < 3, nit, lane);
-          } else {
-            // lane-to-stencil-point map of the deposition (as in flush_component)
-            const int tu = lane % NW1, th = (lane / NW1) % Lay::TH;
-            // strides along A, U = (A+1)%3, L = (A+2)%3 without indexing a local array by a run-time value
-            const long sA = A == 0 ? 1 : (A == 1 ? g.pj : g.pk);
-            const long sU = A == 0 ? g.pj : (A == 1 ? g.pk : 1);
-            const long sL = A == 0 ? g.pk : (A == 1 ? 1 : g.pj);
-            double acc[2][NWP];
-            // part of A: with what A parked in its earlier batches (first visit) or from zero (already flushed)
-            acc_load<I>(sAccA, acc, step >= 3, lane);
-            deposit_range<I>(sW, acc, 0, itA, 0, b.nA, lane);
-            flush_regs<I>(acc, E + (long)A * g.pc + baseA + tu * sU + (2 * th) * sL, sL, sA, lane);
-            // part of B: B starts here (first visit: zero) and parks like any first batch
-            acc_load<I>(sAccA, acc, step < 3, lane);
-            deposit_range<I>(sW, acc, itB, nit, b.nA, nvalid, lane);
-            acc_store<I>(sAccA, acc, lane);
-          }
-          __syncwarp();  // the record area is free again
-        }
-        if (step < 4) {
-          const double f = (A == 0 ? x[0] : (A == 1 ? x[1] : x[2])) - sHl[A];
-          if (step == -1 || step == 0 || step == 3) {
-            eval_w1_in<I>(f, P1);
-            eval_wp_in<I>(f, Pp);
-          } else {
-            eval_w1_in<I>(f, Q1);
-            eval_wp_in<I>(f, Qp);
-          }
-        }
-      }
-
-      // ---- re-file: stayers are compacted in place, per cell -------------------------------------------------
-      const bool stays = valid && alive;
-      const unsigned stayA = __ballot_sync(kFull, stays && !isB), stayB = __ballot_sync(kFull, stays && isB);
-      if (stays) {
-        const unsigned below = (1u << lane) - 1u;
-        const long dst = isB ? tStart[tb * kChunk + ci + 1] + __popc(stayB & below)
-                             : tStart[tb * kChunk + ci] + wp + __popc(stayA & below);
-#pragma unroll
-        for (int d = 0; d < 3; ++d) {
-          p.x[d][dst] = x[d];
-          p.v[d][dst] = v[d];
-        }
-      }
-      wp += __popc(stayA);
-
-      if (b.lastA) {
-        if (!mixed) {  // (a mixed batch has flushed A's accumulators sub-flow by sub-flow)
-          flush_component<I, 0>(sAcc, E, baseA, st, g.pc, lane);
-          flush_component<I, 1>(sAcc + NACC * 32, E, baseA, st, g.pc, lane);
-          flush_component<I, 2>(sAcc + 2 * NACC * 32, E, baseA, st, g.pc, lane);
-        }
-        if (lane == 0) count[(long)chunk * kChunk + ci] = wp;
-      }
-      if (mixed) wp = __popc(stayB);  // B is the current cell from here on
-    }
-    __syncwarp();
-    // ---- advance -----------------------------------------------------------------------------------------------
-    if (in_chunk) {
-      if (new_cell) bb ^= 1;
-      ci = nci;
-      off = noff;
-      pmix = npmix;
-    } else {
-      ci = 0;
-      off = 0;
-      pmix = false;
-      bb ^= 1;
-      more = chunk_next < nchunk;
-      if (more) {
-        chunk = chunk_next;
-        chunk_next = __shfl_sync(kFull, pending, 0);
-        if (chunk_next < nchunk) load_table(chunk_next, tb);
-        pending = grab();
-        tb ^= 1;
       }
     }
   }
@@ -917,11 +600,11 @@ __global__ void __launch_bounds__(128)
 }
 
 template <class I>
-int launch_block(Ctx* c, Species& s, double h) {
+int launch_block(Ctx* c, Species& s, double h, const CellRanges& rg, unsigned list_cap) {
   EngineState* e = eng(c);
-  const long ncell = c->g.cells();
   // persistent: two blocks per SM, every warp draws chunks of kChunk cells from a counter
-  const long nchunk = (ncell + kChunk - 1) / kChunk;
+  const long nchunk = (long)rg.nchunk0 + (rg.n[1] + kChunk - 1) / kChunk;
+  if (nchunk == 0) return SPIC_OK;
   long want = (nchunk + kWarps - 1) / kWarps;
   if (want > 2L * c->sm_count) want = 2L * c->sm_count;
   if (!e->block_work) SPIC_CUDA_CHECK(c, cudaMalloc(&e->block_work, sizeof(unsigned)));
@@ -933,25 +616,15 @@ int launch_block(Ctx* c, Species& s, double h) {
   }
   SPIC_CUDA_CHECK(c, cudaMemsetAsync(e->block_work, 0, sizeof(unsigned), c->stream));
   // unused sort keys = all ones: they sort behind every cell index (fused_axis_continue)
-  SPIC_CUDA_CHECK(c, cudaMemsetAsync(e->cont_key, 0xff, sizeof(unsigned) * (size_t)e->mv.cap, c->stream));
-  if (e->block_stream) {  // batches that may span two cells (opt-in until verified on the GPU)
-    const size_t smem_s = sizeof(double) * kWarps * BlockLayout<I>::PER_WARP_S;
-    static unsigned long long attr_s = 0;
-    if (smem_attr_needed(attr_s, c->cfg.device))
-      SPIC_CUDA_CHECK(c, cudaFuncSetAttribute(k_axis_block_s<I>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                              (int)smem_s));
-    k_axis_block_s<I><<<(int)want, kThreads, smem_s, c->stream>>>(c->g, s.b, s.start, s.count, c->E, c->B, s.q,
-                                                                  s.q / s.m, h, e->mv, c->d_flags, ncell,
-                                                                  e->block_work, e->cont_key);
-    c->launches++;
-    return SPIC_OK;
-  }
+  SPIC_CUDA_CHECK(c, cudaMemsetAsync(e->cont_key, 0xff, sizeof(unsigned) * (size_t)list_cap, c->stream));
+  MoverList mv = e->mv;
+  mv.cap = list_cap;  // (this launch may use a prefix of the list only: what the continuation then sorts)
   const size_t smem = sizeof(double) * kWarps * BlockLayout<I>::PER_WARP;
   static unsigned long long attr = 0;
   if (smem_attr_needed(attr, c->cfg.device))
     SPIC_CUDA_CHECK(c, cudaFuncSetAttribute(k_axis_block<I>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   k_axis_block<I><<<(int)want, kThreads, smem, c->stream>>>(c->g, s.b, s.start, s.count, c->E, c->B, s.q, s.q / s.m,
-                                                            h, e->mv, c->d_flags, ncell, e->block_work, e->cont_key);
+                                                            h, mv, c->d_flags, rg, e->block_work, e->cont_key);
   c->launches++;
   return SPIC_OK;
 }
@@ -963,30 +636,61 @@ bool fused_block_supported(const Ctx* c) {
   return c->cfg.nranks == 1 || c->g.ng >= c->W + 1;
 }
 
-int fused_axis_block(Ctx* c, Species& s, double h) {
-  KernelTimer t(c, KT_BLOCK);
-  return c->cfg.interp == SPIC_INTERP_P8R2 ? launch_block<InterpP8R2>(c, s, h) : launch_block<InterpPWL>(c, s, h);
+// The length of the mover-list prefix a launch over `cells` of the brick's cells may fill (and the continuation
+// sorts): the list's share of those cells, doubled, and never less than 64 Ki entries.
+unsigned fused_list_cap(Ctx* c, long cells) {
+  const unsigned cap = eng(c)->mv.cap;
+  const long ncell = c->g.cells();
+  if (cells >= ncell) return cap;
+  const double want = 2.0 * (double)cap * (double)cells / (double)ncell + 65536.0;
+  return want < (double)cap ? (unsigned)want : cap;
 }
 
-int fused_axis_continue(Ctx* c, Species& s, double h) {
+// part: 0 = every cell; 1 = the nb z planes next to each slab face; 2 = the planes between them
+int fused_axis_block(Ctx* c, Species& s, double h, int part, int nb, unsigned list_cap) {
+  KernelTimer t(c, KT_BLOCK);
+  const Grid& g = c->g;
+  const unsigned plane = (unsigned)g.n[0] * (unsigned)g.n[1], ncell = (unsigned)g.cells();
+  CellRanges rg;
+  rg.cell0[1] = 0xffffffffu;
+  rg.n[1] = 0;
+  if (part == 0 || 2 * nb >= g.n[2]) {
+    if (part == 2) return SPIC_OK;  // (thin slab: the boundary part covered everything)
+    rg.cell0[0] = 0;
+    rg.n[0] = ncell;
+  } else if (part == 1) {
+    rg.cell0[0] = 0;
+    rg.n[0] = (unsigned)nb * plane;
+    rg.cell0[1] = ncell - (unsigned)nb * plane;
+    rg.n[1] = (unsigned)nb * plane;
+  } else {
+    rg.cell0[0] = (unsigned)nb * plane;
+    rg.n[0] = ncell - 2u * (unsigned)nb * plane;
+  }
+  rg.nchunk0 = (rg.n[0] + kChunk - 1) / kChunk;
+  return c->cfg.interp == SPIC_INTERP_P8R2 ? launch_block<InterpP8R2>(c, s, h, rg, list_cap)
+                                           : launch_block<InterpPWL>(c, s, h, rg, list_cap);
+}
+
+int fused_axis_continue(Ctx* c, Species& s, double h, unsigned list_cap) {
   EngineState* e = eng(c);
   // No read-back of the ejected count: the whole mover list (capacity entries) is sorted by home cell, the unused
   // entries carry the key 0xffffffff (set before the block ran) and sort behind the real ones; k_axis_continue
   // reads the count on the device.  One host round trip per block idled the GPU for longer than the extra sort.
-  const unsigned cap = e->mv.cap;
+  const unsigned cap = list_cap;
   if (cap == 0) return SPIC_OK;
   if (cap > 0x7fffffffu) {
     c->err = "mover list too long for one radix sort (lower option mover_frac)";
     return SPIC_ECAPACITY;
   }
-  if (e->cont_sort_cap < cap) {
+  if (e->cont_sort_cap < e->mv.cap) {
     for (unsigned** p : {&e->cont_key2, &e->cont_idx, &e->cont_perm}) {
       if (*p) cudaFree(*p);
       *p = nullptr;
-      SPIC_CUDA_CHECK(c, cudaMalloc(p, sizeof(unsigned) * (size_t)cap));
+      SPIC_CUDA_CHECK(c, cudaMalloc(p, sizeof(unsigned) * (size_t)e->mv.cap));
     }
-    e->cont_sort_cap = cap;
-    k_iota<<<c->sm_count * 4, 256, 0, c->stream>>>(e->cont_idx, cap);
+    e->cont_sort_cap = e->mv.cap;
+    k_iota<<<c->sm_count * 4, 256, 0, c->stream>>>(e->cont_idx, e->mv.cap);
     c->launches++;
   }
   int bits = 1;
@@ -1008,11 +712,13 @@ int fused_axis_continue(Ctx* c, Species& s, double h) {
   long nb = ((long)cap + 127) / 128;
   if (nb > (long)c->sm_count * 16) nb = (long)c->sm_count * 16;
   const double qm = s.q / s.m;
+  MoverList mv = e->mv;
+  mv.cap = cap;
   if (c->cfg.interp == SPIC_INTERP_P8R2)
-    k_axis_continue<InterpP8R2><<<(int)nb, 128, 0, c->stream>>>(c->g, e->mv, e->cont_perm, c->E, c->B, s.q, qm, h,
+    k_axis_continue<InterpP8R2><<<(int)nb, 128, 0, c->stream>>>(c->g, mv, e->cont_perm, c->E, c->B, s.q, qm, h,
                                                               c->d_flags);
   else
-    k_axis_continue<InterpPWL><<<(int)nb, 128, 0, c->stream>>>(c->g, e->mv, e->cont_perm, c->E, c->B, s.q, qm, h,
+    k_axis_continue<InterpPWL><<<(int)nb, 128, 0, c->stream>>>(c->g, mv, e->cont_perm, c->E, c->B, s.q, qm, h,
                                                              c->d_flags);
   c->launches++;
   return SPIC_OK;

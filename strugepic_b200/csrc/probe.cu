@@ -45,6 +45,26 @@ __global__ void __launch_bounds__(256) k_dfma3(double* out, int iters, double a,
   for (int i = 0; i < 8; ++i) s += x[i] + y[i] + z[i];
   out[blockIdx.x * blockDim.x + threadIdx.x] = s;
 }
+// Horner chains with IMMEDIATE coefficients, x = fma(x, t, imm): what the weight and line-integral evaluations of
+// the particle kernels issue (one register operand pair + a constant): the fastest DFMA form of the three
+__global__ void __launch_bounds__(256) k_dfma_imm(double* out, int iters, double t) {
+  double x0 = threadIdx.x * 1e-3, x1 = x0 + 1, x2 = x0 + 2, x3 = x0 + 3, x4 = x0 + 4, x5 = x0 + 5, x6 = x0 + 6,
+         x7 = x0 + 7;
+  for (int i = 0; i < iters; ++i) {
+#pragma unroll
+    for (int u = 0; u < 16; ++u) {
+      x0 = fma(x0, t, 0.25);
+      x1 = fma(x1, t, -0.5);
+      x2 = fma(x2, t, 0.125);
+      x3 = fma(x3, t, -0.75);
+      x4 = fma(x4, t, 0.375);
+      x5 = fma(x5, t, -0.625);
+      x6 = fma(x6, t, 0.875);
+      x7 = fma(x7, t, -0.0625);
+    }
+  }
+  out[blockIdx.x * blockDim.x + threadIdx.x] = ((x0 + x1) + (x2 + x3)) + ((x4 + x5) + (x6 + x7));
+}
 }  // namespace
 
 static int probe_impl(int device, double seconds, int three_operands, double* tflops);
@@ -54,6 +74,9 @@ extern "C" int spic_probe_fp64_tflops(int device, double seconds, double* tflops
 }
 extern "C" int spic_probe_fp64_three_operand_tflops(int device, double seconds, double* tflops) {
   return probe_impl(device, seconds, 1, tflops);
+}
+extern "C" int spic_probe_fp64_immediate_tflops(int device, double seconds, double* tflops) {
+  return probe_impl(device, seconds, 2, tflops);
 }
 
 static int probe_impl(int device, double seconds, int three_operands, double* tflops) {
@@ -68,7 +91,8 @@ static int probe_impl(int device, double seconds, int three_operands, double* tf
   cudaEventCreate(&e0);
   cudaEventCreate(&e1);
   auto launch = [&]() {
-    if (three_operands) k_dfma3<<<blocks, threads>>>(out, iters, 0.999999, 1e-9);
+    if (three_operands == 1) k_dfma3<<<blocks, threads>>>(out, iters, 0.999999, 1e-9);
+    else if (three_operands == 2) k_dfma_imm<<<blocks, threads>>>(out, iters, 0.999999);
     else k_dfma<<<blocks, threads>>>(out, iters, 0.999999, 1e-9);
   };
   launch();  // warm-up

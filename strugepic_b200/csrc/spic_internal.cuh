@@ -66,7 +66,7 @@ struct Ctx;
 // ---- field kernels (field_kernels.cu) ------------------------------------------
 void launch_fill_boundary(Ctx* c, double* F, bool z_too);
 void launch_zero_guards(Ctx* c, double* F);
-void launch_sum_boundary(Ctx* c, double* F, int comp, bool z_too);
+void launch_sum_boundary(Ctx* c, double* F, int comp, bool z_too, bool owner_only = false);
 void launch_curl_E_into_B(Ctx* c, double dt);  // push_B_E
 void launch_curl_B_into_E(Ctx* c, double dt);  // push_E_B
 void launch_source(Ctx* c, int pos, int comp, double amp);

@@ -42,7 +42,6 @@ def main():
     dist.broadcast_object_list(ids, src=0)
     s.comm_init(ids[0])
     s.set_option("fuse", fuse)
-    s.set_option("block_stream", 1 if "stream" in opts else 0)  # batches that span two cells (k_axis_block_s)
     if "serial" in opts:
         s.set_option("overlap", 0)  # exchanges in stream order behind the whole axis block
     k0, k1 = s.lo[2], s.lo[2] + s.n[2]

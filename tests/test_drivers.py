@@ -224,3 +224,36 @@ def test_langmuir_driver_on_two_gpus_matches_one(drivers, tmp_path):
     e1, e2 = energies(one.stdout), energies(outs[0][0])
     assert e1.shape == e2.shape == (6, 2) and energies(outs[1][0]).size == 0  # only the IO rank prints
     assert np.max(np.abs(e2 - e1) / np.abs(e1)) < 1e-11
+
+
+@pytest.mark.gpu
+def test_single_particle_driver_on_two_gpus(drivers, tmp_path):
+    """add_single_particle under a slab decomposition (the reference adds on grid 0 and Redistributes,
+    util.cpp:144-155): every rank adds the species, the owner rank holds the particle, TotalNumberOfParticles is
+    global; the orbit equals the 1-rank run while the particle crosses slab faces."""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    args = ["nsteps=40", "precision=17", "print_every=1", "vel=0.01 0.0 -0.01"]  # starts at z = 6 = the slab face
+    one = run_driver(drivers["single_particle"], "cyclotron", *args)
+    assert one.returncode == 0, one.stderr
+    procs = []
+    for rank in range(2):
+        env = dict(os.environ, RANK=str(rank), WORLD_SIZE="2", LOCAL_RANK=str(rank), MASTER_PORT="29518",
+                   SPIC_ID_FILE=str(tmp_path / "nccl_id_sp"))
+        procs.append(subprocess.Popen([drivers["single_particle"], os.path.join(DECKS, "cyclotron.input")] + args,
+                                      env=env, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True))
+    outs = [p.communicate(timeout=300) for p in procs]
+    assert all(p.returncode == 0 for p in procs), [o[1] for o in outs]
+    assert outs[0][0].splitlines()[0].strip() == "1"  # global count on the IO rank
+    e1, e2 = energies(one.stdout), energies(outs[0][0])
+    assert e1.shape == e2.shape and np.max(np.abs(e2 - e1) / np.maximum(np.abs(e1), 1e-300)) < 1e-11
+
+    def positions(text):
+        return [[float(t) for t in re.findall(r"[-+0-9.e]+", ln[4:])] for ln in text.splitlines() if ln.startswith("POS:")]
+    p1 = np.array(positions(one.stdout))
+    p2 = np.array(positions(outs[0][0]) + positions(outs[1][0]))
+    assert len(p2) == len(p1) == 40  # exactly one rank prints the particle at every step
+    assert len(positions(outs[0][0])) > 0 and len(positions(outs[1][0])) > 0  # the particle changed rank
+    for row in p1:
+        assert np.min(np.max(np.abs(p2 - row), axis=1)) < 1e-9

@@ -336,19 +336,16 @@ def test_fused_axis_block_and_reference_schedule(fuse, interp, mode):
     print(fuse, interp, mode, errs, kt)
 
 
-@pytest.mark.parametrize("block_stream", [0, 1])
 @pytest.mark.parametrize("ppc", [1, 7, 8, 33, 64, 65])
-def test_fused_block_batch_shapes(ppc, block_stream):
-    """The fused axis block with one warp per cell (k_axis_block) and with batches that span two cells
-    (k_axis_block_s, option block_stream = 1) over bins of 1 ... 65+ particles: empty lanes, exactly full batches,
-    a cell of 65 (32 + 32 + 1: the short batch is topped up from the next cell), both W, warm plasma so that the
-    counts drift apart and particles are ejected to the continuation; Gauss residual constant to round-off."""
+def test_fused_block_batch_shapes(ppc):
+    """The fused axis block over bins of 1 ... 65+ particles: empty lanes, exactly full batches, a cell of 65
+    (32 + 32 + 1), both W, warm plasma so that the counts drift apart and particles are ejected to the continuation;
+    Gauss residual constant to round-off."""
     for interp, n_cell, vth, order in ((0, (8, 6, 5), 0.1, 4), (1, (9, 7, 3), 0.15, 2), (0, (16, 2, 2), 0.05, 2)):
         E, B = util.rng_fields(n_cell, 5, 0.3)
         parts = util.plasma(n_cell, ppc, vth, 5)
         o = ora.best_oracle(n_cell, interp=interp)
         s = spic().Simulation(n_cell, interp=interp)
-        s.set_option("block_stream", block_stream)
         s.set_option("time_kernels", 1)
         for t in (o, s):
             util.load_state(t, E, B, parts, -1.0 / ppc, 100.0 / ppc)
@@ -361,13 +358,12 @@ def test_fused_block_batch_shapes(ppc, block_stream):
         assert s.kernel_times()["axis_block"][1] == (9 if order == 4 else 3)
         drift = float(np.max(np.abs(s.gauss_residual() - g0)))
         assert drift < 1e-12 * max(1.0, float(np.max(np.abs(g0)))), drift
-        print(interp, n_cell, ppc, block_stream, errs, drift)
+        print(interp, n_cell, ppc, errs, drift)
         s.close()
 
 
 @pytest.mark.parametrize("engine", ENGINES)
-@pytest.mark.parametrize("block_stream", [0, 1])
-def test_two_species(engine, block_stream):
+def test_two_species(engine):
     """Electrons + ions (two (q, m) pairs: the reference carries q, m per particle, defs.hpp:22-49): the species
     share the mover list, the continuation buffers and the field deposits.  State vs the oracle, and the Gauss
     residual (rho of BOTH species) against the port's."""
@@ -384,8 +380,6 @@ def test_two_species(engine, block_stream):
     o.set_field(1, B)
     o.set_particles(*allp, qa, ma)
     s = spic().Simulation(n_cell, interp=0, engine=engine)
-    if engine == 0:
-        s.set_option("block_stream", block_stream)
     s.set_field(0, E)
     s.set_field(1, B)
     s.add_species(qe, me, *el)
@@ -405,7 +399,7 @@ def test_two_species(engine, block_stream):
     assert np.max(np.abs(gs1 - gs)) < 1e-12 * max(1.0, float(np.max(np.abs(gs))))
     ho, hs = sum(o.energy()), sum(s.get_total_energy())
     assert abs(hs - ho) <= 1e-11 * abs(ho)
-    print(engine, block_stream, errs)
+    print(engine, errs)
 
 
 def test_deferred_half_kick_is_invisible():
