@@ -38,15 +38,57 @@ __device__ __forceinline__ bool image_of(int idx, int n, int per, int& out) {
   return true;
 }
 
-__global__ void k_fill_boundary(Grid g, double* __restrict__ F, int z_too) {
-  const int gx = g.n[0] + 2 * g.ng, gy = g.n[1] + 2 * g.ng, gz = g.n[2] + 2 * g.ng;
-  const long total = (long)gx * gy * gz;
+// Guard-shell enumeration: the guards of a brick are six slabs (two per direction: z slabs span the whole guarded
+// plane, y slabs the valid k range, x slabs the valid k and j ranges), 2 ng (gx gy + gx nz + ny nz) cells -- 7 % of the
+// guarded box at 256^3.  t -> (i, j, k) in guarded coordinates (-ng .. n + ng - 1).
+struct Shell {
+  long nzs, nys, nxs;  // cells in the z, y, x slab pairs
+  int gx, gy, ng, n0, n1, n2;
+  __host__ __device__ long total() const { return nzs + nys + nxs; }
+  __device__ void cell(long t, int& i, int& j, int& k) const {
+    if (t < nzs) {  // z slabs: [2 ng][gy][gx]
+      const int p = (int)(t / ((long)gx * gy));
+      const long r = t - (long)p * gx * gy;
+      k = p < ng ? p - ng : n2 + (p - ng);
+      j = (int)(r / gx) - ng;
+      i = (int)(r % gx) - ng;
+    } else if (t < nzs + nys) {  // y slabs: [n2][2 ng][gx]
+      t -= nzs;
+      k = (int)(t / ((long)2 * ng * gx));
+      const long r = t - (long)k * 2 * ng * gx;
+      const int p = (int)(r / gx);
+      j = p < ng ? p - ng : n1 + (p - ng);
+      i = (int)(r % gx) - ng;
+    } else {  // x slabs: [n2][n1][2 ng]
+      t -= nzs + nys;
+      k = (int)(t / ((long)2 * ng * n1));
+      const long r = t - (long)k * 2 * ng * n1;
+      j = (int)(r / (2 * ng));
+      const int p = (int)(r % (2 * ng));
+      i = p < ng ? p - ng : n0 + (p - ng);
+    }
+  }
+};
+Shell make_shell(const Grid& g) {
+  Shell s;
+  s.gx = g.n[0] + 2 * g.ng;
+  s.gy = g.n[1] + 2 * g.ng;
+  s.ng = g.ng;
+  s.n0 = g.n[0];
+  s.n1 = g.n[1];
+  s.n2 = g.n[2];
+  s.nzs = 2L * g.ng * s.gx * s.gy;
+  s.nys = 2L * g.ng * s.gx * g.n[2];
+  s.nxs = 2L * g.ng * g.n[1] * g.n[2];
+  return s;
+}
+
+__global__ void k_fill_boundary(Grid g, Shell sh, double* __restrict__ F, int z_too) {
+  const long total = sh.total();
   for (long t = blockIdx.x * (long)blockDim.x + threadIdx.x; t < total; t += (long)gridDim.x * blockDim.x) {
-    const int i = (int)(t % gx) - g.ng;
-    const int j = (int)((t / gx) % gy) - g.ng;
-    const int k = (int)(t / ((long)gx * gy)) - g.ng;
-    const bool vi = i >= 0 && i < g.n[0], vj = j >= 0 && j < g.n[1], vk = k >= 0 && k < g.n[2];
-    if (vi && vj && vk) continue;
+    int i, j, k;
+    sh.cell(t, i, j, k);
+    const bool vi = i >= 0 && i < g.n[0], vj = j >= 0 && j < g.n[1];
     int si, sj, sk;
     if (!image_of(i, g.n[0], g.per[0], si)) continue;
     if (!image_of(j, g.n[1], g.per[1], sj)) continue;
@@ -64,14 +106,11 @@ __global__ void k_fill_boundary(Grid g, double* __restrict__ F, int z_too) {
   }
 }
 
-__global__ void k_zero_guards(Grid g, double* __restrict__ F) {
-  const int gx = g.n[0] + 2 * g.ng, gy = g.n[1] + 2 * g.ng, gz = g.n[2] + 2 * g.ng;
-  const long total = (long)gx * gy * gz;
+__global__ void k_zero_guards(Grid g, Shell sh, double* __restrict__ F) {
+  const long total = sh.total();
   for (long t = blockIdx.x * (long)blockDim.x + threadIdx.x; t < total; t += (long)gridDim.x * blockDim.x) {
-    const int i = (int)(t % gx) - g.ng;
-    const int j = (int)((t / gx) % gy) - g.ng;
-    const int k = (int)(t / ((long)gx * gy)) - g.ng;
-    if (i >= 0 && i < g.n[0] && j >= 0 && j < g.n[1] && k >= 0 && k < g.n[2]) continue;
+    int i, j, k;
+    sh.cell(t, i, j, k);
     const long d = g.at(i, j, k);
     F[d] = 0.0;
     F[d + g.pc] = 0.0;
@@ -292,13 +331,13 @@ bool all_periodic(const Grid& g) { return g.per[0] && g.per[1] && g.per[2]; }
 }  // namespace
 
 void launch_fill_boundary(Ctx* c, double* F, bool z_too) {
-  const int gx = c->g.n[0] + 2 * c->g.ng, gy = c->g.n[1] + 2 * c->g.ng, gz = c->g.n[2] + 2 * c->g.ng;
-  k_fill_boundary<<<grid_for(c, (long)gx * gy * gz), kBlock, 0, c->stream>>>(c->g, F, z_too ? 1 : 0);
+  const Shell sh = make_shell(c->g);
+  k_fill_boundary<<<grid_for(c, sh.total()), kBlock, 0, c->stream>>>(c->g, sh, F, z_too ? 1 : 0);
   c->launches++;
 }
 void launch_zero_guards(Ctx* c, double* F) {
-  const int gx = c->g.n[0] + 2 * c->g.ng, gy = c->g.n[1] + 2 * c->g.ng, gz = c->g.n[2] + 2 * c->g.ng;
-  k_zero_guards<<<grid_for(c, (long)gx * gy * gz), kBlock, 0, c->stream>>>(c->g, F);
+  const Shell sh = make_shell(c->g);
+  k_zero_guards<<<grid_for(c, sh.total()), kBlock, 0, c->stream>>>(c->g, sh, F);
   c->launches++;
 }
 void launch_sum_boundary(Ctx* c, double* F, int comp, bool z_too, bool owner_only) {
