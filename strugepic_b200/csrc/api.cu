@@ -107,7 +107,19 @@ int halo_fill(Ctx* c, double* F) {
     if (rc) return rc;
   }
   launch_fill_boundary(c, F, c->g.zlocal != 0);
+  if (F == c->E) c->guards_ok[0] = true;
+  if (F == c->B) c->guards_ok[1] = true;
   return SPIC_OK;
+}
+// FillBoundary on demand: the reference refreshes the guards in front of every consumer (hpp:56, 350; cpp:40, 104);
+// here a refresh is skipped when the valid cells have not changed since the last one
+int ensure_guards(Ctx* c, double* F) {
+  if ((F == c->E && c->guards_ok[0]) || (F == c->B && c->guards_ok[1])) return SPIC_OK;
+  return halo_fill(c, F);
+}
+void touched(Ctx* c, double* F) {  // the valid cells of F changed (or its guards were zeroed)
+  if (F == c->E) c->guards_ok[0] = false;
+  if (F == c->B) c->guards_ok[1] = false;
 }
 int halo_sum(Ctx* c, double* F, int comp) {
   launch_sum_boundary(c, F, comp, c->g.zlocal != 0);
@@ -457,9 +469,10 @@ int spic_get_particles(spic_ctx* c, int species, double* x, double* y, double* z
 }  // extern "C"
 
 static int theta_axis_impl(spic_ctx* c, int comp, double dt) {
-  int rc = halo_fill(c, c->B);  // B.FillBoundary            hpp:350
+  int rc = ensure_guards(c, c->B);  // B.FillBoundary            hpp:350
   if (rc) return rc;
   launch_zero_guards(c, c->E);  // E.setBndry(0)             hpp:351-352
+  touched(c, c->E);
   for (auto& s : c->sp) {       // Theta<comp,W,...> per tile hpp:353-365
     if (s.binned) {
       if ((rc = engine_theta_axis(c, s, comp, dt))) return rc;
@@ -473,7 +486,10 @@ static int theta_axis_impl(spic_ctx* c, int comp, double dt) {
 }
 
 static int theta_E_impl(spic_ctx* c, double dt) {
-  int rc = halo_fill(c, c->E);  // E.FillBoundary  hpp:56
+  int rc = SPIC_OK;
+  // E.FillBoundary hpp:56: for the particle gathers, and for the curl's z neighbours across slab faces (x, y and a
+  // local z are wrapped inside the sweep)
+  if (!c->sp.empty() || c->cfg.nranks > 1) rc = ensure_guards(c, c->E);
   if (rc) return rc;
   for (auto& s : c->sp) {       // push_V_E        hpp:57-62
     if (s.binned) {
@@ -483,13 +499,16 @@ static int theta_E_impl(spic_ctx* c, double dt) {
     }
   }
   launch_curl_E_into_B(c, dt);  // push_B_E        hpp:63-68
+  touched(c, c->B);
   return SPIC_OK;
 }
 
-static int theta_B_impl(spic_ctx* c, double dt) {
-  int rc = halo_fill(c, c->B);  // cpp:104
+// src_pos >= 0: an E_source application (cpp:32-36) folded into the sweep's launch, applied before it
+static int theta_B_impl(spic_ctx* c, double dt, int src_pos = -1, int src_comp = 0, double src_amp = 0.0) {
+  int rc = c->cfg.nranks > 1 ? ensure_guards(c, c->B) : SPIC_OK;  // cpp:104 (only the z guards of a slab are read)
   if (rc) return rc;
-  launch_curl_B_into_E(c, dt);  // cpp:105-110
+  launch_curl_B_into_E(c, dt, src_pos, src_comp, src_amp);  // cpp:105-110
+  touched(c, c->E);
   return SPIC_OK;
 }
 
@@ -518,9 +537,11 @@ static int map2(spic_ctx* c, double dt) {  // hpp:559-572
 // fused pass per species.  Theta_B only adds dt * curl B into E and the axis sub-flows only add their
 // currents into E and read B, which neither changes (hpp:562-569, cpp:102-113): the order is free.
 static int axis_block(spic_ctx* c, double dt) {
-  int rc = theta_B_impl(c, dt);  // fills the guards of B (cpp:104): B does not change until the next Theta_E
+  int rc = theta_B_impl(c, dt);
   if (rc) return rc;
+  if ((rc = ensure_guards(c, c->B))) return rc;  // B.FillBoundary, hpp:350: B does not change until the next Theta_E
   launch_zero_guards(c, c->E);  // E.setBndry(0), hpp:351-352: the guards collect this block's currents
+  touched(c, c->E);
   // With z slabs (option "overlap"): the cells of the W + 2 planes next to each slab face run first -- only they can
   // deposit into the guard z planes or lose particles to a neighbour (a particle moves < 2 cells in a block, its
   // stencil reaches W cells further) -- then ONE exchange carries the guard planes of the three components and the
@@ -612,7 +633,8 @@ int spic_source(spic_ctx* c, int pos, int comp, double E0, double omega, double 
   int rc = flush_pending(c);
   if (rc) return rc;
   if (pos >= 0 && pos < c->g.n[0]) launch_source(c, pos, comp, 2 * E0 * sin(omega * t) * dt);  // cpp:32-36
-  return halo_fill(c, c->E);                                                                   // cpp:40
+  touched(c, c->E);  // (E.FillBoundary of cpp:40 happens in front of the next reader of the guards)
+  return SPIC_OK;
 }
 
 int spic_map(spic_ctx* c, int order, double dt) {
@@ -624,11 +646,15 @@ int spic_map(spic_ctx* c, int order, double dt) {
 }
 
 int spic_field_only_step(spic_ctx* c, int pos, int comp, double E0, double omega, double dt, int step) {
-  int rc;  // examples/field_only/main.cpp:142-145
-  if ((rc = spic_theta_E(c, dt / 2))) return rc;
-  if ((rc = spic_source(c, pos, comp, E0, omega, dt, dt * step))) return rc;
-  if ((rc = spic_theta_B(c, dt))) return rc;
-  return spic_theta_E(c, dt / 2);
+  if (!c || comp < 0 || comp > 2) return SPIC_EINVAL;
+  cudaSetDevice(c->cfg.device);
+  int rc = flush_pending(c);  // examples/field_only/main.cpp:142-145
+  if (rc) return rc;
+  if ((rc = theta_E_impl(c, dt / 2))) return rc;
+  // Source(t) then G_Theta_B(dt): the source plane is added inside the sweep's launch, before MABC and the curl
+  const bool on = pos >= 0 && pos < c->g.n[0];
+  if ((rc = theta_B_impl(c, dt, on ? pos : -1, comp, 2 * E0 * sin(omega * (dt * step)) * dt))) return rc;
+  return theta_E_impl(c, dt / 2);
 }
 
 // ---- diagnostics ---------------------------------------------------------------------
@@ -663,7 +689,7 @@ int spic_gauss_residual(spic_ctx* c, double* host) {
   if (!c || !host) return SPIC_EINVAL;
   cudaSetDevice(c->cfg.device);
   if (int frc = flush_pending(c)) return frc;
-  int rc = halo_fill(c, c->E);
+  int rc = ensure_guards(c, c->E);
   if (rc) return rc;
   // rho is deposited like a current: into one guarded component whose guards are then folded into their owner cells
   // (periodic images, and the neighbour slabs over NCCL) -- so the diagnostic works on every rank of a slab run

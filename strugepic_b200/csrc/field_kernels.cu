@@ -177,11 +177,23 @@ struct Interior {
   int lo[3], hi[3];  // inclusive, local indices
 };
 
+// What a curl sweep folds in besides the curl itself (field-only steps: one launch per sub-flow).
+struct SweepExtras {
+  int mabc;      // 1: MABC_bad<X> of the target on the two global x faces (ExteriorF of push_ff, hpp:516-523), done by
+                 //    the threads of the neighbouring interior columns before they update their own cell
+  int src_pos;   // >= 0: E_source (cpp:32-36) applied to the target first: T(src_pos, j, k, src_comp) += src_amp
+  int src_comp;
+  double src_amp;
+};
+
 // FWD = true : B -= dt * curl+ E   (E_curl, forward differences)
 // FWD = false: E += dt * curl- B   (B_curl, backward differences)
+// Periodic directions that are resolved inside this brick are WRAPPED here (wrap[d] = n[d]: the neighbour of the last
+// / first cell is the first / last one), so the sweep does not depend on the guard cells of S in those directions;
+// wrap[d] = 0: the neighbour is read in place (interior of a wall box, or the z guards a neighbour slab has filled).
 template <bool FWD>
 __global__ void __launch_bounds__(kBlock) k_curl(Grid g, const double* __restrict__ S, double* __restrict__ T,
-                                                 Interior in, double dt) {
+                                                 Interior in, double dt, int wrap0, int wrap1, int wrap2, SweepExtras ex) {
   const int nx = in.hi[0] - in.lo[0] + 1, ny = in.hi[1] - in.lo[1] + 1, nz = in.hi[2] - in.lo[2] + 1;
   const long total = (long)nx * ny * nz;
   const long sj = g.pj, sk = g.pk, sc = g.pc;
@@ -191,21 +203,48 @@ __global__ void __launch_bounds__(kBlock) k_curl(Grid g, const double* __restric
     const int k = (int)(t / ((long)nx * ny)) + in.lo[2];
     const long o = g.at(i, j, k);
     const double sx = S[o], sy = S[o + sc], sz = S[o + 2 * sc];
+    double t0 = T[o], t1 = T[o + sc], t2 = T[o + 2 * sc];
+    if (ex.src_pos >= 0 || ex.mabc) {
+      // the target as E_source leaves it (a plain add, rounded like the reference's separate pass)
+      auto src = [&](int ii, int c, double v) { return ii == ex.src_pos && c == ex.src_comp ? v + ex.src_amp : v; };
+      t0 = src(i, 0, t0);
+      t1 = src(i, 1, t1);
+      t2 = src(i, 2, t2);
+      if (ex.mabc) {  // A <- (1-dt) A + dt A(i +- 1) on the faces, from the values BEFORE the interior update
+        const int Hi = g.gn[0] - 1;
+        if (i == 1) {
+          T[o - 1] = (1 - dt) * src(0, 0, T[o - 1]) + t0 * dt;
+          T[o - 1 + sc] = (1 - dt) * src(0, 1, T[o - 1 + sc]) + t1 * dt;
+          T[o - 1 + 2 * sc] = (1 - dt) * src(0, 2, T[o - 1 + 2 * sc]) + t2 * dt;
+        }
+        if (i == Hi - 1) {
+          T[o + 1] = (1 - dt) * src(Hi, 0, T[o + 1]) + t0 * dt;
+          T[o + 1 + sc] = (1 - dt) * src(Hi, 1, T[o + 1 + sc]) + t1 * dt;
+          T[o + 1 + 2 * sc] = (1 - dt) * src(Hi, 2, T[o + 1 + 2 * sc]) + t2 * dt;
+        }
+      }
+    }
     double r0, r1, r2;
     if (FWD) {
-      r0 = (S[o + sj + 2 * sc] - sz) - (S[o + sk + sc] - sy);
-      r1 = (S[o + sk] - sx) - (S[o + 1 + 2 * sc] - sz);
-      r2 = (S[o + 1 + sc] - sy) - (S[o + sj] - sx);
-      T[o] = T[o] - dt * r0;
-      T[o + sc] = T[o + sc] - dt * r1;
-      T[o + 2 * sc] = T[o + 2 * sc] - dt * r2;
+      const long di = (wrap0 && i + 1 == wrap0) ? 1 - wrap0 : 1;
+      const long dj = (wrap1 && j + 1 == wrap1) ? (1 - wrap1) * sj : sj;
+      const long dk = (wrap2 && k + 1 == wrap2) ? (1 - wrap2) * sk : sk;
+      r0 = (S[o + dj + 2 * sc] - sz) - (S[o + dk + sc] - sy);
+      r1 = (S[o + dk] - sx) - (S[o + di + 2 * sc] - sz);
+      r2 = (S[o + di + sc] - sy) - (S[o + dj] - sx);
+      T[o] = t0 - dt * r0;
+      T[o + sc] = t1 - dt * r1;
+      T[o + 2 * sc] = t2 - dt * r2;
     } else {
-      r0 = (sz - S[o - sj + 2 * sc]) - (sy - S[o - sk + sc]);
-      r1 = (sx - S[o - sk]) - (sz - S[o - 1 + 2 * sc]);
-      r2 = (sy - S[o - 1 + sc]) - (sx - S[o - sj]);
-      T[o] = T[o] + dt * r0;
-      T[o + sc] = T[o + sc] + dt * r1;
-      T[o + 2 * sc] = T[o + 2 * sc] + dt * r2;
+      const long di = (wrap0 && i == 0) ? 1 - wrap0 : 1;
+      const long dj = (wrap1 && j == 0) ? (1 - wrap1) * sj : sj;
+      const long dk = (wrap2 && k == 0) ? (1 - wrap2) * sk : sk;
+      r0 = (sz - S[o - dj + 2 * sc]) - (sy - S[o - dk + sc]);
+      r1 = (sx - S[o - dk]) - (sz - S[o - di + 2 * sc]);
+      r2 = (sy - S[o - di + sc]) - (sx - S[o - dj]);
+      T[o] = t0 + dt * r0;
+      T[o + sc] = t1 + dt * r1;
+      T[o + 2 * sc] = t2 + dt * r2;
     }
   }
 }
@@ -345,29 +384,45 @@ void launch_sum_boundary(Ctx* c, double* F, int comp, bool z_too, bool owner_onl
   k_sum_boundary<<<grid_for(c, total), kBlock, 0, c->stream>>>(c->g, F, comp, z_too ? 1 : 0, owner_only ? 1 : 0);
   c->launches++;
 }
-void launch_curl_E_into_B(Ctx* c, double dt) {
-  if (!all_periodic(c->g)) {  // push_ff: ExteriorF(Target) first (hpp:516-523)
-    k_mabc_x<<<grid_for(c, (long)c->g.n[1] * c->g.n[2]), kBlock, 0, c->stream>>>(c->g, c->B, dt);
+// One field sweep: MABC of the target's x faces (wall boxes), then the interior curl update (push_ff, hpp:512-527);
+// src: an E_source application folded into the same launch (target = E only), or null.
+template <bool FWD>
+static void launch_sweep(Ctx* c, const double* S, double* T, double dt, const SweepExtras* src) {
+  const Grid& g = c->g;
+  const bool walls = !all_periodic(g);
+  const Interior in = make_interior(g);
+  const long total = (long)(in.hi[0] - in.lo[0] + 1) * (in.hi[1] - in.lo[1] + 1) * (in.hi[2] - in.lo[2] + 1);
+  SweepExtras ex{0, -1, 0, 0.0};
+  if (src) ex = *src;
+  // the faces are blended by the interior columns next to them when those exist (x walls, >= 4 cells across, one
+  // brick in x: always) -- else by the stand-alone kernel
+  const bool fold_mabc = walls && !g.per[0] && g.n[0] >= 4 && total > 0;
+  if (walls && !fold_mabc) {
+    if (ex.src_pos >= 0) {
+      k_source<<<grid_for(c, (long)g.n[1] * g.n[2]), kBlock, 0, c->stream>>>(g, T, ex.src_pos, ex.src_comp, ex.src_amp);
+      c->launches++;
+      ex.src_pos = -1;
+    }
+    k_mabc_x<<<grid_for(c, (long)g.n[1] * g.n[2]), kBlock, 0, c->stream>>>(g, T, dt);
     c->launches++;
   }
-  const Interior in = make_interior(c->g);
-  const long total = (long)(in.hi[0] - in.lo[0] + 1) * (in.hi[1] - in.lo[1] + 1) * (in.hi[2] - in.lo[2] + 1);
-  if (total <= 0) return;
+  ex.mabc = fold_mabc ? 1 : 0;
+  if (total <= 0) {
+    if (ex.src_pos >= 0) {
+      k_source<<<grid_for(c, (long)g.n[1] * g.n[2]), kBlock, 0, c->stream>>>(g, T, ex.src_pos, ex.src_comp, ex.src_amp);
+      c->launches++;
+    }
+    return;
+  }
   KernelTimer t(c, KT_CURL);
-  k_curl<true><<<grid_for(c, total), kBlock, 0, c->stream>>>(c->g, c->E, c->B, in, dt);
+  const int w0 = g.per[0] ? g.n[0] : 0, w1 = g.per[1] ? g.n[1] : 0, w2 = g.per[2] && g.zlocal ? g.n[2] : 0;
+  k_curl<FWD><<<grid_for(c, total), kBlock, 0, c->stream>>>(g, S, T, in, dt, w0, w1, w2, ex);
   c->launches++;
 }
-void launch_curl_B_into_E(Ctx* c, double dt) {
-  if (!all_periodic(c->g)) {
-    k_mabc_x<<<grid_for(c, (long)c->g.n[1] * c->g.n[2]), kBlock, 0, c->stream>>>(c->g, c->E, dt);
-    c->launches++;
-  }
-  const Interior in = make_interior(c->g);
-  const long total = (long)(in.hi[0] - in.lo[0] + 1) * (in.hi[1] - in.lo[1] + 1) * (in.hi[2] - in.lo[2] + 1);
-  if (total <= 0) return;
-  KernelTimer t(c, KT_CURL);
-  k_curl<false><<<grid_for(c, total), kBlock, 0, c->stream>>>(c->g, c->B, c->E, in, dt);
-  c->launches++;
+void launch_curl_E_into_B(Ctx* c, double dt) { launch_sweep<true>(c, c->E, c->B, dt, nullptr); }
+void launch_curl_B_into_E(Ctx* c, double dt, int src_pos, int src_comp, double src_amp) {
+  SweepExtras ex{0, src_pos, src_comp, src_amp};
+  launch_sweep<false>(c, c->B, c->E, dt, src_pos >= 0 ? &ex : nullptr);
 }
 void launch_source(Ctx* c, int pos, int comp, double amp) {
   k_source<<<grid_for(c, (long)c->g.n[1] * c->g.n[2]), kBlock, 0, c->stream>>>(c->g, c->E, pos, comp, amp);

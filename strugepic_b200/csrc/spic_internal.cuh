@@ -68,7 +68,8 @@ void launch_fill_boundary(Ctx* c, double* F, bool z_too);
 void launch_zero_guards(Ctx* c, double* F);
 void launch_sum_boundary(Ctx* c, double* F, int comp, bool z_too, bool owner_only = false);
 void launch_curl_E_into_B(Ctx* c, double dt);  // push_B_E
-void launch_curl_B_into_E(Ctx* c, double dt);  // push_E_B
+// push_E_B; src_pos >= 0: E_source (E(src_pos,.,.,src_comp) += src_amp) applied first, in the same launch
+void launch_curl_B_into_E(Ctx* c, double dt, int src_pos = -1, int src_comp = 0, double src_amp = 0.0);
 void launch_source(Ctx* c, int pos, int comp, double amp);
 void launch_set_uniform(Ctx* c, double* F, const double v[3]);
 void field_energy(Ctx* c, double* out_sumsq6);  // sum of squares of the 6 components (valid cells)
@@ -99,6 +100,9 @@ struct Ctx {
   int W = 2;
   double* E = nullptr;
   double* B = nullptr;
+  // guard cells of E / B hold the images of the current valid cells (FillBoundary semantics).  Guards are refreshed
+  // lazily, by the first consumer that reads them: the curl sweeps wrap periodic directions themselves and need none.
+  bool guards_ok[2] = {false, false};
   double* scratch = nullptr;  // >= 3 * cells doubles (pack/unpack, reductions, gauss)
   long scratch_elems = 0;
   int* d_flags = nullptr;     // [0]: CFL violation, [1]: capacity overflow

@@ -128,6 +128,38 @@ def test_empty_species_and_field_only(engine):
     assert s.get_total_energy()[0] == pytest.approx(o.energy()[0], rel=1e-12)
 
 
+@pytest.mark.parametrize("periodic", [(0, 1, 1), (1, 1, 1), (1, 0, 1)])
+def test_field_only_at_scale(periodic):
+    """BASELINE configs[2] shape at a size the oracle runs in seconds: 256 x 32 x 32 vacuum Maxwell, soft plane-wave
+    source, MABC on the x faces (examples/field_only/main.cpp:142-145).  One launch per sub-flow here (source and MABC
+    folded into the curl sweeps, periodic directions wrapped inside them, no guard refresh): equal to the oracle's
+    separate passes to round-off; also fully periodic, and with a y wall (MABC_bad<X> still blends the x faces of a
+    periodic x then: hpp:516-523 applies it whenever the box is not ALL periodic)."""
+    n_cell = (256, 32, 32)
+    o = ora.best_oracle(n_cell, periodic=periodic, interp=0, ng=3)
+    s = spic().Simulation(n_cell, periodic=periodic, interp=0, ng=3)
+    E, B = util.rng_fields(n_cell, 97, 1e-3)
+    for t in (o, s):
+        util.load_state(t, E, B, [np.zeros(0)] * 6, -1.0, 1.0)
+    pos, comp, E0, omega, dt = 32, 1, 0.1, 0.3, 0.5
+    for step in range(60):
+        for op in (("E", dt / 2), ("source", pos, comp, E0, omega, dt, dt * step), ("B", dt), ("E", dt / 2)):
+            util.apply(o, op)
+        s.field_only_step(pos, comp, E0, omega, dt, step)
+    Eo, Bo, _ = util.state_of(o)
+    Es, Bs, _ = util.state_of(s)
+    assert util.rel_err(Es, Eo) < 1e-12 and util.rel_err(Bs, Bo) < 1e-12
+    assert np.max(np.abs(Eo)) > 1e-2
+    # the same sub-flows called one by one (spic_source as its own launch) agree with the folded step
+    s2 = spic().Simulation(n_cell, periodic=periodic, interp=0, ng=3)
+    util.load_state(s2, E, B, [np.zeros(0)] * 6, -1.0, 1.0)
+    for step in range(60):
+        for op in (("E", dt / 2), ("source", pos, comp, E0, omega, dt, dt * step), ("B", dt), ("E", dt / 2)):
+            util.apply(s2, op)
+    E2, B2, _ = util.state_of(s2)
+    assert util.rel_err(E2, Es) < 1e-13 and util.rel_err(B2, Bs) < 1e-13
+
+
 @pytest.mark.parametrize("engine", ENGINES)
 def test_single_particle_decks(engine):
     """cyclotron.input known answers and reflection.input flip steps."""
