@@ -485,7 +485,8 @@ static int theta_axis_impl(spic_ctx* c, int comp, double dt) {
   return deposit_exchange_end(c, 1u << comp);
 }
 
-static int theta_E_impl(spic_ctx* c, double dt) {
+// dt2 != 0 (no species only): the field half is applied twice in a row, dt then dt2, by one sweep
+static int theta_E_impl(spic_ctx* c, double dt, double dt2 = 0.0) {
   int rc = SPIC_OK;
   // E.FillBoundary hpp:56: for the particle gathers, and for the curl's z neighbours across slab faces (x, y and a
   // local z are wrapped inside the sweep)
@@ -498,7 +499,7 @@ static int theta_E_impl(spic_ctx* c, double dt) {
       launch_push_v_e_direct(c, s.d, s.nd, nullptr, s.q, s.m, dt);
     }
   }
-  launch_curl_E_into_B(c, dt);  // push_B_E        hpp:63-68
+  launch_curl_E_into_B(c, dt, dt2);  // push_B_E        hpp:63-68
   touched(c, c->B);
   return SPIC_OK;
 }
@@ -513,7 +514,14 @@ static int theta_B_impl(spic_ctx* c, double dt, int src_pos = -1, int src_comp =
 }
 
 // Applies the deferred trailing Theta_E of the last fused map (see Ctx::pending_E).
+static int flush_pending_field(spic_ctx* c) {
+  if (c->pending_field_E == 0.0) return SPIC_OK;
+  const double d = c->pending_field_E;
+  c->pending_field_E = 0.0;
+  return theta_E_impl(c, d);
+}
 static int flush_pending(spic_ctx* c) {
+  if (int rc = flush_pending_field(c)) return rc;
   if (c->pending_E == 0.0) return SPIC_OK;
   const double d = c->pending_E;
   c->pending_E = 0.0;
@@ -583,6 +591,7 @@ static int fused_maps(spic_ctx* c, const double* d, int n) {
 static int map_body(spic_ctx* c, int order, double dt) {
   int rc;
   const bool fuse = (order == 2 || order == 4) && engine_can_fuse(c);
+  if ((rc = flush_pending_field(c))) return rc;
   if (!fuse && (rc = flush_pending(c))) return rc;
   if (order == 1) {  // hpp:548-557
     if ((rc = theta_B_impl(c, dt))) return rc;
@@ -648,12 +657,24 @@ int spic_map(spic_ctx* c, int order, double dt) {
 int spic_field_only_step(spic_ctx* c, int pos, int comp, double E0, double omega, double dt, int step) {
   if (!c || comp < 0 || comp > 2) return SPIC_EINVAL;
   cudaSetDevice(c->cfg.device);
-  int rc = flush_pending(c);  // examples/field_only/main.cpp:142-145
-  if (rc) return rc;
-  if ((rc = theta_E_impl(c, dt / 2))) return rc;
+  // examples/field_only/main.cpp:142-145: Theta_E(dt/2), Source(t), Theta_B(dt), Theta_E(dt/2)
+  int rc;
+  const bool vacuum = c->sp.empty();
+  if (vacuum && c->pending_field_E != 0.0) {  // the previous step's trailing half + this step's leading half: one sweep
+    const double first = c->pending_field_E;
+    c->pending_field_E = 0.0;
+    if ((rc = theta_E_impl(c, first, dt / 2))) return rc;
+  } else {
+    if ((rc = flush_pending(c))) return rc;
+    if ((rc = theta_E_impl(c, dt / 2))) return rc;
+  }
   // Source(t) then G_Theta_B(dt): the source plane is added inside the sweep's launch, before MABC and the curl
   const bool on = pos >= 0 && pos < c->g.n[0];
   if ((rc = theta_B_impl(c, dt, on ? pos : -1, comp, 2 * E0 * sin(omega * (dt * step)) * dt))) return rc;
+  if (vacuum && c->defer_kick && dt != 0.0) {
+    c->pending_field_E = dt / 2;
+    return SPIC_OK;
+  }
   return theta_E_impl(c, dt / 2);
 }
 

@@ -158,11 +158,11 @@ int main_after_comm(Ctx* c) {
 // guards are folded afterwards)
 __global__ void __launch_bounds__(256)
     k_add_planes(double* __restrict__ F, const double* __restrict__ recv, long cnt, long pc, long off_top, long off_bot,
-                 unsigned mask) {
+                 unsigned mask, unsigned sides) {
   const long total = 6 * cnt;
   for (long t = blockIdx.x * (long)blockDim.x + threadIdx.x; t < total; t += (long)gridDim.x * blockDim.x) {
     const int b = (int)(t / cnt), comp = b >> 1, side = b & 1;
-    if (!((mask >> comp) & 1u)) continue;
+    if (!((mask >> comp) & 1u) || !((sides >> side) & 1u)) continue;
     const long i = t - (long)b * cnt;
     F[(long)comp * pc + (side == 0 ? off_top : off_bot) + i] += recv[((long)side * 3 + comp) * cnt + i];
   }
@@ -368,9 +368,14 @@ int comm_block_end(Ctx* c) {
     long nb = (6 * (long)cnt + 255) / 256;
     if (nb > (long)c->sm_count * 8) nb = (long)c->sm_count * 8;
     // from next: its low guards -> my top owner planes; from prev: its high guards -> my bottom owner planes
-    k_add_planes<<<(int)nb, 256, 0, c->stream>>>(s->F, s->sum_recv, (long)cnt, g.pc, (long)g.n[2] * g.pk,
-                                                 (long)g.ng * g.pk, s->mask);
-    c->launches++;
+    // (a slab thinner than 2 ng planes: the two target regions overlap, one side after the other)
+    const bool overlap = g.n[2] < 2 * g.ng;
+    for (unsigned sides : {overlap ? 1u : 3u, 2u}) {
+      k_add_planes<<<(int)nb, 256, 0, c->stream>>>(s->F, s->sum_recv, (long)cnt, g.pc, (long)g.n[2] * g.pk,
+                                                   (long)g.ng * g.pk, s->mask, sides);
+      c->launches++;
+      if (!overlap) break;
+    }
   }
   if (s->migrate) {
     for (size_t si = 0; si < s->sp.size(); ++si) {

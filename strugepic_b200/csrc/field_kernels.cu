@@ -191,9 +191,13 @@ struct SweepExtras {
 // Periodic directions that are resolved inside this brick are WRAPPED here (wrap[d] = n[d]: the neighbour of the last
 // / first cell is the first / last one), so the sweep does not depend on the guard cells of S in those directions;
 // wrap[d] = 0: the neighbour is read in place (interior of a wall box, or the z guards a neighbour slab has filled).
+// dt2 != 0: the sweep is applied TWICE in a row (steps dt, then dt2) with ONE read of S -- consecutive Theta_E halves
+// of a field-only run see the same E (field_only/main.cpp:142-145: ... Theta_E(dt/2) | Theta_E(dt/2) ...), so the
+// second application costs no memory traffic.  Both roundings and both MABC blends are made in the reference's order.
 template <bool FWD>
 __global__ void __launch_bounds__(kBlock) k_curl(Grid g, const double* __restrict__ S, double* __restrict__ T,
-                                                 Interior in, double dt, int wrap0, int wrap1, int wrap2, SweepExtras ex) {
+                                                 Interior in, double dt, double dt2, int wrap0, int wrap1, int wrap2,
+                                                 SweepExtras ex) {
   const int nx = in.hi[0] - in.lo[0] + 1, ny = in.hi[1] - in.lo[1] + 1, nz = in.hi[2] - in.lo[2] + 1;
   const long total = (long)nx * ny * nz;
   const long sj = g.pj, sk = g.pk, sc = g.pc;
@@ -203,48 +207,53 @@ __global__ void __launch_bounds__(kBlock) k_curl(Grid g, const double* __restric
     const int k = (int)(t / ((long)nx * ny)) + in.lo[2];
     const long o = g.at(i, j, k);
     const double sx = S[o], sy = S[o + sc], sz = S[o + 2 * sc];
-    double t0 = T[o], t1 = T[o + sc], t2 = T[o + 2 * sc];
-    if (ex.src_pos >= 0 || ex.mabc) {
-      // the target as E_source leaves it (a plain add, rounded like the reference's separate pass)
-      auto src = [&](int ii, int c, double v) { return ii == ex.src_pos && c == ex.src_comp ? v + ex.src_amp : v; };
-      t0 = src(i, 0, t0);
-      t1 = src(i, 1, t1);
-      t2 = src(i, 2, t2);
-      if (ex.mabc) {  // A <- (1-dt) A + dt A(i +- 1) on the faces, from the values BEFORE the interior update
-        const int Hi = g.gn[0] - 1;
-        if (i == 1) {
-          T[o - 1] = (1 - dt) * src(0, 0, T[o - 1]) + t0 * dt;
-          T[o - 1 + sc] = (1 - dt) * src(0, 1, T[o - 1 + sc]) + t1 * dt;
-          T[o - 1 + 2 * sc] = (1 - dt) * src(0, 2, T[o - 1 + 2 * sc]) + t2 * dt;
-        }
-        if (i == Hi - 1) {
-          T[o + 1] = (1 - dt) * src(Hi, 0, T[o + 1]) + t0 * dt;
-          T[o + 1 + sc] = (1 - dt) * src(Hi, 1, T[o + 1 + sc]) + t1 * dt;
-          T[o + 1 + 2 * sc] = (1 - dt) * src(Hi, 2, T[o + 1 + 2 * sc]) + t2 * dt;
-        }
-      }
-    }
-    double r0, r1, r2;
+    double tv[3] = {T[o], T[o + sc], T[o + 2 * sc]};
+    double r[3];
     if (FWD) {
       const long di = (wrap0 && i + 1 == wrap0) ? 1 - wrap0 : 1;
       const long dj = (wrap1 && j + 1 == wrap1) ? (1 - wrap1) * sj : sj;
       const long dk = (wrap2 && k + 1 == wrap2) ? (1 - wrap2) * sk : sk;
-      r0 = (S[o + dj + 2 * sc] - sz) - (S[o + dk + sc] - sy);
-      r1 = (S[o + dk] - sx) - (S[o + di + 2 * sc] - sz);
-      r2 = (S[o + di + sc] - sy) - (S[o + dj] - sx);
-      T[o] = t0 - dt * r0;
-      T[o + sc] = t1 - dt * r1;
-      T[o + 2 * sc] = t2 - dt * r2;
+      r[0] = (S[o + dj + 2 * sc] - sz) - (S[o + dk + sc] - sy);
+      r[1] = (S[o + dk] - sx) - (S[o + di + 2 * sc] - sz);
+      r[2] = (S[o + di + sc] - sy) - (S[o + dj] - sx);
     } else {
       const long di = (wrap0 && i == 0) ? 1 - wrap0 : 1;
       const long dj = (wrap1 && j == 0) ? (1 - wrap1) * sj : sj;
       const long dk = (wrap2 && k == 0) ? (1 - wrap2) * sk : sk;
-      r0 = (sz - S[o - dj + 2 * sc]) - (sy - S[o - dk + sc]);
-      r1 = (sx - S[o - dk]) - (sz - S[o - di + 2 * sc]);
-      r2 = (sy - S[o - di + sc]) - (sx - S[o - dj]);
-      T[o] = t0 + dt * r0;
-      T[o + sc] = t1 + dt * r1;
-      T[o + 2 * sc] = t2 + dt * r2;
+      r[0] = (sz - S[o - dj + 2 * sc]) - (sy - S[o - dk + sc]);
+      r[1] = (sx - S[o - dk]) - (sz - S[o - di + 2 * sc]);
+      r[2] = (sy - S[o - di + sc]) - (sx - S[o - dj]);
+    }
+    const int Hi = g.gn[0] - 1;
+    const bool lo_face = ex.mabc && i == 1, hi_face = ex.mabc && i == Hi - 1;
+    double flo[3] = {0, 0, 0}, fhi[3] = {0, 0, 0};
+    if (ex.src_pos >= 0 || ex.mabc) {
+      // the target as E_source leaves it (a plain add, rounded like the reference's separate pass)
+      auto src = [&](int ii, int c, double v) { return ii == ex.src_pos && c == ex.src_comp ? v + ex.src_amp : v; };
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        tv[c] = src(i, c, tv[c]);
+        if (lo_face) flo[c] = src(0, c, T[o - 1 + c * sc]);
+        if (hi_face) fhi[c] = src(Hi, c, T[o + 1 + c * sc]);
+      }
+    }
+    // one application: MABC_bad<X> on the faces from the values BEFORE the interior update (ExteriorF first, hpp:516-525:
+    // A <- (1-dt) A + dt A(i +- 1)), then the interior update
+    auto apply = [&](double h) {
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        if (lo_face) flo[c] = (1 - h) * flo[c] + tv[c] * h;
+        if (hi_face) fhi[c] = (1 - h) * fhi[c] + tv[c] * h;
+        tv[c] = FWD ? tv[c] - h * r[c] : tv[c] + h * r[c];
+      }
+    };
+    apply(dt);
+    if (dt2 != 0.0) apply(dt2);
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      T[o + c * sc] = tv[c];
+      if (lo_face) T[o - 1 + c * sc] = flo[c];
+      if (hi_face) T[o + 1 + c * sc] = fhi[c];
     }
   }
 }
@@ -387,7 +396,7 @@ void launch_sum_boundary(Ctx* c, double* F, int comp, bool z_too, bool owner_onl
 // One field sweep: MABC of the target's x faces (wall boxes), then the interior curl update (push_ff, hpp:512-527);
 // src: an E_source application folded into the same launch (target = E only), or null.
 template <bool FWD>
-static void launch_sweep(Ctx* c, const double* S, double* T, double dt, const SweepExtras* src) {
+static void launch_sweep(Ctx* c, const double* S, double* T, double dt, const SweepExtras* src, double dt2 = 0.0) {
   const Grid& g = c->g;
   const bool walls = !all_periodic(g);
   const Interior in = make_interior(g);
@@ -396,7 +405,12 @@ static void launch_sweep(Ctx* c, const double* S, double* T, double dt, const Sw
   if (src) ex = *src;
   // the faces are blended by the interior columns next to them when those exist (x walls, >= 4 cells across, one
   // brick in x: always) -- else by the stand-alone kernel
-  const bool fold_mabc = walls && !g.per[0] && g.n[0] >= 4 && total > 0;
+  const bool fold_mabc = walls && !g.per[0] && g.per[1] && g.per[2] && g.n[0] >= 4 && total > 0;
+  if (dt2 != 0.0 && walls && !fold_mabc) {  // the stand-alone MABC kernel cannot be doubled: two plain sweeps
+    launch_sweep<FWD>(c, S, T, dt, src);
+    launch_sweep<FWD>(c, S, T, dt2, nullptr);
+    return;
+  }
   if (walls && !fold_mabc) {
     if (ex.src_pos >= 0) {
       k_source<<<grid_for(c, (long)g.n[1] * g.n[2]), kBlock, 0, c->stream>>>(g, T, ex.src_pos, ex.src_comp, ex.src_amp);
@@ -416,10 +430,10 @@ static void launch_sweep(Ctx* c, const double* S, double* T, double dt, const Sw
   }
   KernelTimer t(c, KT_CURL);
   const int w0 = g.per[0] ? g.n[0] : 0, w1 = g.per[1] ? g.n[1] : 0, w2 = g.per[2] && g.zlocal ? g.n[2] : 0;
-  k_curl<FWD><<<grid_for(c, total), kBlock, 0, c->stream>>>(g, S, T, in, dt, w0, w1, w2, ex);
+  k_curl<FWD><<<grid_for(c, total), kBlock, 0, c->stream>>>(g, S, T, in, dt, dt2, w0, w1, w2, ex);
   c->launches++;
 }
-void launch_curl_E_into_B(Ctx* c, double dt) { launch_sweep<true>(c, c->E, c->B, dt, nullptr); }
+void launch_curl_E_into_B(Ctx* c, double dt, double dt2) { launch_sweep<true>(c, c->E, c->B, dt, nullptr, dt2); }
 void launch_curl_B_into_E(Ctx* c, double dt, int src_pos, int src_comp, double src_amp) {
   SweepExtras ex{0, src_pos, src_comp, src_amp};
   launch_sweep<false>(c, c->B, c->E, dt, src_pos >= 0 ? &ex : nullptr);

@@ -67,7 +67,8 @@ struct Ctx;
 void launch_fill_boundary(Ctx* c, double* F, bool z_too);
 void launch_zero_guards(Ctx* c, double* F);
 void launch_sum_boundary(Ctx* c, double* F, int comp, bool z_too, bool owner_only = false);
-void launch_curl_E_into_B(Ctx* c, double dt);  // push_B_E
+// push_B_E; dt2 != 0: applied twice in a row (dt, then dt2) with one read of E
+void launch_curl_E_into_B(Ctx* c, double dt, double dt2 = 0.0);
 // push_E_B; src_pos >= 0: E_source (E(src_pos,.,.,src_comp) += src_amp) applied first, in the same launch
 void launch_curl_B_into_E(Ctx* c, double dt, int src_pos = -1, int src_comp = 0, double src_amp = 0.0);
 void launch_source(Ctx* c, int pos, int comp, double amp);
@@ -117,6 +118,10 @@ struct Ctx {
   // (getters, setters, single sub-flows, diagnostics, IO, sync) applies it first: the state a caller can observe
   // is always the fully stepped one.  Option "defer_kick" = 0 turns it off.
   double pending_E = 0.0;
+  // Field-only runs (no species): the trailing Theta_E(dt/2) of spic_field_only_step is left pending the same way and
+  // applied TOGETHER with the leading one of the next step by one sweep that reads E once (two applications in the
+  // reference's order and rounding: MABC makes Theta_E(s) o Theta_E(t) != Theta_E(s + t) on wall boxes).
+  double pending_field_E = 0.0;
   bool defer_kick = true;
   struct TimedLaunch {
     cudaEvent_t e0, e1;

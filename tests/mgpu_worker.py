@@ -29,7 +29,9 @@ def main():
     case = sys.argv[1] if len(sys.argv) > 1 else "p8"
     interp = 0 if case.startswith("p8") else 1
     opts = case.split("_")[1:]
-    nz = 4 * world if "thin" in opts else 6 * world
+    # slab thickness: thin = 4 planes (< 2 ng: the halo-sum targets overlap), tall = 12 (> 2 (W + 2): the axis block
+    # is split into slab-face planes + interior planes and the exchange overlaps the interior), default 6
+    nz = (4 if "thin" in opts else 12 if "tall" in opts else 6) * world
     fuse = 0 if "nofuse" in opts else 1  # fused axis blocks (guard width W + 1) / launch per sub-flow
     n_cell = (12, 10, nz)
     ppc, vth = 6, 0.25
