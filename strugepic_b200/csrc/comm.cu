@@ -170,13 +170,14 @@ __global__ void __launch_bounds__(256)
 
 // movers flagged dest == -1 / -2 -> the low / high message (count in the message header)
 __global__ void k_collect_leavers(const double* mx0, const double* mx1, const double* mx2, const double* mv0,
-                                  const double* mv1, const double* mv2, const int* __restrict__ dest,
+                                  const double* mv1, const double* mv2, int* __restrict__ dest,
                                   const unsigned* __restrict__ n_dev, unsigned mcap, double* lo, double* hi,
                                   unsigned Mlo, unsigned Mhi, int* __restrict__ flags) {
   const unsigned n = min(*n_dev, mcap);
   for (unsigned m = blockIdx.x * blockDim.x + threadIdx.x; m < n; m += gridDim.x * blockDim.x) {
     const int d = dest[m];
-    if (d >= 0) continue;
+    if (d != -1 && d != -2) continue;
+    dest[m] = kMoverDone;
     const int side = d == -1 ? 0 : 1;
     double* out = side == 0 ? lo : hi;
     const unsigned M = side == 0 ? Mlo : Mhi;
@@ -419,7 +420,7 @@ int comm_exchange_sum(Ctx* c, double* F, int comp) {
 // ---- particle migration: packing -----------------------------------------------------------------------
 // movers with dest -1 / -2 (left through the low / high z face) and the leavers of the overflow tail are copied into
 // this species' two messages; the exchange itself is comm_block_begin(.., migrate = true)
-int comm_collect_leavers(Ctx* c, Species& sp, double* const mx[3], double* const mv[3], const int* dest,
+int comm_collect_leavers(Ctx* c, Species& sp, double* const mx[3], double* const mv[3], int* dest,
                          const unsigned* n, unsigned mcap) {
   int rc = need_comm(c);
   if (rc) return rc;

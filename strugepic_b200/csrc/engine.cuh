@@ -5,10 +5,11 @@
 
 namespace spic {
 
+constexpr int kMoverDone = -3;  // mover-list entry that has been filed / packed already
 struct MoverList {
   double* x[3];
   double* v[3];
-  int* dest;  // >= 0: local cell; -1 / -2: leaves through the low / high z face of the slab
+  int* dest;  // >= 0: local cell; -1 / -2: leaves through the low / high z face of the slab; kMoverDone
   unsigned* n;
   unsigned cap;
 };
@@ -32,6 +33,11 @@ struct EngineState {
   // nranks > 1: 1 = the slab-face cells of an axis block run first and their halo sums / migration travel on a side
   // stream while the interior cells compute; 0 = every exchange in stream order behind the whole block
   int overlap = 1;
+  // 1: the fused axis block stages its batches with TMA (cp.async.bulk + a 4-D tensor map for the B stencil, completed
+  // on an mbarrier) instead of cp.async
+  int tma = 0;
+  alignas(64) unsigned char map_B[128];  // CUtensorMap of the B stencil box
+  bool map_B_ok = false;
   unsigned* block_work = nullptr;   // chunk counter of the fused axis-block kernel
   // continuation of the ejected particles: sort key (home cell) per mover-list entry + radix-sort buffers
   unsigned* cont_key = nullptr;
@@ -122,7 +128,7 @@ int comm_block_begin(Ctx* c, double* F, unsigned mask, bool migrate);
 int comm_block_end(Ctx* c);
 int comm_init(Ctx* c, const void* id128);                            // particles that crossed a slab face change rank
 // movers with dest -1 / -2 (left through the low / high z face) are copied to the send buffers
-int comm_collect_leavers(Ctx* c, Species& s, double* const mx[3], double* const mv[3], const int* dest,
+int comm_collect_leavers(Ctx* c, Species& s, double* const mx[3], double* const mv[3], int* dest,
                          const unsigned* n, unsigned cap);
 int comm_allreduce_sum(Ctx* c, double* v, int n);
 void comm_destroy(Ctx* c);

@@ -640,14 +640,20 @@ __global__ void __launch_bounds__(kThreads, 2)
   cp_async_wait<0>();
 }
 
-// movers -> their new bin (or the tail when the bin is full)
+// movers -> their new bin (or the tail when the bin is full).  Only destinations inside [lo0, hi0) or [lo1, hi1) are
+// filed (a split axis block must not put a particle into a cell that has not run yet); a filed entry is marked done
+// (dest = kMoverDone), the others stay in the list for a later call.
 __global__ void __launch_bounds__(256)
     k_insert_movers(MoverList mv, ParticleSoA b, const long* __restrict__ start, int* __restrict__ count,
-                    ParticleSoA tail, unsigned long long* __restrict__ tail_n, long tail_cap, int* __restrict__ flags) {
+                    ParticleSoA tail, unsigned long long* __restrict__ tail_n, long tail_cap, int* __restrict__ flags,
+                    unsigned lo0, unsigned hi0, unsigned lo1, unsigned hi1) {
   const unsigned n = min(*mv.n, mv.cap);
   for (unsigned m = blockIdx.x * blockDim.x + threadIdx.x; m < n; m += gridDim.x * blockDim.x) {
     const int dest = mv.dest[m];
-    if (dest < 0) continue;  // handled by the migration kernels (comm.cu)
+    if (dest < 0) continue;  // leavers: handled by the migration kernels (comm.cu); kMoverDone: already filed
+    const unsigned ud = (unsigned)dest;
+    if (!((ud >= lo0 && ud < hi0) || (ud >= lo1 && ud < hi1))) continue;
+    mv.dest[m] = kMoverDone;
     const int cap = (int)(start[dest + 1] - start[dest]);
     const int slot = atomicAdd(&count[dest], 1);
     if (slot < cap) {
@@ -1435,7 +1441,8 @@ int engine_theta_axis(Ctx* c, Species& s, int comp, double dt) {
   launch_theta_axis_direct(c, s.d, s.capd, s.d_nd, s.q, s.m, comp, dt);
   int nb = (int)((e->mv.cap + 255) / 256);
   if (nb > c->sm_count * 8) nb = c->sm_count * 8;
-  k_insert_movers<<<nb, 256, 0, c->stream>>>(e->mv, s.b, s.start, s.count, s.d, s.d_nd, s.capd, c->d_flags);
+  k_insert_movers<<<nb, 256, 0, c->stream>>>(e->mv, s.b, s.start, s.count, s.d, s.d_nd, s.capd, c->d_flags, 0u,
+                                             0xffffffffu, 0u, 0u);
   c->launches++;
   if (c->cfg.nranks > 1 && comp == 2) {
     int rc = comm_collect_leavers(c, s, e->mv.x, e->mv.v, e->mv.dest, e->mv.n, e->mv.cap);
@@ -1460,11 +1467,14 @@ int engine_axis_block(Ctx* c, Species& s, double h, int part, int nb) {
   if (!s.binned) return SPIC_OK;
   EngineState* e = eng(c);
   int rc;
-  const long plane = (long)c->g.n[0] * c->g.n[1];
+  const unsigned plane = (unsigned)c->g.n[0] * (unsigned)c->g.n[1], ncell = (unsigned)c->g.cells();
   const bool split = part != 0 && 2 * nb < c->g.n[2];
   if (part == 2 && !split) return SPIC_OK;  // (thin slab: part 1 covered every cell)
-  const long cells = !split ? c->g.cells() : (part == 1 ? 2 * nb * plane : c->g.cells() - 2 * nb * plane);
-  const unsigned list_cap = fused_list_cap(c, cells);
+  // Split block: part 1 (slab-face planes) fills a short prefix of the mover list and files only the movers that end
+  // in its own planes; those that entered the interior stay in the list (a particle filed there now would be pushed
+  // a second time by part 2), part 2 appends behind them and the final call files everything that is left.
+  const bool first_of_two = split && part == 1;
+  const unsigned list_cap = first_of_two ? fused_list_cap(c, 2L * nb * plane) : e->mv.cap;
   if ((rc = fused_axis_block(c, s, h, part, nb, list_cap))) return rc;
   // the overflow tail takes the general per-particle code BEFORE new overflow can join it
   if (part != 2 && (rc = fused_axis_tail(c, s, h))) return rc;
@@ -1473,15 +1483,21 @@ int engine_axis_block(Ctx* c, Species& s, double h, int part, int nb) {
   mv.cap = list_cap;
   int nbk = (int)((list_cap + 255) / 256);
   if (nbk > c->sm_count * 8) nbk = c->sm_count * 8;
-  k_insert_movers<<<nbk, 256, 0, c->stream>>>(mv, s.b, s.start, s.count, s.d, s.d_nd, s.capd, c->d_flags);
+  const unsigned nbp = (unsigned)nb * plane;
+  if (first_of_two)
+    k_insert_movers<<<nbk, 256, 0, c->stream>>>(mv, s.b, s.start, s.count, s.d, s.d_nd, s.capd, c->d_flags, 0u, nbp,
+                                                ncell - nbp, ncell);
+  else
+    k_insert_movers<<<nbk, 256, 0, c->stream>>>(mv, s.b, s.start, s.count, s.d, s.d_nd, s.capd, c->d_flags, 0u,
+                                                0xffffffffu, 0u, 0u);
   c->launches++;
-  // movers that left the slab (dest -1 / -2) -> this species' migration messages; none can come from the interior
-  // part (a particle moves < 2 cells in a block and nb >= 2)
+  // movers that left the slab (dest -1 / -2) -> this species' migration messages (and marked done); none can come
+  // from the interior part (a particle moves < 2 cells in a block and nb >= 2)
   if (c->cfg.nranks > 1 && part != 2) {
     rc = comm_collect_leavers(c, s, e->mv.x, e->mv.v, e->mv.dest, e->mv.n, list_cap);
     if (rc) return rc;
   }
-  SPIC_CUDA_CHECK(c, cudaMemsetAsync(e->mv.n, 0, sizeof(unsigned), c->stream));
+  if (!first_of_two) SPIC_CUDA_CHECK(c, cudaMemsetAsync(e->mv.n, 0, sizeof(unsigned), c->stream));
   return SPIC_OK;
 }
 
@@ -1622,6 +1638,10 @@ int engine_set_option(Ctx* c, const char* name, double value) {
   }
   if (!strcmp(name, "pushve_kernel")) {
     e->pushve_kernel = (int)value;
+    return SPIC_OK;
+  }
+  if (!strcmp(name, "tma")) {
+    e->tma = value != 0;
     return SPIC_OK;
   }
   if (!strcmp(name, "overlap")) {

@@ -40,6 +40,8 @@
 // Only for fully periodic boxes (walls need the reference's order around MABC, hpp:516).  With z slabs over
 // several ranks the guard width must be W + 1: a particle that left the slab in Theta_z finishes its
 // Theta_y, Theta_x one cell outside before it migrates (Redistribute once per block, hpp:368).
+#include <cuda.h>  // CUtensorMap (the encoder is fetched with cudaGetDriverEntryPoint: no link-time libcuda)
+
 #include <cub/device/device_radix_sort.cuh>
 
 #include "engine.cuh"
@@ -72,6 +74,7 @@ struct BlockLayout {
   static constexpr int NW1 = I::NW1, NWP = I::NWP;
   static constexpr int NS = NW1 * NW1 * NW1;            // stencil points per B component
   static constexpr int SB = 3 * NS;                     // one stencil buffer [comp][k][j][i]
+  static constexpr int SBS = (SB + 15) / 16 * 16;       // its stride: both buffers on 128-byte boundaries (TMA target)
   static constexpr int SP = 6 * 32;                     // one particle batch
   // deposition record a[NW1] b[NW1] I[NWP] (+ pad).  W8: 12 doubles = 24 banks, and every group of four records
   // is followed by 2 pad doubles (rec()): the four records read together in one deposition iteration (one per
@@ -98,10 +101,45 @@ struct BlockLayout {
 #define SPIC_WARP_ALIGN 16  // doubles: every warp's buffer starts on a 128-byte boundary
 #endif
   static constexpr int PER_WARP =
-      (kTableDoubles + SP + 2 * SB + SWA + SA + SPIC_WARP_ALIGN - 1) / SPIC_WARP_ALIGN * SPIC_WARP_ALIGN;
+      (kTableDoubles + SP + 2 * SBS + SWA + SA + SPIC_WARP_ALIGN - 1) / SPIC_WARP_ALIGN * SPIC_WARP_ALIGN;
   static_assert(SB % 2 == 0 && SW % 2 == 0 && NW1 % 2 == 0 && kTableDoubles % 2 == 0,
                 "16-byte alignment of the sub-buffers");
 };
+
+// ---- TMA staging (option "tma"): bulk copies global -> shared that complete on a per-warp mbarrier ----------------
+SPIC_DI unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+SPIC_DI void mbar_init(unsigned long long* bar, unsigned count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+  asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+}
+SPIC_DI void mbar_expect_tx(unsigned long long* bar, unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+SPIC_DI void mbar_wait(unsigned long long* bar, unsigned parity) {
+  unsigned done = 0;
+  while (!done) {
+    asm volatile(
+        "{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}\n"
+        : "=r"(done)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+  }
+}
+// n bytes (multiple of 16; source and destination 16-byte aligned) global -> shared: one UBLKCP
+SPIC_DI void tma_copy_1d(void* dst, const void* src, unsigned bytes, unsigned long long* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n" ::"r"(
+                   smem_u32(dst)),
+               "l"(src), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+// one box of a 4-D tensor map (x, y, z, component) -> shared (128-byte aligned, dense [c][z][y][x]): one UTMALDG
+SPIC_DI void tma_load_4d(void* dst, const CUtensorMap* map, int x, int y, int z, int comp, unsigned long long* bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5}], [%6];\n" ::"r"(
+          smem_u32(dst)),
+      "l"(map), "r"(x), "r"(y), "r"(z), "r"(comp), "r"(smem_u32(bar))
+      : "memory");
+}
 
 // sum_k w2[k] sum_j w1[j] sum_i w0[i] blk[k][j][i] over a staged NW1^3 block (i fastest); rows are read
 // with LDS.128 (every lane reads the same address: broadcast).  First terms are plain products:
@@ -269,24 +307,30 @@ SPIC_DI void flush_component(const double* sAccA, double* __restrict__ E, long b
     }
 }
 
-template <class I>
+// TMA = true: the particle rows of a batch travel as six bulk copies (UBLKCP) and the cell's 4x4x4x3 B stencil as ONE
+// box of a 4-D tensor map (UTMALDG), issued by lane 0 and completed on the warp's mbarrier; TMA = false: cp.async
+// (LDGSTS) from every lane.  Same shared-memory layout, same arithmetic.
+template <class I, bool TMA>
 __global__ void __launch_bounds__(kThreads, 2)
     k_axis_block(Grid g, ParticleSoA p, const long* __restrict__ start, int* __restrict__ count,
                  double* __restrict__ E, const double* __restrict__ B, double q, double qm, double h, MoverList mv,
-                 int* __restrict__ flags, CellRanges rg, unsigned* __restrict__ work, unsigned* __restrict__ ekey) {
+                 int* __restrict__ flags, CellRanges rg, unsigned* __restrict__ work, unsigned* __restrict__ ekey,
+                 const __grid_constant__ CUtensorMap mapB) {
   constexpr int NW1 = I::NW1, NWP = I::NWP;
   using Lay = BlockLayout<I>;
-  constexpr int NS = Lay::NS, SB = Lay::SB, SP = Lay::SP, NACC = Lay::NACC, NSUB = Lay::NSUB;
+  constexpr int NS = Lay::NS, SB = Lay::SB, SBS = Lay::SBS, SP = Lay::SP, NACC = Lay::NACC, NSUB = Lay::NSUB;
   constexpr unsigned kNone = 0xffffffffu;
-  extern __shared__ __align__(16) double smem[];
+  extern __shared__ __align__(128) double smem[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   double* sWarp = smem + warp * Lay::PER_WARP;
-  long* tStart = reinterpret_cast<long*>(sWarp);           // [2][kChunk]  bin starts of two chunks
-  int* tCnt = reinterpret_cast<int*>(sWarp + 2 * kChunk);   // [2][kChunk]  bin counts
-  double* sH = sWarp + 3 * kChunk;                          // [3] (+ pad)  the cell's global coordinates
-  double* sPart = sWarp + kTableDoubles;                    // [6][32]
-  double* sBst = sPart + SP;                                // [2][3][NW1][NW1][NW1]
-  double* sW = sBst + 2 * SB;                               // [32][SW]
+  double* sBst = sWarp;                                     // [2][3][NW1][NW1][NW1] (stride SBS: 128-byte aligned)
+  double* sPart = sBst + 2 * SBS;                           // [6][32]
+  double* sTab = sPart + SP;
+  long* tStart = reinterpret_cast<long*>(sTab);            // [2][kChunk]  bin starts of two chunks
+  int* tCnt = reinterpret_cast<int*>(sTab + 2 * kChunk);    // [2][kChunk]  bin counts
+  double* sH = sTab + 3 * kChunk;                           // [3]  the cell's global coordinates
+  unsigned long long* sBar = reinterpret_cast<unsigned long long*>(sH + 3);  // the warp's mbarrier (TMA staging)
+  double* sW = sTab + kTableDoubles;                        // [32][SW]
   double* sAcc = sW + Lay::SWA;                             // [3][NACC][32]
   const long st[3] = {1, g.pj, g.pk};
   const double nq = -q;  // -E_coef (hpp:114; Ics = Cs = 1)
@@ -329,6 +373,31 @@ __global__ void __launch_bounds__(kThreads, 2)
   // stage batch `off` of cell (chunk, tb, ci); with off == 0 also the cell's stencil into buffer bb
   auto stage = [&](unsigned cbase, int tb, int ci, int off, int bb) {
     const int n = tCnt[tb * kChunk + ci];
+    if (TMA) {
+      if (lane == 0) {
+        // rows of min(32, n - off) doubles, rounded up to 16 bytes (bins are 64-byte aligned with an even capacity)
+        const int rem = n - off;
+        const unsigned rowb = rem <= 0 ? 0u : (unsigned)(((rem < 32 ? rem : 32) + 1) & ~1) * 8u;
+        const bool stencil = off == 0 && n > 0;
+        mbar_expect_tx(sBar, 6u * rowb + (stencil ? (unsigned)(SB * sizeof(double)) : 0u));
+        if (rowb) {
+          const long src = tStart[tb * kChunk + ci] + off;
+          tma_copy_1d(sPart + 0 * 32, p.x[0] + src, rowb, sBar);
+          tma_copy_1d(sPart + 1 * 32, p.x[1] + src, rowb, sBar);
+          tma_copy_1d(sPart + 2 * 32, p.x[2] + src, rowb, sBar);
+          tma_copy_1d(sPart + 3 * 32, p.v[0] + src, rowb, sBar);
+          tma_copy_1d(sPart + 4 * 32, p.v[1] + src, rowb, sBar);
+          tma_copy_1d(sPart + 5 * 32, p.v[2] + src, rowb, sBar);
+        }
+        if (stencil) {
+          int cc[3];
+          corner_of(cbase + ci, cc);
+          tma_load_4d(sBst + bb * SBS, &mapB, cc[0] + g.ng + 1 - I::W, cc[1] + g.ng + 1 - I::W, cc[2] + g.ng + 1 - I::W, 0,
+                      sBar);
+        }
+      }
+      return;
+    }
     if (off + lane < n) {
       const long src = tStart[tb * kChunk + ci] + off + lane;
       double* d = sPart + lane;
@@ -342,7 +411,7 @@ __global__ void __launch_bounds__(kThreads, 2)
     if (off == 0 && n > 0) {
       int cc[3];
       const double* src = B + corner_of(cbase + ci, cc);
-      double* d = sBst + bb * SB;
+      double* d = sBst + bb * SBS;
 #pragma unroll
       for (int s = lane; s < SB; s += 32) {
         const int comp = s / NS, r = s % NS;
@@ -355,6 +424,11 @@ __global__ void __launch_bounds__(kThreads, 2)
   // ---- prologue: first chunk's table, then the second chunk's table and the first batch ------------
   unsigned cbase = to_base(__shfl_sync(kFull, grab(), 0));  // first cell of the current chunk
   if (cbase == kNone) return;
+  unsigned phase = 0;  // parity of the mbarrier phase the next wait completes on
+  if (TMA) {
+    if (lane == 0) mbar_init(sBar, 1);
+    __syncwarp();
+  }
   load_table(cbase, 0);
   cp_async_commit();
   unsigned pending = grab();  // lane 0 holds the id of the chunk after next
@@ -374,6 +448,10 @@ __global__ void __launch_bounds__(kThreads, 2)
 
   while (more) {
     cp_async_wait<0>();  // this batch (at a new cell its stencil, at a new chunk the next table) has landed
+    if (TMA) {
+      mbar_wait(sBar, phase);
+      phase ^= 1;
+    }
     __syncwarp();
     if (off == 0) {  // new cell
       int cc[3];
@@ -409,7 +487,7 @@ __global__ void __launch_bounds__(kThreads, 2)
     cp_async_commit();
 
     if (nvalid > 0) {
-      const double* sB = sBst + bb * SB;
+      const double* sB = sBst + bb * SBS;
       const int nit = (nvalid + NSUB - 1) / NSUB;
       const bool first = off == 0;
       bool alive = valid;
@@ -599,6 +677,60 @@ __global__ void __launch_bounds__(128)
   }
 }
 
+// 4-D tensor map over a guarded field [comp][k][j][i] with a box of NW1^3 x 3 (the B stencil of one cell): dimensions
+// and strides of the Grid, no swizzle, no interleave (the kernel reads the box as a dense array).
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+int make_stencil_map(Ctx* c, const double* F, int nw1, CUtensorMap* out) {
+  static EncodeTiledFn encode = nullptr;
+  if (!encode) {
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) != cudaSuccess || !fn) {
+      c->err = "cuTensorMapEncodeTiled is not available from this driver";
+      return SPIC_ECUDA;
+    }
+    encode = reinterpret_cast<EncodeTiledFn>(fn);
+  }
+  const Grid& g = c->g;
+  const cuuint64_t dims[4] = {(cuuint64_t)g.pj, (cuuint64_t)(g.n[1] + 2 * g.ng), (cuuint64_t)(g.n[2] + 2 * g.ng), 3};
+  const cuuint64_t strides[3] = {(cuuint64_t)g.pj * 8, (cuuint64_t)g.pk * 8, (cuuint64_t)g.pc * 8};
+  const cuuint32_t box[4] = {(cuuint32_t)nw1, (cuuint32_t)nw1, (cuuint32_t)nw1, 3};
+  const cuuint32_t estr[4] = {1, 1, 1, 1};
+  const CUresult r = encode(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 4, const_cast<double*>(F), dims, strides, box, estr,
+                            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    c->err = "cuTensorMapEncodeTiled failed (" + std::to_string((int)r) + ")";
+    return SPIC_ECUDA;
+  }
+  return SPIC_OK;
+}
+
+template <class I, bool TMA>
+int launch_block_t(Ctx* c, Species& s, double h, const CellRanges& rg, const MoverList& mv, long want) {
+  EngineState* e = eng(c);
+  CUtensorMap map;
+  memset(&map, 0, sizeof map);
+  if (TMA) {
+    if (!e->map_B_ok) {
+      int rc = make_stencil_map(c, c->B, I::NW1, reinterpret_cast<CUtensorMap*>(e->map_B));
+      if (rc) return rc;
+      e->map_B_ok = true;
+    }
+    memcpy(&map, e->map_B, sizeof map);
+  }
+  const size_t smem = sizeof(double) * kWarps * BlockLayout<I>::PER_WARP;
+  static unsigned long long attr = 0;
+  if (smem_attr_needed(attr, c->cfg.device))
+    SPIC_CUDA_CHECK(c, cudaFuncSetAttribute(k_axis_block<I, TMA>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  k_axis_block<I, TMA><<<(int)want, kThreads, smem, c->stream>>>(c->g, s.b, s.start, s.count, c->E, c->B, s.q, s.q / s.m,
+                                                                 h, mv, c->d_flags, rg, e->block_work, e->cont_key, map);
+  c->launches++;
+  return SPIC_OK;
+}
+
 template <class I>
 int launch_block(Ctx* c, Species& s, double h, const CellRanges& rg, unsigned list_cap) {
   EngineState* e = eng(c);
@@ -619,14 +751,7 @@ int launch_block(Ctx* c, Species& s, double h, const CellRanges& rg, unsigned li
   SPIC_CUDA_CHECK(c, cudaMemsetAsync(e->cont_key, 0xff, sizeof(unsigned) * (size_t)list_cap, c->stream));
   MoverList mv = e->mv;
   mv.cap = list_cap;  // (this launch may use a prefix of the list only: what the continuation then sorts)
-  const size_t smem = sizeof(double) * kWarps * BlockLayout<I>::PER_WARP;
-  static unsigned long long attr = 0;
-  if (smem_attr_needed(attr, c->cfg.device))
-    SPIC_CUDA_CHECK(c, cudaFuncSetAttribute(k_axis_block<I>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  k_axis_block<I><<<(int)want, kThreads, smem, c->stream>>>(c->g, s.b, s.start, s.count, c->E, c->B, s.q, s.q / s.m,
-                                                            h, mv, c->d_flags, rg, e->block_work, e->cont_key);
-  c->launches++;
-  return SPIC_OK;
+  return e->tma ? launch_block_t<I, true>(c, s, h, rg, mv, want) : launch_block_t<I, false>(c, s, h, rg, mv, want);
 }
 
 }  // namespace

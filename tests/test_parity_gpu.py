@@ -368,17 +368,20 @@ def test_fused_axis_block_and_reference_schedule(fuse, interp, mode):
     print(fuse, interp, mode, errs, kt)
 
 
+@pytest.mark.parametrize("tma", [0, 1])
 @pytest.mark.parametrize("ppc", [1, 7, 8, 33, 64, 65])
-def test_fused_block_batch_shapes(ppc):
+def test_fused_block_batch_shapes(ppc, tma):
     """The fused axis block over bins of 1 ... 65+ particles: empty lanes, exactly full batches, a cell of 65
     (32 + 32 + 1), both W, warm plasma so that the counts drift apart and particles are ejected to the continuation;
-    Gauss residual constant to round-off."""
+    Gauss residual constant to round-off.  tma = 1: batches staged with cp.async.bulk + a 4-D tensor map (odd row
+    lengths are rounded up to 16 bytes) instead of cp.async -- same results to the bit."""
     for interp, n_cell, vth, order in ((0, (8, 6, 5), 0.1, 4), (1, (9, 7, 3), 0.15, 2), (0, (16, 2, 2), 0.05, 2)):
         E, B = util.rng_fields(n_cell, 5, 0.3)
         parts = util.plasma(n_cell, ppc, vth, 5)
         o = ora.best_oracle(n_cell, interp=interp)
         s = spic().Simulation(n_cell, interp=interp)
         s.set_option("time_kernels", 1)
+        s.set_option("tma", tma)
         for t in (o, s):
             util.load_state(t, E, B, parts, -1.0 / ppc, 100.0 / ppc)
         g0 = s.gauss_residual()
