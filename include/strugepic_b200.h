@@ -46,7 +46,9 @@ extern "C" {
 /* The user's own W1 / Wp / I_W1 / I_Wp / interpolation_range, linked into the library the way the
  * reference lets a user override its weak defaults (include/strugepic_w.hpp:12-16;
  * src/interpolation/interpolation.cpp:10,14,20,89): see include/strugepic_user_w.h.  The stock
- * library carries the cubic B-spline pair in this slot.  One GPU, thread-per-particle engine. */
+ * library carries the cubic B-spline pair in this slot.  Runs on the same kernels as the shipped variants (fused axis
+ * block, particle-stream kernels, every engine, any number of ranks): the W evaluations are calls into the user's
+ * device functions instead of inlined polynomials. */
 #define SPIC_INTERP_USER 2
 
 #define SPIC_FIELD_E 0

@@ -49,20 +49,23 @@ def _stale(out, deps):
 # linked with each other at the final link; USER_W_DEFAULT is replaced by the user's file with --user-w
 RDC = {"user_w.cu", "user_w_default.cu"}
 USER_W_DEFAULT = "user_w_default.cu"
+# the warp-per-cell kernels over the user-supplied W: these sources are compiled a second time with -DSPIC_USER_W_TU
+# (relocatable device code, entry points prefixed user_; csrc/engine.cuh)
+USER_W_TWICE = ["particles_fused.cu", "particles_stream.cu"]
 
 
-def _compile(src, verbose, path=None, obj=None):
-    rdc = src in RDC or path is not None
-    obj = obj or os.path.join(OBJ, src[:-3] + ".o")
+def _compile(src, verbose, path=None, obj=None, user_tu=False):
+    rdc = src in RDC or path is not None or user_tu
+    obj = obj or os.path.join(OBJ, ("userw_tu_" if user_tu else "") + src[:-3] + ".o")
     path = path or os.path.join(CSRC, src)
     if not _stale(obj, [path] + _headers()):
         return obj, ""
-    cmd = [NVCC] + ARCH + FLAGS + (["-rdc=true", "-I", os.path.join(HERE, "..", "include")] if rdc else []) + [
-        "-x", "cu", "-c", path, "-o", obj]
+    cmd = [NVCC] + ARCH + FLAGS + (["-rdc=true", "-I", os.path.join(HERE, "..", "include")] if rdc else []) + (
+        ["-DSPIC_USER_W_TU"] if user_tu else []) + ["-x", "cu", "-c", path, "-o", obj]
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:
         raise RuntimeError("nvcc failed for %s:\n%s" % (src, r.stderr[-6000:]))
-    log = os.path.join(OBJ, src[:-3] + ".ptxas.log")
+    log = os.path.join(OBJ, ("userw_tu_" if user_tu else "") + src[:-3] + ".ptxas.log")
     with open(log, "w") as f:
         f.write(r.stderr)
     return obj, (r.stderr if verbose else "")
@@ -78,8 +81,9 @@ def build(force=False, verbose=False, user_w=None, out=None):
         for f in os.listdir(OBJ):
             os.remove(os.path.join(OBJ, f))
     srcs = [s for s in _sources() if not (user_w and s == USER_W_DEFAULT)]
+    jobs = [(s, False) for s in srcs] + [(s, True) for s in USER_W_TWICE]
     with ThreadPoolExecutor(max_workers=8) as ex:
-        res = list(ex.map(lambda s: _compile(s, verbose), srcs))
+        res = list(ex.map(lambda j: _compile(j[0], verbose, user_tu=j[1]), jobs))
     lib = LIB
     if user_w:
         lib = out or os.path.join(LIBDIR, "libstrugepic_b200_userw.so")

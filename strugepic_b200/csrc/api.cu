@@ -169,8 +169,6 @@ int spic_create(const spic_config* cfg, spic_ctx** out) {
   const int W = spic_interpolation_range(cfg->interp);
   if (W != 1 && W != 2) return fail(nullptr, SPIC_EINVAL, "spic_user_interpolation_range must be 1 or 2");
   const int nranks = cfg->nranks <= 0 ? 1 : cfg->nranks;
-  if (cfg->interp == SPIC_INTERP_USER && nranks > 1)
-    return fail(nullptr, SPIC_EINVAL, "SPIC_INTERP_USER runs on one GPU (thread-per-particle engine)");
   // default guard width: the interpolation range; one more with z slabs on a periodic box, so that the fused axis
   // block can let a particle finish its sub-flows one cell outside the slab before it migrates
   const bool all_periodic = cfg->periodic[0] && cfg->periodic[1] && cfg->periodic[2];
@@ -197,8 +195,6 @@ int spic_create(const spic_config* cfg, spic_ctx** out) {
   c->cfg = *cfg;
   c->cfg.ng = ng;
   c->cfg.nranks = nranks;
-  // the warp-per-cell kernels are specialised per tap for the two shipped variants; a user W runs thread per particle
-  if (cfg->interp == SPIC_INTERP_USER) c->cfg.engine = SPIC_ENGINE_DIRECT;
   c->W = W;
   c->sm_count = prop.multiProcessorCount;
   Grid& g = c->g;

@@ -3,6 +3,22 @@
 #pragma once
 #include "spic_internal.cuh"
 
+// ---- the user-W slot on the warp-per-cell kernels ---------------------------------------------------------------
+// particles_fused.cu and particles_stream.cu are compiled TWICE: whole-program for the two shipped interpolation
+// variants, and once more with -DSPIC_USER_W_TU -rdc=true, where the same kernels are instantiated for InterpUser<R>
+// (interp_user.cuh: the W functions are external device functions, device-linked with the user's file) and the
+// public entry points carry the prefix user_.  The whole-program entry points forward SPIC_INTERP_USER to those.
+#ifdef SPIC_USER_W_TU
+#include "interp_user.cuh"
+#define SPIC_PUBLIC(name) user_##name
+#define SPIC_BY_INTERP(ctx, FN, ...) \
+  (spic_user_interpolation_range == 2 ? FN<InterpUser<2>>(__VA_ARGS__) : FN<InterpUser<1>>(__VA_ARGS__))
+#else
+#define SPIC_PUBLIC(name) name
+#define SPIC_BY_INTERP(ctx, FN, ...) \
+  ((ctx)->cfg.interp == SPIC_INTERP_P8R2 ? FN<InterpP8R2>(__VA_ARGS__) : FN<InterpPWL>(__VA_ARGS__))
+#endif
+
 namespace spic {
 
 constexpr int kMoverDone = -3;  // mover-list entry that has been filed / packed already
@@ -33,11 +49,9 @@ struct EngineState {
   // nranks > 1: 1 = the slab-face cells of an axis block run first and their halo sums / migration travel on a side
   // stream while the interior cells compute; 0 = every exchange in stream order behind the whole block
   int overlap = 1;
-  // 1: the fused axis block stages its batches with TMA (cp.async.bulk + a 4-D tensor map for the B stencil, completed
-  // on an mbarrier) instead of cp.async
+  // 1: the fused axis block stages the particle rows of its batches with TMA bulk copies (cp.async.bulk completed on
+  // an mbarrier) instead of cp.async
   int tma = 0;
-  alignas(64) unsigned char map_B[128];  // CUtensorMap of the B stencil box
-  bool map_B_ok = false;
   unsigned* block_work = nullptr;   // chunk counter of the fused axis-block kernel
   // continuation of the ejected particles: sort key (home cell) per mover-list entry + radix-sort buffers
   unsigned* cont_key = nullptr;
@@ -86,6 +100,12 @@ __device__ __forceinline__ void lds_row(const double* src, double (&out)[N]) {
 // ---- particle-stream kernels (particles_stream.cu) ------------------------------------------
 int stream_theta_axis(Ctx* c, Species& s, int comp, double dt);
 int stream_push_v_e(Ctx* c, Species& s, double dt);
+// the same entry points over the user-supplied W (second compilation of the two files, see above)
+int user_stream_theta_axis(Ctx* c, Species& s, int comp, double dt);
+int user_stream_push_v_e(Ctx* c, Species& s, double dt);
+int user_fused_axis_block(Ctx* c, Species& s, double h, int part, int nb, unsigned list_cap);
+int user_fused_axis_continue(Ctx* c, Species& s, double h, unsigned list_cap);
+int user_fused_axis_tail(Ctx* c, Species& s, double h);
 
 // ---- fused axis block (particles_fused.cu) ------------------------------------------------
 bool fused_block_supported(const Ctx* c);                 // fully periodic box (guard width W + 1 with z slabs)

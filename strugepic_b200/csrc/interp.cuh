@@ -120,6 +120,8 @@ struct InterpP8R2 {
   static SPIC_HDI double wp_in(double a) { return wp_piece<2 - T>(a); }
   template <int T>
   static SPIC_HDI double iwp_in(double a) { return iwp_piece<2 - T>(a); }
+  template <int T>
+  static SPIC_HDI double iwp_seg_in(double a, double b) { return iwp_in<T>(b) - iwp_in<T>(a); }
 
   // general-argument forms (diagnostics, tests): dynamic piece like the reference
   static SPIC_HDI double W1(double x) {
@@ -193,6 +195,8 @@ struct InterpPWL {
   static SPIC_HDI double wp_in(double a) { return Wp(a); }
   template <int T>
   static SPIC_HDI double iwp_in(double a) { return IWp_cdf(a); }
+  template <int T>
+  static SPIC_HDI double iwp_seg_in(double a, double b) { return IWp_cdf(b) - IWp_cdf(a); }
 };
 
 // Fill w1[0..NW1) and wp[0..NWP) for a particle at normalised coordinate x in cell c:
@@ -274,11 +278,11 @@ template <class I>
 SPIC_HDI void eval_iwp_in(double s, double e, double hc, double (&out)[I::NWP]) {
   if (I::NWP == 3) {
     const double c0 = hc - 1.0, c2 = hc + 1.0;
-    out[0] = I::template iwp_in<0>(e - c0) - I::template iwp_in<0>(s - c0);
-    out[I::NWP > 1 ? 1 : 0] = I::template iwp_in<1>(e - hc) - I::template iwp_in<1>(s - hc);
-    out[I::NWP > 2 ? 2 : 0] = I::template iwp_in<2>(e - c2) - I::template iwp_in<2>(s - c2);
+    out[0] = I::template iwp_seg_in<0>(s - c0, e - c0);
+    out[I::NWP > 1 ? 1 : 0] = I::template iwp_seg_in<1>(s - hc, e - hc);
+    out[I::NWP > 2 ? 2 : 0] = I::template iwp_seg_in<2>(s - c2, e - c2);
   } else {
-    out[0] = I::template iwp_in<0>(e - hc) - I::template iwp_in<0>(s - hc);
+    out[0] = I::template iwp_seg_in<0>(s - hc, e - hc);
   }
 }
 

@@ -1423,6 +1423,7 @@ int engine_theta_axis(Ctx* c, Species& s, int comp, double dt) {
     KernelTimer t(c, KT_AXIS);
     int variant = e->axis_kernel;
     if (variant == 0) variant = s.n_total < 40 * c->g.cells() ? 3 : 2;
+    if (c->cfg.interp == SPIC_INTERP_USER) variant = 3;  // (the user-W slot exists for the stream and fused kernels)
     if (variant == 3) {
       const int rc = stream_theta_axis(c, s, comp, dt);
       if (rc) return rc;
@@ -1525,7 +1526,7 @@ int engine_push_v_e(Ctx* c, Species& s, double dt) {
   const double coef = dt * s.q / s.m;  // hpp:267
   {
     KernelTimer t(c, KT_PUSHVE);
-    if (e->pushve_kernel == 3 || e->pushve_kernel == 4 || e->pushve_kernel == 0) {
+    if (e->pushve_kernel == 3 || e->pushve_kernel == 4 || e->pushve_kernel == 0 || c->cfg.interp == SPIC_INTERP_USER) {
       const int rc = stream_push_v_e(c, s, dt);
       if (rc) return rc;
       c->launches--;  // counted below
@@ -1565,9 +1566,43 @@ int engine_kinetic(Ctx* c, Species& s, double* acc) {
 
 // Gauss diagnostic: rho of the binned particles, cell-centric (one reduction per stencil point and cell); the tail
 // takes the thread-per-particle kernel.  rho = one guarded component.
+// the binned positions of a species as one packed list (diagnostics over a user-supplied W: the thread-per-particle
+// kernels of the user-W slot then do the work); the caller frees tmp.x[0..2]
+static int pack_positions(Ctx* c, Species& s, ParticleSoA& tmp, long* live) {
+  const long ncell = c->g.cells();
+  int rc = engine_count(c, s, live);
+  if (rc) return rc;
+  long* prefix = nullptr;
+  SPIC_CUDA_CHECK(c, cudaMalloc(&prefix, sizeof(long) * (ncell + 1)));
+  cub::TransformInputIterator<long, ToLong, const int*> it(s.count, ToLong());
+  size_t bytes = 0;
+  cub::DeviceScan::ExclusiveSum(nullptr, bytes, it, prefix, (int)ncell, c->stream);
+  if ((rc = ensure_cub(c, bytes))) return rc;
+  cub::DeviceScan::ExclusiveSum(eng(c)->cub_tmp, bytes, it, prefix, (int)ncell, c->stream);
+  for (int d = 0; d < 3; ++d) {
+    SPIC_CUDA_CHECK(c, cudaMalloc(&tmp.x[d], sizeof(double) * (size_t)(*live + 1)));
+    k_pack_bins<<<grid_warps(c, ncell), 256, 0, c->stream>>>(s.b.x[d], s.start, s.count, prefix, ncell, tmp.x[d]);
+    c->launches++;
+  }
+  SPIC_CUDA_CHECK(c, cudaStreamSynchronize(c->stream));
+  cudaFree(prefix);
+  return SPIC_OK;
+}
+
 int engine_deposit_rho(Ctx* c, Species& s, double* rho) {
   if (!s.binned) return SPIC_OK;
   const long ncell = c->g.cells();
+  if (c->cfg.interp == SPIC_INTERP_USER) {
+    ParticleSoA tmp{};
+    long live = 0;
+    int rc = pack_positions(c, s, tmp, &live);
+    if (rc) return rc;
+    launch_deposit_rho(c, tmp, live, nullptr, s.q, rho);
+    launch_deposit_rho(c, s.d, s.capd, s.d_nd, s.q, rho);
+    SPIC_CUDA_CHECK(c, cudaStreamSynchronize(c->stream));
+    for (int d = 0; d < 3; ++d) cudaFree(tmp.x[d]);
+    return SPIC_OK;
+  }
   if (c->cfg.interp == SPIC_INTERP_P8R2)
     k_rho_binned<InterpP8R2><<<grid_warps(c, ncell), 256, 0, c->stream>>>(c->g, s.b, s.start, s.count, ncell, -s.q, rho);
   else
@@ -1580,6 +1615,17 @@ int engine_deposit_rho(Ctx* c, Species& s, double* rho) {
 int engine_number_density(Ctx* c, Species& s, double* nd) {
   if (!s.binned) return SPIC_OK;
   const long ncell = c->g.cells();
+  if (c->cfg.interp == SPIC_INTERP_USER) {
+    ParticleSoA tmp{};
+    long live = 0;
+    int rc = pack_positions(c, s, tmp, &live);
+    if (rc) return rc;
+    launch_number_density(c, tmp, live, nullptr, nd);
+    launch_number_density(c, s.d, s.capd, s.d_nd, nd);
+    SPIC_CUDA_CHECK(c, cudaStreamSynchronize(c->stream));
+    for (int d = 0; d < 3; ++d) cudaFree(tmp.x[d]);
+    return SPIC_OK;
+  }
   if (c->cfg.interp == SPIC_INTERP_P8R2)
     k_number_density_binned<InterpP8R2><<<grid_warps(c, ncell), 256, 0, c->stream>>>(c->g, s.b, s.start, s.count, ncell, nd);
   else

@@ -40,8 +40,6 @@
 // Only for fully periodic boxes (walls need the reference's order around MABC, hpp:516).  With z slabs over
 // several ranks the guard width must be W + 1: a particle that left the slab in Theta_z finishes its
 // Theta_y, Theta_x one cell outside before it migrates (Redistribute once per block, hpp:368).
-#include <cuda.h>  // CUtensorMap (the encoder is fetched with cudaGetDriverEntryPoint: no link-time libcuda)
-
 #include <cub/device/device_radix_sort.cuh>
 
 #include "engine.cuh"
@@ -132,15 +130,6 @@ SPIC_DI void tma_copy_1d(void* dst, const void* src, unsigned bytes, unsigned lo
                "l"(src), "r"(bytes), "r"(smem_u32(bar))
                : "memory");
 }
-// one box of a 4-D tensor map (x, y, z, component) -> shared (128-byte aligned, dense [c][z][y][x]): one UTMALDG
-SPIC_DI void tma_load_4d(void* dst, const CUtensorMap* map, int x, int y, int z, int comp, unsigned long long* bar) {
-  asm volatile(
-      "cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5}], [%6];\n" ::"r"(
-          smem_u32(dst)),
-      "l"(map), "r"(x), "r"(y), "r"(z), "r"(comp), "r"(smem_u32(bar))
-      : "memory");
-}
-
 // sum_k w2[k] sum_j w1[j] sum_i w0[i] blk[k][j][i] over a staged NW1^3 block (i fastest); rows are read
 // with LDS.128 (every lane reads the same address: broadcast).  First terms are plain products:
 // fma(a, b, +0) has the same bits and would cost a zeroed register.
@@ -307,15 +296,14 @@ SPIC_DI void flush_component(const double* sAccA, double* __restrict__ E, long b
     }
 }
 
-// TMA = true: the particle rows of a batch travel as six bulk copies (UBLKCP) and the cell's 4x4x4x3 B stencil as ONE
-// box of a 4-D tensor map (UTMALDG), issued by lane 0 and completed on the warp's mbarrier; TMA = false: cp.async
-// (LDGSTS) from every lane.  Same shared-memory layout, same arithmetic.
+// TMA = true: the six particle rows of a batch travel as bulk copies (cp.async.bulk = UBLKCP) issued by lane 0 and
+// completed on the warp's mbarrier; TMA = false: cp.async (LDGSTS) from every lane.  Same shared-memory layout, same
+// arithmetic.  (The stencil box cannot be a tensor-map tile: see stage().)
 template <class I, bool TMA>
 __global__ void __launch_bounds__(kThreads, 2)
     k_axis_block(Grid g, ParticleSoA p, const long* __restrict__ start, int* __restrict__ count,
                  double* __restrict__ E, const double* __restrict__ B, double q, double qm, double h, MoverList mv,
-                 int* __restrict__ flags, CellRanges rg, unsigned* __restrict__ work, unsigned* __restrict__ ekey,
-                 const __grid_constant__ CUtensorMap mapB) {
+                 int* __restrict__ flags, CellRanges rg, unsigned* __restrict__ work, unsigned* __restrict__ ekey) {
   constexpr int NW1 = I::NW1, NWP = I::NWP;
   using Lay = BlockLayout<I>;
   constexpr int NS = Lay::NS, SB = Lay::SB, SBS = Lay::SBS, SP = Lay::SP, NACC = Lay::NACC, NSUB = Lay::NSUB;
@@ -378,8 +366,7 @@ __global__ void __launch_bounds__(kThreads, 2)
         // rows of min(32, n - off) doubles, rounded up to 16 bytes (bins are 64-byte aligned with an even capacity)
         const int rem = n - off;
         const unsigned rowb = rem <= 0 ? 0u : (unsigned)(((rem < 32 ? rem : 32) + 1) & ~1) * 8u;
-        const bool stencil = off == 0 && n > 0;
-        mbar_expect_tx(sBar, 6u * rowb + (stencil ? (unsigned)(SB * sizeof(double)) : 0u));
+        mbar_expect_tx(sBar, 6u * rowb);
         if (rowb) {
           const long src = tStart[tb * kChunk + ci] + off;
           tma_copy_1d(sPart + 0 * 32, p.x[0] + src, rowb, sBar);
@@ -389,16 +376,8 @@ __global__ void __launch_bounds__(kThreads, 2)
           tma_copy_1d(sPart + 4 * 32, p.v[1] + src, rowb, sBar);
           tma_copy_1d(sPart + 5 * 32, p.v[2] + src, rowb, sBar);
         }
-        if (stencil) {
-          int cc[3];
-          corner_of(cbase + ci, cc);
-          tma_load_4d(sBst + bb * SBS, &mapB, cc[0] + g.ng + 1 - I::W, cc[1] + g.ng + 1 - I::W, cc[2] + g.ng + 1 - I::W, 0,
-                      sBar);
-        }
       }
-      return;
-    }
-    if (off + lane < n) {
+    } else if (off + lane < n) {
       const long src = tStart[tb * kChunk + ci] + off + lane;
       double* d = sPart + lane;
       cp_async8(d + 0 * 32, p.x[0] + src);
@@ -408,6 +387,10 @@ __global__ void __launch_bounds__(kThreads, 2)
       cp_async8(d + 4 * 32, p.v[1] + src);
       cp_async8(d + 5 * 32, p.v[2] + src);
     }
+    // The 4x4x4x3 stencil box stays on cp.async in both variants: a tensor-map tile (UTMALDG) must start on a 16-byte
+    // boundary of the innermost dimension, and the box of a cell starts at x = cell + ng + 1 - W doubles -- odd for
+    // every other cell (scripts/micro/tma_probe3.cu, profiles/r02_tma_probe.txt: "illegal instruction" for a 24-byte
+    // start, fine for a 32-byte one).
     if (off == 0 && n > 0) {
       int cc[3];
       const double* src = B + corner_of(cbase + ci, cc);
@@ -677,56 +660,15 @@ __global__ void __launch_bounds__(128)
   }
 }
 
-// 4-D tensor map over a guarded field [comp][k][j][i] with a box of NW1^3 x 3 (the B stencil of one cell): dimensions
-// and strides of the Grid, no swizzle, no interleave (the kernel reads the box as a dense array).
-typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
-                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
-                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-int make_stencil_map(Ctx* c, const double* F, int nw1, CUtensorMap* out) {
-  static EncodeTiledFn encode = nullptr;
-  if (!encode) {
-    void* fn = nullptr;
-    cudaDriverEntryPointQueryResult qres;
-    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) != cudaSuccess || !fn) {
-      c->err = "cuTensorMapEncodeTiled is not available from this driver";
-      return SPIC_ECUDA;
-    }
-    encode = reinterpret_cast<EncodeTiledFn>(fn);
-  }
-  const Grid& g = c->g;
-  const cuuint64_t dims[4] = {(cuuint64_t)g.pj, (cuuint64_t)(g.n[1] + 2 * g.ng), (cuuint64_t)(g.n[2] + 2 * g.ng), 3};
-  const cuuint64_t strides[3] = {(cuuint64_t)g.pj * 8, (cuuint64_t)g.pk * 8, (cuuint64_t)g.pc * 8};
-  const cuuint32_t box[4] = {(cuuint32_t)nw1, (cuuint32_t)nw1, (cuuint32_t)nw1, 3};
-  const cuuint32_t estr[4] = {1, 1, 1, 1};
-  const CUresult r = encode(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 4, const_cast<double*>(F), dims, strides, box, estr,
-                            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
-                            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  if (r != CUDA_SUCCESS) {
-    c->err = "cuTensorMapEncodeTiled failed (" + std::to_string((int)r) + ")";
-    return SPIC_ECUDA;
-  }
-  return SPIC_OK;
-}
-
 template <class I, bool TMA>
 int launch_block_t(Ctx* c, Species& s, double h, const CellRanges& rg, const MoverList& mv, long want) {
   EngineState* e = eng(c);
-  CUtensorMap map;
-  memset(&map, 0, sizeof map);
-  if (TMA) {
-    if (!e->map_B_ok) {
-      int rc = make_stencil_map(c, c->B, I::NW1, reinterpret_cast<CUtensorMap*>(e->map_B));
-      if (rc) return rc;
-      e->map_B_ok = true;
-    }
-    memcpy(&map, e->map_B, sizeof map);
-  }
   const size_t smem = sizeof(double) * kWarps * BlockLayout<I>::PER_WARP;
   static unsigned long long attr = 0;
   if (smem_attr_needed(attr, c->cfg.device))
     SPIC_CUDA_CHECK(c, cudaFuncSetAttribute(k_axis_block<I, TMA>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   k_axis_block<I, TMA><<<(int)want, kThreads, smem, c->stream>>>(c->g, s.b, s.start, s.count, c->E, c->B, s.q, s.q / s.m,
-                                                                 h, mv, c->d_flags, rg, e->block_work, e->cont_key, map);
+                                                                 h, mv, c->d_flags, rg, e->block_work, e->cont_key);
   c->launches++;
   return SPIC_OK;
 }
@@ -754,8 +696,20 @@ int launch_block(Ctx* c, Species& s, double h, const CellRanges& rg, unsigned li
   return e->tma ? launch_block_t<I, true>(c, s, h, rg, mv, want) : launch_block_t<I, false>(c, s, h, rg, mv, want);
 }
 
+template <class I>
+int launch_continue(Ctx* c, int nb, const MoverList& mv, const unsigned* perm, double q, double qm, double h) {
+  k_axis_continue<I><<<nb, 128, 0, c->stream>>>(c->g, mv, perm, c->E, c->B, q, qm, h, c->d_flags);
+  return SPIC_OK;
+}
+template <class I>
+int launch_tail(Ctx* c, int nb, Species& s, double qm, double h) {
+  k_axis_tail<I><<<nb, 128, 0, c->stream>>>(c->g, s.d, s.d_nd, s.capd, c->E, c->B, s.q, qm, h, c->d_flags);
+  return SPIC_OK;
+}
+
 }  // namespace
 
+#ifndef SPIC_USER_W_TU
 bool fused_block_supported(const Ctx* c) {
   if (!(c->g.per[0] && c->g.per[1] && c->g.per[2])) return false;
   return c->cfg.nranks == 1 || c->g.ng >= c->W + 1;
@@ -771,8 +725,13 @@ unsigned fused_list_cap(Ctx* c, long cells) {
   return want < (double)cap ? (unsigned)want : cap;
 }
 
+#endif  // SPIC_USER_W_TU
+
 // part: 0 = every cell; 1 = the nb z planes next to each slab face; 2 = the planes between them
-int fused_axis_block(Ctx* c, Species& s, double h, int part, int nb, unsigned list_cap) {
+int SPIC_PUBLIC(fused_axis_block)(Ctx* c, Species& s, double h, int part, int nb, unsigned list_cap) {
+#ifndef SPIC_USER_W_TU
+  if (c->cfg.interp == SPIC_INTERP_USER) return user_fused_axis_block(c, s, h, part, nb, list_cap);
+#endif
   KernelTimer t(c, KT_BLOCK);
   const Grid& g = c->g;
   const unsigned plane = (unsigned)g.n[0] * (unsigned)g.n[1], ncell = (unsigned)g.cells();
@@ -793,11 +752,13 @@ int fused_axis_block(Ctx* c, Species& s, double h, int part, int nb, unsigned li
     rg.n[0] = ncell - 2u * (unsigned)nb * plane;
   }
   rg.nchunk0 = (rg.n[0] + kChunk - 1) / kChunk;
-  return c->cfg.interp == SPIC_INTERP_P8R2 ? launch_block<InterpP8R2>(c, s, h, rg, list_cap)
-                                           : launch_block<InterpPWL>(c, s, h, rg, list_cap);
+  return SPIC_BY_INTERP(c, launch_block, c, s, h, rg, list_cap);
 }
 
-int fused_axis_continue(Ctx* c, Species& s, double h, unsigned list_cap) {
+int SPIC_PUBLIC(fused_axis_continue)(Ctx* c, Species& s, double h, unsigned list_cap) {
+#ifndef SPIC_USER_W_TU
+  if (c->cfg.interp == SPIC_INTERP_USER) return user_fused_axis_continue(c, s, h, list_cap);
+#endif
   EngineState* e = eng(c);
   // No read-back of the ejected count: the whole mover list (capacity entries) is sorted by home cell, the unused
   // entries carry the key 0xffffffff (set before the block ran) and sort behind the real ones; k_axis_continue
@@ -839,26 +800,21 @@ int fused_axis_continue(Ctx* c, Species& s, double h, unsigned list_cap) {
   const double qm = s.q / s.m;
   MoverList mv = e->mv;
   mv.cap = cap;
-  if (c->cfg.interp == SPIC_INTERP_P8R2)
-    k_axis_continue<InterpP8R2><<<(int)nb, 128, 0, c->stream>>>(c->g, mv, e->cont_perm, c->E, c->B, s.q, qm, h,
-                                                              c->d_flags);
-  else
-    k_axis_continue<InterpPWL><<<(int)nb, 128, 0, c->stream>>>(c->g, mv, e->cont_perm, c->E, c->B, s.q, qm, h,
-                                                             c->d_flags);
+  SPIC_BY_INTERP(c, launch_continue, c, (int)nb, mv, e->cont_perm, s.q, qm, h);
   c->launches++;
   return SPIC_OK;
 }
 
-int fused_axis_tail(Ctx* c, Species& s, double h) {
+int SPIC_PUBLIC(fused_axis_tail)(Ctx* c, Species& s, double h) {
+#ifndef SPIC_USER_W_TU
+  if (c->cfg.interp == SPIC_INTERP_USER) return user_fused_axis_tail(c, s, h);
+#endif
   if (s.capd <= 0 || !s.d_nd) return SPIC_OK;
   KernelTimer t(c, KT_OTHER);
   long nb = (s.capd + 127) / 128;
   if (nb > (long)c->sm_count * 16) nb = (long)c->sm_count * 16;
   const double qm = s.q / s.m;
-  if (c->cfg.interp == SPIC_INTERP_P8R2)
-    k_axis_tail<InterpP8R2><<<(int)nb, 128, 0, c->stream>>>(c->g, s.d, s.d_nd, s.capd, c->E, c->B, s.q, qm, h, c->d_flags);
-  else
-    k_axis_tail<InterpPWL><<<(int)nb, 128, 0, c->stream>>>(c->g, s.d, s.d_nd, s.capd, c->E, c->B, s.q, qm, h, c->d_flags);
+  SPIC_BY_INTERP(c, launch_tail, c, (int)nb, s, qm, h);
   c->launches++;
   return SPIC_OK;
 }

@@ -902,13 +902,18 @@ int push_dispatch(Ctx* c, Species& s, double dt) {
 
 }  // namespace
 
-int stream_theta_axis(Ctx* c, Species& s, int comp, double dt) {
-  return c->cfg.interp == SPIC_INTERP_P8R2 ? axis_dispatch<InterpP8R2>(c, s, comp, dt)
-                                           : axis_dispatch<InterpPWL>(c, s, comp, dt);
+int SPIC_PUBLIC(stream_theta_axis)(Ctx* c, Species& s, int comp, double dt) {
+#ifndef SPIC_USER_W_TU
+  if (c->cfg.interp == SPIC_INTERP_USER) return user_stream_theta_axis(c, s, comp, dt);
+#endif
+  return SPIC_BY_INTERP(c, axis_dispatch, c, s, comp, dt);
 }
 
-int stream_push_v_e(Ctx* c, Species& s, double dt) {
-  return c->cfg.interp == SPIC_INTERP_P8R2 ? push_dispatch<InterpP8R2>(c, s, dt) : push_dispatch<InterpPWL>(c, s, dt);
+int SPIC_PUBLIC(stream_push_v_e)(Ctx* c, Species& s, double dt) {
+#ifndef SPIC_USER_W_TU
+  if (c->cfg.interp == SPIC_INTERP_USER) return user_stream_push_v_e(c, s, dt);
+#endif
+  return SPIC_BY_INTERP(c, push_dispatch, c, s, dt);
 }
 
 }  // namespace spic

@@ -14,7 +14,7 @@ def _ngpu():
     return torch.cuda.device_count()
 
 
-@pytest.mark.parametrize("case", ["p8", "pwl", "p8_thin", "p8_nofuse", "p8_tall", "pwl_tall", "p8_tall_serial", "pwl_serial_thin"])
+@pytest.mark.parametrize("case", ["p8", "pwl", "p8_thin", "p8_nofuse", "p8_tall", "pwl_tall", "p8_tall_serial", "pwl_serial_thin", "user_tall", "user_nofuse"])
 @pytest.mark.parametrize("world", [2, 4, 8])
 def test_slab_decomposition_matches_oracle(world, case):
     if _ngpu() < world:

@@ -165,10 +165,11 @@ def test_user_w_conserves_charge():
 
 
 @pytest.mark.gpu
-def test_user_pwl_library_equals_the_shipped_pwl(user_pwl_library):
+@pytest.mark.parametrize("engine", [1, 0])
+def test_user_pwl_library_equals_the_shipped_pwl(user_pwl_library, engine):
     """A library built with --user-w (PWL restated by a user, range 1) run in a subprocess against the stock
-    library's PWL kernels (thread-per-particle engine on both sides: the particle order is kept): same
-    particles and fields after maps of every order."""
+    library's PWL kernels: same particles and fields after maps of every order -- on the thread-per-particle engine
+    and on the binned engine (fused axis block + particle-stream kernels instantiated over the user's functions)."""
     import subprocess
     code = r'''
 import sys, numpy as np
@@ -177,11 +178,12 @@ import strugepic_b200 as spic, util
 n_cell = (9, 7, 6)
 E, B = util.rng_fields(n_cell, 71, 0.4)
 parts = util.plasma(n_cell, 5, 0.2, 71)
-s = spic.Simulation(n_cell, interp=int(sys.argv[1]), engine=1)
+s = spic.Simulation(n_cell, interp=int(sys.argv[1]), engine=int(sys.argv[3]))
 util.load_state(s, E, B, parts, -0.2, 20.0)
 for order in (1, 2, 4):
     s.map(order, 0.5)
 E1, B1, P1 = util.state_of(s)
+P1 = P1[:, np.lexsort(np.round(P1[::-1], 9))]  # (the binned engine returns the particles in cell order)
 np.savez(sys.argv[2], E=E1, B=B1, P=P1)
 ''' % (os.path.dirname(HERE), HERE)
     d = os.path.dirname(user_pwl_library)
@@ -191,8 +193,8 @@ np.savez(sys.argv[2], E=E1, B=B1, P=P1)
         if lib:
             env["SPIC_B200_LIBRARY"] = lib
         out = os.path.join(d, "userpwl_%s.npz" % tag)
-        r = subprocess.run([sys.executable, "-c", code, str(interp), out], env=env, capture_output=True, text=True,
-                           timeout=300)
+        r = subprocess.run([sys.executable, "-c", code, str(interp), out, str(engine)], env=env, capture_output=True,
+                           text=True, timeout=300)
         assert r.returncode == 0, r.stderr
         outs.append(np.load(out))
         os.remove(out)
