@@ -537,14 +537,14 @@ static int map2(spic_ctx* c, double dt) {  // hpp:559-572
   return theta_E_impl(c, dt / 2);
 }
 
-// The axis block of one Theta_map2(dt): Theta_B(dt), then x(h) y(h) z(h) z(h) y(h) x(h) with h = dt/2 as one
-// fused pass per species.  Theta_B only adds dt * curl B into E and the axis sub-flows only add their
-// currents into E and read B, which neither changes (hpp:562-569, cpp:102-113): the order is free.
-static int axis_block(spic_ctx* c, double dt) {
-  int rc = theta_B_impl(c, dt);
+// The position sub-flows of one Theta_map2(dt) as fused passes over the particles, h = dt/2.
+//   half = 0: x(h) y(h) z(h) z(h) y(h) x(h) in one pass per species (the caller has applied Theta_B(dt) already);
+//   half = 1 / 2: x(h) y(h) z(h) / z(h) y(h) x(h) only (boxes with walls: the caller runs Theta_B between them).
+// Guards of E are zeroed before and folded after every pass (hpp:351-352, 367), particles migrate once per pass.
+static int axis_pass(spic_ctx* c, double dt, int half) {
+  int rc = ensure_guards(c, c->B);  // B.FillBoundary, hpp:350: B does not change until the next Theta_E
   if (rc) return rc;
-  if ((rc = ensure_guards(c, c->B))) return rc;  // B.FillBoundary, hpp:350: B does not change until the next Theta_E
-  launch_zero_guards(c, c->E);  // E.setBndry(0), hpp:351-352: the guards collect this block's currents
+  launch_zero_guards(c, c->E);  // E.setBndry(0), hpp:351-352: the guards collect this pass's currents
   touched(c, c->E);
   // With z slabs (option "overlap"): the cells of the W + 2 planes next to each slab face run first -- only they can
   // deposit into the guard z planes or lose particles to a neighbour (a particle moves < 2 cells in a block, its
@@ -554,12 +554,21 @@ static int axis_block(spic_ctx* c, double dt) {
   const int nb = c->W + 2;
   const bool split = c->cfg.nranks > 1 && engine_overlap(c) && 2 * nb < c->g.n[2];
   for (auto& s : c->sp)
-    if ((rc = engine_axis_block(c, s, dt / 2, split ? 1 : 0, nb))) return rc;
+    if ((rc = engine_axis_block(c, s, dt / 2, split ? 1 : 0, nb, half))) return rc;
   if ((rc = deposit_exchange_begin(c, 7u, true))) return rc;
   if (split)
     for (auto& s : c->sp)
-      if ((rc = engine_axis_block(c, s, dt / 2, 2, nb))) return rc;
+      if ((rc = engine_axis_block(c, s, dt / 2, 2, nb, half))) return rc;
   return deposit_exchange_end(c, 7u);
+}
+
+// The axis block of one Theta_map2(dt) on a periodic box: Theta_B(dt) first, then the six axis sub-flows as one pass.
+// Theta_B only adds dt * curl B into E and the axis sub-flows only add their currents into E and read B, which
+// neither changes (hpp:562-569, cpp:102-113): the order is free.
+static int axis_block(spic_ctx* c, double dt) {
+  int rc = theta_B_impl(c, dt);
+  if (rc) return rc;
+  return axis_pass(c, dt, 0);
 }
 
 // Theta_map2(d_0) o ... o Theta_map2(d_{n-1}) with fused axis blocks; adjacent Theta_E halves are merged:
@@ -568,6 +577,21 @@ static int axis_block(spic_ctx* c, double dt) {
 // of this call is left pending in turn (option "defer_kick") and applied by whatever entry point runs next.
 static int fused_maps(spic_ctx* c, const double* d, int n) {
   int rc;
+  if (!(c->g.per[0] && c->g.per[1] && c->g.per[2])) {
+    // Walls.  (1) Theta_B cannot move: its MABC_bad blend (hpp:447-476) reads E on the plane next to the high x face,
+    // which the W1 stencil of the last particle cell reaches -- the deposits of the first three sub-flows must be in E
+    // when it runs and those of the last three must not.  So every map2 is  Theta_E, [x y z], Theta_B, [z y x],
+    // Theta_E  with each bracket one fused pass.  (2) Theta_E's own MABC blend of B is not additive in dt: adjacent
+    // halves are not merged and nothing is deferred.
+    for (int i = 0; i < n; ++i) {
+      if ((rc = theta_E_impl(c, d[i] / 2))) return rc;
+      if ((rc = axis_pass(c, d[i], 1))) return rc;
+      if ((rc = theta_B_impl(c, d[i]))) return rc;
+      if ((rc = axis_pass(c, d[i], 2))) return rc;
+      if ((rc = theta_E_impl(c, d[i] / 2))) return rc;
+    }
+    return SPIC_OK;
+  }
   const double lead = d[0] / 2 + c->pending_E;
   c->pending_E = 0.0;
   if ((rc = theta_E_impl(c, lead))) return rc;

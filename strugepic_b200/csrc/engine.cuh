@@ -63,6 +63,14 @@ struct EngineState {
   void* cont_tmp = nullptr;
   size_t cont_tmp_bytes = 0;
   unsigned long long* d_scalar = nullptr;  // small device scratch (8 words)
+  // spic_get_particles: persistent staging (two buffers, packed by cell chunk on the compute stream while the previous
+  // chunk travels to the host on the copy stream)
+  long* gather_prefix = nullptr;
+  long gather_prefix_cells = 0;
+  double* gather_stage[2] = {nullptr, nullptr};
+  long gather_stage_cap = 0;
+  cudaStream_t copy_stream = nullptr;
+  cudaEvent_t gather_packed[2] = {nullptr, nullptr}, gather_copied[2] = {nullptr, nullptr};
 };
 EngineState* eng(Ctx* c);
 
@@ -103,18 +111,19 @@ int stream_push_v_e(Ctx* c, Species& s, double dt);
 // the same entry points over the user-supplied W (second compilation of the two files, see above)
 int user_stream_theta_axis(Ctx* c, Species& s, int comp, double dt);
 int user_stream_push_v_e(Ctx* c, Species& s, double dt);
-int user_fused_axis_block(Ctx* c, Species& s, double h, int part, int nb, unsigned list_cap);
-int user_fused_axis_continue(Ctx* c, Species& s, double h, unsigned list_cap);
-int user_fused_axis_tail(Ctx* c, Species& s, double h);
+int user_fused_axis_block(Ctx* c, Species& s, double h, int part, int nb, unsigned list_cap, int half);
+int user_fused_axis_continue(Ctx* c, Species& s, double h, unsigned list_cap, int half);
+int user_fused_axis_tail(Ctx* c, Species& s, double h, int half);
 
 // ---- fused axis block (particles_fused.cu) ------------------------------------------------
-bool fused_block_supported(const Ctx* c);                 // fully periodic box (guard width W + 1 with z slabs)
+bool fused_block_supported(const Ctx* c);                 // (with z slabs: periodic z, guard width W + 1)
 // x(h) y(h) z(2h) y(h) x(h) over the bins of: part 0 = every cell, 1 = the nb z planes next to each slab face,
-// 2 = the planes between them; list_cap = the mover-list prefix the launch may fill (fused_list_cap)
-int fused_axis_block(Ctx* c, Species& s, double h, int part, int nb, unsigned list_cap);
+// 2 = the planes between them; list_cap = the mover-list prefix the launch may fill (fused_list_cap);
+// half: 0 = the whole block, 1 = x(h) y(h) z(h) only, 2 = z(h) y(h) x(h) only (boxes with walls)
+int fused_axis_block(Ctx* c, Species& s, double h, int part, int nb, unsigned list_cap, int half);
 unsigned fused_list_cap(Ctx* c, long cells);
-int fused_axis_continue(Ctx* c, Species& s, double h, unsigned list_cap);  // finishes the particles the block ejected
-int fused_axis_tail(Ctx* c, Species& s, double h);        // the same six sub-flows for the overflow tail
+int fused_axis_continue(Ctx* c, Species& s, double h, unsigned list_cap, int half);  // finishes the ejected particles
+int fused_axis_tail(Ctx* c, Species& s, double h, int half);  // the same sub-flows for the overflow tail
 
 // ---- cell-binned engine ------------------------------------------------------------
 int engine_ingest(Ctx* c, Species& s);  // move s.d (direct list) into cell bins (no-op for ENGINE_DIRECT)
@@ -128,7 +137,7 @@ bool engine_overlap(Ctx* c);                       // option "overlap"
 bool engine_can_fuse(Ctx* c);                      // option "fuse" on, box supported, every species binned
 // the six Theta of a map2 (step h each) for one species over part 0 / 1 / 2 of the cells (fused_axis_block); with
 // nranks > 1 parts 0 and 1 also pack the particles that left the slab into the species' migration messages
-int engine_axis_block(Ctx* c, Species& s, double h, int part = 0, int nb = 0);
+int engine_axis_block(Ctx* c, Species& s, double h, int part = 0, int nb = 0, int half = 0);
 int engine_kinetic(Ctx* c, Species& s, double* acc);
 int engine_deposit_rho(Ctx* c, Species& s, double* out);
 int engine_number_density(Ctx* c, Species& s, double* nd);  // nd: one guarded component

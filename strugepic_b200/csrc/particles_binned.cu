@@ -29,6 +29,8 @@
 
 #include <string.h>
 
+#include <algorithm>
+
 #include "engine.cuh"
 #include "particle_math.cuh"
 
@@ -1350,6 +1352,13 @@ void engine_destroy(Ctx* c) {
   if (e->cub_tmp) cudaFree(e->cub_tmp);
   if (e->d_scalar) cudaFree(e->d_scalar);
   if (e->block_work) cudaFree(e->block_work);
+  if (e->gather_prefix) cudaFree(e->gather_prefix);
+  for (int k = 0; k < 2; ++k) {
+    if (e->gather_stage[k]) cudaFree(e->gather_stage[k]);
+    if (e->gather_packed[k]) cudaEventDestroy(e->gather_packed[k]);
+    if (e->gather_copied[k]) cudaEventDestroy(e->gather_copied[k]);
+  }
+  if (e->copy_stream) cudaStreamDestroy(e->copy_stream);
   for (void* p : {(void*)e->cont_key, (void*)e->cont_key2, (void*)e->cont_idx, (void*)e->cont_perm, e->cont_tmp})
     if (p) cudaFree(p);
   delete e;
@@ -1385,33 +1394,111 @@ int engine_count(Ctx* c, Species& s, long* nb) {
   return SPIC_OK;
 }
 
+// packed[prefix[cell] - base + i] = arr[start[cell] + i] for the cells [c0, c1)
+__global__ void __launch_bounds__(256)
+    k_pack_bins_range(const double* __restrict__ arr, const long* __restrict__ start, const int* __restrict__ count,
+                      const long* __restrict__ prefix, long c0, long c1, long base, double* __restrict__ packed) {
+  const int lane = threadIdx.x & 31;
+  const long wid = (blockIdx.x * (long)blockDim.x + threadIdx.x) >> 5, nw = ((long)gridDim.x * blockDim.x) >> 5;
+  for (long cell = c0 + wid; cell < c1; cell += nw) {
+    const int cnt = count[cell];
+    const long s0 = start[cell], d0 = prefix[cell] - base;
+    for (int i = lane; i < cnt; i += 32) packed[d0 + i] = arr[s0 + i];
+  }
+}
+__global__ void k_sample_prefix(const long* __restrict__ prefix, long ncell, long cells_per_chunk, int nchunk,
+                                long* __restrict__ out) {
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j <= nchunk) {
+    const long cell = (long)j * cells_per_chunk;
+    out[j] = prefix[cell < ncell ? cell : ncell];
+  }
+}
+
+// Binned particles -> host arrays in cell order.  The bins carry slack, so every component is packed on the device
+// first: chunk by chunk (~32 Mi particles) into one of two persistent staging buffers on the compute stream, while the
+// previous chunk travels to the host on the copy stream -- no allocation per call, the copies never wait for a pack.
 int engine_gather(Ctx* c, Species& s, double* hx[3], double* hv[3], long* nb) {
   *nb = 0;
   if (!s.binned) return SPIC_OK;
+  EngineState* e = eng(c);
   const long ncell = c->g.cells();
+  int rc;
+  if (e->gather_prefix_cells < ncell + 1) {
+    if (e->gather_prefix) cudaFree(e->gather_prefix);
+    e->gather_prefix = nullptr;
+    SPIC_CUDA_CHECK(c, cudaMalloc(&e->gather_prefix, sizeof(long) * (ncell + 1)));
+    e->gather_prefix_cells = ncell + 1;
+  }
+  if (!e->copy_stream) {
+    SPIC_CUDA_CHECK(c, cudaStreamCreateWithFlags(&e->copy_stream, cudaStreamNonBlocking));
+    for (int k = 0; k < 2; ++k) {
+      SPIC_CUDA_CHECK(c, cudaEventCreateWithFlags(&e->gather_packed[k], cudaEventDisableTiming));
+      SPIC_CUDA_CHECK(c, cudaEventCreateWithFlags(&e->gather_copied[k], cudaEventDisableTiming));
+    }
+  }
+  long* prefix = e->gather_prefix;
+  {  // exclusive prefix of the live counts, ncell + 1 entries (the last one is the total)
+    cub::TransformInputIterator<long, ToLong, const int*> it(s.count, ToLong());
+    size_t bytes = 0;
+    // (the scan reads one element past the counts when asked for ncell + 1 items: scan ncell, add the total below)
+    cub::DeviceScan::ExclusiveSum(nullptr, bytes, it, prefix, (int)ncell, c->stream);
+    if ((rc = ensure_cub(c, bytes))) return rc;
+    cub::DeviceScan::ExclusiveSum(e->cub_tmp, bytes, it, prefix, (int)ncell, c->stream);
+    c->launches++;
+  }
   long live = 0;
-  int rc = engine_count(c, s, &live);
-  if (rc) return rc;
-  long* prefix = nullptr;
-  double* packed = nullptr;
-  SPIC_CUDA_CHECK(c, cudaMalloc(&prefix, sizeof(long) * (ncell + 1)));
-  SPIC_CUDA_CHECK(c, cudaMalloc(&packed, sizeof(double) * (size_t)(live + 1)));
-  cub::TransformInputIterator<long, ToLong, const int*> it(s.count, ToLong());
-  size_t bytes = 0;
-  cub::DeviceScan::ExclusiveSum(nullptr, bytes, it, prefix, (int)ncell, c->stream);
-  if ((rc = ensure_cub(c, bytes))) return rc;
-  cub::DeviceScan::ExclusiveSum(eng(c)->cub_tmp, bytes, it, prefix, (int)ncell, c->stream);
-  c->launches++;
+  if ((rc = engine_count(c, s, &live))) return rc;  // (synchronises)
+  SPIC_CUDA_CHECK(c, cudaMemcpyAsync(prefix + ncell, &live, sizeof(long), cudaMemcpyHostToDevice, c->stream));
+  // chunks of whole cells, ~32 Mi particles each at the mean density
+  const long target = 32L << 20;
+  long cpc = live > 0 ? (long)((double)ncell * (double)target / (double)live) : ncell;
+  if (cpc < 1) cpc = 1;
+  if (cpc > ncell) cpc = ncell;
+  const int nchunk = (int)((ncell + cpc - 1) / cpc);
+  std::vector<long> bounds((size_t)nchunk + 1);
+  {
+    long* d_bounds = reinterpret_cast<long*>(c->scratch);  // (nchunk + 1 <= cells + 1 longs: fits)
+    if ((long)(nchunk + 1) > c->scratch_elems) {
+      c->err = "engine_gather: scratch too small";
+      return SPIC_EINVAL;
+    }
+    k_sample_prefix<<<(nchunk + 256) / 256, 256, 0, c->stream>>>(prefix, ncell, cpc, nchunk, d_bounds);
+    c->launches++;
+    SPIC_CUDA_CHECK(c, cudaMemcpyAsync(bounds.data(), d_bounds, sizeof(long) * (nchunk + 1), cudaMemcpyDeviceToHost, c->stream));
+    SPIC_CUDA_CHECK(c, cudaStreamSynchronize(c->stream));
+  }
+  long biggest = 1;
+  for (int j = 0; j < nchunk; ++j) biggest = std::max(biggest, bounds[j + 1] - bounds[j]);
+  if (e->gather_stage_cap < biggest) {
+    for (int k = 0; k < 2; ++k) {
+      if (e->gather_stage[k]) cudaFree(e->gather_stage[k]);
+      e->gather_stage[k] = nullptr;
+      SPIC_CUDA_CHECK(c, cudaMalloc(&e->gather_stage[k], sizeof(double) * (size_t)(biggest + biggest / 8)));
+    }
+    e->gather_stage_cap = biggest + biggest / 8;
+  }
+  int turn = 0;
+  bool used[2] = {false, false};
   for (int a = 0; a < 6; ++a) {
     const double* src = a < 3 ? s.b.x[a] : s.b.v[a - 3];
     double* dst = a < 3 ? hx[a] : hv[a - 3];
-    k_pack_bins<<<grid_warps(c, ncell), 256, 0, c->stream>>>(src, s.start, s.count, prefix, ncell, packed);
-    c->launches++;
-    SPIC_CUDA_CHECK(c, cudaMemcpyAsync(dst, packed, sizeof(double) * (size_t)live, cudaMemcpyDeviceToHost, c->stream));
-    SPIC_CUDA_CHECK(c, cudaStreamSynchronize(c->stream));
+    for (int j = 0; j < nchunk; ++j, turn ^= 1) {
+      const long c0 = (long)j * cpc, c1 = std::min(ncell, c0 + cpc), n = bounds[j + 1] - bounds[j];
+      if (n <= 0) continue;
+      if (used[turn]) SPIC_CUDA_CHECK(c, cudaStreamWaitEvent(c->stream, e->gather_copied[turn], 0));
+      k_pack_bins_range<<<grid_warps(c, c1 - c0), 256, 0, c->stream>>>(src, s.start, s.count, prefix, c0, c1, bounds[j],
+                                                                       e->gather_stage[turn]);
+      c->launches++;
+      SPIC_CUDA_CHECK(c, cudaEventRecord(e->gather_packed[turn], c->stream));
+      SPIC_CUDA_CHECK(c, cudaStreamWaitEvent(e->copy_stream, e->gather_packed[turn], 0));
+      SPIC_CUDA_CHECK(c, cudaMemcpyAsync(dst + bounds[j], e->gather_stage[turn], sizeof(double) * (size_t)n,
+                                         cudaMemcpyDeviceToHost, e->copy_stream));
+      SPIC_CUDA_CHECK(c, cudaEventRecord(e->gather_copied[turn], e->copy_stream));
+      used[turn] = true;
+    }
   }
-  cudaFree(prefix);
-  cudaFree(packed);
+  SPIC_CUDA_CHECK(c, cudaStreamSynchronize(e->copy_stream));
   *nb = live;
   return SPIC_OK;
 }
@@ -1464,7 +1551,7 @@ bool engine_can_fuse(Ctx* c) {
 
 // Theta_x(h) Theta_y(h) Theta_z(h) Theta_z(h) Theta_y(h) Theta_x(h) for one species
 // (include/strugepic_propagators.hpp:562-569 without the Theta_B in the middle, which commutes)
-int engine_axis_block(Ctx* c, Species& s, double h, int part, int nb) {
+int engine_axis_block(Ctx* c, Species& s, double h, int part, int nb, int half) {
   if (!s.binned) return SPIC_OK;
   EngineState* e = eng(c);
   int rc;
@@ -1476,10 +1563,10 @@ int engine_axis_block(Ctx* c, Species& s, double h, int part, int nb) {
   // a second time by part 2), part 2 appends behind them and the final call files everything that is left.
   const bool first_of_two = split && part == 1;
   const unsigned list_cap = first_of_two ? fused_list_cap(c, 2L * nb * plane) : e->mv.cap;
-  if ((rc = fused_axis_block(c, s, h, part, nb, list_cap))) return rc;
+  if ((rc = fused_axis_block(c, s, h, part, nb, list_cap, half))) return rc;
   // the overflow tail takes the general per-particle code BEFORE new overflow can join it
-  if (part != 2 && (rc = fused_axis_tail(c, s, h))) return rc;
-  if ((rc = fused_axis_continue(c, s, h, list_cap))) return rc;
+  if (part != 2 && (rc = fused_axis_tail(c, s, h, half))) return rc;
+  if ((rc = fused_axis_continue(c, s, h, list_cap, half))) return rc;
   MoverList mv = e->mv;
   mv.cap = list_cap;
   int nbk = (int)((list_cap + 255) / 256);

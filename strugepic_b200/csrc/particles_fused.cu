@@ -299,7 +299,11 @@ SPIC_DI void flush_component(const double* sAccA, double* __restrict__ E, long b
 // TMA = true: the six particle rows of a batch travel as bulk copies (cp.async.bulk = UBLKCP) issued by lane 0 and
 // completed on the warp's mbarrier; TMA = false: cp.async (LDGSTS) from every lane.  Same shared-memory layout, same
 // arithmetic.  (The stencil box cannot be a tensor-map tile: see stage().)
-template <class I, bool TMA>
+// HALF = 0: the whole block; 1: x(h) y(h) z(h) only; 2: z(h) y(h) x(h) only -- on boxes with walls Theta_B cannot be
+// moved in front of the block (MABC_bad reads E at the plane next to the high x face, which the W1 stencil of the
+// last particle cell reaches: a deposit there and the blend do not commute), so the two halves run on either side
+// of it, hpp:562-569 in the reference's own order.
+template <class I, bool TMA, int HALF>
 __global__ void __launch_bounds__(kThreads, 2)
     k_axis_block(Grid g, ParticleSoA p, const long* __restrict__ start, int* __restrict__ count,
                  double* __restrict__ E, const double* __restrict__ B, double q, double qm, double h, MoverList mv,
@@ -487,16 +491,20 @@ __global__ void __launch_bounds__(kThreads, 2)
       //   P,Q after   -,z  y,z| x,z   x,y   x,z   y,z
       double P1[NW1] = {}, Pp[NWP] = {}, Q1[NW1] = {}, Qp[NWP] = {};
 #pragma unroll 1
-      for (int step = -2; step < 5; ++step) {
-        const int A = step < 0 ? -step : (step < 3 ? step : 4 - step);
+      // (HALF = 1 stops after step 2; HALF = 2 evaluates x -> P, y -> Q first and runs steps 2, 3, 4)
+      for (int step = -2; step < (HALF == 1 ? 3 : 5); ++step) {
+        if (HALF == 2 && (step == 0 || step == 1)) continue;
+        const int A = step < 0 ? (HALF == 2 ? step + 2 : -step) : (step < 3 ? step : 4 - step);
         if (step >= 0) {
           const double xa = A == 0 ? x[0] : (A == 1 ? x[1] : x[2]);
           const double va = A == 0 ? v[0] : (A == 1 ? v[1] : v[2]);
           const double hA = sH[A];
-          double x1 = xa + (step == 2 ? 2.0 * h : h) * va;  // hpp:237
+          double x1 = xa + (step == 2 && HALF == 0 ? 2.0 * h : h) * va;  // hpp:237
           // construct_segments (util.cpp:160-174): one segment  <=>  floor(x1) == cell  <=>  hA <= x1 < hA + 1
           const bool leaves = alive && !(x1 >= hA && x1 < hA + 1.0);
-          eject(leaves, kContBase - (step < 3 ? step : step + 1), cbase + ci, ekey, x, v, sH, alive, mv, flags, lane);
+          // (code = position in the program x y z z y x of the first sub-flow the continuation has to do)
+          eject(leaves, kContBase - (step < 3 && HALF != 2 ? step : step + 1), cbase + ci, ekey, x, v, sH, alive, mv, flags,
+                lane);
           const double xs = leaves ? hA + 0.5 : xa;  // an ejected lane is a resting padding particle from here on
           if (leaves) x1 = xs;
           double I0[NWP];
@@ -505,13 +513,13 @@ __global__ void __launch_bounds__(kThreads, 2)
           else if (A == 1) axis_part<I, 1>(x, v, x1, I0, Q1, Qp, P1, Pp, sB, sW, nq, qm, lane);  // U = z in Q, L = x in P
           else axis_part<I, 2>(x, v, x1, I0, P1, Pp, Q1, Qp, sB, sW, nq, qm, lane);              // U = x in P, L = y in Q
           __syncwarp();
-          deposit_records<I>(sW, sAcc + A * (NACC * 32), first && step < 3, nit, lane);
+          deposit_records<I>(sW, sAcc + A * (NACC * 32), first && (step < 3 || HALF == 2), nit, lane);
           __syncwarp();  // the record area is free again
         }
-        if (step < 4) {
+        if (step < (HALF == 1 ? 2 : 4)) {
           // f = x - cell is exact: the particle lies inside its bin cell
           const double f = (A == 0 ? x[0] : (A == 1 ? x[1] : x[2])) - sH[A];
-          if (step == -1 || step == 0 || step == 3) {
+          if (HALF == 2 && step < 0 ? step == -2 : (step == -1 || step == 0 || step == 3)) {
             eval_w1_in<I>(f, P1);
             eval_wp_in<I>(f, Pp);
           } else {
@@ -570,14 +578,15 @@ __global__ void __launch_bounds__(kThreads, 2)
 // that the CFL limit of the reference, |v h| < 1 cell, is the one that applies) for one particle, general code.
 // With z slabs over several ranks z is NOT wrapped between the sub-flows: the particle keeps its coordinate
 // relative to this slab (at most one cell outside: guard width W + 1) and is wrapped when it is handed over.
+// `end`: one past the last program position to run (6; 3 for the first half-block of a wall box)
 template <class I>
-SPIC_DI void finish_program(const Grid& g, int resume, double (&x)[3], double (&v)[3], double* __restrict__ E,
+SPIC_DI void finish_program(const Grid& g, int resume, int end, double (&x)[3], double (&v)[3], double* __restrict__ E,
                             const double* __restrict__ B, double q, double qm, double h, int* __restrict__ flags) {
   // Every thread walks the whole program and skips the sub-flows it has behind it, so that the lanes of a
   // warp run the SAME sub-flow at the same time: with the list sorted by cell their gathers and reductions then
   // fall into shared 32-byte sectors (this code is bound by L1/L2 sector operations, not by issue slots).
 #pragma unroll 1
-  for (int k = 0; k < 6; ++k) {
+  for (int k = 0; k < end; ++k) {
     if (k < resume) continue;
     const int axis = k < 3 ? k : 5 - k;
     if (axis == 0) theta_axis_one<I, 0>(g, x, v, E, B, q, qm, h, flags);
@@ -617,14 +626,14 @@ SPIC_DI int finish_dest(const Grid& g, double (&x)[3], int* __restrict__ flags) 
 template <class I>
 __global__ void __launch_bounds__(128, 4)
     k_axis_continue(Grid g, MoverList mv, const unsigned* __restrict__ perm, double* __restrict__ E,
-                    const double* __restrict__ B, double q, double qm, double h, int* __restrict__ flags) {
+                    const double* __restrict__ B, double q, double qm, double h, int* __restrict__ flags, int end) {
   const unsigned n = min(*mv.n, mv.cap);
   for (unsigned t = blockIdx.x * blockDim.x + threadIdx.x; t < n; t += gridDim.x * blockDim.x) {
     const unsigned m = perm ? perm[t] : t;
     const int code = mv.dest[m];
     if (code > kContBase) continue;
     double x[3] = {mv.x[0][m], mv.x[1][m], mv.x[2][m]}, v[3] = {mv.v[0][m], mv.v[1][m], mv.v[2][m]};
-    finish_program<I>(g, kContBase - code, x, v, E, B, q, qm, h, flags);
+    finish_program<I>(g, kContBase - code, end, x, v, E, B, q, qm, h, flags);
     const int dest = finish_dest(g, x, flags);
 #pragma unroll
     for (int d = 0; d < 3; ++d) {
@@ -646,11 +655,11 @@ template <class I>
 __global__ void __launch_bounds__(128)
     k_axis_tail(Grid g, ParticleSoA t, const unsigned long long* __restrict__ n_dev, long cap,
                 double* __restrict__ E, const double* __restrict__ B, double q, double qm, double h,
-                int* __restrict__ flags) {
+                int* __restrict__ flags, int begin, int end) {
   const long n = min((long)*n_dev, cap);
   for (long m = blockIdx.x * (long)blockDim.x + threadIdx.x; m < n; m += (long)gridDim.x * blockDim.x) {
     double x[3] = {t.x[0][m], t.x[1][m], t.x[2][m]}, v[3] = {t.v[0][m], t.v[1][m], t.v[2][m]};
-    finish_program<I>(g, 0, x, v, E, B, q, qm, h, flags);
+    finish_program<I>(g, begin, end, x, v, E, B, q, qm, h, flags);
     finish_dest(g, x, flags);  // (wraps z when the particle left the slab)
 #pragma unroll
     for (int d = 0; d < 3; ++d) {
@@ -660,21 +669,22 @@ __global__ void __launch_bounds__(128)
   }
 }
 
-template <class I, bool TMA>
+template <class I, bool TMA, int HALF>
 int launch_block_t(Ctx* c, Species& s, double h, const CellRanges& rg, const MoverList& mv, long want) {
   EngineState* e = eng(c);
   const size_t smem = sizeof(double) * kWarps * BlockLayout<I>::PER_WARP;
   static unsigned long long attr = 0;
   if (smem_attr_needed(attr, c->cfg.device))
-    SPIC_CUDA_CHECK(c, cudaFuncSetAttribute(k_axis_block<I, TMA>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  k_axis_block<I, TMA><<<(int)want, kThreads, smem, c->stream>>>(c->g, s.b, s.start, s.count, c->E, c->B, s.q, s.q / s.m,
+    SPIC_CUDA_CHECK(c, cudaFuncSetAttribute(k_axis_block<I, TMA, HALF>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                            (int)smem));
+  k_axis_block<I, TMA, HALF><<<(int)want, kThreads, smem, c->stream>>>(c->g, s.b, s.start, s.count, c->E, c->B, s.q, s.q / s.m,
                                                                  h, mv, c->d_flags, rg, e->block_work, e->cont_key);
   c->launches++;
   return SPIC_OK;
 }
 
 template <class I>
-int launch_block(Ctx* c, Species& s, double h, const CellRanges& rg, unsigned list_cap) {
+int launch_block(Ctx* c, Species& s, double h, const CellRanges& rg, unsigned list_cap, int half) {
   EngineState* e = eng(c);
   // persistent: two blocks per SM, every warp draws chunks of kChunk cells from a counter
   const long nchunk = (long)rg.nchunk0 + (rg.n[1] + kChunk - 1) / kChunk;
@@ -693,26 +703,30 @@ int launch_block(Ctx* c, Species& s, double h, const CellRanges& rg, unsigned li
   SPIC_CUDA_CHECK(c, cudaMemsetAsync(e->cont_key, 0xff, sizeof(unsigned) * (size_t)list_cap, c->stream));
   MoverList mv = e->mv;
   mv.cap = list_cap;  // (this launch may use a prefix of the list only: what the continuation then sorts)
-  return e->tma ? launch_block_t<I, true>(c, s, h, rg, mv, want) : launch_block_t<I, false>(c, s, h, rg, mv, want);
+  if (half == 1) return launch_block_t<I, false, 1>(c, s, h, rg, mv, want);
+  if (half == 2) return launch_block_t<I, false, 2>(c, s, h, rg, mv, want);
+  return e->tma ? launch_block_t<I, true, 0>(c, s, h, rg, mv, want) : launch_block_t<I, false, 0>(c, s, h, rg, mv, want);
 }
 
 template <class I>
-int launch_continue(Ctx* c, int nb, const MoverList& mv, const unsigned* perm, double q, double qm, double h) {
-  k_axis_continue<I><<<nb, 128, 0, c->stream>>>(c->g, mv, perm, c->E, c->B, q, qm, h, c->d_flags);
+int launch_continue(Ctx* c, int nb, const MoverList& mv, const unsigned* perm, double q, double qm, double h, int end) {
+  k_axis_continue<I><<<nb, 128, 0, c->stream>>>(c->g, mv, perm, c->E, c->B, q, qm, h, c->d_flags, end);
   return SPIC_OK;
 }
 template <class I>
-int launch_tail(Ctx* c, int nb, Species& s, double qm, double h) {
-  k_axis_tail<I><<<nb, 128, 0, c->stream>>>(c->g, s.d, s.d_nd, s.capd, c->E, c->B, s.q, qm, h, c->d_flags);
+int launch_tail(Ctx* c, int nb, Species& s, double qm, double h, int begin, int end) {
+  k_axis_tail<I><<<nb, 128, 0, c->stream>>>(c->g, s.d, s.d_nd, s.capd, c->E, c->B, s.q, qm, h, c->d_flags, begin, end);
   return SPIC_OK;
 }
 
 }  // namespace
 
 #ifndef SPIC_USER_W_TU
+// Periodic boxes run whole blocks, boxes with walls the two half-blocks around Theta_B (api.cu).  A particle that
+// would reach a reflect cell (util.hpp:172-180) crosses a cell face first: it is ejected and reflected by the general
+// code.  With z slabs z must be periodic and the guard width W + 1 (a particle finishes a block one cell outside).
 bool fused_block_supported(const Ctx* c) {
-  if (!(c->g.per[0] && c->g.per[1] && c->g.per[2])) return false;
-  return c->cfg.nranks == 1 || c->g.ng >= c->W + 1;
+  return c->cfg.nranks == 1 || (c->g.per[2] && c->g.ng >= c->W + 1);
 }
 
 // The length of the mover-list prefix a launch over `cells` of the brick's cells may fill (and the continuation
@@ -728,9 +742,9 @@ unsigned fused_list_cap(Ctx* c, long cells) {
 #endif  // SPIC_USER_W_TU
 
 // part: 0 = every cell; 1 = the nb z planes next to each slab face; 2 = the planes between them
-int SPIC_PUBLIC(fused_axis_block)(Ctx* c, Species& s, double h, int part, int nb, unsigned list_cap) {
+int SPIC_PUBLIC(fused_axis_block)(Ctx* c, Species& s, double h, int part, int nb, unsigned list_cap, int half) {
 #ifndef SPIC_USER_W_TU
-  if (c->cfg.interp == SPIC_INTERP_USER) return user_fused_axis_block(c, s, h, part, nb, list_cap);
+  if (c->cfg.interp == SPIC_INTERP_USER) return user_fused_axis_block(c, s, h, part, nb, list_cap, half);
 #endif
   KernelTimer t(c, KT_BLOCK);
   const Grid& g = c->g;
@@ -752,12 +766,12 @@ int SPIC_PUBLIC(fused_axis_block)(Ctx* c, Species& s, double h, int part, int nb
     rg.n[0] = ncell - 2u * (unsigned)nb * plane;
   }
   rg.nchunk0 = (rg.n[0] + kChunk - 1) / kChunk;
-  return SPIC_BY_INTERP(c, launch_block, c, s, h, rg, list_cap);
+  return SPIC_BY_INTERP(c, launch_block, c, s, h, rg, list_cap, half);
 }
 
-int SPIC_PUBLIC(fused_axis_continue)(Ctx* c, Species& s, double h, unsigned list_cap) {
+int SPIC_PUBLIC(fused_axis_continue)(Ctx* c, Species& s, double h, unsigned list_cap, int half) {
 #ifndef SPIC_USER_W_TU
-  if (c->cfg.interp == SPIC_INTERP_USER) return user_fused_axis_continue(c, s, h, list_cap);
+  if (c->cfg.interp == SPIC_INTERP_USER) return user_fused_axis_continue(c, s, h, list_cap, half);
 #endif
   EngineState* e = eng(c);
   // No read-back of the ejected count: the whole mover list (capacity entries) is sorted by home cell, the unused
@@ -800,21 +814,21 @@ int SPIC_PUBLIC(fused_axis_continue)(Ctx* c, Species& s, double h, unsigned list
   const double qm = s.q / s.m;
   MoverList mv = e->mv;
   mv.cap = cap;
-  SPIC_BY_INTERP(c, launch_continue, c, (int)nb, mv, e->cont_perm, s.q, qm, h);
+  SPIC_BY_INTERP(c, launch_continue, c, (int)nb, mv, e->cont_perm, s.q, qm, h, half == 1 ? 3 : 6);
   c->launches++;
   return SPIC_OK;
 }
 
-int SPIC_PUBLIC(fused_axis_tail)(Ctx* c, Species& s, double h) {
+int SPIC_PUBLIC(fused_axis_tail)(Ctx* c, Species& s, double h, int half) {
 #ifndef SPIC_USER_W_TU
-  if (c->cfg.interp == SPIC_INTERP_USER) return user_fused_axis_tail(c, s, h);
+  if (c->cfg.interp == SPIC_INTERP_USER) return user_fused_axis_tail(c, s, h, half);
 #endif
   if (s.capd <= 0 || !s.d_nd) return SPIC_OK;
   KernelTimer t(c, KT_OTHER);
   long nb = (s.capd + 127) / 128;
   if (nb > (long)c->sm_count * 16) nb = (long)c->sm_count * 16;
   const double qm = s.q / s.m;
-  SPIC_BY_INTERP(c, launch_tail, c, (int)nb, s, qm, h);
+  SPIC_BY_INTERP(c, launch_tail, c, (int)nb, s, qm, h, half == 2 ? 3 : 0, half == 1 ? 3 : 6);
   c->launches++;
   return SPIC_OK;
 }

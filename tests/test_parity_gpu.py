@@ -437,6 +437,53 @@ def test_two_species(engine):
     print(engine, errs)
 
 
+@pytest.mark.parametrize("interp", [0, 1])
+@pytest.mark.parametrize("fuse", [0, 1])
+@pytest.mark.parametrize("periodic", [(0, 1, 1), (1, 0, 0)])
+def test_fused_half_blocks_with_walls(periodic, fuse, interp):
+    """Walls (MABC + reflecting particles, the reference's production decks: examples/full/bernstein_main.cpp).
+    Theta_B cannot be moved in front of the axis sub-flows there (its MABC blend reads E on a plane the deposits
+    reach), so a map2 runs as Theta_E [x y z] Theta_B [z y x] Theta_E with each bracket ONE fused pass; a particle
+    that reaches a reflect cell crosses a cell face first and is reflected by the general code (util.hpp:172-186).
+    Hot plasma, 14 steps: the walls are reached."""
+    n_cell = (18, 12, 10)
+    W = 2 if interp == 0 else 1
+    E, B = util.rng_fields(n_cell, 93, 0.2)
+    parts = np.stack(util.plasma(n_cell, 20, 0.3, 93))
+    keep = np.ones(parts.shape[1], bool)
+    for d in range(3):  # nothing starts within W + 2 cells of a wall (SURVEY 0 quirk 4)
+        if not periodic[d]:
+            keep &= (parts[d] >= W + 2) & (parts[d] < n_cell[d] - W - 2)
+    parts = [np.ascontiguousarray(t) for t in parts[:, keep]]
+    q, m = -1.0 / 20, 100.0 / 20
+    o = ora.best_oracle(n_cell, periodic=periodic, interp=interp)
+    s = spic().Simulation(n_cell, periodic=periodic, interp=interp)
+    s.set_option("fuse", fuse)
+    s.set_option("time_kernels", 1)
+    for t in (o, s):
+        util.load_state(t, E, B, parts, q, m)
+    for k in range(14):
+        order = 4 if k % 7 == 3 else 2
+        o.map(order, 0.5)
+        s.map(order, 0.5)
+    nmaps2 = 12 + 2 * 3
+    errs = util.compare_states(util.state_of(o), util.state_of(s), TOL_STEP * nmaps2, TOL_STEP * nmaps2, box=n_cell)
+    kt = s.kernel_times()
+    assert kt["axis_block"][1] == (2 * nmaps2 if fuse else 0), kt
+    assert kt["theta_axis"][1] == (0 if fuse else 6 * nmaps2), kt
+    assert kt["push_V_E"][1] == 2 * nmaps2, kt   # no merged halves with walls
+    Po = np.stack(o.get_particles())
+    assert s.num_particles() == Po.shape[1]
+    reached = 0
+    for d in range(3):
+        if not periodic[d]:
+            lo, hi = W + 1, n_cell[d] - 1 - W
+            assert np.all((Po[d] >= lo) & (Po[d] < hi)), "a particle entered a reflect cell"
+            reached += np.sum(Po[d] - lo < 0.5) + np.sum(hi - Po[d] < 0.5)
+    assert reached > 0  # the walls were reached
+    print(periodic, fuse, interp, errs, kt)
+
+
 def test_deferred_half_kick_is_invisible():
     """The last Theta_E half of a fused map is deferred and merged with the first half of the next one
     (Theta_E(s) o Theta_E(t) = Theta_E(s + t)); any observation applies it first.  Three chained Theta_map4 with
