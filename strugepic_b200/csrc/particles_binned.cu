@@ -1773,6 +1773,10 @@ int engine_set_option(Ctx* c, const char* name, double value) {
     e->pushve_kernel = (int)value;
     return SPIC_OK;
   }
+  if (!strcmp(name, "pair_kernel")) {
+    e->pair_kernel = (int)value;
+    return SPIC_OK;
+  }
   if (!strcmp(name, "tma")) {
     e->tma = value != 0;
     return SPIC_OK;

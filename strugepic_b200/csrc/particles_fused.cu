@@ -52,6 +52,7 @@ namespace {
 constexpr int kWarps = 8;
 constexpr int kThreads = kWarps * 32;
 constexpr unsigned kFull = 0xffffffffu;
+constexpr long kPairBelow = 12;  // mean particles per cell below which the two-cells-per-batch kernel runs
 constexpr int kContBase = -100;  // mover-list code of an ejected particle: kContBase - first sub-flow still to do
 #ifndef SPIC_CHUNK
 #define SPIC_CHUNK 8
@@ -100,6 +101,7 @@ struct BlockLayout {
 #endif
   static constexpr int PER_WARP =
       (kTableDoubles + SP + 2 * SBS + SWA + SA + SPIC_WARP_ALIGN - 1) / SPIC_WARP_ALIGN * SPIC_WARP_ALIGN;
+  static constexpr int PER_WARP_PAIR = PER_WARP + 16;   // (k_axis_block_pair: buffer 1 shifted by 2 doubles)
   static_assert(SB % 2 == 0 && SW % 2 == 0 && NW1 % 2 == 0 && kTableDoubles % 2 == 0,
                 "16-byte alignment of the sub-buffers");
 };
@@ -197,13 +199,13 @@ SPIC_DI void eject(bool go, int code, unsigned cell, unsigned* __restrict__ ekey
 template <class I, int A>
 SPIC_DI void axis_part(double (&x)[3], double (&v)[3], double x1, const double (&I0)[I::NWP],
                        const double (&uW1)[I::NW1], const double (&uWp)[I::NWP], const double (&lW1)[I::NW1],
-                       const double (&lWp)[I::NWP], const double* sB, double* sW, double nq, double qm, int lane) {
+                       const double (&lWp)[I::NWP], const double* sB, double* sW, double nq, double qm, int rslot) {
   constexpr int U = (A + 1) % 3, L = (A + 2) % 3;  // hpp:90-91
   constexpr int NW1 = I::NW1, NWP = I::NWP;
   using Lay = BlockLayout<I>;
   constexpr int NS = Lay::NS;
-  {  // deposition record of this particle: -q W1_l, W1_u, I   (hpp:194,215)
-    double* wr = sW + Lay::rec(lane);
+  {  // deposition record of this particle (slot rslot of the record area): -q W1_l, W1_u, I   (hpp:194,215)
+    double* wr = sW + Lay::rec(rslot);
     double2* w = reinterpret_cast<double2*>(wr);
 #pragma unroll
     for (int t = 0; t < NW1 / 2; ++t) w[t] = make_double2(nq * lW1[2 * t], nq * lW1[2 * t + 1]);
@@ -277,13 +279,16 @@ SPIC_DI void deposit_records(const double* sW, double* sAccA, bool fresh, int ni
 
 // End of a cell: sum the parked accumulators of E(A) over the particle subsets (lane bits above LPP)
 // and issue one native FP64 reduction per stencil point.
-template <class I, int A>
+// PAIR: the upper and the lower half of the particle subsets belong to two different cells (k_axis_block_pair): the
+// sums stay inside each half and `base` is the lane's own cell.
+template <class I, int A, bool PAIR = false>
 SPIC_DI void flush_component(const double* sAccA, double* __restrict__ E, long base, const long (&st)[3], long pc,
                              int lane) {
   constexpr int U = (A + 1) % 3, L = (A + 2) % 3;
   constexpr int NW1 = I::NW1, NWP = I::NWP;
   using Lay = BlockLayout<I>;
-  const int tu = lane % NW1, th = (lane / NW1) % Lay::TH, sub = lane / Lay::LPP;
+  const int tu = lane % NW1, th = (lane / NW1) % Lay::TH;
+  const int sub = (PAIR ? (lane & 15) : lane) / Lay::LPP;
   double* Ea = E + (long)A * pc + base + tu * st[U] + (2 * th) * st[L];
 #pragma unroll
   for (int j = 0; j < 2; ++j)
@@ -291,7 +296,7 @@ SPIC_DI void flush_component(const double* sAccA, double* __restrict__ E, long b
     for (int t = 0; t < NWP; ++t) {
       double a = sAccA[(j * NWP + t) * 32 + lane];
 #pragma unroll
-      for (int m = Lay::LPP; m < 32; m <<= 1) a += __shfl_xor_sync(kFull, a, m);
+      for (int m = Lay::LPP; m < (PAIR ? 16 : 32); m <<= 1) a += __shfl_xor_sync(kFull, a, m);
       if (sub == 0) atomicAdd(Ea + j * st[L] + t * st[A], a);  // hpp:215, summed over the cell's particles
     }
 }
@@ -574,6 +579,212 @@ __global__ void __launch_bounds__(kThreads, 2)
   cp_async_wait<0>();
 }
 
+// ------------------------------------------------------------------------------------------------------------------
+// k_axis_block_pair: the same block for LOW particle counts per cell (host: mean count < kPairBelow).  With one cell
+// per batch a cell of 8 particles leaves 24 of 32 lanes idle through all five sub-flows (512^3 x 8 ppc ran 3.1x slower
+// per particle than 256^3 x 64 ppc).  Here two consecutive cells of a chunk with <= 16 particles each share a batch:
+// lanes 0-15 carry cell A, lanes 16-31 cell B.
+//   * cell data is per lane: coordinates sH / sH + 4, stencil buffer 0 / 1 (buffer 1 sits 16 bytes further in bank
+//     space, so the two broadcast reads of an LDS.128 never meet in a bank);
+//   * deposition: a particle's record goes to a slot whose subset (slot mod NSUB) lies in its cell's half of the
+//     subsets, so deposit_records -- unchanged -- accumulates the two cells in disjoint lanes; the flush sums inside
+//     each half and every half issues the reductions of its own cell;
+//   * both cells begin and end in the batch: nothing is parked across batches.
+// A cell with more than 16 particles (or without a partner) runs alone, as in k_axis_block.  Staging is synchronous
+// (both stencil buffers belong to the current batch): the other 15 warps of the SM cover the wait.
+// ------------------------------------------------------------------------------------------------------------------
+template <class I>
+__global__ void __launch_bounds__(kThreads, 2)
+    k_axis_block_pair(Grid g, ParticleSoA p, const long* __restrict__ start, int* __restrict__ count,
+                      double* __restrict__ E, const double* __restrict__ B, double q, double qm, double h, MoverList mv,
+                      int* __restrict__ flags, CellRanges rg, unsigned* __restrict__ work, unsigned* __restrict__ ekey) {
+  constexpr int NW1 = I::NW1, NWP = I::NWP;
+  using Lay = BlockLayout<I>;
+  constexpr int NS = Lay::NS, SB = Lay::SB, SBS = Lay::SBS, SP = Lay::SP, NACC = Lay::NACC, NSUB = Lay::NSUB;
+  constexpr int HALF_SUB = NSUB / 2;  // particle subsets per cell of a pair
+  constexpr unsigned kNone = 0xffffffffu;
+  extern __shared__ __align__(128) double smem[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  double* sWarp = smem + warp * Lay::PER_WARP_PAIR;
+  double* sBst = sWarp;                                     // buffer 0 at 0, buffer 1 at SBS + 2
+  double* sPart = sBst + 2 * SBS + 16;                      // [6][32]
+  double* sTab = sPart + SP;
+  long* tStart = reinterpret_cast<long*>(sTab);            // [kChunk]
+  int* tCnt = reinterpret_cast<int*>(sTab + kChunk);        // [kChunk]
+  double* sH = sTab + 2 * kChunk;                           // [2][4] global coordinates of cell A / cell B
+  double* sW = sTab + kTableDoubles;                        // [32][SW]
+  double* sAcc = sW + Lay::SWA;                             // [3][NACC][32]
+  const long st[3] = {1, g.pj, g.pk};
+  const double nq = -q;
+  const unsigned nchunk = rg.nchunk0 + (rg.n[1] + kChunk - 1) / kChunk;
+  auto corner_of = [&](unsigned cell, int (&cc)[3]) -> long {
+    const unsigned row = cell / (unsigned)g.n[0];
+    cc[0] = (int)(cell - row * (unsigned)g.n[0]);
+    cc[2] = (int)(row / (unsigned)g.n[1]);
+    cc[1] = (int)(row - (unsigned)cc[2] * (unsigned)g.n[1]);
+    return g.at(cc[0], cc[1], cc[2]) + (1 - I::W) * (1 + g.pj + g.pk);
+  };
+  auto stage_stencil = [&](unsigned cell, double* d) {
+    int cc[3];
+    const double* src = B + corner_of(cell, cc);
+#pragma unroll
+    for (int s = lane; s < SB; s += 32) {
+      const int comp = s / NS, r = s % NS;
+      const int ti = r % NW1, tj = (r / NW1) % NW1, tk = r / (NW1 * NW1);
+      cp_async8(d + s, src + (long)comp * g.pc + ti + tj * g.pj + tk * g.pk);
+    }
+  };
+
+  for (;;) {
+    unsigned id = 0;
+    if (lane == 0) id = atomicAdd(work, 1u);
+    id = __shfl_sync(kFull, id, 0);
+    if (id >= nchunk) break;
+    const unsigned cbase = id < rg.nchunk0 ? rg.cell0[0] + id * kChunk : rg.cell0[1] + (id - rg.nchunk0) * kChunk;
+    __syncwarp();
+    if (lane < kChunk) {
+      const unsigned cell = cbase + lane;
+      const unsigned end = cbase >= rg.cell0[1] ? rg.cell0[1] + rg.n[1] : rg.cell0[0] + rg.n[0];
+      tCnt[lane] = cell < end ? count[cell] : 0;
+      tStart[lane] = cell < end ? start[cell] : 0;
+    }
+    __syncwarp();
+    int ci = 0, off = 0, wp = 0;
+    while (ci < kChunk) {
+      const int cntA = tCnt[ci];
+      if (cntA == 0) {
+        ++ci;
+        continue;
+      }
+      // batch: particles [off, off + 32) of cell A alone, or the whole of A (lanes 0-15) + the whole of B (lanes 16-31)
+      const bool pair = off == 0 && cntA <= 16 && ci + 1 < kChunk && tCnt[ci + 1] <= 16 && tCnt[ci + 1] > 0;
+      const int cntB = pair ? tCnt[ci + 1] : 0;
+      const bool isB = pair && lane >= 16;
+      const int slot = pair ? (lane & 15) : off + lane;           // index inside the lane's bin
+      const bool valid = slot < (isB ? cntB : cntA);
+      const int nvalidA = pair ? cntA : (cntA - off < 32 ? cntA - off : 32);
+      const bool last_of_cell = pair || off + 32 >= cntA;
+      // ---- stage (synchronous) ------------------------------------------------------------------------------
+      if (valid) {
+        const long src = tStart[ci + (isB ? 1 : 0)] + slot;
+        double* d = sPart + lane;
+        cp_async8(d + 0 * 32, p.x[0] + src);
+        cp_async8(d + 1 * 32, p.x[1] + src);
+        cp_async8(d + 2 * 32, p.x[2] + src);
+        cp_async8(d + 3 * 32, p.v[0] + src);
+        cp_async8(d + 4 * 32, p.v[1] + src);
+        cp_async8(d + 5 * 32, p.v[2] + src);
+      }
+      if (off == 0) stage_stencil(cbase + ci, sBst);
+      if (pair) stage_stencil(cbase + ci + 1, sBst + SBS + 2);
+      cp_async_commit();
+      if (off == 0) {
+        int cc[3];
+        corner_of(cbase + ci, cc);
+        if (lane < 3) sH[lane] = (double)(cc[lane] + (lane == 2 ? g.z0 : 0));
+        if (pair) {
+          corner_of(cbase + ci + 1, cc);
+          if (lane < 3) sH[4 + lane] = (double)(cc[lane] + (lane == 2 ? g.z0 : 0));
+        }
+        wp = 0;
+      }
+      cp_async_wait<0>();
+      __syncwarp();
+      const double* sHl = sH + (isB ? 4 : 0);
+      const double* sB = sBst + (isB ? SBS + 2 : 0);
+      double x[3] = {sHl[0] + 0.5, sHl[1] + 0.5, sHl[2] + 0.5}, v[3] = {0.0, 0.0, 0.0};
+      if (valid) {
+        const double* sP = sPart + lane;
+        x[0] = sP[0 * 32];
+        x[1] = sP[1 * 32];
+        x[2] = sP[2 * 32];
+        v[0] = sP[3 * 32];
+        v[1] = sP[4 * 32];
+        v[2] = sP[5 * 32];
+      }
+      // record slot: in a pair, particle i of a cell goes to subset (i mod HALF_SUB) of the cell's half of the subsets
+      const int rslot = pair ? ((lane & 15) / HALF_SUB) * NSUB + (isB ? HALF_SUB : 0) + (lane & 15) % HALF_SUB : lane;
+      const int nit = pair ? ((cntA > cntB ? cntA : cntB) + HALF_SUB - 1) / HALF_SUB : (nvalidA + NSUB - 1) / NSUB;
+      const bool first = off == 0;
+      bool alive = valid;
+      const unsigned my_cell = cbase + ci + (isB ? 1 : 0);
+
+      double P1[NW1] = {}, Pp[NWP] = {}, Q1[NW1] = {}, Qp[NWP] = {};
+#pragma unroll 1
+      for (int step = -2; step < 5; ++step) {  // (the loop of k_axis_block, HALF = 0)
+        const int A = step < 0 ? -step : (step < 3 ? step : 4 - step);
+        if (step >= 0) {
+          const double xa = A == 0 ? x[0] : (A == 1 ? x[1] : x[2]);
+          const double va = A == 0 ? v[0] : (A == 1 ? v[1] : v[2]);
+          const double hA = sHl[A];
+          double x1 = xa + (step == 2 ? 2.0 * h : h) * va;  // hpp:237
+          const bool leaves = alive && !(x1 >= hA && x1 < hA + 1.0);
+          eject(leaves, kContBase - (step < 3 ? step : step + 1), my_cell, ekey, x, v, sHl, alive, mv, flags, lane);
+          const double xs = leaves ? hA + 0.5 : xa;
+          if (leaves) x1 = xs;
+          double I0[NWP];
+          eval_iwp_in<I>(xs, x1, hA, I0);  // hpp:178-186
+          if (A == 0) axis_part<I, 0>(x, v, x1, I0, P1, Pp, Q1, Qp, sB, sW, nq, qm, rslot);
+          else if (A == 1) axis_part<I, 1>(x, v, x1, I0, Q1, Qp, P1, Pp, sB, sW, nq, qm, rslot);
+          else axis_part<I, 2>(x, v, x1, I0, P1, Pp, Q1, Qp, sB, sW, nq, qm, rslot);
+          __syncwarp();
+          deposit_records<I>(sW, sAcc + A * (NACC * 32), first && step < 3, nit, lane);
+          __syncwarp();
+        }
+        if (step < 4) {
+          const double f = (A == 0 ? x[0] : (A == 1 ? x[1] : x[2])) - sHl[A];
+          if (step == -1 || step == 0 || step == 3) {
+            eval_w1_in<I>(f, P1);
+            eval_wp_in<I>(f, Pp);
+          } else {
+            eval_w1_in<I>(f, Q1);
+            eval_wp_in<I>(f, Qp);
+          }
+        }
+      }
+
+      // ---- re-file: stayers are compacted in place, per cell ---------------------------------------------------
+      const bool stays = valid && alive;
+      const unsigned stayA = __ballot_sync(kFull, stays && !isB), stayB = __ballot_sync(kFull, stays && isB);
+      if (stays) {
+        const unsigned below = (1u << lane) - 1u;
+        const long dst = isB ? tStart[ci + 1] + __popc(stayB & below) : tStart[ci] + wp + __popc(stayA & below);
+#pragma unroll
+        for (int d = 0; d < 3; ++d) {
+          p.x[d][dst] = x[d];
+          p.v[d][dst] = v[d];
+        }
+      }
+      wp += __popc(stayA);
+      if (last_of_cell) {
+        int cc[3];
+        const long base = corner_of(my_cell, cc);  // (per lane: the lane's own cell)
+        if (pair) {
+          flush_component<I, 0, true>(sAcc, E, base, st, g.pc, lane);
+          flush_component<I, 1, true>(sAcc + NACC * 32, E, base, st, g.pc, lane);
+          flush_component<I, 2, true>(sAcc + 2 * NACC * 32, E, base, st, g.pc, lane);
+          if (lane == 0) {
+            count[cbase + ci] = wp;
+            count[cbase + ci + 1] = __popc(stayB);
+          }
+        } else {
+          flush_component<I, 0>(sAcc, E, base, st, g.pc, lane);
+          flush_component<I, 1>(sAcc + NACC * 32, E, base, st, g.pc, lane);
+          flush_component<I, 2>(sAcc + 2 * NACC * 32, E, base, st, g.pc, lane);
+          if (lane == 0) count[cbase + ci] = wp;
+        }
+      }
+      __syncwarp();
+      if (last_of_cell) {
+        ci += pair ? 2 : 1;
+        off = 0;
+      } else {
+        off += 32;
+      }
+    }
+  }
+}
+
 // Sub-flows resume..5 of the program x y z z y x (step h each; the merged z(2h) of the block is undone here so
 // that the CFL limit of the reference, |v h| < 1 cell, is the one that applies) for one particle, general code.
 // With z slabs over several ranks z is NOT wrapped between the sub-flows: the particle keeps its coordinate
@@ -703,6 +914,18 @@ int launch_block(Ctx* c, Species& s, double h, const CellRanges& rg, unsigned li
   SPIC_CUDA_CHECK(c, cudaMemsetAsync(e->cont_key, 0xff, sizeof(unsigned) * (size_t)list_cap, c->stream));
   MoverList mv = e->mv;
   mv.cap = list_cap;  // (this launch may use a prefix of the list only: what the continuation then sorts)
+  // low particle counts per cell: two cells per batch (k_axis_block_pair); option "pair_kernel": -1 auto, 0 off, 1 on
+  const bool pairs = e->pair_kernel < 0 ? s.n_total < kPairBelow * c->g.cells() : e->pair_kernel != 0;
+  if (half == 0 && pairs) {
+    const size_t smem = sizeof(double) * kWarps * BlockLayout<I>::PER_WARP_PAIR;
+    static unsigned long long attr = 0;
+    if (smem_attr_needed(attr, c->cfg.device))
+      SPIC_CUDA_CHECK(c, cudaFuncSetAttribute(k_axis_block_pair<I>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k_axis_block_pair<I><<<(int)want, kThreads, smem, c->stream>>>(c->g, s.b, s.start, s.count, c->E, c->B, s.q, s.q / s.m,
+                                                                  h, mv, c->d_flags, rg, e->block_work, e->cont_key);
+    c->launches++;
+    return SPIC_OK;
+  }
   if (half == 1) return launch_block_t<I, false, 1>(c, s, h, rg, mv, want);
   if (half == 2) return launch_block_t<I, false, 2>(c, s, h, rg, mv, want);
   return e->tma ? launch_block_t<I, true, 0>(c, s, h, rg, mv, want) : launch_block_t<I, false, 0>(c, s, h, rg, mv, want);
