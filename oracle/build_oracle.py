@@ -81,6 +81,36 @@ def build_ref(force=False):
     return outs
 
 
+def build_ref_adapter(force=False):
+    """The reference + include/strugepic_amrex_adapter.hpp (ref_driver.cpp with -DSPIC_ADAPTER): its maps and
+    sub-flows go through the C ABI of ../strugepic_b200/lib/libstrugepic_b200.so (linked with an rpath relative to
+    the output) -- the literal drop-in of INTEGRATION.md, compiled against the AMReX stand-in.  Needs the library to
+    be built first; [] without /root/reference."""
+    lib_dir = os.path.join(HERE, "..", "strugepic_b200", "lib")
+    if not reference_present() or not os.path.isfile(os.path.join(lib_dir, "libstrugepic_b200.so")):
+        return []
+    os.makedirs(REFOUT, exist_ok=True)
+    srcs = [
+        os.path.join(REF, "src", "strugepic_propagators.cpp"),
+        os.path.join(REF, "src", "strugepic_util.cpp"),
+        os.path.join(REF, "src", "interpolation", "interpolation.cpp"),
+        os.path.join(HERE, "ref_driver.cpp"),
+    ]
+    pub = os.path.join(HERE, "..", "include")
+    deps = srcs + [os.path.join(HERE, "amrex_shim", "amrex_standin.H"), os.path.join(pub, "strugepic_amrex_adapter.hpp"),
+                   os.path.join(pub, "strugepic_b200.h")]
+    inc = ["-I" + os.path.join(HERE, "amrex_shim"), "-I" + os.path.join(REF, "include"),
+           "-I" + os.path.join(REF, "src", "interpolation"), "-I" + pub]
+    outs = []
+    for tag, defs in (("p8", ["-DINTERPOLATION_P8R2=1", "-DWRANGE=2"]), ("pwl", ["-DINTERPOLATION_PWL=1", "-DWRANGE=1"])):
+        out = os.path.join(REFOUT, "liboracle_adapter_%s.so" % tag)
+        if force or not _newer(out, deps):
+            _run(["g++", "-std=c++14", "-fPIC", "-shared", "-w", "-DSPIC_ADAPTER=1"] + PARITY + defs + inc + srcs +
+                 ["-o", out, "-L" + lib_dir, "-lstrugepic_b200", "-Wl,-rpath,$ORIGIN/../../strugepic_b200/lib"])
+        outs.append(out)
+    return outs
+
+
 DEFAULT_USER_W = os.path.join(HERE, "..", "strugepic_b200", "csrc", "user_w_default.cu")
 
 
@@ -109,5 +139,5 @@ def build_ref_user(user_src=DEFAULT_USER_W, wrange=2, tag="user", force=False):
 
 if __name__ == "__main__":
     force = "--force" in sys.argv
-    for o in build_port(force) + build_ref(force) + build_ref_user(force=force):
+    for o in build_port(force) + build_ref(force) + build_ref_user(force=force) + build_ref_adapter(force):
         print("built", os.path.relpath(o, HERE))

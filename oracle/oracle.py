@@ -47,6 +47,11 @@ def ref_lib_path(interp, fast=False):
                                                                   "_fast" if fast else ""))
 
 
+def adapter_lib_path(interp):
+    """The reference driven through include/strugepic_amrex_adapter.hpp (build_oracle.build_ref_adapter)."""
+    return os.path.join(HERE, "_ref", "liboracle_adapter_%s.so" % ("p8" if interp == P8R2 else "pwl"))
+
+
 def have_ref(interp=P8R2, fast=False):
     return os.path.isfile(ref_lib_path(interp, fast))
 
@@ -60,6 +65,7 @@ def ensure_built():
         build_oracle.build_port()
         build_oracle.build_ref()
         build_oracle.build_ref_user()
+        build_oracle.build_ref_adapter()
     finally:
         sys.path.pop(0)
 
@@ -205,8 +211,11 @@ class RefOracle(_Base):
     prefix = "oref_"
     kind = "reference"
 
-    def __init__(self, n_cell, periodic=(1, 1, 1), ng=None, interp=P8R2, fast=False):
-        path = ref_lib_path(interp, fast)
+    def __init__(self, n_cell, periodic=(1, 1, 1), ng=None, interp=P8R2, fast=False, adapter=False):
+        # adapter: the same shell, but maps and sub-flows run through the drop-in adapter -> the GPU library
+        path = adapter_lib_path(interp) if adapter else ref_lib_path(interp, fast)
+        if adapter:
+            self.kind = "adapter"
         if not os.path.isfile(path):
             ensure_built()
         if not os.path.isfile(path):

@@ -19,6 +19,15 @@
 #include "strugepic_propagators.hpp"
 #include "strugepic_util.hpp"
 #include "strugepic_w.hpp"
+// -DSPIC_ADAPTER: the sub-flows and maps below run through include/strugepic_amrex_adapter.hpp instead -- the literal
+// drop-in a maintainer of the reference would use (stand-in MultiFab / AoS particles -> C ABI -> GPU -> back); every
+// other entry point (state in / out, energy, W functions) stays the reference's.  -> oracle/_ref/liboracle_adapter_*.so
+#ifdef SPIC_ADAPTER
+#include "strugepic_amrex_adapter.hpp"
+#define SPIC_CALL strugepic_b200_amrex::
+#else
+#define SPIC_CALL
+#endif
 
 #ifndef WRANGE
 #error "define WRANGE (2 for P8R2, 1 for PWL)"
@@ -124,23 +133,27 @@ void oref_get_particles(void* h, double* x, double* y, double* z, double* vx, do
 
 void oref_theta_axis(void* h, int comp, double dt) {
   Sim* s = static_cast<Sim*>(h);
-  if (comp == 0) G_Theta<X, WRANGE>(s->geom, *s->P, *s->E, *s->B, dt);
-  if (comp == 1) G_Theta<Y, WRANGE>(s->geom, *s->P, *s->E, *s->B, dt);
-  if (comp == 2) G_Theta<Z, WRANGE>(s->geom, *s->P, *s->E, *s->B, dt);
+  if (comp == 0) SPIC_CALL G_Theta<X, WRANGE>(s->geom, *s->P, *s->E, *s->B, dt);
+  if (comp == 1) SPIC_CALL G_Theta<Y, WRANGE>(s->geom, *s->P, *s->E, *s->B, dt);
+  if (comp == 2) SPIC_CALL G_Theta<Z, WRANGE>(s->geom, *s->P, *s->E, *s->B, dt);
 }
 void oref_theta_E(void* h, double dt) {
   Sim* s = static_cast<Sim*>(h);
-  G_Theta_E<WRANGE>(s->geom, *s->P, *s->E, *s->B, dt);
+  SPIC_CALL G_Theta_E<WRANGE>(s->geom, *s->P, *s->E, *s->B, dt);
 }
 void oref_theta_B(void* h, double dt) {
   Sim* s = static_cast<Sim*>(h);
+#ifdef SPIC_ADAPTER
+  strugepic_b200_amrex::G_Theta_B<WRANGE>(s->geom, *s->P, *s->E, *s->B, dt);
+#else
   G_Theta_B(s->geom, *s->P, *s->E, *s->B, dt);
+#endif
 }
 void oref_map(void* h, int order, double dt) {
   Sim* s = static_cast<Sim*>(h);
-  if (order == 1) Theta_map1<WRANGE>(s->geom, *s->P, *s->E, *s->B, dt);
-  if (order == 2) Theta_map2<WRANGE>(s->geom, *s->P, *s->E, *s->B, dt);
-  if (order == 4) Theta_map4<WRANGE>(s->geom, *s->P, *s->E, *s->B, dt);
+  if (order == 1) SPIC_CALL Theta_map1<WRANGE>(s->geom, *s->P, *s->E, *s->B, dt);
+  if (order == 2) SPIC_CALL Theta_map2<WRANGE>(s->geom, *s->P, *s->E, *s->B, dt);
+  if (order == 4) SPIC_CALL Theta_map4<WRANGE>(s->geom, *s->P, *s->E, *s->B, dt);
 }
 void oref_source(void* h, int pos, int comp, double E0, double omega, double dt, double t) {
   Sim* s = static_cast<Sim*>(h);

@@ -52,8 +52,8 @@ struct EngineState {
   // 1: the fused axis block stages the particle rows of its batches with TMA bulk copies (cp.async.bulk completed on
   // an mbarrier) instead of cp.async
   int tma = 0;
-  // fused axis block with two cells per batch (k_axis_block_pair): -1 = when the mean particle count per cell is
-  // below 12, 0 = never, 1 = always
+  // low particle counts per cell: fused axis block with two cells per batch (k_axis_block_pair) and push_V_E with up
+  // to four (k_push_v_e_quad): -1 = when the mean particle count per cell is below 18, 0 = never, 1 = always
   int pair_kernel = -1;
   unsigned* block_work = nullptr;   // chunk counter of the fused axis-block kernel
   // continuation of the ejected particles: sort key (home cell) per mover-list entry + radix-sort buffers

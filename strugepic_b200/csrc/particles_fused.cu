@@ -52,7 +52,7 @@ namespace {
 constexpr int kWarps = 8;
 constexpr int kThreads = kWarps * 32;
 constexpr unsigned kFull = 0xffffffffu;
-constexpr long kPairBelow = 12;  // mean particles per cell below which the two-cells-per-batch kernel runs
+constexpr long kPairBelow = 18;  // mean particles per cell below which the two-cells-per-batch kernel runs
 constexpr int kContBase = -100;  // mover-list code of an ejected particle: kContBase - first sub-flow still to do
 #ifndef SPIC_CHUNK
 #define SPIC_CHUNK 8

@@ -33,6 +33,7 @@ constexpr int kMaxCells = 64;          // cells per block (option cells_per_bloc
 constexpr int kSpan = 2;               // a batch spans at most kSpan non-empty cells
 constexpr int kRing = 2 * kSpan;       // stencil slots per warp: cells of the current + of the next batch
 constexpr unsigned kFull = 0xffffffffu;
+constexpr long kLowPpc = 18;           // mean particles per cell below which the low-count kernels run
 
 struct BlockTables {
   int cnt[kMaxCells];
@@ -281,6 +282,155 @@ __global__ void __launch_bounds__(kThreads, 2)
     pb ^= 1;
   }
   cp_async_wait<0>();
+}
+
+// ------------------------------------------------------------------------------------------------
+// k_push_v_e_quad: push_V_E for LOW particle counts per cell (host: mean count below kLowPpc).  The v3 stream cuts a
+// batch over at most kSpan = 2 cells -- 16 of 32 lanes at 8 particles per cell.  Here a warp draws chunks of 8
+// consecutive cells and packs up to FOUR of them into a batch (as many as fit 32 lanes); their stencils sit in four
+// slots 16 bytes apart in bank space and are staged synchronously with the batch (the other warps of the SM cover the
+// wait: 3 blocks per SM at 62 KB).  A cell with more than 32 particles takes batches of its own.  Same arithmetic as
+// k_push_v_e_v3.
+// ------------------------------------------------------------------------------------------------
+constexpr int kQuad = 4, kQuadChunk = 8;
+template <class I>
+__global__ void __launch_bounds__(kThreads, 3)
+    k_push_v_e_quad(Grid g, ParticleSoA p, const long* __restrict__ start, const int* __restrict__ count,
+                    const double* __restrict__ E, double coef, long ncell, unsigned* __restrict__ work) {
+  constexpr int NW1 = I::NW1, NWP = I::NWP;
+  using Lay = PushLayout<I>;
+  constexpr int NS = Lay::NS, SE = Lay::SE, SES = Lay::SES, SP = Lay::SP;
+  constexpr int PER_WARP = SP + kQuad * SES + 3 * kQuadChunk;
+  extern __shared__ __align__(16) double smem[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  double* sPart = smem + warp * PER_WARP;                          // [6][32]
+  double* sEst = sPart + SP;                                       // [kQuad][SES]
+  long* tStart = reinterpret_cast<long*>(sEst + kQuad * SES);      // [kQuadChunk]
+  long* tBase = tStart + kQuadChunk;                               // [kQuadChunk] stencil corners
+  int* tCnt = reinterpret_cast<int*>(tBase + kQuadChunk);          // [kQuadChunk]
+  const unsigned nchunk = (unsigned)((ncell + kQuadChunk - 1) / kQuadChunk);
+  const long corner_off = (1 - I::W) * (1 + g.pj + g.pk);
+  for (;;) {
+    unsigned id = 0;
+    if (lane == 0) id = atomicAdd(work, 1u);
+    id = __shfl_sync(kFull, id, 0);
+    if (id >= nchunk) break;
+    __syncwarp();
+    if (lane < kQuadChunk) {
+      const long cell = (long)id * kQuadChunk + lane;
+      if (cell < ncell) {
+        const int cx = (int)(cell % g.n[0]), cy = (int)((cell / g.n[0]) % g.n[1]);
+        const int cz = (int)(cell / ((long)g.n[0] * g.n[1]));
+        tCnt[lane] = count[cell];
+        tStart[lane] = start[cell];
+        tBase[lane] = g.at(cx, cy, cz) + corner_off;
+      } else {
+        tCnt[lane] = 0;
+        tStart[lane] = 0;
+        tBase[lane] = 0;
+      }
+    }
+    __syncwarp();
+    int ci = 0, off = 0;
+    while (ci < kQuadChunk) {
+      // batch: particles [off, ..) of cell ci, then whole cells ci+1.. while they fit (<= kQuad cells, <= 32 lanes)
+      int nc = 1, tot = tCnt[ci] - off < 32 ? tCnt[ci] - off : 32;
+      int b1 = tot, b2 = tot, b3 = tot;  // lane boundaries: cell k holds lanes [b_k, b_{k+1})
+      const bool whole0 = off + tot >= tCnt[ci];
+      if (whole0) {
+        while (nc < kQuad && ci + nc < kQuadChunk && tot + tCnt[ci + nc] <= 32) {
+          tot += tCnt[ci + nc];
+          if (nc == 1) b2 = b3 = tot;
+          else if (nc == 2) b3 = tot;
+          ++nc;
+        }
+      }
+      const int k = lane < b1 ? 0 : (lane < b2 ? 1 : (lane < b3 ? 2 : 3));  // my cell of the batch
+      const bool valid = lane < tot;
+      const long idx = valid ? tStart[ci + k] + (k == 0 ? off + lane : lane - (k == 1 ? b1 : (k == 2 ? b2 : b3))) : 0;
+      if (valid) {
+        double* d = sPart + lane;
+        cp_async8(d + 0 * 32, p.x[0] + idx);
+        cp_async8(d + 1 * 32, p.x[1] + idx);
+        cp_async8(d + 2 * 32, p.x[2] + idx);
+        cp_async8(d + 3 * 32, p.v[0] + idx);
+        cp_async8(d + 4 * 32, p.v[1] + idx);
+        cp_async8(d + 5 * 32, p.v[2] + idx);
+      }
+      for (int c = 0; c < nc; ++c) {
+        if (tCnt[ci + c] == 0 || (c == 0 && off > 0)) continue;  // (empty, or the stencil is still in slot 0)
+        const double* src = E + tBase[ci + c];
+        double* d = sEst + c * SES;
+#pragma unroll
+        for (int s = lane; s < SE; s += 32) {
+          const int comp = s / NS, r = s % NS;
+          cp_async8(d + s, src + (r % NW1) + ((r / NW1) % NW1) * g.pj + (r / (NW1 * NW1)) * g.pk + (long)comp * g.pc);
+        }
+      }
+      cp_async_commit();
+      cp_async_wait<0>();
+      __syncwarp();
+      if (valid) {
+        const double* sP = sPart + lane;
+        const double* sE = sEst + k * SES;
+        const double x = sP[0], y = sP[32], z = sP[64];
+        const double fx = x - floor(x), fy = y - floor(y), fz = z - floor(z);
+        double w1x[NW1], w1y[NW1], w1z[NW1], wpx[NWP], wpy[NWP], wpz[NWP];
+        eval_w1_in<I>(fx, w1x);
+        eval_w1_in<I>(fy, w1y);
+        eval_w1_in<I>(fz, w1z);
+        eval_wp_in<I>(fx, wpx);
+        eval_wp_in<I>(fy, wpy);
+        eval_wp_in<I>(fz, wpz);
+        // hpp:322-338, factorised as in k_push_v_e_v3
+        double ax = 0, ay = 0, az = 0;
+#pragma unroll
+        for (int tk = 0; tk < NW1; ++tk) {
+          double bx = 0, by = 0, bz = 0;
+#pragma unroll
+          for (int tj = 0; tj < NW1; ++tj) {
+            const double* row = sE + (tk * NW1 + tj) * NW1;
+            double ex[NW1];
+            lds_row<NW1>(row, ex);
+            double cx = ex[0] * wpx[0];
+#pragma unroll
+            for (int ti = 1; ti < NWP; ++ti) cx = fma(ex[ti], wpx[ti], cx);
+            bx = tj == 0 ? w1y[0] * cx : fma(w1y[tj], cx, bx);
+            if (tj < NWP) {
+              double ey[NW1];
+              lds_row<NW1>(row + NS, ey);
+              double cy = ey[0] * w1x[0];
+#pragma unroll
+              for (int ti = 1; ti < NW1; ++ti) cy = fma(ey[ti], w1x[ti], cy);
+              by = tj == 0 ? wpy[0] * cy : fma(wpy[tj < NWP ? tj : 0], cy, by);
+            }
+            if (tk < NWP) {
+              double ez[NW1];
+              lds_row<NW1>(row + 2 * NS, ez);
+              double cz = ez[0] * w1x[0];
+#pragma unroll
+              for (int ti = 1; ti < NW1; ++ti) cz = fma(ez[ti], w1x[ti], cz);
+              bz = tj == 0 ? w1y[0] * cz : fma(w1y[tj], cz, bz);
+            }
+          }
+          ax = tk == 0 ? w1z[0] * bx : fma(w1z[tk], bx, ax);
+          ay = tk == 0 ? w1z[0] * by : fma(w1z[tk], by, ay);
+          if (tk < NWP) az = tk == 0 ? wpz[0] * bz : fma(wpz[tk < NWP ? tk : 0], bz, az);
+          asm volatile("" ::: "memory");  // bound load hoisting (register pressure)
+        }
+        p.v[0][idx] = fma(ax, coef, sP[96]);  // hpp:339-341
+        p.v[1][idx] = fma(ay, coef, sP[128]);
+        p.v[2][idx] = fma(az, coef, sP[160]);
+      }
+      __syncwarp();  // the buffers are free again
+      if (whole0) {
+        ci += nc;
+        off = 0;
+      } else {
+        off += 32;
+      }
+    }
+  }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -884,6 +1034,24 @@ int push_dispatch(Ctx* c, Species& s, double dt) {
   const int grid = (int)((ncell + cpb - 1) / cpb);
   const double coef = dt * s.q / s.m;  // hpp:267
   int rc;
+  // low particle counts per cell: up to four cells per batch (option "pair_kernel": -1 auto, 0 off, 1 on)
+  const int pk = eng(c)->pair_kernel;
+  if (pk < 0 ? s.n_total < kLowPpc * ncell : pk != 0) {
+    EngineState* e = eng(c);
+    if (!e->block_work) SPIC_CUDA_CHECK(c, cudaMalloc(&e->block_work, sizeof(unsigned)));
+    SPIC_CUDA_CHECK(c, cudaMemsetAsync(e->block_work, 0, sizeof(unsigned), c->stream));
+    constexpr int per_warp = PushLayout<I>::SP + kQuad * PushLayout<I>::SES + 3 * kQuadChunk;
+    const size_t smemq = sizeof(double) * kWarps * per_warp;
+    static unsigned long long attrq = 0;
+    if ((rc = set_smem(c, k_push_v_e_quad<I>, smemq, attrq))) return rc;
+    const long nchunk = (ncell + kQuadChunk - 1) / kQuadChunk;
+    long want = (nchunk + kWarps - 1) / kWarps;
+    if (want > 3L * c->sm_count) want = 3L * c->sm_count;
+    k_push_v_e_quad<I><<<(int)want, kThreads, smemq, c->stream>>>(c->g, s.b, s.start, s.count, c->E, coef, ncell,
+                                                                  e->block_work);
+    c->launches++;
+    return SPIC_OK;
+  }
   if (eng(c)->pushve_kernel == 4) {  // two particles per lane (opt-in: option pushve_kernel = 4)
     const size_t smem4 = sizeof(double) * kWarps * PushLayout4<I>::PER_WARP;
     static unsigned long long attr4 = 0;
