@@ -16,10 +16,10 @@ npart = s.num_particles()
 print("fp64 probe TFLOP/s:", spic.probe_fp64_tflops(0, 0.5), "particles", npart)
 s.set_option("time_kernels", 1)
 s.set_option("fuse", 0)
-for variant in (() if 'fusedonly' in sys.argv else (1, 2, 3)):
+for variant in (() if "fusedonly" in sys.argv else (2, 3)):
     s.set_option("axis_kernel", variant)
     s.set_option("pushve_kernel", variant)
-    for cpb in ((64,) if variant == 1 else (32, 64)):
+    for cpb in (32, 64):
         s.set_option("cells_per_block", cpb)
         for _ in range(2):
             s.Theta_map2(0.5)

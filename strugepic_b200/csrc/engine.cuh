@@ -36,11 +36,11 @@ struct EngineState {
   size_t cub_bytes = 0;
   double mover_frac = 0.0;  // 0: automatic
   int cells_per_block = 64;
-  // particle-kernel generation: 1 warp-per-cell (k_*_binned), 2 cp.async pipelined warp-per-cell
-  // (k_*_v2), 3 particle-stream batches that span cells (k_*_v3, particles_stream.cu)
-  // 0 = automatic: theta_axis uses v3 below ~40 particles per cell (batches would be mostly padding
-  // with one warp per cell) and v2 above (its per-batch bookkeeping is cheaper); push_V_E uses v3.
-  // pushve_kernel = 4: the v3 stream with two particles per lane (k_push_v_e_v4), opt-in.
+  // particle-kernel generation of the single sub-flows: 2 = cp.async pipelined warp-per-cell (k_*_v2), 3 = particle-stream
+  // batches that span cells (k_*_v3, particles_stream.cu); 0 = automatic: theta_axis uses v3 below ~40 particles per cell
+  // (batches would be mostly padding with one warp per cell) and v2 above (its per-batch bookkeeping is cheaper); push_V_E
+  // uses v3 (k_push_v_e_quad at low counts).  Generation 1 (unpipelined) and the pair-blocked k_push_v_e_v4 were removed in
+  // round 2: no A/B kept them.
   int axis_kernel = 0;
   int pushve_kernel = 0;
   // 1: Theta_map2 / Theta_map4 run the six position sub-flows of every map2 as one fused axis block

@@ -51,235 +51,10 @@ constexpr int kWarps = 8;
 constexpr int kThreads = kWarps * 32;
 
 // ------------------------------------------------------------------------------------
-// theta_axis, binned
-// ------------------------------------------------------------------------------------
-template <class I, int A>
-__global__ void __launch_bounds__(kThreads, 2)
-    k_theta_axis_binned(Grid g, ParticleSoA p, const long* __restrict__ start, int* __restrict__ count,
-                        double* __restrict__ E, const double* __restrict__ B, double q, double qm, double dt,
-                        MoverList mv, int* __restrict__ flags, long ncell, int cells_per_block) {
-  constexpr int U = (A + 1) % 3, L = (A + 2) % 3;  // hpp:90-91
-  constexpr int NW1 = I::NW1, NWP = I::NWP;
-  constexpr int LU = NW1 * NW1;     // stencil columns (l,u)
-  constexpr int PER = 32 / LU;      // particles handled per phase-B iteration
-  constexpr int SW = 2 * NW1 + NWP; // doubles per particle in the weight scratch
-  constexpr int NST = NWP * LU;     // stencil points per component
-  extern __shared__ double smem[];
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  double* sB = smem + warp * (2 * NST + 32 * SW);  // [2][NST]: B_u then B_l
-  double* sW = sB + 2 * NST;                       // [32][SW]
-  const long st[3] = {1, g.pj, g.pk};
-  const int lu = lane % LU, sub = lane / LU;
-  const int my_tl = lu / NW1, my_tu = lu % NW1;
-  const double nq = -q;  // -E_coef (hpp:114; Ics = Cs = 1)
-  double* Ea = E + (long)A * g.pc;
-  const double* Bu = B + (long)U * g.pc;
-  const double* Bl = B + (long)L * g.pc;
-  const long cstride[3] = {1, g.n[0], (long)g.n[0] * g.n[1]};
-
-  const long cbeg = (long)blockIdx.x * cells_per_block;
-  long cend = cbeg + cells_per_block;
-  if (cend > ncell) cend = ncell;
-  for (long cell = cbeg + warp; cell < cend; cell += kWarps) {
-    const int cnt = count[cell];
-    if (cnt == 0) continue;
-    const long s0 = start[cell];
-    int cc[3];  // local cell coordinates
-    cc[0] = (int)(cell % g.n[0]);
-    cc[1] = (int)((cell / g.n[0]) % g.n[1]);
-    cc[2] = (int)(cell / cstride[2]);
-    const int homeA = cc[A] + (A == 2 ? g.z0 : 0);  // global index along the push axis
-    const int homeU = cc[U] + (U == 2 ? g.z0 : 0);
-    const int homeL = cc[L] + (L == 2 ? g.z0 : 0);
-    const long base = g.at(cc[0], cc[1], cc[2]) + (1 - I::W) * (st[A] + st[U] + st[L]);
-
-    __syncwarp();
-    for (int s = lane; s < 2 * NST; s += 32) {  // stage the B stencil of this cell
-      const int r = s % NST;
-      const int tc = r % NWP, tu = (r / NWP) % NW1, tl = r / (NWP * NW1);
-      const long idx = base + tc * st[A] + tu * st[U] + tl * st[L];
-      sB[s] = __ldg(s < NST ? &Bu[idx] : &Bl[idx]);
-    }
-    __syncwarp();
-
-    double acc[NWP];
-#pragma unroll
-    for (int t = 0; t < NWP; ++t) acc[t] = 0.0;
-    int wp = 0;  // stayers written so far (compaction pointer)
-
-    for (int off = 0; off < cnt; off += 32) {
-      const bool valid = off + lane < cnt;
-      const long idx = s0 + off + lane;
-      // ---- phase A: thread per particle -------------------------------------------------
-      double xa = (double)homeA + 0.5, xu = (double)homeU + 0.5, xl = (double)homeL + 0.5;
-      double va = 0.0, vu = 0.0, vl = 0.0;
-      if (valid) {
-        xa = p.x[A][idx];
-        xu = p.x[U][idx];
-        xl = p.x[L][idx];
-        va = p.v[A][idx];
-        vu = p.v[U][idx];
-        vl = p.v[L][idx];
-      }
-      double uW1[NW1], lW1[NW1], uWp[NWP], lWp[NWP];
-      eval_w1<I>(xl, homeL, lW1);
-      eval_wp<I>(xl, homeL, lWp);
-      eval_w1<I>(xu, homeU, uW1);
-      eval_wp<I>(xu, homeU, uWp);
-      Segments sg = make_segments<I, A>(g, xa, xa + dt * va, flags);
-      double I0[NWP];
-      eval_iwp<I>(sg.pt[0], sg.pt[1], homeA, I0);
-
-      double r1 = 0, r2 = 0;
-#pragma unroll
-      for (int tl = 0; tl < NW1; ++tl) {  // first segment: B gather from the staged stencil
-        double a1 = 0, a2 = 0;
-#pragma unroll
-        for (int tu = 0; tu < NW1; ++tu) {
-          double s1 = 0, s2 = 0;
-#pragma unroll
-          for (int tc = 0; tc < NWP; ++tc) {
-            s1 = fma(sB[(tl * NW1 + tu) * NWP + tc], I0[tc], s1);
-            if (tu < NWP) s2 = fma(sB[NST + (tl * NW1 + tu) * NWP + tc], I0[tc], s2);
-          }
-          a1 = fma(uW1[tu], s1, a1);
-          if (tu < NWP) a2 = fma(uWp[tu], s2, a2);
-        }
-        if (tl < NWP) r1 = fma(lWp[tl], a1, r1);  // hpp:216
-        r2 = fma(-lW1[tl], a2, r2);               // hpp:217
-        asm volatile("" ::: "memory");            // bound load hoisting (register pressure)
-      }
-      if (sg.n == 2) {  // second segment lives in another stencil: per-particle path (rare)
-        double I1[NWP];
-        eval_iwp<I>(sg.pt[1], sg.pt[2], sg.cell[1], I1);
-        const long base2 = base + (long)(sg.cell[1] - homeA) * st[A];
-#pragma unroll
-        for (int tl = 0; tl < NW1; ++tl) {
-          double a1 = 0, a2 = 0;
-#pragma unroll
-          for (int tu = 0; tu < NW1; ++tu) {
-            const long row = base2 + tl * st[L] + tu * st[U];
-            const double mul = nq * (lW1[tl] * uW1[tu]);
-            double s1 = 0, s2 = 0;
-#pragma unroll
-            for (int tc = 0; tc < NWP; ++tc) {
-              const long j = row + tc * st[A];
-              atomicAdd(&Ea[j], mul * I1[tc]);  // hpp:215
-              s1 = fma(__ldg(&Bu[j]), I1[tc], s1);
-              if (tu < NWP) s2 = fma(__ldg(&Bl[j]), I1[tc], s2);
-            }
-            a1 = fma(uW1[tu], s1, a1);
-            if (tu < NWP) a2 = fma(uWp[tu], s2, a2);
-          }
-          if (tl < NWP) r1 = fma(lWp[tl], a1, r1);
-          r2 = fma(-lW1[tl], a2, r2);
-        }
-      }
-      // position / velocity update (hpp:230-241) and periodic wrap (Redistribute, hpp:368)
-      double xa_new;
-      if (sg.reflected) {
-        xa_new = sg.pt[2];
-        va = -va;
-      } else {
-        xa_new = xa + dt * va;
-      }
-      xa_new = wrap_periodic(xa_new, g.gn[A], g.per[A], flags);
-      vl = fma(qm, r1, vl);
-      vu = fma(qm, r2, vu);
-      const int newA = (int)floor(xa_new);
-      const bool moves = valid && newA != homeA;
-
-      // weights of the first segment for phase B: -q*W1_l, W1_u, I   (hpp:194,215)
-      {
-        double* w = sW + lane * SW;
-#pragma unroll
-        for (int t = 0; t < NW1; ++t) w[t] = nq * lW1[t];
-#pragma unroll
-        for (int t = 0; t < NW1; ++t) w[NW1 + t] = uW1[t];
-#pragma unroll
-        for (int t = 0; t < NWP; ++t) w[2 * NW1 + t] = valid ? I0[t] : 0.0;
-      }
-      __syncwarp();
-      // ---- phase B: lane (l,u) accumulates its stencil column over the warp's particles ----
-#pragma unroll 4
-      for (int it = 0; it < 32 / PER; ++it) {
-        const double* w = sW + (it * PER + sub) * SW;
-        const double ab = w[my_tl] * w[NW1 + my_tu];
-#pragma unroll
-        for (int t = 0; t < NWP; ++t) acc[t] = fma(ab, w[2 * NW1 + t], acc[t]);
-      }
-      __syncwarp();
-
-      // ---- re-file: stayers compacted in place, movers to the list ---------------------------
-      const unsigned stay_mask = __ballot_sync(0xffffffffu, valid && !moves);
-      const unsigned move_mask = __ballot_sync(0xffffffffu, moves);
-      const int nstay = __popc(stay_mask);
-      if (valid && !moves) {
-        const long dst = s0 + wp + __popc(stay_mask & ((1u << lane) - 1u));
-        if (dst == idx) {  // nothing ahead of us left: only the changed components move
-          p.x[A][dst] = xa_new;
-          p.v[U][dst] = vu;
-          p.v[L][dst] = vl;
-          if (!g.per[A]) p.v[A][dst] = va;
-        } else {
-          p.x[A][dst] = xa_new;
-          p.x[U][dst] = xu;
-          p.x[L][dst] = xl;
-          p.v[A][dst] = va;
-          p.v[U][dst] = vu;
-          p.v[L][dst] = vl;
-        }
-      }
-      if (move_mask) {
-        unsigned basei = 0;
-        const int leader = __ffs(move_mask) - 1;
-        if (lane == leader) basei = atomicAdd(mv.n, (unsigned)__popc(move_mask));
-        basei = __shfl_sync(0xffffffffu, basei, leader);
-        if (moves) {
-          const unsigned m = basei + __popc(move_mask & ((1u << lane) - 1u));
-          if (m < mv.cap) {
-            int dest;
-            if (A == 2) {
-              dest = z_dest(g, cell, homeA, newA);
-            } else {
-              dest = (int)(cell + (long)(newA - homeA) * cstride[A]);
-            }
-            mv.x[A][m] = xa_new;
-            mv.x[U][m] = xu;
-            mv.x[L][m] = xl;
-            mv.v[A][m] = va;
-            mv.v[U][m] = vu;
-            mv.v[L][m] = vl;
-            mv.dest[m] = dest;
-          } else {
-            atomicOr(&flags[1], 1);
-          }
-        }
-      }
-      wp += nstay;
-      __syncwarp();
-    }
-
-    // ---- flush: one reduction per stencil point and cell -----------------------------------
-#pragma unroll
-    for (int t = 0; t < NWP; ++t) {
-#pragma unroll
-      for (int s = LU; s < 32; s <<= 1) acc[t] += __shfl_xor_sync(0xffffffffu, acc[t], s);
-    }
-    if (sub == 0) {
-      const long row = base + my_tl * st[L] + my_tu * st[U];
-#pragma unroll
-      for (int t = 0; t < NWP; ++t) atomicAdd(&Ea[row + t * st[A]], acc[t]);
-    }
-    if (lane == 0) count[cell] = wp;
-  }
-}
-
-// ------------------------------------------------------------------------------------
 // theta_axis, binned, v2: software-pipelined warp-per-cell kernel.
 //
-// Same algorithm and data layout as k_theta_axis_binned above; what changes is how the
-// warp is fed (ncu of v1: 28-41 % of the stall samples were long_scoreboard on the particle /
+// The algorithm of the file header; what matters is how the warp is fed (ncu of the first,
+// unpipelined generation -- removed in round 2, it earned nothing --: 28-41 % of the stall samples were long_scoreboard on the particle /
 // stencil loads, 21 % of the instructions were the LDS-bound deposition loop):
 //   * the block's bin counts / starts are read once into shared memory;
 //   * particle batches (32 x 6 doubles) and the B stencil of the NEXT batch / cell are staged
@@ -717,55 +492,6 @@ __global__ void __launch_bounds__(256)
       } else {
         atomicOr(&flags[1], 2);
       }
-    }
-  }
-}
-
-// ------------------------------------------------------------------------------------
-// push_V_E, binned
-// ------------------------------------------------------------------------------------
-template <class I>
-__global__ void __launch_bounds__(kThreads, 2)
-    k_push_v_e_binned(Grid g, ParticleSoA p, const long* __restrict__ start, const int* __restrict__ count,
-                      const double* __restrict__ E, double coef, long ncell, int cells_per_block) {
-  constexpr int NW1 = I::NW1, NWP = I::NWP;
-  constexpr int NS = NW1 * NW1 * NW1;
-  extern __shared__ double smem[];
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  double* sE = smem + warp * 3 * NS;  // [3][NW1][NW1][NW1]
-  const long cstride2 = (long)g.n[0] * g.n[1];
-  const long cbeg = (long)blockIdx.x * cells_per_block;
-  long cend = cbeg + cells_per_block;
-  if (cend > ncell) cend = ncell;
-  for (long cell = cbeg + warp; cell < cend; cell += kWarps) {
-    const int cnt = count[cell];
-    if (cnt == 0) continue;
-    const long s0 = start[cell];
-    const int ci = (int)(cell % g.n[0]), cj = (int)((cell / g.n[0]) % g.n[1]), ck = (int)(cell / cstride2);
-    const long base = g.at(ci, cj, ck) + (1 - I::W) * (1 + g.pj + g.pk);
-    __syncwarp();
-    for (int s = lane; s < 3 * NS; s += 32) {
-      const int comp = s / NS, r = s % NS;
-      const int ti = r % NW1, tj = (r / NW1) % NW1, tk = r / (NW1 * NW1);
-      sE[s] = __ldg(&E[base + ti + tj * g.pj + tk * g.pk + comp * g.pc]);
-    }
-    __syncwarp();
-    for (int off = lane; off < cnt; off += 32) {
-      const long idx = s0 + off;
-      const double x = p.x[0][idx], y = p.x[1][idx], z = p.x[2][idx];
-      double w1x[NW1], w1y[NW1], w1z[NW1], wpx[NWP], wpy[NWP], wpz[NWP];
-      eval_w1<I>(x, ci, w1x);
-      eval_w1<I>(y, cj, w1y);
-      eval_w1<I>(z, ck + g.z0, w1z);
-      eval_wp<I>(x, ci, wpx);
-      eval_wp<I>(y, cj, wpy);
-      eval_wp<I>(z, ck + g.z0, wpz);
-      double dv[3];
-      gather_E<I>(sE, (long)NW1, (long)NW1 * NW1, (long)NS, w1x, w1y, w1z, wpx, wpy, wpz, dv,
-                  [](const double* ptr) { return *ptr; });
-      p.v[0][idx] = fma(dv[0], coef, p.v[0][idx]);  // hpp:339-341
-      p.v[1][idx] = fma(dv[1], coef, p.v[1][idx]);
-      p.v[2][idx] = fma(dv[2], coef, p.v[2][idx]);
     }
   }
 }
@@ -1286,27 +1012,6 @@ int theta_axis_v2_dispatch(Ctx* c, Species& s, int comp, double dt) {
   return SPIC_OK;
 }
 
-template <class I>
-void theta_axis_binned_dispatch(Ctx* c, Species& s, int comp, double dt) {
-  EngineState* e = eng(c);
-  const long ncell = c->g.cells();
-  const int cpb = e->cells_per_block;
-  const int grid = (int)((ncell + cpb - 1) / cpb);
-  constexpr int per_warp = 2 * I::NWP * I::NW1 * I::NW1 + 32 * (2 * I::NW1 + I::NWP);
-  const size_t smem = sizeof(double) * kWarps * per_warp;
-  const double qm = s.q / s.m;
-  if (comp == 0)
-    k_theta_axis_binned<I, 0><<<grid, kThreads, smem, c->stream>>>(c->g, s.b, s.start, s.count, c->E, c->B, s.q, qm, dt,
-                                                                  e->mv, c->d_flags, ncell, cpb);
-  else if (comp == 1)
-    k_theta_axis_binned<I, 1><<<grid, kThreads, smem, c->stream>>>(c->g, s.b, s.start, s.count, c->E, c->B, s.q, qm, dt,
-                                                                  e->mv, c->d_flags, ncell, cpb);
-  else
-    k_theta_axis_binned<I, 2><<<grid, kThreads, smem, c->stream>>>(c->g, s.b, s.start, s.count, c->E, c->B, s.q, qm, dt,
-                                                                  e->mv, c->d_flags, ncell, cpb);
-  c->launches++;
-}
-
 }  // namespace
 
 // ---- engine interface -------------------------------------------------------------------
@@ -1514,11 +1219,6 @@ int engine_theta_axis(Ctx* c, Species& s, int comp, double dt) {
     if (variant == 3) {
       const int rc = stream_theta_axis(c, s, comp, dt);
       if (rc) return rc;
-    } else if (variant == 1) {
-      if (c->cfg.interp == SPIC_INTERP_P8R2)
-        theta_axis_binned_dispatch<InterpP8R2>(c, s, comp, dt);
-      else
-        theta_axis_binned_dispatch<InterpPWL>(c, s, comp, dt);
     } else {
       const int rc = c->cfg.interp == SPIC_INTERP_P8R2 ? theta_axis_v2_dispatch<InterpP8R2>(c, s, comp, dt)
                                                        : theta_axis_v2_dispatch<InterpPWL>(c, s, comp, dt);
@@ -1613,28 +1313,20 @@ int engine_push_v_e(Ctx* c, Species& s, double dt) {
   const double coef = dt * s.q / s.m;  // hpp:267
   {
     KernelTimer t(c, KT_PUSHVE);
-    if (e->pushve_kernel == 3 || e->pushve_kernel == 4 || e->pushve_kernel == 0 || c->cfg.interp == SPIC_INTERP_USER) {
+    if (e->pushve_kernel != 2 || c->cfg.interp == SPIC_INTERP_USER) {
       const int rc = stream_push_v_e(c, s, dt);
       if (rc) return rc;
       c->launches--;  // counted below
-    } else if (e->pushve_kernel != 1) {
-      if (c->cfg.interp == SPIC_INTERP_P8R2) {
-        const size_t smem = sizeof(double) * kWarps * PushV2Layout<InterpP8R2>::PER_WARP;
-        static unsigned long long attr = 0;
-        if (smem_attr_needed(attr, c->cfg.device))
-          SPIC_CUDA_CHECK(c, cudaFuncSetAttribute(k_push_v_e_v2<InterpP8R2>,
-                                                  cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        k_push_v_e_v2<InterpP8R2><<<grid, kThreads, smem, c->stream>>>(c->g, s.b, s.start, s.count, c->E, coef, ncell, cpb);
-      } else {
-        const size_t smem = sizeof(double) * kWarps * PushV2Layout<InterpPWL>::PER_WARP;
-        k_push_v_e_v2<InterpPWL><<<grid, kThreads, smem, c->stream>>>(c->g, s.b, s.start, s.count, c->E, coef, ncell, cpb);
-      }
     } else if (c->cfg.interp == SPIC_INTERP_P8R2) {
-      const size_t smem = sizeof(double) * kWarps * 3 * 64;
-      k_push_v_e_binned<InterpP8R2><<<grid, kThreads, smem, c->stream>>>(c->g, s.b, s.start, s.count, c->E, coef, ncell, cpb);
+      const size_t smem = sizeof(double) * kWarps * PushV2Layout<InterpP8R2>::PER_WARP;
+      static unsigned long long attr = 0;
+      if (smem_attr_needed(attr, c->cfg.device))
+        SPIC_CUDA_CHECK(c, cudaFuncSetAttribute(k_push_v_e_v2<InterpP8R2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                (int)smem));
+      k_push_v_e_v2<InterpP8R2><<<grid, kThreads, smem, c->stream>>>(c->g, s.b, s.start, s.count, c->E, coef, ncell, cpb);
     } else {
-      const size_t smem = sizeof(double) * kWarps * 3 * 8;
-      k_push_v_e_binned<InterpPWL><<<grid, kThreads, smem, c->stream>>>(c->g, s.b, s.start, s.count, c->E, coef, ncell, cpb);
+      const size_t smem = sizeof(double) * kWarps * PushV2Layout<InterpPWL>::PER_WARP;
+      k_push_v_e_v2<InterpPWL><<<grid, kThreads, smem, c->stream>>>(c->g, s.b, s.start, s.count, c->E, coef, ncell, cpb);
     }
     c->launches++;
   }

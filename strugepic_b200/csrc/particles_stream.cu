@@ -433,205 +433,10 @@ __global__ void __launch_bounds__(kThreads, 3)
   }
 }
 
-// ------------------------------------------------------------------------------------------------
-// k_push_v_e_v4: the same stream, TWO particles per lane (register blocking of the gather).
-//
-// ncu on v3: the FP64 pipe is 61 % busy with the L1/shared-memory pipe at 82 % -- every stencil double costs
-// one broadcast wavefront per warp instruction whatever the number of lanes it serves (144 per batch of 32
-// particles against ~180 FP64 cycles).  Here a lane owns the particles 2q and 2q+1 of its cell: each stencil
-// row is read once and feeds both, so the shared-memory traffic per particle halves while the FP64 work is
-// unchanged.  The stream is cut in PAIRS: the cutter sees ceil(count / 2) per cell, a cell with an odd count
-// leaves the second half of its last lane empty (<= 1 slot per cell), and the two particles of a lane always
-// share one stencil slot; lanes of different cells in one batch read different slots as in v3.
-// Measured (128^3 x 64 ppc, profiles/r01_ncu_push_v_e_v4_summary.txt): 11 % fewer warp instructions, L1 pipe
-// 82 -> 65 %, FP64 pipe 61 -> 65 %, and the SAME time (4.57 vs 4.58 ms): what binds these gathers is neither
-// pipe alone but the register file feeding the FP64 pipe -- a DFMA with three distinct register operands
-// issues every 3 cycles instead of 2 (profiles/r01_micro_dfma_operands.txt).  Kept as option
-// pushve_kernel = 4; v3 stays the default.
-// ------------------------------------------------------------------------------------------------
-template <class I>
-struct PushLayout4 {
-  static constexpr int NW1 = I::NW1;
-  static constexpr int NS = NW1 * NW1 * NW1;
-  static constexpr int SE = 3 * NS;
-  static constexpr int SES = SE + 2;          // (see PushLayout)
-  static constexpr int SP = 2 * 3 * 32;       // positions of the two particles of every lane
-  static constexpr int PER_WARP = 2 * SP + kRing * SES;
-};
-
-#ifndef SPIC_PUSH4_MIN_BLOCKS
-#define SPIC_PUSH4_MIN_BLOCKS 2  // 128 registers without spills; one block per SM (166 registers) is 18 % slower
-#endif
-template <class I>
-__global__ void __launch_bounds__(kThreads, SPIC_PUSH4_MIN_BLOCKS)
-    k_push_v_e_v4(Grid g, ParticleSoA p, const long* __restrict__ start, const int* __restrict__ count,
-                  const double* __restrict__ E, double coef, long ncell, int cells_per_block) {
-  constexpr int NW1 = I::NW1, NWP = I::NWP;
-  using Lay = PushLayout4<I>;
-  constexpr int NS = Lay::NS, SE = Lay::SE, SES = Lay::SES, SP = Lay::SP;
-  extern __shared__ __align__(16) double smem[];
-  __shared__ BlockTables T;          // T.cnt holds PAIR counts (what the cutter walks)
-  __shared__ int s_cnt[kMaxCells];   // particles per cell
-  __shared__ long s_soff[SE];
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  double* sPart = smem + warp * Lay::PER_WARP;  // [2][2][3][32]
-  double* sEst = sPart + 2 * SP;                // [kRing][SES]
-  const long cbeg_blk = (long)blockIdx.x * cells_per_block;
-  int nloc = cells_per_block;
-  if (cbeg_blk + nloc > ncell) nloc = (int)(ncell - cbeg_blk);
-  load_tables(T, g, start, count, cbeg_blk, nloc, (1 - I::W) * (1 + g.pj + g.pk));
-  for (int t = threadIdx.x; t < SE; t += kThreads) {
-    const int comp = t / NS, r = t % NS;
-    s_soff[t] = (r % NW1) + ((r / NW1) % NW1) * g.pj + (r / (NW1 * NW1)) * g.pk + comp * g.pc;
-  }
-  __syncthreads();
-  for (int t = threadIdx.x; t < nloc; t += kThreads) {  // (each thread rewrites only what it wrote itself)
-    const int n = T.cnt[t];
-    s_cnt[t] = n;
-    T.cnt[t] = (n + 1) >> 1;
-  }
-  __syncthreads();
-  const int ncw = cells_per_block / kWarps;
-  const int wbeg = warp * ncw < nloc ? warp * ncw : nloc, wend = wbeg + ncw < nloc ? wbeg + ncw : nloc;
-  Cutter cut;
-  cut.init(T, wbeg, wend);
-
-  auto stage = [&](int X, int sl) {
-    const double* src = E + T.base[X];
-    double* d = sEst + sl * SES;
-#pragma unroll
-    for (int s = lane; s < SE; s += 32) cp_async8(d + s, src + s_soff[s]);
-  };
-  // this lane's pair in batch b: index of its first particle, and whether the second one exists
-  auto my_pair = [&](const Batch& b, bool& two) {
-    const int c = lane < b.n0 ? b.c0 : b.c1;
-    const int q = lane < b.n0 ? b.off0 + lane : lane - b.n0;
-    two = 2 * q + 1 < s_cnt[c];
-    return T.start[c] + 2 * q;
-  };
-  auto prefetch = [&](const Batch& b, bool st0, bool st1, int pb) {
-    if (lane < b.n()) {
-      bool two;
-      const long src = my_pair(b, two);
-      double* d = sPart + pb * SP + lane;
-      cp_async8(d + 0 * 32, p.x[0] + src);
-      cp_async8(d + 1 * 32, p.x[1] + src);
-      cp_async8(d + 2 * 32, p.x[2] + src);
-      if (two) {
-        cp_async8(d + 3 * 32, p.x[0] + src + 1);
-        cp_async8(d + 4 * 32, p.x[1] + src + 1);
-        cp_async8(d + 5 * 32, p.x[2] + src + 1);
-      }
-    }
-    if (st0) stage(b.c0, b.slot0);
-    if (st1) stage(b.c1, b.slot1);
-    cp_async_commit();
-  };
-
-  bool st0, st1;
-  Batch b = cut.next(T, st0, st1);
-  int pb = 0;
-  if (b.n() > 0) prefetch(b, st0, st1, 0);
-  while (b.n() > 0) {
-    unsigned nb_w;
-    int nb_off;
-    {
-      const Batch nb = cut.next(T, st0, st1);
-      if (nb.n() > 0) prefetch(nb, st0, st1, pb ^ 1);
-      else cp_async_commit();
-      nb_w = nb.pack();
-      nb_off = nb.off0;
-    }
-    cp_async_wait<1>();
-    __syncwarp();
-
-    if (lane < b.n()) {
-      bool two;
-      const long idx = my_pair(b, two);
-      const double* sP = sPart + pb * SP + lane;
-      const double* sE = sEst + (lane < b.n0 ? b.slot0 : b.slot1) * SES;
-      // velocities are needed once, at the end: straight from global memory (long latency, hidden by the gather)
-      const double va0 = p.v[0][idx], va1 = p.v[1][idx], va2 = p.v[2][idx];
-      const long idx2 = two ? idx + 1 : idx;  // a missing second particle shadows the first (its result is dropped)
-      const double vb0 = p.v[0][idx2], vb1 = p.v[1][idx2], vb2 = p.v[2][idx2];
-      const int o2 = two ? 96 : 0;
-      double w1x[2][NW1], w1y[2][NW1], w1z[2][NW1], wpx[2][NWP], wpy[2][NWP], wpz[2][NWP];
-#pragma unroll
-      for (int h = 0; h < 2; ++h) {
-        const int o = h ? o2 : 0;
-        const double x = sP[o], y = sP[o + 32], z = sP[o + 64];
-        // the particle lies inside its bin cell: x - floor(x) is the exact in-cell coordinate
-        const double fx = x - floor(x), fy = y - floor(y), fz = z - floor(z);
-        eval_w1_in<I>(fx, w1x[h]);
-        eval_w1_in<I>(fy, w1y[h]);
-        eval_w1_in<I>(fz, w1z[h]);
-        eval_wp_in<I>(fx, wpx[h]);
-        eval_wp_in<I>(fy, wpy[h]);
-        eval_wp_in<I>(fz, wpz[h]);
-      }
-      // hpp:322-338, factorised as in v3; every stencil row is loaded once and used by both particles
-      double ax[2] = {0, 0}, ay[2] = {0, 0}, az[2] = {0, 0};
-#pragma unroll
-      for (int tk = 0; tk < NW1; ++tk) {
-        double bx[2] = {0, 0}, by[2] = {0, 0}, bz[2] = {0, 0};
-#pragma unroll
-        for (int tj = 0; tj < NW1; ++tj) {
-          const double* row = sE + (tk * NW1 + tj) * NW1;
-          double ex[NW1];
-          lds_row<NW1>(row, ex);
-#pragma unroll
-          for (int h = 0; h < 2; ++h) {
-            double cx = ex[0] * wpx[h][0];
-#pragma unroll
-            for (int ti = 1; ti < NWP; ++ti) cx = fma(ex[ti], wpx[h][ti], cx);
-            bx[h] = tj == 0 ? w1y[h][0] * cx : fma(w1y[h][tj], cx, bx[h]);
-          }
-          if (tj < NWP) {
-            double ey[NW1];
-            lds_row<NW1>(row + NS, ey);
-#pragma unroll
-            for (int h = 0; h < 2; ++h) {
-              double cy = ey[0] * w1x[h][0];
-#pragma unroll
-              for (int ti = 1; ti < NW1; ++ti) cy = fma(ey[ti], w1x[h][ti], cy);
-              by[h] = tj == 0 ? wpy[h][0] * cy : fma(wpy[h][tj < NWP ? tj : 0], cy, by[h]);
-            }
-          }
-          if (tk < NWP) {
-            double ez[NW1];
-            lds_row<NW1>(row + 2 * NS, ez);
-#pragma unroll
-            for (int h = 0; h < 2; ++h) {
-              double cz = ez[0] * w1x[h][0];
-#pragma unroll
-              for (int ti = 1; ti < NW1; ++ti) cz = fma(ez[ti], w1x[h][ti], cz);
-              bz[h] = tj == 0 ? w1y[h][0] * cz : fma(w1y[h][tj], cz, bz[h]);
-            }
-          }
-        }
-#pragma unroll
-        for (int h = 0; h < 2; ++h) {
-          ax[h] = tk == 0 ? w1z[h][0] * bx[h] : fma(w1z[h][tk], bx[h], ax[h]);
-          ay[h] = tk == 0 ? w1z[h][0] * by[h] : fma(w1z[h][tk], by[h], ay[h]);
-          if (tk < NWP) az[h] = tk == 0 ? wpz[h][0] * bz[h] : fma(wpz[h][tk < NWP ? tk : 0], bz[h], az[h]);
-        }
-        asm volatile("" ::: "memory");  // bound load hoisting (register pressure)
-      }
-      p.v[0][idx] = fma(ax[0], coef, va0);  // hpp:339-341
-      p.v[1][idx] = fma(ay[0], coef, va1);
-      p.v[2][idx] = fma(az[0], coef, va2);
-      if (two) {
-        p.v[0][idx + 1] = fma(ax[1], coef, vb0);
-        p.v[1][idx + 1] = fma(ay[1], coef, vb1);
-        p.v[2][idx + 1] = fma(az[1], coef, vb2);
-      }
-    }
-    __syncwarp();  // every lane is done with this batch's buffers before they are refilled
-    b.unpack(nb_w, nb_off);
-    pb ^= 1;
-  }
-  cp_async_wait<0>();
-}
+// (k_push_v_e_v4 -- the same stream with TWO particles per lane, every stencil row read once for both -- was removed in
+// round 2: 11 % fewer instructions, L1 pipe 82 -> 65 %, FP64 pipe 61 -> 65 %, and the SAME 4.57 ms at 128^3 x 64 ppc
+// (profiles/r01_ncu_push_v_e_v4_summary.txt): what binds these gathers is the register file feeding the FP64 pipe, a DFMA
+// with three distinct register operands issues every 3 cycles instead of 2 (profiles/r01_micro_dfma_operands.txt).)
 
 // ====================================================================================
 // theta_axis
@@ -1049,14 +854,6 @@ int push_dispatch(Ctx* c, Species& s, double dt) {
     if (want > 3L * c->sm_count) want = 3L * c->sm_count;
     k_push_v_e_quad<I><<<(int)want, kThreads, smemq, c->stream>>>(c->g, s.b, s.start, s.count, c->E, coef, ncell,
                                                                   e->block_work);
-    c->launches++;
-    return SPIC_OK;
-  }
-  if (eng(c)->pushve_kernel == 4) {  // two particles per lane (opt-in: option pushve_kernel = 4)
-    const size_t smem4 = sizeof(double) * kWarps * PushLayout4<I>::PER_WARP;
-    static unsigned long long attr4 = 0;
-    if ((rc = set_smem(c, k_push_v_e_v4<I>, smem4, attr4))) return rc;
-    k_push_v_e_v4<I><<<grid, kThreads, smem4, c->stream>>>(c->g, s.b, s.start, s.count, c->E, coef, ncell, cpb);
     c->launches++;
     return SPIC_OK;
   }

@@ -8,12 +8,14 @@ import torch.multiprocessing as mp
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))  # decomp.py: the host-side twin of the slab logic
 
 
 def _worker(rank, world, port, out):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
     dist.init_process_group("gloo", rank=rank, world_size=world)
-    from strugepic_b200 import decomp, synthetic
+    import decomp
+    from strugepic_b200 import synthetic
     n_cell, ppc = (6, 5, 8), 4
     # unique-id plumbing exactly as bench.py / tests/mgpu_worker.py do it (a fake 128-byte id here)
     ids = [bytes(range(128)) if rank == 0 else None]
@@ -60,7 +62,7 @@ def test_slab_partition_and_ring_world2():
 
 
 def test_decomp_helpers():
-    from strugepic_b200 import decomp
+    import decomp
     assert decomp.slab_range(16, 4, 2) == (8, 12)
     assert decomp.ring_neighbours(0, 4) == (3, 1) and decomp.ring_neighbours(3, 4) == (2, 0)
     g = decomp.guard_planes(8, 2)
