@@ -22,7 +22,7 @@ def test_slab_decomposition_matches_oracle(world, case):
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(world),
            "--master-addr", "127.0.0.1", "--master-port", str(29400 + world), os.path.join(HERE, "mgpu_worker.py"), case]
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
-    print(r.stdout[-3000:])
+    print(r.stdout[-3000:])  # (the "multi-gpu parity ok ..." line of rank 0)
     print("\n".join(ln for ln in r.stderr.splitlines() if "OMP_NUM_THREADS" not in ln and "****" not in ln)[-3000:])
     assert r.returncode == 0
     assert "multi-gpu parity ok" in r.stdout
