@@ -22,11 +22,19 @@ import util  # noqa: E402
 
 
 def main():
+    """python mgpu_worker.py case [case ...]: several cases in one rendezvous (one interpreter start-up per rank)."""
     rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
     local = int(os.environ.get("LOCAL_RANK", rank))
     dist.init_process_group("gloo")
     torch.cuda.set_device(local)
-    case = sys.argv[1] if len(sys.argv) > 1 else "p8"
+    ok = True
+    for case in (sys.argv[1:] or ["p8"]):
+        ok = run_case(case, rank, world, local) and ok
+    dist.destroy_process_group()
+    sys.exit(0 if ok else 1)
+
+
+def run_case(case, rank, world, local):
     interp = {"p8": 0, "pwl": 1, "user": 2}[case.split("_")[0]]  # user: the user-W slot (cubic B-spline pair, range 2)
     opts = case.split("_")[1:]
     # slab thickness: thin = 4 planes (< 2 ng: the halo-sum targets overlap), tall = 12 (> 2 (W + 2): the axis block
@@ -99,8 +107,7 @@ def main():
     flag = [ok]
     dist.broadcast_object_list(flag, src=0)
     s.close()
-    dist.destroy_process_group()
-    sys.exit(0 if flag[0] else 1)
+    return flag[0]
 
 
 if __name__ == "__main__":
