@@ -65,6 +65,9 @@ def parse():
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--opt", action="append", default=[], metavar="NAME=VALUE",
                     help="library option for A/B runs (spic_set_option), e.g. --opt fuse=0")
+    ap.add_argument("--walls", action="store_true",
+                    help="x walls (MABC + reflecting particles, as examples/full/bernstein_main.cpp): the plasma stays "
+                         "W + 2 cells away from them; A/B of the half-block schedule with --no-fuse")
     ap.add_argument("--no-secondary", action="store_true", help="skip the secondary records (low ppc, PWL, field_only)")
     ap.add_argument("--secondary-all-ranks", action="store_true", help="run the secondary records at N > 1 too")
     ap.add_argument("--e2e-steps", type=int, default=2)
@@ -74,9 +77,10 @@ def parse():
 
 
 def workload_name(a, n_gpus):
-    return ("uniform plasma %dx%dx%d cells, %d ppc, %s, Theta_map%d, dt=0.5, v_th=0.01 "
+    return ("uniform plasma %dx%dx%d cells%s, %d ppc, %s, Theta_map%d, dt=0.5, v_th=0.01 "
             "(stand-in for examples/full 512^3 x 64 ppc = 412 GB, which does not fit one B200)"
-            % (a.n, a.n, a.n * n_gpus, a.ppc, "W8/P8R2" if a.interp == "p8r2" else "PWL", a.order))
+            % (a.n, a.n, a.n * n_gpus, " with x walls (MABC, reflection)" if a.walls else "", a.ppc,
+               "W8/P8R2" if a.interp == "p8r2" else "PWL", a.order))
 
 
 # ------------------------------------------------------------------------------------------
@@ -277,7 +281,7 @@ class Env:
     def allsum(self, x):
         return self._red(x, self.dist.ReduceOp.SUM) if self.dist else x
 
-    def make_sim(self, n, interp, ppc, periodic=(1, 1, 1), opts=()):
+    def make_sim(self, n, interp, ppc, periodic=(1, 1, 1), opts=(), slab_profile=False):
         """One brick of n^3 cells per GPU (z slabs), E = 0, B = (0,0,1), uniform thermal plasma (ppc = 0: vacuum)."""
         spic, torch = self.spic, self.torch
         sim = spic.Simulation((n, n, n * self.world), periodic=periodic, interp=interp, device=self.local,
@@ -290,7 +294,11 @@ class Env:
             sim.comm_init(bytes(uid.cpu().tolist()))
         sim.set_uniform_field(spic.FIELD_E, [0.0, 0.0, 0.0])
         sim.set_uniform_field(spic.FIELD_B, [0.0, 0.0, 1.0] if ppc else [0.0, 0.0, 0.0])
-        if ppc:
+        if ppc and slab_profile:  # nothing within W + 2 cells of an x wall (the reflect cells)
+            margin = sim.W + 2
+            sim.add_particle_density(lambda nc, i, j, k: ((i >= margin) & (i < nc[0] - margin)) * 1.0 + 0.0 * (j + k),
+                                     ppc, 100.0, -1.0, 0.01, seed=12345)
+        elif ppc:
             sim.add_particle_density_uniform(ppc, 100.0, -1.0, 0.01, seed=12345)
         for kv in opts:
             k, v = kv.split("=")
@@ -495,7 +503,7 @@ def ours_main(a):
     spic, np, torch, dist, local = env.spic, env.np, env.torch, env.dist, env.local
     interp = spic.P8R2 if a.interp == "p8r2" else spic.PWL
     opts = list(a.opt) + (["fuse=0"] if a.no_fuse else [])
-    sim = env.make_sim(a.n, interp, a.ppc, opts=opts)
+    sim = env.make_sim(a.n, interp, a.ppc, periodic=(0, 1, 1) if a.walls else (1, 1, 1), opts=opts, slab_profile=a.walls)
     npart_local = sim.num_particles()
     npart = int(env.allsum(float(npart_local)))
     roof = fp64_roof(env)
