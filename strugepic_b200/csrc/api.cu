@@ -481,23 +481,33 @@ static int theta_axis_impl(spic_ctx* c, int comp, double dt) {
   return deposit_exchange_end(c, 1u << comp);
 }
 
-// dt2 != 0 (no species only): the field half is applied twice in a row, dt then dt2, by one sweep
-static int theta_E_impl(spic_ctx* c, double dt, double dt2 = 0.0) {
-  int rc = SPIC_OK;
-  // E.FillBoundary hpp:56: for the particle gathers, and for the curl's z neighbours across slab faces (x, y and a
-  // local z are wrapped inside the sweep)
-  if (!c->sp.empty() || c->cfg.nranks > 1) rc = ensure_guards(c, c->E);
+// Theta_E (hpp:52-71) in its two halves.  The particle half (push_V_E, hpp:57-62) is additive in dt: it reads E, which
+// Theta_E does not change, and moves nothing.  The field half (push_B_E, hpp:63-68) is additive on periodic boxes only
+// (MABC_bad blends B on wall boxes), but two applications in a row read the same E: one sweep applies both (dt, dt2).
+static int theta_E_particles(spic_ctx* c, double dt) {
+  if (c->sp.empty()) return SPIC_OK;
+  int rc = ensure_guards(c, c->E);  // E.FillBoundary hpp:56 (the gathers read the guards)
   if (rc) return rc;
-  for (auto& s : c->sp) {       // push_V_E        hpp:57-62
+  for (auto& s : c->sp) {
     if (s.binned) {
       if ((rc = engine_push_v_e(c, s, dt))) return rc;
     } else {
       launch_push_v_e_direct(c, s.d, s.nd, nullptr, s.q, s.m, dt);
     }
   }
-  launch_curl_E_into_B(c, dt, dt2);  // push_B_E        hpp:63-68
+  return SPIC_OK;
+}
+static int theta_E_fields(spic_ctx* c, double dt, double dt2 = 0.0) {
+  // (the sweep wraps x, y and a local z itself; only the z neighbours across slab faces come from the guards)
+  int rc = c->cfg.nranks > 1 ? ensure_guards(c, c->E) : SPIC_OK;
+  if (rc) return rc;
+  launch_curl_E_into_B(c, dt, dt2);
   touched(c, c->B);
   return SPIC_OK;
+}
+static int theta_E_impl(spic_ctx* c, double dt) {
+  int rc = theta_E_particles(c, dt);
+  return rc ? rc : theta_E_fields(c, dt);
 }
 
 // src_pos >= 0: an E_source application (cpp:32-36) folded into the sweep's launch, applied before it
@@ -509,19 +519,15 @@ static int theta_B_impl(spic_ctx* c, double dt, int src_pos = -1, int src_comp =
   return SPIC_OK;
 }
 
-// Applies the deferred trailing Theta_E of the last fused map (see Ctx::pending_E).
-static int flush_pending_field(spic_ctx* c) {
-  if (c->pending_field_E == 0.0) return SPIC_OK;
-  const double d = c->pending_field_E;
-  c->pending_field_E = 0.0;
-  return theta_E_impl(c, d);
-}
+// Applies what a fused map or a field-only step left pending (Ctx::pending_E: the particle kick; Ctx::pending_field_E:
+// one application of the field half).
 static int flush_pending(spic_ctx* c) {
-  if (int rc = flush_pending_field(c)) return rc;
-  if (c->pending_E == 0.0) return SPIC_OK;
-  const double d = c->pending_E;
-  c->pending_E = 0.0;
-  return theta_E_impl(c, d);
+  const double pk = c->pending_E, pf = c->pending_field_E;
+  c->pending_E = c->pending_field_E = 0.0;
+  int rc = SPIC_OK;
+  if (pk != 0.0) rc = theta_E_particles(c, pk);
+  if (!rc && pf != 0.0) rc = theta_E_fields(c, pf);
+  return rc;
 }
 
 static int map2(spic_ctx* c, double dt) {  // hpp:559-572
@@ -571,36 +577,36 @@ static int axis_block(spic_ctx* c, double dt) {
   return axis_pass(c, dt, 0);
 }
 
-// Theta_map2(d_0) o ... o Theta_map2(d_{n-1}) with fused axis blocks; adjacent Theta_E halves are merged:
-// Theta_E(s) o Theta_E(t) = Theta_E(s + t) exactly, because Theta_E changes neither E nor the positions
-// (hpp:52-71, 339-341; cpp:93-95).  That includes the half kick a previous call left pending; the last half kick
-// of this call is left pending in turn (option "defer_kick") and applied by whatever entry point runs next.
+// Theta_map2(d_0) o ... o Theta_map2(d_{n-1}) with fused axis blocks; adjacent Theta_E halves run together: the kicks
+// of the particle half add up exactly (Theta_E changes neither E nor the positions, hpp:52-71, 339-341), the two
+// applications of the field half read the same E and are made by one sweep (cpp:93-95; on wall boxes they cannot be
+// summed: MABC_bad).  That includes the half a previous call left pending; the last half of this call is left pending in
+// turn (option "defer_kick") and applied by whatever entry point runs next.
 static int fused_maps(spic_ctx* c, const double* d, int n) {
   int rc;
-  if (!(c->g.per[0] && c->g.per[1] && c->g.per[2])) {
-    // Walls.  (1) Theta_B cannot move: its MABC_bad blend (hpp:447-476) reads E on the plane next to the high x face,
-    // which the W1 stencil of the last particle cell reaches -- the deposits of the first three sub-flows must be in E
-    // when it runs and those of the last three must not.  So every map2 is  Theta_E, [x y z], Theta_B, [z y x],
-    // Theta_E  with each bracket one fused pass.  (2) Theta_E's own MABC blend of B is not additive in dt: adjacent
-    // halves are not merged and nothing is deferred.
-    for (int i = 0; i < n; ++i) {
-      if ((rc = theta_E_impl(c, d[i] / 2))) return rc;
+  // Walls.  Theta_B cannot move in front of the axis sub-flows there: its MABC_bad blend (hpp:447-476) reads E on the
+  // plane next to the high x face, which the W1 stencil of the last particle cell reaches -- the deposits of the first
+  // three sub-flows must be in E when it runs and those of the last three must not.  So a map2 is
+  // Theta_E, [x y z], Theta_B, [z y x], Theta_E with each bracket one fused pass.
+  const bool walls = !(c->g.per[0] && c->g.per[1] && c->g.per[2]);
+  // leading Theta_E(d0/2) together with what the previous call left pending: ONE kick, ONE sweep (two applications)
+  const double pk = c->pending_E, pf = c->pending_field_E;
+  c->pending_E = c->pending_field_E = 0.0;
+  if ((rc = theta_E_particles(c, pk + d[0] / 2))) return rc;
+  if ((rc = pf != 0.0 ? theta_E_fields(c, pf, d[0] / 2) : theta_E_fields(c, d[0] / 2))) return rc;
+  for (int i = 0; i < n; ++i) {
+    if (walls) {
       if ((rc = axis_pass(c, d[i], 1))) return rc;
       if ((rc = theta_B_impl(c, d[i]))) return rc;
       if ((rc = axis_pass(c, d[i], 2))) return rc;
-      if ((rc = theta_E_impl(c, d[i] / 2))) return rc;
+    } else if ((rc = axis_block(c, d[i]))) {
+      return rc;
     }
-    return SPIC_OK;
-  }
-  const double lead = d[0] / 2 + c->pending_E;
-  c->pending_E = 0.0;
-  if ((rc = theta_E_impl(c, lead))) return rc;
-  for (int i = 0; i < n; ++i) {
-    if ((rc = axis_block(c, d[i]))) return rc;
-    if (i + 1 < n) {
-      if ((rc = theta_E_impl(c, d[i] / 2 + d[i + 1] / 2))) return rc;
+    if (i + 1 < n) {  // Theta_E(d_i / 2) o Theta_E(d_{i+1} / 2): the kicks add up, the sweep applies both
+      if ((rc = theta_E_particles(c, d[i] / 2 + d[i + 1] / 2))) return rc;
+      if ((rc = theta_E_fields(c, d[i] / 2, d[i + 1] / 2))) return rc;
     } else if (c->defer_kick) {
-      c->pending_E = d[i] / 2;
+      c->pending_E = c->pending_field_E = d[i] / 2;
     } else if ((rc = theta_E_impl(c, d[i] / 2))) {
       return rc;
     }
@@ -611,7 +617,6 @@ static int fused_maps(spic_ctx* c, const double* d, int n) {
 static int map_body(spic_ctx* c, int order, double dt) {
   int rc;
   const bool fuse = (order == 2 || order == 4) && engine_can_fuse(c);
-  if ((rc = flush_pending_field(c))) return rc;
   if (!fuse && (rc = flush_pending(c))) return rc;
   if (order == 1) {  // hpp:548-557
     if ((rc = theta_B_impl(c, dt))) return rc;
@@ -683,7 +688,7 @@ int spic_field_only_step(spic_ctx* c, int pos, int comp, double E0, double omega
   if (vacuum && c->pending_field_E != 0.0) {  // the previous step's trailing half + this step's leading half: one sweep
     const double first = c->pending_field_E;
     c->pending_field_E = 0.0;
-    if ((rc = theta_E_impl(c, first, dt / 2))) return rc;
+    if ((rc = theta_E_fields(c, first, dt / 2))) return rc;
   } else {
     if ((rc = flush_pending(c))) return rc;
     if ((rc = theta_E_impl(c, dt / 2))) return rc;

@@ -113,10 +113,11 @@ struct Ctx {
   int sm_count = 148;
   int64_t launches = 0;
   bool time_kernels = false;
-  // Deferred trailing Theta_E of the last fused Theta_map2/4 (0 = none).  Theta_E(s) o Theta_E(t) = Theta_E(s + t),
-  // so the last half kick of one step and the first of the next run as one launch; every other entry point
-  // (getters, setters, single sub-flows, diagnostics, IO, sync) applies it first: the state a caller can observe
-  // is always the fully stepped one.  Option "defer_kick" = 0 turns it off.
+  // Deferred trailing Theta_E of the last fused Theta_map2/4 (0 = none): pending_E = the particle kick (additive: it
+  // merges with the first kick of the next call), pending_field_E = one application of the field half (the next call's
+  // first sweep applies it together with its own).  Every other entry point (getters, setters, single sub-flows,
+  // diagnostics, IO, sync) applies both first: the state a caller can observe is always the fully stepped one.
+  // Option "defer_kick" = 0 turns it off.
   double pending_E = 0.0;
   // Field-only runs (no species): the trailing Theta_E(dt/2) of spic_field_only_step is left pending the same way and
   // applied TOGETHER with the leading one of the next step by one sweep that reads E once (two applications in the
