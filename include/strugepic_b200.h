@@ -177,6 +177,15 @@ int spic_kernel_time_ms(spic_ctx* ctx, int reset, double* particle_ms, int64_t* 
  * the context's stream (no synchronisation); this call synchronises and sums them. */
 #define SPIC_KERNEL_KINDS 5
 int spic_kernel_times(spic_ctx* ctx, int reset, double ms[SPIC_KERNEL_KINDS], int64_t launches[SPIC_KERNEL_KINDS]);
+/* Options (none changes results beyond FP64 round-off; defaults in brackets):
+ *   fuse [1]         Theta_map2/4 as fused axis blocks (half-blocks around Theta_B on wall boxes); 0: the reference's
+ *                    launch-per-sub-flow order
+ *   defer_kick [1]   leave the trailing Theta_E of a fused map pending for the next call
+ *   overlap [1]      nranks > 1: slab-face planes of an axis block first, their exchange under the interior planes
+ *   pair_kernel [-1] low-count kernels (two / four cells per batch): -1 = below 18 particles per cell, 0 never, 1 always
+ *   tma [0]          stage the particle rows of the fused block with cp.async.bulk + mbarrier instead of cp.async
+ *   axis_kernel, pushve_kernel [0]  single-sub-flow kernel generation: 2 warp per cell, 3 particle stream, 0 automatic
+ *   cells_per_block [64], mover_frac [0 = automatic], rebin (value ignored: re-bin now), time_kernels [0] */
 int spic_set_option(spic_ctx* ctx, const char* name, double value);
 void* spic_stream(spic_ctx* ctx); /* cudaStream_t */
 /* FP64 FMA micro-benchmark for the roofline denominator: returns TFLOP/s */

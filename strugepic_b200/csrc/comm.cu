@@ -316,8 +316,8 @@ int comm_exchange_fill(Ctx* c, double* F) {
 //     my high guards to next's bottom ones), raw: the x / y guards travel along and are folded by the receiver;
 //   * when `migrate`: the leaver messages of every species that packed one (comm_collect_leavers).
 // The compute stream is NOT made to wait: comm_block_end does that, adds the received planes into the owner planes and
-// files the arrivals.  Work enqueued on the compute stream in between must not touch the guard planes of F, the
-// messages or the bins' arrival targets' guard... (it may deposit into owner planes: the sums commute).
+// files the arrivals.  Work enqueued on the compute stream in between must leave the guard z planes of F and the
+// messages alone; it may deposit into owner planes (the sums commute) and re-file particles inside the slab.
 int comm_block_begin(Ctx* c, double* F, unsigned mask, bool migrate) {
   int rc = need_comm(c);
   if (rc) return rc;

@@ -52,6 +52,13 @@ namespace {
 constexpr int kWarps = 8;
 constexpr int kThreads = kWarps * 32;
 constexpr unsigned kFull = 0xffffffffu;
+// Resident blocks per SM of the fused block kernel.  W8 needs its 128 registers (2 blocks); the 2-tap variants carry a
+// third of the live values and are latency-bound at 2 blocks (PWL: 55 % of the issue slots), so they are compiled for
+// SPIC_PWL_BLOCKS blocks per SM (<= 80 registers at 3) and launched that way.
+#ifndef SPIC_PWL_BLOCKS
+#define SPIC_PWL_BLOCKS 3
+#endif
+#define SPIC_BLOCKS_PER_SM(I) (I::NW1 == 2 ? SPIC_PWL_BLOCKS : 2)
 constexpr long kPairBelow = 18;  // mean particles per cell below which the two-cells-per-batch kernel runs
 constexpr int kContBase = -100;  // mover-list code of an ejected particle: kContBase - first sub-flow still to do
 #ifndef SPIC_CHUNK
@@ -309,7 +316,7 @@ SPIC_DI void flush_component(const double* sAccA, double* __restrict__ E, long b
 // last particle cell reaches: a deposit there and the blend do not commute), so the two halves run on either side
 // of it, hpp:562-569 in the reference's own order.
 template <class I, bool TMA, int HALF>
-__global__ void __launch_bounds__(kThreads, 2)
+__global__ void __launch_bounds__(kThreads, SPIC_BLOCKS_PER_SM(I))
     k_axis_block(Grid g, ParticleSoA p, const long* __restrict__ start, int* __restrict__ count,
                  double* __restrict__ E, const double* __restrict__ B, double q, double qm, double h, MoverList mv,
                  int* __restrict__ flags, CellRanges rg, unsigned* __restrict__ work, unsigned* __restrict__ ekey) {
@@ -901,7 +908,8 @@ int launch_block(Ctx* c, Species& s, double h, const CellRanges& rg, unsigned li
   const long nchunk = (long)rg.nchunk0 + (rg.n[1] + kChunk - 1) / kChunk;
   if (nchunk == 0) return SPIC_OK;
   long want = (nchunk + kWarps - 1) / kWarps;
-  if (want > 2L * c->sm_count) want = 2L * c->sm_count;
+  const long per_sm = SPIC_BLOCKS_PER_SM(I);
+  if (want > per_sm * c->sm_count) want = per_sm * c->sm_count;
   if (!e->block_work) SPIC_CUDA_CHECK(c, cudaMalloc(&e->block_work, sizeof(unsigned)));
   if (e->cont_key_cap < e->mv.cap) {  // home cell of every ejected particle: the sort key of the continuation
     if (e->cont_key) cudaFree(e->cont_key);
