@@ -84,3 +84,24 @@ def test_density_profile_twin_is_decomposition_independent():
     assert np.array_equal(uni, np.stack(synthetic.uniform_plasma(n_cell, 5, 0.05, 42)))
     over, stride2 = synthetic.density_counts((40, 1, 1), synthetic.simple_line_density, 10)
     assert stride2 == 19 and over[0, 0, 39] == 19  # a profile above 1 widens the RNG key stride
+
+
+def test_amrex_adapter_compiles_against_the_stand_in(tmp_path):
+    """include/strugepic_amrex_adapter.hpp (the literal drop-in of INTEGRATION.md) is C++14 over the AMReX calls the
+    reference itself makes: it must compile next to the reference's own headers against oracle/amrex_shim.  Needs the
+    reference's headers (this container); on the GPU box the prebuilt oracle/_ref/liboracle_adapter_*.so is what runs
+    (tests/test_adapter_gpu.py)."""
+    import subprocess
+    ref = "/root/reference/include"
+    if not os.path.isdir(ref):
+        pytest.skip("no /root/reference here")
+    src = tmp_path / "use_adapter.cpp"
+    src.write_text('#include "strugepic_propagators.hpp"\n#include "strugepic_amrex_adapter.hpp"\n'
+                   'void step(amrex::Geometry g, CParticleContainer& P, amrex::MultiFab& E, amrex::MultiFab& B) {\n'
+                   '  strugepic_b200_amrex::Theta_map4<2>(g, P, E, B, 0.5);\n'
+                   '  strugepic_b200_amrex::G_Theta<0, 1>(g, P, E, B, 0.5);\n'
+                   '  strugepic_b200_amrex::G_Theta_E<2>(g, P, E, B, 0.5);\n'
+                   '  strugepic_b200_amrex::G_Theta_B<2>(g, P, E, B, 0.5);\n}\n')
+    r = subprocess.run(["g++", "-std=c++14", "-fsyntax-only", "-w", "-I", os.path.join(ROOT, "oracle", "amrex_shim"), "-I", ref,
+                        "-I", os.path.join(ROOT, "include"), str(src)], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr[-3000:]
