@@ -589,13 +589,14 @@ __global__ void __launch_bounds__(kThreads, SPIC_BLOCKS_PER_SM(I))
 // ------------------------------------------------------------------------------------------------------------------
 // k_axis_block_pair: the same block for LOW particle counts per cell (host: mean count < kPairBelow).  With one cell
 // per batch a cell of 8 particles leaves 24 of 32 lanes idle through all five sub-flows (512^3 x 8 ppc ran 3.1x slower
-// per particle than 256^3 x 64 ppc).  Here two consecutive cells of a chunk with <= 16 particles each share a batch:
-// lanes 0-15 carry cell A, lanes 16-31 cell B.
+// per particle than 256^3 x 64 ppc).  Here two consecutive cells of a chunk with <= 16 particles each share a batch,
+// 16 lanes each.
 //   * cell data is per lane: coordinates sH / sH + 4, stencil buffer 0 / 1 (buffer 1 sits 16 bytes further in bank
 //     space, so the two broadcast reads of an LDS.128 never meet in a bank);
-//   * deposition: a particle's record goes to a slot whose subset (slot mod NSUB) lies in its cell's half of the
-//     subsets, so deposit_records -- unchanged -- accumulates the two cells in disjoint lanes; the flush sums inside
-//     each half and every half issues the reductions of its own cell;
+//   * deposition: lanes are dealt to the two cells so that a lane's record slot (= its lane, the conflict-free store
+//     pattern) falls into its cell's half of the particle subsets; deposit_records -- unchanged -- then accumulates
+//     the two cells in disjoint lanes, the flush sums inside each half and every half issues the reductions of its
+//     own cell (the first version permuted the slots instead: 13 % of its shared-memory wavefronts were replays);
 //   * both cells begin and end in the batch: nothing is parked across batches.
 // A cell with more than 16 particles (or without a partner) runs alone, as in k_axis_block.  Staging is synchronous
 // (both stencil buffers belong to the current batch): the other 15 warps of the SM cover the wait.
@@ -666,8 +667,11 @@ __global__ void __launch_bounds__(kThreads, 2)
       // batch: particles [off, off + 32) of cell A alone, or the whole of A (lanes 0-15) + the whole of B (lanes 16-31)
       const bool pair = off == 0 && cntA <= 16 && ci + 1 < kChunk && tCnt[ci + 1] <= 16 && tCnt[ci + 1] > 0;
       const int cntB = pair ? tCnt[ci + 1] : 0;
-      const bool isB = pair && lane >= 16;
-      const int slot = pair ? (lane & 15) : off + lane;           // index inside the lane's bin
+      // Lane -> (cell, particle).  The deposition hands record slot p to particle subset p mod NSUB, and a lane writes its
+      // record to slot = lane (the store pattern the record layout is conflict-free for), so in a pair the lanes whose
+      // subset lies in the upper half of the subsets carry cell B: lanes 0 1 | 2 3 | 4 5 | ... = A A | B B | A A | ... for W8.
+      const bool isB = pair && (lane % NSUB) >= HALF_SUB;
+      const int slot = pair ? (lane / NSUB) * HALF_SUB + lane % HALF_SUB : off + lane;  // index inside the lane's bin
       const bool valid = slot < (isB ? cntB : cntA);
       const int nvalidA = pair ? cntA : (cntA - off < 32 ? cntA - off : 32);
       const bool last_of_cell = pair || off + 32 >= cntA;
@@ -709,8 +713,7 @@ __global__ void __launch_bounds__(kThreads, 2)
         v[1] = sP[4 * 32];
         v[2] = sP[5 * 32];
       }
-      // record slot: in a pair, particle i of a cell goes to subset (i mod HALF_SUB) of the cell's half of the subsets
-      const int rslot = pair ? ((lane & 15) / HALF_SUB) * NSUB + (isB ? HALF_SUB : 0) + (lane & 15) % HALF_SUB : lane;
+      const int rslot = lane;
       const int nit = pair ? ((cntA > cntB ? cntA : cntB) + HALF_SUB - 1) / HALF_SUB : (nvalidA + NSUB - 1) / NSUB;
       const bool first = off == 0;
       bool alive = valid;
@@ -765,7 +768,8 @@ __global__ void __launch_bounds__(kThreads, 2)
       wp += __popc(stayA);
       if (last_of_cell) {
         int cc[3];
-        const long base = corner_of(my_cell, cc);  // (per lane: the lane's own cell)
+        // (the deposition lanes: subsets 0 .. HALF_SUB-1 = lanes 0-15 hold cell A's sums, lanes 16-31 cell B's)
+        const long base = corner_of(cbase + ci + (pair && lane >= 16 ? 1 : 0), cc);
         if (pair) {
           flush_component<I, 0, true>(sAcc, E, base, st, g.pc, lane);
           flush_component<I, 1, true>(sAcc + NACC * 32, E, base, st, g.pc, lane);
