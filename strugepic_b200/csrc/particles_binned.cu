@@ -423,10 +423,13 @@ __global__ void __launch_bounds__(kThreads, 2)
 __global__ void __launch_bounds__(256)
     k_insert_movers(MoverList mv, ParticleSoA b, const long* __restrict__ start, int* __restrict__ count,
                     ParticleSoA tail, unsigned long long* __restrict__ tail_n, long tail_cap, int* __restrict__ flags,
-                    unsigned lo0, unsigned hi0, unsigned lo1, unsigned hi1) {
+                    unsigned lo0, unsigned hi0, unsigned lo1, unsigned hi1, int leavers_are_errors) {
   const unsigned n = min(*mv.n, mv.cap);
   for (unsigned m = blockIdx.x * blockDim.x + threadIdx.x; m < n; m += gridDim.x * blockDim.x) {
     const int dest = mv.dest[m];
+    // (the interior part of a split block runs after the exchange was packed: a particle that leaves the slab from
+    // there -- more than W + 2 cells from a face in one block -- has nowhere to go: the slab limit of SPIC_ECFL)
+    if (leavers_are_errors && (dest == -1 || dest == -2)) atomicOr(&flags[0], 4);
     if (dest < 0) continue;  // leavers: handled by the migration kernels (comm.cu); kMoverDone: already filed
     const unsigned ud = (unsigned)dest;
     if (!((ud >= lo0 && ud < hi0) || (ud >= lo1 && ud < hi1))) continue;
@@ -1230,7 +1233,7 @@ int engine_theta_axis(Ctx* c, Species& s, int comp, double dt) {
   int nb = (int)((e->mv.cap + 255) / 256);
   if (nb > c->sm_count * 8) nb = c->sm_count * 8;
   k_insert_movers<<<nb, 256, 0, c->stream>>>(e->mv, s.b, s.start, s.count, s.d, s.d_nd, s.capd, c->d_flags, 0u,
-                                             0xffffffffu, 0u, 0u);
+                                             0xffffffffu, 0u, 0u, 0);
   c->launches++;
   if (c->cfg.nranks > 1 && comp == 2) {
     int rc = comm_collect_leavers(c, s, e->mv.x, e->mv.v, e->mv.dest, e->mv.n, e->mv.cap);
@@ -1274,10 +1277,10 @@ int engine_axis_block(Ctx* c, Species& s, double h, int part, int nb, int half) 
   const unsigned nbp = (unsigned)nb * plane;
   if (first_of_two)
     k_insert_movers<<<nbk, 256, 0, c->stream>>>(mv, s.b, s.start, s.count, s.d, s.d_nd, s.capd, c->d_flags, 0u, nbp,
-                                                ncell - nbp, ncell);
+                                                ncell - nbp, ncell, 0);
   else
     k_insert_movers<<<nbk, 256, 0, c->stream>>>(mv, s.b, s.start, s.count, s.d, s.d_nd, s.capd, c->d_flags, 0u,
-                                                0xffffffffu, 0u, 0u);
+                                                0xffffffffu, 0u, 0u, split && part == 2 ? 1 : 0);
   c->launches++;
   // movers that left the slab (dest -1 / -2) -> this species' migration messages (and marked done); none can come
   // from the interior part (a particle moves < 2 cells in a block and nb >= 2)

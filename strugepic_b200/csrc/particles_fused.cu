@@ -58,7 +58,11 @@ constexpr unsigned kFull = 0xffffffffu;
 #ifndef SPIC_PWL_BLOCKS
 #define SPIC_PWL_BLOCKS 3
 #endif
+#ifdef SPIC_USER_W_TU  // (calls into the user's W functions need their registers: 2 blocks)
+#define SPIC_BLOCKS_PER_SM(I) 2
+#else
 #define SPIC_BLOCKS_PER_SM(I) (I::NW1 == 2 ? SPIC_PWL_BLOCKS : 2)
+#endif
 constexpr long kPairBelow = 18;  // mean particles per cell below which the two-cells-per-batch kernel runs
 constexpr int kContBase = -100;  // mover-list code of an ejected particle: kContBase - first sub-flow still to do
 #ifndef SPIC_CHUNK

@@ -302,6 +302,12 @@ __global__ void __launch_bounds__(kThreads, 3)
   constexpr int NS = Lay::NS, SE = Lay::SE, SES = Lay::SES, SP = Lay::SP;
   constexpr int PER_WARP = SP + kQuad * SES + 3 * kQuadChunk;
   extern __shared__ __align__(16) double smem[];
+  __shared__ long s_soff[SE];  // offset of stencil point s from the stencil corner (as in k_push_v_e_v3)
+  for (int t = threadIdx.x; t < SE; t += kThreads) {
+    const int comp = t / NS, r = t % NS;
+    s_soff[t] = (r % NW1) + ((r / NW1) % NW1) * g.pj + (r / (NW1 * NW1)) * g.pk + comp * g.pc;
+  }
+  __syncthreads();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   double* sPart = smem + warp * PER_WARP;                          // [6][32]
   double* sEst = sPart + SP;                                       // [kQuad][SES]
@@ -362,10 +368,7 @@ __global__ void __launch_bounds__(kThreads, 3)
         const double* src = E + tBase[ci + c];
         double* d = sEst + c * SES;
 #pragma unroll
-        for (int s = lane; s < SE; s += 32) {
-          const int comp = s / NS, r = s % NS;
-          cp_async8(d + s, src + (r % NW1) + ((r / NW1) % NW1) * g.pj + (r / (NW1 * NW1)) * g.pk + (long)comp * g.pc);
-        }
+        for (int s = lane; s < SE; s += 32) cp_async8(d + s, src + s_soff[s]);
       }
       cp_async_commit();
       cp_async_wait<0>();
