@@ -410,6 +410,10 @@ def particle_rooflines(a, env, r, npart_local, ppc, interp_name, order, steps, r
                 "fused_bytes_achieved_gbs": fused_bytes / (ax_avg * 1e-3) / 1e9 if fused and ax_n else None,
                 "fused_bytes_frac": fused_bytes / (ax_avg * 1e-3) / 1e9 / peaks["hbm_gbs"] if fused and ax_n else None,
                 "share_of_step": ax_ms / ms if ms else None,
+                # the whole step in contract bytes: 24 sub-flows x 72 B on the reference schedule, and the
+                # lower bound once the sub-flows are fused by the exact commutations (3 x 96 + 4 x 72 B)
+                "whole_step_reference_bytes_gbs": 1728.0 * npart_local * steps / (ms * 1e-3) / 1e9 if order == 4 else None,
+                "whole_step_fused_bound_bytes_gbs": 576.0 * npart_local * steps / (ms * 1e-3) / 1e9 if order == 4 else None,
                 "note": ("W8 is FP64-pipe bound (10 flop/B > ridge 5.8): see roofline_fp64 for the binding roof"
                          if interp_name == "p8r2" else
                          "PWL is HBM bound; `achieved` counts reference-schedule bytes (6 x 72 B per particle and "
@@ -469,7 +473,7 @@ def secondary_field_only(a, env, n=256):
     state = {"k": 0}
 
     def step():
-        sim.field_only_step(n // 8, 1, 0.1, 0.3, 0.5, state["k"])
+        sim.field_only_step(4, 1, 0.1, 0.02, 0.5, state["k"])  # sp = 4, comp Y, Es = 0.1, omega = 0.02: source_absorb.input
         state["k"] += 1
 
     steps = 200

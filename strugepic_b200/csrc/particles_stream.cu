@@ -302,12 +302,6 @@ __global__ void __launch_bounds__(kThreads, 3)
   constexpr int NS = Lay::NS, SE = Lay::SE, SES = Lay::SES, SP = Lay::SP;
   constexpr int PER_WARP = SP + kQuad * SES + 3 * kQuadChunk;
   extern __shared__ __align__(16) double smem[];
-  __shared__ long s_soff[SE];  // offset of stencil point s from the stencil corner (as in k_push_v_e_v3)
-  for (int t = threadIdx.x; t < SE; t += kThreads) {
-    const int comp = t / NS, r = t % NS;
-    s_soff[t] = (r % NW1) + ((r / NW1) % NW1) * g.pj + (r / (NW1 * NW1)) * g.pk + comp * g.pc;
-  }
-  __syncthreads();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   double* sPart = smem + warp * PER_WARP;                          // [6][32]
   double* sEst = sPart + SP;                                       // [kQuad][SES]
@@ -367,8 +361,13 @@ __global__ void __launch_bounds__(kThreads, 3)
         if (tCnt[ci + c] == 0 || (c == 0 && off > 0)) continue;  // (empty, or the stencil is still in slot 0)
         const double* src = E + tBase[ci + c];
         double* d = sEst + c * SES;
+        // (offsets computed, not tabulated: the kernel is shared-memory bound -- a table in shared memory cost 17 %,
+        // 222 -> 261 ms per step at 512^3 x 8 ppc, profiles/r02_s15_bench_lowppc.txt)
 #pragma unroll
-        for (int s = lane; s < SE; s += 32) cp_async8(d + s, src + s_soff[s]);
+        for (int s = lane; s < SE; s += 32) {
+          const int comp = s / NS, r = s % NS;
+          cp_async8(d + s, src + (r % NW1) + ((r / NW1) % NW1) * g.pj + (r / (NW1 * NW1)) * g.pk + (long)comp * g.pc);
+        }
       }
       cp_async_commit();
       cp_async_wait<0>();
