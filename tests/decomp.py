@@ -45,3 +45,29 @@ def guard_planes(nz_local, ng):
         "send_to_next": (nz_local - ng, nz_local), "recv_from_prev": (-ng, 0),
         "send_to_prev": (0, ng), "recv_from_next": (nz_local, nz_local + ng),
     }
+
+
+# ---- migration messages without a count read-back (csrc/comm.cu: plan_messages) ---------------------------------------
+def message_capacity(count_two_exchanges_ago, cap):
+    """Capacity M (particles) of a migration message: a function of the count that crossed the same face two
+    exchanges ago -- a number BOTH ends of the pair hold (the sender counted it, the receiver read it from the
+    message header), so they agree on M without talking to each other; None = no history yet: the whole buffer."""
+    if count_two_exchanges_ago is None:
+        return cap
+    return min(cap, 4 * int(count_two_exchanges_ago) + 65536)
+
+
+class MigrationPlanner:
+    """One rank's view of the protocol: history of {sent low, sent high, received from prev, received from next}."""
+
+    def __init__(self, cap):
+        self.cap = cap
+        self.hist = []  # one (sent_lo, sent_hi, recv_prev, recv_next) per completed exchange
+
+    def plan(self):
+        """(M_send_lo, M_send_hi, M_recv_prev, M_recv_next) of the next exchange."""
+        h = self.hist[-2] if len(self.hist) >= 2 else (None,) * 4
+        return tuple(message_capacity(c, self.cap) for c in h)
+
+    def record(self, sent_lo, sent_hi, recv_prev, recv_next):
+        self.hist.append((sent_lo, sent_hi, recv_prev, recv_next))

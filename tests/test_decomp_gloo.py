@@ -3,6 +3,7 @@ import os
 import sys
 
 import numpy as np
+import pytest
 import torch.distributed as dist
 import torch.multiprocessing as mp
 
@@ -53,6 +54,58 @@ def test_slab_partition_and_ring_world2():
     out = ctx.Queue()
     port = 29531
     procs = [ctx.Process(target=_worker, args=(r, 2, port, out)) for r in range(2)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(timeout=120)
+        assert p.exitcode == 0
+    assert out.get(timeout=5) == "ok"
+
+
+def _planner_worker(rank, world, port, out):
+    """Every rank runs the migration-message protocol of csrc/comm.cu with gloo in place of NCCL: capacities are
+    planned from local history only, the payload carries its count in the header, and the receiver must have planned
+    exactly the capacity the sender used -- at every exchange, for counts that jump around."""
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    import decomp
+    import torch
+    prev, nxt = decomp.ring_neighbours(rank, world)
+    plan = decomp.MigrationPlanner(cap=200000)
+    rng = np.random.default_rng(100 + rank)
+    ok = True
+    for k in range(12):
+        m_lo, m_hi, m_rp, m_rn = plan.plan()
+        n_lo, n_hi = (int(rng.integers(0, 30000)) for _ in range(2))  # leavers through my low / high face
+        assert n_lo <= m_lo and n_hi <= m_hi, "4 x head-room over the count two exchanges ago"
+        send_lo = torch.zeros(1 + m_lo, dtype=torch.float64)
+        send_hi = torch.zeros(1 + m_hi, dtype=torch.float64)
+        send_lo[0], send_hi[0] = n_lo, n_hi
+        send_lo[1:1 + n_lo] = rank + 0.25
+        send_hi[1:1 + n_hi] = rank + 0.75
+        recv_prev = torch.empty(1 + m_rp, dtype=torch.float64)  # what prev sent through ITS high face
+        recv_next = torch.empty(1 + m_rn, dtype=torch.float64)  # what next sent through ITS low face
+        # (gloo checks the sizes of a matched send / recv pair: a mismatch in the planned capacities fails here)
+        reqs = [dist.isend(send_lo, prev, tag=2 * k), dist.irecv(recv_next, nxt, tag=2 * k),
+                dist.isend(send_hi, nxt, tag=2 * k + 1), dist.irecv(recv_prev, prev, tag=2 * k + 1)]
+        for r in reqs:
+            r.wait()
+        c_prev, c_next = int(recv_prev[0]), int(recv_next[0])
+        ok = ok and bool(torch.all(recv_prev[1:1 + c_prev] == prev + 0.75)) and bool(torch.all(recv_next[1:1 + c_next] == nxt + 0.25))
+        plan.record(n_lo, n_hi, c_prev, c_next)
+    flags = [None] * world
+    dist.all_gather_object(flags, ok)
+    if rank == 0:
+        out.put("ok" if all(flags) else "bad")
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_migration_messages_agree_without_a_count_exchange(world):
+    ctx = mp.get_context("spawn")
+    out = ctx.Queue()
+    procs = [ctx.Process(target=_planner_worker, args=(r, world, 29540 + world, out)) for r in range(world)]
     for p in procs:
         p.start()
     for p in procs:
