@@ -189,14 +189,19 @@ struct InterpPWL {
   static SPIC_HDI double iwp_tap(double a) { return IWp_cdf(a); }
   template <int T>
   static SPIC_HDI double iwp_seg(double a, double b) { return IWp_cdf(b) - IWp_cdf(a); }
+  // In-cell tap forms (the binned kernels): the argument is KNOWN to lie in the tap's range -- tap 0 gets f in [0,1),
+  // tap 1 gets f - 1 in [-1,0), the running integral gets s - cell in [0,1] -- so the range tests and the fabs of the
+  // general forms are decided at compile time: 1 - |f| = 1 - f, 1 - |f - 1| = 1 + (f - 1), Wp = 1, clamp(a) = a.  Same
+  // bits as the general forms for every such argument (tests/test_interp_host.py), without DSETP / FSEL: the PWL block
+  // kernel is issue-bound (profiles/r02_ncu_axis_block_pwl_summary.txt).
   template <int T>
-  static SPIC_HDI double w1_in(double a) { return W1(a); }
+  static SPIC_HDI double w1_in(double a) { return T == 0 ? 1.0 - a : 1.0 + a; }
   template <int T>
-  static SPIC_HDI double wp_in(double a) { return Wp(a); }
+  static SPIC_HDI double wp_in(double) { return 1.0; }
   template <int T>
-  static SPIC_HDI double iwp_in(double a) { return IWp_cdf(a); }
+  static SPIC_HDI double iwp_in(double a) { return a; }
   template <int T>
-  static SPIC_HDI double iwp_seg_in(double a, double b) { return IWp_cdf(b) - IWp_cdf(a); }
+  static SPIC_HDI double iwp_seg_in(double a, double b) { return b - a; }
 };
 
 // Fill w1[0..NW1) and wp[0..NWP) for a particle at normalised coordinate x in cell c:
