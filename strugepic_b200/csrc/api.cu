@@ -499,7 +499,7 @@ static int theta_E_particles(spic_ctx* c, double dt) {
 }
 static int theta_E_fields(spic_ctx* c, double dt, double dt2 = 0.0) {
   // (the sweep wraps x, y and a local z itself; only the z neighbours across slab faces come from the guards)
-  int rc = c->cfg.nranks > 1 ? ensure_guards(c, c->E) : SPIC_OK;
+  int rc = c->cfg.nranks > 1 || c->curl_tma ? ensure_guards(c, c->E) : SPIC_OK;
   if (rc) return rc;
   launch_curl_E_into_B(c, dt, dt2);
   touched(c, c->B);
@@ -512,7 +512,7 @@ static int theta_E_impl(spic_ctx* c, double dt) {
 
 // src_pos >= 0: an E_source application (cpp:32-36) folded into the sweep's launch, applied before it
 static int theta_B_impl(spic_ctx* c, double dt, int src_pos = -1, int src_comp = 0, double src_amp = 0.0) {
-  int rc = c->cfg.nranks > 1 ? ensure_guards(c, c->B) : SPIC_OK;  // cpp:104 (only the z guards of a slab are read)
+  int rc = c->cfg.nranks > 1 || c->curl_tma ? ensure_guards(c, c->B) : SPIC_OK;  // cpp:104 (z guards of a slab; TMA tiles)
   if (rc) return rc;
   launch_curl_B_into_E(c, dt, src_pos, src_comp, src_amp);  // cpp:105-110
   touched(c, c->E);
@@ -1021,6 +1021,10 @@ int spic_set_option(spic_ctx* c, const char* name, double value) {
   if (int frc = flush_pending(c)) return frc;  // (options may change the schedule)
   if (!strcmp(name, "defer_kick")) {
     c->defer_kick = value != 0;
+    return SPIC_OK;
+  }
+  if (!strcmp(name, "curl_tma")) {
+    c->curl_tma = value != 0;
     return SPIC_OK;
   }
   return engine_set_option(c, name, value);

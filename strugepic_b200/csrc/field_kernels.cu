@@ -10,6 +10,9 @@
 //                           include/strugepic_propagators.hpp:56, 350-352, 367
 // These are HBM-streaming stencils (72 B per cell per curl sweep); grids are sized
 // in whole waves of the SM count and rows are read with the x index fastest.
+#include <cuda.h>  // CUtensorMap (the encoder is fetched with cudaGetDriverEntryPoint: no link-time libcuda)
+#include <string.h>
+
 #include "spic_internal.cuh"
 
 namespace spic {
@@ -258,6 +261,108 @@ __global__ void __launch_bounds__(kBlock) k_curl(Grid g, const double* __restric
   }
 }
 
+// ---- the same sweep with TMA tile staging (option "curl_tma"; periodic boxes, guards of S filled) ------------------
+// One block = one tile of kTX x kTY x kTZ cells.  Its S values, with the one-cell halo the differences reach, arrive
+// as ONE box of a 4-D tensor map (x, y, z, component) -- UTMALDG, completed on an mbarrier -- instead of per-thread
+// loads through L1; T is read and written in place.  A tensor-map tile must start on a 16-byte boundary of the
+// innermost dimension (profiles/r02_s4_tma_probe3.txt): the box is kTX + 2 wide and starts on the even column at or
+// below the first one the tile needs, `xoff` says where the tile begins inside it.
+constexpr int kTX = 32, kTY = 8, kTZ = 4;
+constexpr int kBoxX = kTX + 2, kBoxY = kTY + 1, kBoxZ = kTZ + 1;
+constexpr int kBoxElems = kBoxX * kBoxY * kBoxZ * 3;
+
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+
+template <bool FWD>
+__global__ void __launch_bounds__(kBlock) k_curl_tma(Grid g, const __grid_constant__ CUtensorMap mapS, double* __restrict__ T,
+                                                     double dt, double dt2, int tiles_x, int tiles_y) {
+  extern __shared__ __align__(128) double sS[];  // [3][kBoxZ][kBoxY][kBoxX]
+  __shared__ __align__(8) unsigned long long bar;
+  const int tx = blockIdx.x % tiles_x, ty = (blockIdx.x / tiles_x) % tiles_y, tz = blockIdx.x / (tiles_x * tiles_y);
+  const int i0 = tx * kTX, j0 = ty * kTY, k0 = tz * kTZ;  // first cell of the tile (valid-cell coordinates)
+  // first guarded column / row / plane the tile reads: its own for forward differences, one below for backward ones
+  const int gx = g.ng + i0 - (FWD ? 0 : 1), gy = g.ng + j0 - (FWD ? 0 : 1), gz = g.ng + k0 - (FWD ? 0 : 1);
+  const int bx = gx & ~1, xoff = gx - bx;
+  if (threadIdx.x == 0) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;\n" ::"r"(smem_u32(&bar)) : "memory");
+    asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(smem_u32(&bar)),
+                 "r"((unsigned)(kBoxElems * sizeof(double)))
+                 : "memory");
+    asm volatile(
+        "cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5}], [%6];\n" ::"r"(
+            smem_u32(sS)),
+        "l"(&mapS), "r"(bx), "r"(gy), "r"(gz), "r"(0), "r"(smem_u32(&bar))
+        : "memory");
+  }
+  __syncthreads();  // (the barrier's initialisation is visible to the waiters)
+  unsigned done = 0;
+  while (!done)
+    asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}\n"
+                 : "=r"(done)
+                 : "r"(smem_u32(&bar)), "r"(0)
+                 : "memory");
+  constexpr int sj = kBoxX, sk = kBoxX * kBoxY, sc = kBoxX * kBoxY * kBoxZ;
+  const int o0 = FWD ? 0 : 1;  // the tile's first cell sits o0 rows / planes (and xoff + o0 columns) inside the box
+  for (int t = threadIdx.x; t < kTX * kTY * kTZ; t += kBlock) {
+    const int li = t % kTX, lj = (t / kTX) % kTY, lk = t / (kTX * kTY);
+    const int i = i0 + li, j = j0 + lj, k = k0 + lk;
+    if (i >= g.n[0] || j >= g.n[1] || k >= g.n[2]) continue;
+    const int s = (lk + o0) * sk + (lj + o0) * sj + li + xoff + o0;
+    const double sx = sS[s], sy = sS[s + sc], sz = sS[s + 2 * sc];
+    double r0, r1, r2;
+    if (FWD) {
+      r0 = (sS[s + sj + 2 * sc] - sz) - (sS[s + sk + sc] - sy);
+      r1 = (sS[s + sk] - sx) - (sS[s + 1 + 2 * sc] - sz);
+      r2 = (sS[s + 1 + sc] - sy) - (sS[s + sj] - sx);
+    } else {
+      r0 = (sz - sS[s - sj + 2 * sc]) - (sy - sS[s - sk + sc]);
+      r1 = (sx - sS[s - sk]) - (sz - sS[s - 1 + 2 * sc]);
+      r2 = (sy - sS[s - 1 + sc]) - (sx - sS[s - sj]);
+    }
+    const long o = g.at(i, j, k);
+    double t0 = T[o], t1 = T[o + g.pc], t2 = T[o + 2 * g.pc];
+    if (FWD) {
+      t0 -= dt * r0;
+      t1 -= dt * r1;
+      t2 -= dt * r2;
+      if (dt2 != 0.0) {
+        t0 -= dt2 * r0;
+        t1 -= dt2 * r1;
+        t2 -= dt2 * r2;
+      }
+    } else {
+      t0 += dt * r0;
+      t1 += dt * r1;
+      t2 += dt * r2;
+    }
+    T[o] = t0;
+    T[o + g.pc] = t1;
+    T[o + 2 * g.pc] = t2;
+  }
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+// tensor map over a guarded field [comp][k][j][i] with the tile box of k_curl_tma; false: no encoder in this driver
+bool make_field_map(const Grid& g, const double* F, CUtensorMap* out) {
+  static EncodeTiledFn encode = nullptr;
+  if (!encode) {
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) != cudaSuccess || !fn) return false;
+    encode = reinterpret_cast<EncodeTiledFn>(fn);
+  }
+  const cuuint64_t dims[4] = {(cuuint64_t)g.pj, (cuuint64_t)(g.n[1] + 2 * g.ng), (cuuint64_t)(g.n[2] + 2 * g.ng), 3};
+  const cuuint64_t strides[3] = {(cuuint64_t)g.pj * 8, (cuuint64_t)g.pk * 8, (cuuint64_t)g.pc * 8};
+  const cuuint32_t box[4] = {kBoxX, kBoxY, kBoxZ, 3};
+  const cuuint32_t estr[4] = {1, 1, 1, 1};
+  return encode(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 4, const_cast<double*>(F), dims, strides, box, estr,
+                CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
 __global__ void k_source(Grid g, double* __restrict__ E, int pos, int comp, double amp) {
   const long total = (long)g.n[1] * g.n[2];
   for (long t = blockIdx.x * (long)blockDim.x + threadIdx.x; t < total; t += (long)gridDim.x * blockDim.x) {
@@ -429,6 +534,29 @@ static void launch_sweep(Ctx* c, const double* S, double* T, double dt, const Sw
     return;
   }
   KernelTimer t(c, KT_CURL);
+  if (c->curl_tma && !walls && ex.src_pos < 0) {  // (the caller has refreshed the guards of S: api.cu)
+    const int m = FWD ? 0 : 1;
+    CUtensorMap* maps = reinterpret_cast<CUtensorMap*>(c->curl_maps);
+    if (c->curl_mapped[m] != S) {
+      if (!make_field_map(g, S, &maps[m])) {
+        c->curl_tma = false;  // no encoder: the plain sweep below
+      } else {
+        c->curl_mapped[m] = S;
+      }
+    }
+    if (c->curl_tma) {
+      const int txs = (g.n[0] + kTX - 1) / kTX, tys = (g.n[1] + kTY - 1) / kTY, tzs = (g.n[2] + kTZ - 1) / kTZ;
+      const size_t smem = sizeof(double) * kBoxElems;
+      static bool attr_set[2] = {false, false};
+      if (!attr_set[m]) {
+        cudaFuncSetAttribute(k_curl_tma<FWD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        attr_set[m] = true;
+      }
+      k_curl_tma<FWD><<<txs * tys * tzs, kBlock, smem, c->stream>>>(g, maps[m], T, dt, dt2, txs, tys);
+      c->launches++;
+      return;
+    }
+  }
   const int w0 = g.per[0] ? g.n[0] : 0, w1 = g.per[1] ? g.n[1] : 0, w2 = g.per[2] && g.zlocal ? g.n[2] : 0;
   k_curl<FWD><<<grid_for(c, total), kBlock, 0, c->stream>>>(g, S, T, in, dt, dt2, w0, w1, w2, ex);
   c->launches++;

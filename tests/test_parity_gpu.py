@@ -160,6 +160,39 @@ def test_field_only_at_scale(periodic):
     assert util.rel_err(E2, Es) < 1e-13 and util.rel_err(B2, Bs) < 1e-13
 
 
+@pytest.mark.parametrize("n_cell", [(64, 16, 8), (37, 9, 5), (256, 32, 32)])
+def test_curl_sweeps_with_tma_tiles(n_cell):
+    """Option curl_tma: the curl sweeps of a periodic box stage their S tiles with ONE 4-D tensor-map box per block
+    (UTMALDG + mbarrier) and read the periodic neighbours from the guards.  Same arithmetic as the plain sweep:
+    bit-identical fields, on boxes that are and are not multiples of the 32 x 8 x 4 tile, incl. the double Theta_E sweep
+    of the field-only step and a PIC step."""
+    E, B = util.rng_fields(n_cell, 99, 0.5)
+    out = []
+    for tma in (0, 1):
+        s = spic().Simulation(n_cell, interp=0)
+        s.set_option("curl_tma", tma)
+        s.set_field(0, E)
+        s.set_field(1, B)
+        for k in range(4):
+            s.G_Theta_E(0.3)
+            s.G_Theta_B(0.4)
+        for k in range(5):  # periodic box, no species: pending half + leading half in one sweep (dt, dt2)
+            s.field_only_step(3, 1, 0.1, 0.3, 0.5, k)
+        out.append((s.get_field(0), s.get_field(1)))
+        s.close()
+    assert np.array_equal(out[0][0], out[1][0]) and np.array_equal(out[0][1], out[1][1])
+    if n_cell[0] == 37:  # and inside a PIC step, against the oracle
+        parts = util.plasma(n_cell, 6, 0.1, 99)
+        o = ora.best_oracle(n_cell, interp=0)
+        s = spic().Simulation(n_cell, interp=0)
+        s.set_option("curl_tma", 1)
+        for t in (o, s):
+            util.load_state(t, E, B, parts, -1.0 / 6, 100.0 / 6)
+            t.map(4, 0.5)
+            t.map(2, 0.5)
+        util.compare_states(util.state_of(o), util.state_of(s), 4 * TOL_STEP, 4 * TOL_STEP, box=n_cell)
+
+
 @pytest.mark.parametrize("engine", ENGINES)
 def test_single_particle_decks(engine):
     """cyclotron.input known answers and reflection.input flip steps."""
