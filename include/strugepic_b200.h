@@ -184,6 +184,7 @@ int spic_kernel_times(spic_ctx* ctx, int reset, double ms[SPIC_KERNEL_KINDS], in
  *   overlap [1]      nranks > 1: slab-face planes of an axis block first, their exchange under the interior planes
  *   pair_kernel [-1] low-count kernels (two / four cells per batch): -1 = below 18 particles per cell, 0 never, 1 always
  *   tma [0]          stage the particle rows of the fused block with cp.async.bulk + mbarrier instead of cp.async
+ *   curl_tma [1]     curl sweeps of periodic boxes with TMA-staged tiles whenever the guards of their source are valid
  *   axis_kernel, pushve_kernel [0]  single-sub-flow kernel generation: 2 warp per cell, 3 particle stream, 0 automatic
  *   cells_per_block [64], mover_frac [0 = automatic], rebin (value ignored: re-bin now), time_kernels [0] */
 int spic_set_option(spic_ctx* ctx, const char* name, double value);

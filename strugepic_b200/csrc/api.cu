@@ -499,7 +499,7 @@ static int theta_E_particles(spic_ctx* c, double dt) {
 }
 static int theta_E_fields(spic_ctx* c, double dt, double dt2 = 0.0) {
   // (the sweep wraps x, y and a local z itself; only the z neighbours across slab faces come from the guards)
-  int rc = c->cfg.nranks > 1 || c->curl_tma ? ensure_guards(c, c->E) : SPIC_OK;
+  int rc = c->cfg.nranks > 1 ? ensure_guards(c, c->E) : SPIC_OK;
   if (rc) return rc;
   launch_curl_E_into_B(c, dt, dt2);
   touched(c, c->B);
@@ -512,7 +512,7 @@ static int theta_E_impl(spic_ctx* c, double dt) {
 
 // src_pos >= 0: an E_source application (cpp:32-36) folded into the sweep's launch, applied before it
 static int theta_B_impl(spic_ctx* c, double dt, int src_pos = -1, int src_comp = 0, double src_amp = 0.0) {
-  int rc = c->cfg.nranks > 1 || c->curl_tma ? ensure_guards(c, c->B) : SPIC_OK;  // cpp:104 (z guards of a slab; TMA tiles)
+  int rc = c->cfg.nranks > 1 ? ensure_guards(c, c->B) : SPIC_OK;  // cpp:104 (only the z guards of a slab are read)
   if (rc) return rc;
   launch_curl_B_into_E(c, dt, src_pos, src_comp, src_amp);  // cpp:105-110
   touched(c, c->E);
@@ -572,8 +572,11 @@ static int axis_pass(spic_ctx* c, double dt, int half) {
 // Theta_B only adds dt * curl B into E and the axis sub-flows only add their currents into E and read B, which
 // neither changes (hpp:562-569, cpp:102-113): the order is free.
 static int axis_block(spic_ctx* c, double dt) {
-  int rc = theta_B_impl(c, dt);
+  // (B.FillBoundary first -- the axis pass needs it anyway, hpp:350 -- so that Theta_B's sweep finds the guards of B
+  // valid and takes the TMA-tiled kernel)
+  int rc = c->sp.empty() ? SPIC_OK : ensure_guards(c, c->B);
   if (rc) return rc;
+  if ((rc = theta_B_impl(c, dt))) return rc;
   return axis_pass(c, dt, 0);
 }
 

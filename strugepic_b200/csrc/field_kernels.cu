@@ -261,7 +261,10 @@ __global__ void __launch_bounds__(kBlock) k_curl(Grid g, const double* __restric
   }
 }
 
-// ---- the same sweep with TMA tile staging (option "curl_tma"; periodic boxes, guards of S filled) ------------------
+// ---- the same sweep with TMA tile staging (option "curl_tma", default 1; periodic boxes, guards of S valid) ---------
+// ncu at 256^3 (profiles/r02_ncu_curl_tma_summary.txt vs r02_ncu_curl_summary.txt): 209 us per sweep against 243 / 258,
+// DRAM reads 821 MB against 970 MB (the halo planes come once per tile instead of through L1 misses), 5.8 TB/s = 0.88 of
+// the measured copy bandwidth in algorithmic bytes.
 // One block = one tile of kTX x kTY x kTZ cells.  Its S values, with the one-cell halo the differences reach, arrive
 // as ONE box of a 4-D tensor map (x, y, z, component) -- UTMALDG, completed on an mbarrier -- instead of per-thread
 // loads through L1; T is read and written in place.  A tensor-map tile must start on a 16-byte boundary of the
@@ -534,7 +537,9 @@ static void launch_sweep(Ctx* c, const double* S, double* T, double dt, const Sw
     return;
   }
   KernelTimer t(c, KT_CURL);
-  if (c->curl_tma && !walls && ex.src_pos < 0) {  // (the caller has refreshed the guards of S: api.cu)
+  // TMA-tiled sweep: periodic boxes, when the guards of S happen to be valid (the tiles read the periodic neighbours from
+  // them; after a particle sub-flow's FillBoundary they are) -- it never asks for a refresh of its own
+  if (c->curl_tma && !walls && ex.src_pos < 0 && c->guards_ok[S == c->E ? 0 : 1]) {
     const int m = FWD ? 0 : 1;
     CUtensorMap* maps = reinterpret_cast<CUtensorMap*>(c->curl_maps);
     if (c->curl_mapped[m] != S) {

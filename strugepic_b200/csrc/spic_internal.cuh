@@ -104,8 +104,9 @@ struct Ctx {
   // guard cells of E / B hold the images of the current valid cells (FillBoundary semantics).  Guards are refreshed
   // lazily, by the first consumer that reads them: the curl sweeps wrap periodic directions themselves and need none.
   bool guards_ok[2] = {false, false};
-  // option "curl_tma": the curl sweeps of periodic boxes stage their tiles with TMA (k_curl_tma) and read the guards
-  bool curl_tma = false;
+  // option "curl_tma" (default 1): on periodic boxes a curl sweep that finds the guards of its source valid stages its
+  // tiles with TMA (k_curl_tma: one tensor-map box per block); otherwise the plain sweep, which wraps by itself
+  bool curl_tma = true;
   alignas(64) unsigned char curl_maps[2][128];      // CUtensorMap of E (forward sweep) and of B (backward sweep)
   const double* curl_mapped[2] = {nullptr, nullptr};
   double* scratch = nullptr;  // >= 3 * cells doubles (pack/unpack, reductions, gauss)

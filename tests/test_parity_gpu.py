@@ -171,11 +171,14 @@ def test_curl_sweeps_with_tma_tiles(n_cell):
     for tma in (0, 1):
         s = spic().Simulation(n_cell, interp=0)
         s.set_option("curl_tma", tma)
-        s.set_field(0, E)
+        s.set_field(0, E)   # (spic_set_field refreshes the guards: the first sweeps below find them valid)
         s.set_field(1, B)
+        s.set_option("time_kernels", 1)
         for k in range(4):
             s.G_Theta_E(0.3)
+            s.set_field(1, s.get_field(1))  # guards of B valid again: Theta_B takes the tiled sweep when tma = 1
             s.G_Theta_B(0.4)
+            s.set_field(0, s.get_field(0))
         for k in range(5):  # periodic box, no species: pending half + leading half in one sweep (dt, dt2)
             s.field_only_step(3, 1, 0.1, 0.3, 0.5, k)
         out.append((s.get_field(0), s.get_field(1)))
