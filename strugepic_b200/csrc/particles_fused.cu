@@ -614,7 +614,6 @@ __global__ void __launch_bounds__(kThreads, 2)
   using Lay = BlockLayout<I>;
   constexpr int NS = Lay::NS, SB = Lay::SB, SBS = Lay::SBS, SP = Lay::SP, NACC = Lay::NACC, NSUB = Lay::NSUB;
   constexpr int HALF_SUB = NSUB / 2;  // particle subsets per cell of a pair
-  constexpr unsigned kNone = 0xffffffffu;
   extern __shared__ __align__(128) double smem[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   double* sWarp = smem + warp * Lay::PER_WARP_PAIR;
