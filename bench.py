@@ -15,14 +15,18 @@ q = -1, m = 100, E = 0, B = (0,0,1), fully periodic.  Wit
 global box is 256 x 256 x (256 N) cut into z slabs (weak scaling).
 
 Keys: `value` = particle-steps/s with the state resident in HBM, CUDA-event timed on the
-library's stream, max over ranks; `e2e` = the same step driven through the C ABI with HOST
-buffers: fields and particles uploaded from pinned host memory (spic_set_field /
-spic_set_particles), one spic_map(4), fields and particles read back (spic_get_*), all inside
-the timed region; `roofline` = the dominant kernel (theta_axis, 18 of the 24 particle launches
-of a step) in algorithmic bytes (72 B per particle per sub-flow) over its own CUDA-event
-duration against MEASURED_PEAKS.json; `roofline_fp64` = the same launch in algorithmic FP64
-flops (718 per particle per sub-flow) against the DFMA rate measured here by
-spic_probe_fp64_tflops -- W8 is FP64-pipe bound, so that is the binding roof;
+library's stream (the closing event after the spic_sync that applies the deferred half kick),
+max over ranks; `e2e` = the same step driven through the C ABI with HOST buffers: fields and
+particles uploaded from pinned host memory (spic_set_field / spic_set_particles), one
+spic_map(4), fields and particles read back (spic_get_*), all inside the timed region;
+`checks` = particle count, discrete Gauss residual drift and energy before / after the timed
+region (no oracle needed; collective over the slabs at N > 1); `roofline` = the dominant
+kernel (k_axis_block: one axis block = the six Theta of a map2) in algorithmic bytes of the
+REFERENCE schedule (6 x 72 B per particle) over its own CUDA-event duration against
+MEASURED_PEAKS.json, with the fused byte bound beside it; `roofline_fp64` = the same block in
+algorithmic FP64 flops (6 x 718 per particle) against the better of two DFMA probes
+measured here -- W8 is FP64-pipe bound, so that is the binding roof; `secondary` (N = 1) =
+512^3 x 8 ppc, the PWL variant and the vacuum field_only step of BASELINE configs[2];
 `cpu_baseline` / `--impl reference` = the reference's own sources (oracle/_ref, compiled
 unmodified; else the C port) on every host core, one independent 16^3 x 64 ppc brick per
 core (the communication-free upper bound of its MPI build).
