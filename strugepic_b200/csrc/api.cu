@@ -6,7 +6,9 @@
 // SumBoundary / Redistribute replaced by device kernels (+ NCCL across z slabs).
 #include <math.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
+#include <time.h>
 
 #include "engine.cuh"
 #include "spic_internal.cuh"
@@ -308,6 +310,27 @@ int spic_get_field(spic_ctx* c, int which, double* host) {
 }
 
 // ---- particles --------------------------------------------------------------------
+namespace spic {
+double PhaseTrace::now() {
+  timespec ts;
+  clock_gettime(CLOCK_MONOTONIC, &ts);
+  return ts.tv_sec * 1e3 + ts.tv_nsec * 1e-6;
+}
+PhaseTrace::PhaseTrace(const char* w, cudaStream_t s) : on(getenv("SPIC_TRACE_PHASES") != nullptr), st(s), what(w), t0(0) {
+  if (on) {
+    cudaStreamSynchronize(st);
+    t0 = now();
+  }
+}
+void PhaseTrace::mark(const char* phase) {
+  if (!on) return;
+  cudaStreamSynchronize(st);
+  const double t = now();
+  fprintf(stderr, "[spic trace] %s: %-18s %9.2f ms\n", what, phase, t - t0);
+  t0 = t;
+}
+}  // namespace spic
+
 int spic_num_species(const spic_ctx* c) { return c ? (int)c->sp.size() : SPIC_EINVAL; }
 
 static int upload_list(spic_ctx* c, Species& s, int64_t n, const double* const* hx, const double* const* hv) {
@@ -338,6 +361,9 @@ int spic_add_species(spic_ctx* c, double q, double m, int64_t n, const double* x
   const int id = (int)c->sp.size() - 1;
   int rc = spic_set_particles(c, id, n, x, y, z, vx, vy, vz);
   if (rc) {
+    free_soa(c->sp.back().d);
+    c->sp.back().nd = c->sp.back().capd = 0;
+    engine_free_species(c, c->sp.back());
     c->sp.pop_back();
     return rc;
   }
@@ -353,6 +379,8 @@ int spic_set_particles(spic_ctx* c, int species, int64_t n, const double* x, con
   if (n > 0 && (!x || !y || !z || !vx || !vy || !vz)) return fail(c, SPIC_EINVAL, "null particle array");
   const double* hx[3] = {x, y, z};
   const double* hv[3] = {vx, vy, vz};
+  if (c->cfg.engine == SPIC_ENGINE_BINNED && n > 0)  // bins, upload list and permutation of the last call are reused
+    return engine_upload(c, s, n, hx, hv, c->d_flags + 2);
   engine_free_species(c, s);
   int rc = upload_list(c, s, n, hx, hv);
   if (rc) return rc;
@@ -372,7 +400,7 @@ int spic_set_particles(spic_ctx* c, int species, int64_t n, const double* x, con
       return fail(c, SPIC_EINVAL, "particle outside this rank's brick");
     }
   }
-  return engine_ingest(c, s);  // BINNED: move the list into cell bins
+  return engine_ingest(c, s);  // BINNED (n == 0 on a decomposed run): an empty set of bins
 }
 
 int spic_load_uniform_plasma(spic_ctx* c, double q, double m, int32_t ppc, double v_th, uint64_t seed) {

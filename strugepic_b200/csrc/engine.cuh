@@ -131,6 +131,9 @@ int fused_axis_tail(Ctx* c, Species& s, double h, int half);  // the same sub-fl
 // ---- cell-binned engine ------------------------------------------------------------
 int engine_ingest(Ctx* c, Species& s);  // move s.d (direct list) into cell bins (no-op for ENGINE_DIRECT)
 void engine_free_species(Ctx* c, Species& s);
+// spic_set_particles, engine BINNED: replace the particles of s by the n particles of the host arrays; the bin
+// arrays, the upload list and the permutation of the previous call are reused when they fit
+int engine_upload(Ctx* c, Species& s, long n, const double* const* hx, const double* const* hv, int* bad_flag);
 void engine_destroy(Ctx* c);
 int engine_count(Ctx* c, Species& s, long* nb);
 int engine_gather(Ctx* c, Species& s, double* hx[3], double* hv[3], long* nb);

@@ -876,8 +876,11 @@ long tail_capacity(long n_total) {
 }
 
 // Rebuild the bins of species s from its current bins + tail (tail_n_host < 0: read *d_nd).
-int rebin(Ctx* c, Species& s, long tail_n_host) {
+// `upload` != null: the tail_n_host particles of that list replace everything (no live bins); the parked bin arrays
+// are written in place when they fit and the permutation buffer of the species is reused
+int rebin(Ctx* c, Species& s, long tail_n_host, const ParticleSoA* upload = nullptr) {
   const long ncell = c->g.cells();
+  const ParticleSoA& list = upload ? *upload : s.d;
   int rc;
   if (!s.d_nd) {
     SPIC_CUDA_CHECK(c, cudaMalloc(&s.d_nd, sizeof(unsigned long long)));
@@ -893,6 +896,7 @@ int rebin(Ctx* c, Species& s, long tail_n_host) {
   int* ncount = nullptr;
   int* fill = nullptr;
   long* nstart = nullptr;
+  PhaseTrace tr("rebin", c->stream);
   SPIC_CUDA_CHECK(c, cudaMalloc(&ncount, sizeof(int) * (ncell + 1)));
   SPIC_CUDA_CHECK(c, cudaMalloc(&nstart, sizeof(long) * (ncell + 1)));
   if (s.count)
@@ -903,7 +907,7 @@ int rebin(Ctx* c, Species& s, long tail_n_host) {
   if (tail_n > 0) {
     long b = (tail_n + 255) / 256;
     if (b > (long)c->sm_count * 32) b = (long)c->sm_count * 32;
-    k_count_tail<<<(int)b, 256, 0, c->stream>>>(c->g, s.d, tail_n, nullptr, ncount);
+    k_count_tail<<<(int)b, 256, 0, c->stream>>>(c->g, list, tail_n, nullptr, ncount);
     c->launches++;
   }
   // capacities -> exclusive scan -> new starts (ncell + 1 entries; the last is the slot total)
@@ -924,8 +928,21 @@ int rebin(Ctx* c, Species& s, long tail_n_host) {
     c->err = "more than 2^32 particle slots on one rank: decompose over more GPUs";
     return SPIC_EINVAL;
   }
+  tr.mark("count + scan");
   unsigned* perm = nullptr;
-  SPIC_CUDA_CHECK(c, cudaMalloc(&perm, sizeof(unsigned) * (size_t)(new_slots + 1)));
+  if (upload) {
+    if (s.perm_cap < new_slots + 1 || s.perm_cap > 2 * (new_slots + 1)) {
+      if (s.perm_buf) cudaFree(s.perm_buf);
+      s.perm_buf = nullptr;
+      s.perm_cap = 0;
+      const long cap = new_slots + 1 + (new_slots + 1) / 64;
+      SPIC_CUDA_CHECK(c, cudaMalloc(&s.perm_buf, sizeof(unsigned) * (size_t)cap));
+      s.perm_cap = cap;
+    }
+    perm = s.perm_buf;
+  } else {
+    SPIC_CUDA_CHECK(c, cudaMalloc(&perm, sizeof(unsigned) * (size_t)(new_slots + 1)));
+  }
   if (s.count) {
     k_perm_bins<<<grid_warps(c, ncell), 256, 0, c->stream>>>(s.start, s.count, nstart, ncell, perm);
     c->launches++;
@@ -938,22 +955,36 @@ int rebin(Ctx* c, Species& s, long tail_n_host) {
       SPIC_CUDA_CHECK(c, cudaMemsetAsync(fill, 0, sizeof(int) * ncell, c->stream));
     long b = (tail_n + 255) / 256;
     if (b > (long)c->sm_count * 32) b = (long)c->sm_count * 32;
-    k_perm_tail<<<(int)b, 256, 0, c->stream>>>(c->g, s.d, tail_n, nullptr, nstart, fill, s.slots, perm);
+    k_perm_tail<<<(int)b, 256, 0, c->stream>>>(c->g, list, tail_n, nullptr, nstart, fill, s.slots, perm);
     c->launches++;
   }
-  // permute the six arrays one at a time (peak extra memory: one array + perm)
+  tr.mark("perm");
+  // permute the six arrays one at a time (peak extra memory: one array + perm); an upload has no live bins, so the
+  // parked arrays of the previous store are the destination when they fit (nothing is read from them: s.slots == 0)
+  const long need = new_slots + 1;
+  const bool in_place = upload && s.b.x[0] && need <= s.b_cap && s.b_cap <= need + need / 2;
+  if (upload && !in_place) {
+    free_soa_local(s.b);  // too small (or far too large): released BEFORE the new arrays are allocated
+    s.b_cap = 0;
+  }
+  const long new_cap = upload ? need + need / 64 : need;
   for (int a = 0; a < 6; ++a) {
     double*& old_b = a < 3 ? s.b.x[a] : s.b.v[a - 3];
-    const double* tl = a < 3 ? s.d.x[a] : s.d.v[a - 3];
-    double* out = nullptr;
-    SPIC_CUDA_CHECK(c, cudaMalloc(&out, sizeof(double) * (size_t)(new_slots + 1)));
-    k_gather_perm<<<grid_warps(c, ncell), 256, 0, c->stream>>>(old_b, tl, s.slots, perm, nstart, ncount, ncell, out);
+    const double* tl = a < 3 ? list.x[a] : list.v[a - 3];
+    double* out = old_b;
+    if (!in_place) SPIC_CUDA_CHECK(c, cudaMalloc(&out, sizeof(double) * (size_t)new_cap));
+    k_gather_perm<<<grid_warps(c, ncell), 256, 0, c->stream>>>(in_place ? nullptr : old_b, tl, s.slots, perm, nstart,
+                                                                ncount, ncell, out);
     c->launches++;
-    SPIC_CUDA_CHECK(c, cudaStreamSynchronize(c->stream));
-    if (old_b) cudaFree(old_b);
-    old_b = out;
+    if (!in_place) {
+      SPIC_CUDA_CHECK(c, cudaStreamSynchronize(c->stream));
+      if (old_b) cudaFree(old_b);
+      old_b = out;
+    }
   }
-  cudaFree(perm);
+  if (!in_place) s.b_cap = new_cap;
+  tr.mark("6 x gather");
+  if (!upload) cudaFree(perm);
   if (fill) cudaFree(fill);
   if (s.start) cudaFree(s.start);
   if (s.count) cudaFree(s.count);
@@ -986,7 +1017,10 @@ int rebin(Ctx* c, Species& s, long tail_n_host) {
   }
   s.nd = 0;
   SPIC_CUDA_CHECK(c, cudaMemsetAsync(s.d_nd, 0, sizeof(unsigned long long), c->stream));
-  return ensure_movers(c, s.n_total);
+  tr.mark("free list, new tail");
+  rc = ensure_movers(c, s.n_total);
+  tr.mark("ensure_movers");
+  return rc;
 }
 
 template <class I>
@@ -1034,6 +1068,12 @@ void engine_free_species(Ctx*, Species& s) {
   s.h_tail = nullptr;
   s.tail_pending = false;
   free_soa_local(s.b);
+  s.b_cap = 0;
+  free_soa_local(s.up);
+  s.up_cap = 0;
+  if (s.perm_buf) cudaFree(s.perm_buf);
+  s.perm_buf = nullptr;
+  s.perm_cap = 0;
   if (s.start) cudaFree(s.start);
   if (s.count) cudaFree(s.count);
   if (s.d_nd) cudaFree(s.d_nd);
@@ -1046,6 +1086,65 @@ void engine_free_species(Ctx*, Species& s) {
   s.d_nd = nullptr;
   s.slots = 0;
   s.binned = false;
+}
+
+__global__ void __launch_bounds__(256) k_check_inside_list(Grid g, ParticleSoA p, long n, int* bad) {
+  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x) {
+    const double x = p.x[0][i], y = p.x[1][i], z = p.x[2][i];  // (global coordinates; the slab owns [z0, z0 + n2))
+    if (!(x >= 0.0 && x < g.gn[0] && y >= 0.0 && y < g.gn[1] && z >= (double)g.z0 && z < (double)(g.z0 + g.n[2])))
+      *bad = 1;
+  }
+}
+
+int engine_upload(Ctx* c, Species& s, long n, const double* const* hx, const double* const* hv, int* bad_flag) {
+  PhaseTrace tr("engine_upload", c->stream);
+  // the old store is dead from here on: no live bins, an empty tail; the arrays stay allocated
+  if (s.tail_pending) {
+    cudaEventSynchronize(s.tail_ev);
+    s.tail_pending = false;
+  }
+  if (s.start) cudaFree(s.start);
+  if (s.count) cudaFree(s.count);
+  s.start = nullptr;
+  s.count = nullptr;
+  s.slots = 0;
+  s.binned = false;
+  s.nd = 0;
+  s.n_total = 0;
+  if (s.d_nd) SPIC_CUDA_CHECK(c, cudaMemsetAsync(s.d_nd, 0, sizeof(unsigned long long), c->stream));
+  if (s.up_cap < n || s.up_cap > n + n / 2 + 65536) {
+    free_soa_local(s.up);
+    s.up_cap = 0;
+    const long cap = n + n / 64 + 1;
+    for (int d = 0; d < 3; ++d) {
+      SPIC_CUDA_CHECK(c, cudaMalloc(&s.up.x[d], sizeof(double) * (size_t)cap));
+      SPIC_CUDA_CHECK(c, cudaMalloc(&s.up.v[d], sizeof(double) * (size_t)cap));
+    }
+    s.up_cap = cap;
+  }
+  s.maps_since_upload = 0;
+  tr.mark("reset");
+  for (int d = 0; d < 3; ++d) {
+    SPIC_CUDA_CHECK(c, cudaMemcpyAsync(s.up.x[d], hx[d], sizeof(double) * (size_t)n, cudaMemcpyHostToDevice, c->stream));
+    SPIC_CUDA_CHECK(c, cudaMemcpyAsync(s.up.v[d], hv[d], sizeof(double) * (size_t)n, cudaMemcpyHostToDevice, c->stream));
+  }
+  // every particle must sit inside this rank's slab (and inside the domain): checked on the device
+  SPIC_CUDA_CHECK(c, cudaMemsetAsync(bad_flag, 0, sizeof(int), c->stream));
+  long b = (n + 255) / 256;
+  if (b > (long)c->sm_count * 16) b = (long)c->sm_count * 16;
+  k_check_inside_list<<<(int)b, 256, 0, c->stream>>>(c->g, s.up, n, bad_flag);
+  c->launches++;
+  int bad = 0;
+  SPIC_CUDA_CHECK(c, cudaMemcpyAsync(&bad, bad_flag, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+  SPIC_CUDA_CHECK(c, cudaStreamSynchronize(c->stream));
+  tr.mark("h2d + check");
+  if (bad) {
+    c->err = "particle outside this rank's brick";
+    return SPIC_EINVAL;  // (the species is left empty and unbinned)
+  }
+  int rc = rebin(c, s, n, &s.up);
+  tr.mark("bins");
+  return rc;
 }
 
 void engine_destroy(Ctx* c) {
@@ -1423,6 +1522,13 @@ int engine_maintain(Ctx* c) {
   // previous call once its event has completed -- the decision lags by one step, the step path has no host sync
   // (each one idled the GPU for a host round trip; on a busy host that was 5-20 % of the step).
   for (auto& s : c->sp) {
+    if (s.up_cap && ++s.maps_since_upload >= 2) {  // no re-upload between two maps: not that kind of caller
+      free_soa_local(s.up);
+      s.up_cap = 0;
+      if (s.perm_buf) cudaFree(s.perm_buf);
+      s.perm_buf = nullptr;
+      s.perm_cap = 0;
+    }
     if (!s.binned || !s.d_nd) continue;
     if (!s.h_tail) {
       SPIC_CUDA_CHECK(c, cudaMallocHost(&s.h_tail, sizeof(unsigned long long)));

@@ -50,7 +50,16 @@ struct Species {
   unsigned long long* d2_nd = nullptr;
   long capd2 = 0;
   ParticleSoA b{};
-  long slots = 0;         // allocated slots in b
+  long slots = 0;         // slots of b in use (start[cells])
+  long b_cap = 0;         // doubles allocated per array of b (>= slots + 1)
+  // spic_set_particles keeps its upload list and the permutation across calls (a caller that re-uploads every step
+  // would otherwise pay a cudaFree + cudaMalloc of the whole particle store per call: 0.3-1.1 s at 52 GB, measured);
+  // released by the second spic_map in a row without an upload in between (engine_maintain)
+  ParticleSoA up{};
+  long up_cap = 0;
+  unsigned* perm_buf = nullptr;
+  long perm_cap = 0;
+  int maps_since_upload = 0;
   long* start = nullptr;  // [cells+1]
   int* count = nullptr;   // [cells]
   long n_total = 0;       // particles of this species on this rank at the last rebin
@@ -62,6 +71,18 @@ struct Species {
 };
 
 struct Ctx;
+
+// Phase timer of the upload / download paths, printed to stderr when SPIC_TRACE_PHASES is set in the environment
+// (synchronises the stream at every mark: a diagnostic, never on by default).
+struct PhaseTrace {
+  bool on;
+  cudaStream_t st;
+  const char* what;
+  double t0;
+  static double now();
+  PhaseTrace(const char* w, cudaStream_t s);
+  void mark(const char* phase);
+};
 
 // ---- field kernels (field_kernels.cu) ------------------------------------------
 void launch_fill_boundary(Ctx* c, double* F, bool z_too);

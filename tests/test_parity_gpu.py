@@ -474,6 +474,61 @@ def test_two_species(engine):
     print(engine, errs)
 
 
+def _sorted_cols(P):
+    P = np.stack(P)
+    return P[:, np.lexsort(P[::-1])]
+
+
+@pytest.mark.parametrize("engine", ENGINES)
+def test_reupload_reuses_the_particle_store(engine):
+    """spic_set_particles on a species that already holds particles (what a caller does that keeps its particles
+    on the host and hands them over every step): the bin arrays, the upload list and the permutation of the previous
+    call are reused when they fit (csrc/particles_binned.cu: engine_upload).  Every upload must replace the whole
+    store -- smaller, larger, the same size, after one map and after two (the retained list is released by the second)
+    -- and a step after the n-th upload must equal the step of a context that was loaded once."""
+    n_cell = (12, 10, 8)
+    E, B = util.rng_fields(n_cell, 91, 0.3)
+    sets = {k: util.plasma(n_cell, ppc, 0.1, 91 + k) for k, ppc in enumerate((20, 31, 7, 20))}
+    q, m = -1.0 / 20, 1.0 / 20
+
+    def fresh(parts):
+        t = spic().Simulation(n_cell, interp=0, engine=engine)
+        t.set_field(0, E)
+        t.set_field(1, B)
+        t.add_species(q, m, *parts)
+        return t
+
+    s = fresh(sets[0])
+    for k in (1, 2, 3, 0):  # larger (new arrays), much smaller (arrays far too large), the first size again
+        s.set_particles(0, *sets[k])
+        assert s.num_particles(0) == len(sets[k][0])
+        assert np.array_equal(_sorted_cols(s.get_particles(0)), _sorted_cols(sets[k]))
+    ref = fresh(sets[0])
+    for t in (s, ref):
+        t.set_field(0, E)
+        t.set_field(1, B)
+        t.map(2, 0.5)
+    util.compare_states(util.state_of(ref), util.state_of(s), 1e-12, 1e-12, box=n_cell)  # (deposits are atomic sums)
+    # upload -> map -> upload (buffers kept), then -> map -> map (released) -> upload again
+    for rounds in (1, 2):
+        P = [np.ascontiguousarray(x) for x in s.get_particles(0)]
+        s.set_particles(0, *P)
+        assert np.array_equal(_sorted_cols(s.get_particles(0)), _sorted_cols(P))
+        for _ in range(rounds):
+            s.map(4, 0.5)
+            ref.map(4, 0.5)
+    a, b = util.state_of(s), util.state_of(ref)
+    errs = util.compare_states(b, a, 1e-12, 1e-12, box=n_cell)
+    # a particle outside the box: refused, the species is left empty, and the next upload works
+    badp = [x.copy() for x in sets[2]]
+    badp[0][3] = n_cell[0] + 0.5
+    with pytest.raises(Exception):
+        s.set_particles(0, *badp)
+    s.set_particles(0, *sets[2])
+    assert np.array_equal(_sorted_cols(s.get_particles(0)), _sorted_cols(sets[2]))
+    print(engine, errs)
+
+
 @pytest.mark.parametrize("interp", [0, 1])
 @pytest.mark.parametrize("fuse", [0, 1])
 @pytest.mark.parametrize("periodic", [(0, 1, 1), (1, 0, 0)])
