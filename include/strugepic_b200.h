@@ -118,6 +118,10 @@ int spic_num_particles(spic_ctx* ctx, int species, int64_t* n);
 int spic_num_particles_global(spic_ctx* ctx, int species, int64_t* n);
 int spic_get_particles(spic_ctx* ctx, int species, double* x, double* y, double* z, double* vx,
                        double* vy, double* vz);
+/* Replaces the particles of `species`.  Every particle must lie inside this rank's brick (SPIC_EINVAL otherwise; the
+ * species is then left empty).  The device copy of the list and the bin arrays of the previous call are kept and reused
+ * when the new set fits, so calling this every step costs the transfer and one counting sort; the list is released by
+ * the second spic_map in a row that was not preceded by an upload. */
 int spic_set_particles(spic_ctx* ctx, int species, int64_t n, const double* x, const double* y,
                        const double* z, const double* vx, const double* vy, const double* vz);
 
